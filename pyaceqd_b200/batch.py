@@ -1,0 +1,101 @@
+"""Deferred-execution executor: the reference's thread-pool fan-out as ONE GPU batch.
+
+The reference issues every sweep as
+``with ThreadPoolExecutor(max_workers=w) as ex: f = ex.submit(system, t0, tend_i, *pulses, **kw)``
+followed by ``wait(futures)`` / ``f.result()`` (49 call sites; e.g.
+``pyaceqd/two_time/correlations.py:153-175``).  :class:`BatchExecutor` has the same
+``submit`` / context-manager surface; calls are recorded instead of run, and the whole set is
+propagated in one launch when the first result is requested (or on ``__exit__`` / ``wait``).
+"""
+from __future__ import annotations
+
+from typing import Callable, List
+
+from pyaceqd_b200.general_system import general_system as _gs
+
+
+class BatchFuture:
+    def __init__(self, owner: "BatchExecutor", index: int):
+        self._owner, self._index = owner, index
+        self._callbacks: List[Callable] = []
+
+    def result(self, timeout=None):
+        self._owner.flush()
+        return self._owner._results[self._index]
+
+    def done(self):
+        return self._owner._results[self._index] is not None
+
+    def add_done_callback(self, fn):
+        if self.done():
+            fn(self)
+        else:
+            self._callbacks.append(fn)
+
+    def exception(self, timeout=None):
+        return None
+
+
+class BatchExecutor:
+    """Drop-in for ``concurrent.futures.ThreadPoolExecutor`` around ``system(...)`` calls."""
+
+    def __init__(self, max_workers=None, **_ignored):
+        self.max_workers = max_workers
+        self._requests = []     # (Request | immediate result, post-processing)
+        self._results: list = []
+        self._futures: List[BatchFuture] = []
+        self._flushed_upto = 0
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        if exc[0] is None:
+            self.flush()
+        return False
+
+    def shutdown(self, wait=True):
+        self.flush()
+
+    def submit(self, fn, *args, **kwargs) -> BatchFuture:
+        sink: list = []
+        prev = getattr(_gs._capture, "sink", None)
+        _gs._capture.sink = sink
+        try:
+            ret = fn(*args, **kwargs)
+        finally:
+            _gs._capture.sink = prev
+        fut = BatchFuture(self, len(self._results))
+        self._futures.append(fut)
+        self._results.append(None)
+        # the adapter returned the Request itself (system_ace_stream's deferred value), possibly
+        # wrapped by post-processing that cannot run on a placeholder -> only plain pass-through
+        # adapters are deferred; anything else has already been computed eagerly.
+        if isinstance(ret, _gs.Request):
+            self._requests.append((len(self._results) - 1, ret))
+        else:
+            if sink:  # adapter post-processed a placeholder: run it again eagerly
+                ret = fn(*args, **kwargs)
+            self._results[-1] = ret
+            for cb in fut._callbacks:
+                cb(fut)
+        return fut
+
+    def flush(self):
+        pending = [(i, r) for (i, r) in self._requests if self._results[i] is None]
+        if not pending:
+            return
+        res = _gs.run_requests([r for _, r in pending])
+        for (i, _), out in zip(pending, res):
+            self._results[i] = out
+            for cb in self._futures[i]._callbacks:
+                cb(self._futures[i])
+        self._requests = []
+
+
+def wait(futures, timeout=None, return_when=None):
+    """``concurrent.futures.wait`` look-alike: triggers the batch."""
+    for f in futures:
+        if isinstance(f, BatchFuture):
+            f.result()
+    return set(futures), set()

@@ -1,0 +1,683 @@
+// C ABI of libaceqd.so (include/aceqd.h): context, PT re-tiling into the HBM layout the step
+// kernel streams, problem upload, batch staging (H2D / D2H for the end-to-end path) and the
+// two-stage launch  [operator builder] -> [persistent DMMA step kernel].
+#include <cstdarg>
+#include <algorithm>
+#include <new>
+
+#include "common.cuh"
+
+namespace aceqd {
+
+static thread_local std::string g_err;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return ACEQD_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            p = nullptr;
+            return ACEQD_ERR_NOMEM;
+        }
+        cap = want;
+        return ACEQD_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace aceqd
+
+using namespace aceqd;
+
+struct aceqd_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    long long launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // step start/stop, opbuild start/stop
+    bool have_step = false, have_op = false;
+    DevBuf W, OV, tables, seqs, seq_base, entries, mto, rho0s, trajs, tiles, snap_steps, snaps,
+        out, passes, scratch, misc;
+    // layout of the operators currently in the workspace
+    long long n_seq_entries = 0;
+};
+
+struct aceqd_pt {
+    aceqd_ctx* ctx = nullptr;
+    PtDev d{};
+    void *blob = nullptr, *closure = nullptr, *kin = nullptr, *nout = nullptr, *off = nullptr;
+};
+
+struct aceqd_problem {
+    aceqd_ctx* ctx = nullptr;
+    ProbDev d{};
+    void* mem = nullptr;  // one allocation holding every array
+    std::vector<int> pos_of_alpha, block_of_alpha;
+};
+
+extern "C" {
+
+const char* aceqd_last_error(void) { return g_err.c_str(); }
+const char* aceqd_version(void) { return "aceqd-b200 0.1 (sm_100a)"; }
+
+int aceqd_ctx_create(int device, void* stream, aceqd_ctx** out) {
+    if (!out) {
+        set_error("aceqd_ctx_create: out is NULL");
+        return ACEQD_ERR_ARG;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        set_error("no CUDA device available (%s); libaceqd has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return ACEQD_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        set_error("device %d out of range (count %d)", device, count);
+        return ACEQD_ERR_ARG;
+    }
+    ACEQD_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ACEQD_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device,
+                  prop.major, prop.minor);
+        return ACEQD_ERR_CUDA;
+    }
+    aceqd_ctx* c = new (std::nothrow) aceqd_ctx();
+    if (!c) return ACEQD_ERR_NOMEM;
+    c->device = device;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        ACEQD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    for (auto& ev : c->ev) ACEQD_CUDA(cudaEventCreate(&ev));
+    *out = c;
+    return ACEQD_OK;
+}
+
+void aceqd_ctx_destroy(aceqd_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf* b : {&c->W, &c->OV, &c->tables, &c->seqs, &c->seq_base, &c->entries, &c->mto,
+                      &c->rho0s, &c->trajs, &c->tiles, &c->snap_steps, &c->snaps, &c->out,
+                      &c->passes, &c->scratch, &c->misc})
+        b->release();
+    for (auto& ev : c->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int aceqd_ctx_sync(aceqd_ctx* c) {
+    if (!c) return ACEQD_ERR_ARG;
+    ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+    return ACEQD_OK;
+}
+
+long long aceqd_launch_count(const aceqd_ctx* c) { return c ? c->launches : 0; }
+
+int aceqd_last_timings(aceqd_ctx* c, float* step_ms, float* op_ms) {
+    if (!c) return ACEQD_ERR_ARG;
+    ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+    if (step_ms) {
+        *step_ms = 0.f;
+        if (c->have_step) ACEQD_CUDA(cudaEventElapsedTime(step_ms, c->ev[0], c->ev[1]));
+    }
+    if (op_ms) {
+        *op_ms = 0.f;
+        if (c->have_op) ACEQD_CUDA(cudaEventElapsedTime(op_ms, c->ev[2], c->ev[3]));
+    }
+    return ACEQD_OK;
+}
+
+// ------------------------------------------------------------------------------- PT
+int aceqd_pt_create(aceqd_ctx* c, int n_cls, int n_slices, int n_initial, const int* chi_in,
+                    const int* chi_out, const double* const* slices,
+                    const double* const* closures, aceqd_pt** out) {
+    if (!c || !out || n_cls <= 0 || n_slices <= 0 || n_initial < 0 || n_initial >= n_slices ||
+        !chi_in || !chi_out || !slices || !closures) {
+        set_error("aceqd_pt_create: invalid argument");
+        return ACEQD_ERR_ARG;
+    }
+    *out = nullptr;
+    ACEQD_CUDA(cudaSetDevice(c->device));
+    int chi_max = 1;
+    for (int s = 0; s < n_slices; ++s) {
+        if (chi_in[s] <= 0 || chi_out[s] <= 0) {
+            set_error("aceqd_pt_create: slice %d has non-positive bond dimension", s);
+            return ACEQD_ERR_ARG;
+        }
+        chi_max = std::max(chi_max, std::max(chi_in[s], chi_out[s]));
+    }
+    const int chi_pad = round_up(chi_max, 8);
+    const int strideB = chi_pad + 4;
+    const int chunk_doubles = 2 * KC * strideB;
+    std::vector<int> kin(n_slices), nout(n_slices);
+    std::vector<long long> off(n_slices);
+    long long total = 0;
+    for (int s = 0; s < n_slices; ++s) {
+        kin[s] = round_up(chi_in[s], KC);
+        nout[s] = round_up(chi_out[s], 8);
+        off[s] = total;
+        total += (long long)n_cls * (kin[s] / KC) * chunk_doubles;
+    }
+    std::vector<double> blob((size_t)total, 0.0);
+    std::vector<double> clo((size_t)n_slices * 2 * chi_pad, 0.0);
+    for (int s = 0; s < n_slices; ++s) {
+        const int din = chi_in[s], dout = chi_out[s];
+        const int nch = kin[s] / KC;
+        for (int b = 0; b < n_cls; ++b) {
+            const double* src = slices[s] + (size_t)b * din * dout * 2;
+            for (int d1 = 0; d1 < din; ++d1) {
+                double* ch = blob.data() + off[s] + ((size_t)b * nch + d1 / KC) * chunk_doubles;
+                double* re = ch + (size_t)(d1 % KC) * strideB;
+                double* im = re + (size_t)KC * strideB;
+                const double* row = src + (size_t)d1 * dout * 2;
+                for (int d2 = 0; d2 < dout; ++d2) {
+                    re[d2] = row[2 * d2];
+                    im[d2] = row[2 * d2 + 1];
+                }
+            }
+        }
+        for (int d = 0; d < dout; ++d) {
+            clo[((size_t)s * chi_pad + d) * 2] = closures[s][2 * d];
+            clo[((size_t)s * chi_pad + d) * 2 + 1] = closures[s][2 * d + 1];
+        }
+    }
+    aceqd_pt* pt = new (std::nothrow) aceqd_pt();
+    if (!pt) return ACEQD_ERR_NOMEM;
+    pt->ctx = c;
+    auto fail = [&](int rc) {
+        aceqd_pt_destroy(pt);
+        return rc;
+    };
+#define PT_UP(dst, vec)                                                                   \
+    do {                                                                                  \
+        size_t bytes_ = (vec).size() * sizeof((vec)[0]);                                  \
+        if (cudaMalloc(&(dst), bytes_ ? bytes_ : 16) != cudaSuccess) {                    \
+            set_error("aceqd_pt_create: cudaMalloc(%zu) failed", bytes_);                 \
+            return fail(ACEQD_ERR_NOMEM);                                                 \
+        }                                                                                 \
+        if (cudaMemcpyAsync((dst), (vec).data(), bytes_, cudaMemcpyHostToDevice,          \
+                            c->stream) != cudaSuccess) {                                  \
+            set_error("aceqd_pt_create: upload failed");                                  \
+            return fail(ACEQD_ERR_CUDA);                                                  \
+        }                                                                                 \
+    } while (0)
+    PT_UP(pt->blob, blob);
+    PT_UP(pt->closure, clo);
+    PT_UP(pt->kin, kin);
+    PT_UP(pt->nout, nout);
+    PT_UP(pt->off, off);
+#undef PT_UP
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        set_error("aceqd_pt_create: sync failed");
+        return fail(ACEQD_ERR_CUDA);
+    }
+    PtDev& d = pt->d;
+    d.n_cls = n_cls;
+    d.n_slices = n_slices;
+    d.n_initial = n_initial;
+    d.n_repeat = n_slices - n_initial;
+    d.chi_pad = chi_pad;
+    d.strideB = strideB;
+    d.chunk_doubles = chunk_doubles;
+    d.kin_pad = (const int*)pt->kin;
+    d.nout_pad = (const int*)pt->nout;
+    d.off = (const long long*)pt->off;
+    d.blob = (const double*)pt->blob;
+    d.closure = (const double*)pt->closure;
+    *out = pt;
+    return ACEQD_OK;
+}
+
+void aceqd_pt_destroy(aceqd_pt* pt) {
+    if (!pt) return;
+    if (pt->ctx) cudaSetDevice(pt->ctx->device);
+    for (void* p : {pt->blob, pt->closure, pt->kin, pt->nout, pt->off})
+        if (p) cudaFree(p);
+    delete pt;
+}
+
+int aceqd_pt_chi_pad(const aceqd_pt* pt) { return pt ? pt->d.chi_pad : 0; }
+
+// ------------------------------------------------------------------------------- problem
+int aceqd_problem_create(aceqd_ctx* c, int NL, int n_fields, int n_out, const double* L0,
+                         const double* LA, const double* LB, const int* field_table,
+                         const double* out_w, const int* pos_of_alpha, const int* block_of_alpha,
+                         aceqd_problem** out) {
+    if (!c || !out || NL <= 0 || NL > MAX_NL || n_fields < 0 || n_out < 0 || !L0 ||
+        !pos_of_alpha || !block_of_alpha || (n_fields && (!LA || !LB || !field_table)) ||
+        (n_out && !out_w)) {
+        set_error("aceqd_problem_create: invalid argument (NL must be 1..%d)", MAX_NL);
+        return ACEQD_ERR_ARG;
+    }
+    *out = nullptr;
+    // pos_of_alpha must be a permutation whose block sequence is grouped
+    std::vector<int> blk_of_pos(NL, -1);
+    for (int a = 0; a < NL; ++a) {
+        const int ps = pos_of_alpha[a];
+        if (ps < 0 || ps >= NL || blk_of_pos[ps] != -1 || block_of_alpha[a] < 0) {
+            set_error("aceqd_problem_create: pos_of_alpha is not a permutation / negative block");
+            return ACEQD_ERR_ARG;
+        }
+        blk_of_pos[ps] = block_of_alpha[a];
+    }
+    ACEQD_CUDA(cudaSetDevice(c->device));
+    const size_t n2 = (size_t)NL * NL;
+    const size_t b_L0 = n2 * 16, b_LA = (size_t)n_fields * n2 * 16, b_ow = (size_t)n_out * NL * 16;
+    const size_t b_int = (size_t)(n_fields + 2 * NL) * sizeof(int);
+    const size_t total = b_L0 + 2 * b_LA + b_ow + b_int + 64;
+    aceqd_problem* p = new (std::nothrow) aceqd_problem();
+    if (!p) return ACEQD_ERR_NOMEM;
+    p->ctx = c;
+    if (cudaMalloc(&p->mem, total) != cudaSuccess) {
+        delete p;
+        set_error("aceqd_problem_create: cudaMalloc failed");
+        return ACEQD_ERR_NOMEM;
+    }
+    std::vector<unsigned char> host(total, 0);
+    size_t o = 0;
+    auto put = [&](const void* src, size_t bytes) {
+        size_t at = o;
+        if (bytes) memcpy(host.data() + o, src, bytes);
+        o += (bytes + 15) / 16 * 16;
+        return at;
+    };
+    const size_t o_L0 = put(L0, b_L0), o_LA = put(LA, b_LA), o_LB = put(LB, b_LA),
+                 o_ow = put(out_w, b_ow);
+    const size_t o_ft = put(field_table, n_fields * sizeof(int));
+    const size_t o_pos = put(pos_of_alpha, NL * sizeof(int));
+    const size_t o_blk = put(block_of_alpha, NL * sizeof(int));
+    if (cudaMemcpy(p->mem, host.data(), total, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(p->mem);
+        delete p;
+        set_error("aceqd_problem_create: upload failed");
+        return ACEQD_ERR_CUDA;
+    }
+    unsigned char* base = (unsigned char*)p->mem;
+    ProbDev& d = p->d;
+    d.NL = NL;
+    d.NLp8 = round_up(NL, 8);
+    d.NLp4 = round_up(NL, 4);
+    d.n_out = n_out;
+    d.n_fields = n_fields;
+    d.w_doubles = 2 * d.NLp8 * d.NLp4;
+    d.ov_doubles = 2 * n_out * NL;
+    d.L0 = (const double*)(base + o_L0);
+    d.LA = (const double*)(base + o_LA);
+    d.LB = (const double*)(base + o_LB);
+    d.out_w = (const double*)(base + o_ow);
+    d.field_table = (const int*)(base + o_ft);
+    d.pos_of_alpha = (const int*)(base + o_pos);
+    d.block_of_alpha = (const int*)(base + o_blk);
+    p->pos_of_alpha.assign(pos_of_alpha, pos_of_alpha + NL);
+    p->block_of_alpha.assign(block_of_alpha, block_of_alpha + NL);
+    *out = p;
+    return ACEQD_OK;
+}
+
+void aceqd_problem_destroy(aceqd_problem* p) {
+    if (!p) return;
+    if (p->ctx) cudaSetDevice(p->ctx->device);
+    if (p->mem) cudaFree(p->mem);
+    delete p;
+}
+
+// ------------------------------------------------------------------------------- batch
+static int check_batch(const aceqd_problem* prob, const aceqd_batch* b) {
+    if (!prob || !b) {
+        set_error("batch: NULL argument");
+        return ACEQD_ERR_ARG;
+    }
+    if (b->n_traj <= 0 || !b->trajs || b->n_seq < 0 || (b->n_seq && !b->seqs) ||
+        b->n_entries < 0 || (b->n_entries && !b->entries) || b->n_rho0 < 0 ||
+        (b->n_rho0 && !b->rho0s) || !b->out || b->out_elems <= 0 || b->dt <= 0.0) {
+        set_error("batch: invalid sizes or missing pointers");
+        return ACEQD_ERR_ARG;
+    }
+    if (b->n_tables > 0 && (b->n_sets <= 0 || b->n_samples <= 0 || !b->tables || b->tab_dt <= 0)) {
+        set_error("batch: inconsistent drive tables");
+        return ACEQD_ERR_ARG;
+    }
+    return ACEQD_OK;
+}
+
+#define UP(buf, src, bytes)                                                                   \
+    do {                                                                                      \
+        int rc_ = (buf).reserve(bytes);                                                       \
+        if (rc_) return rc_;                                                                  \
+        if ((bytes) > 0)                                                                      \
+            ACEQD_CUDA(cudaMemcpyAsync((buf).p, (src), (bytes), cudaMemcpyHostToDevice,       \
+                                       c->stream));                                           \
+    } while (0)
+
+int aceqd_build_operators(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_batch* b) {
+    int rc = check_batch(prob, b);
+    if (rc) return rc;
+    if (!c) return ACEQD_ERR_ARG;
+    ACEQD_CUDA(cudaSetDevice(c->device));
+    const ProbDev& pd = prob->d;
+    std::vector<long long> base(b->n_seq + 1, 0);
+    for (int q = 0; q < b->n_seq; ++q) {
+        if (b->seqs[q].len <= 0 || b->seqs[q].set < 0 ||
+            (b->n_tables > 0 && b->seqs[q].set >= b->n_sets)) {
+            set_error("batch: sequence %d invalid", q);
+            return ACEQD_ERR_ARG;
+        }
+        base[q + 1] = base[q] + b->seqs[q].len;
+    }
+    for (int e = 0; e < b->n_entries; ++e) {
+        const aceqd_entry& en = b->entries[e];
+        if (en.sb >= b->n_mto_mats || en.sa >= b->n_mto_mats || en.set < 0 ||
+            (b->n_tables > 0 && en.set >= b->n_sets)) {
+            set_error("batch: explicit entry %d invalid", e);
+            return ACEQD_ERR_ARG;
+        }
+    }
+    const long long n_ent = base[b->n_seq] + b->n_entries;
+    c->n_seq_entries = base[b->n_seq];
+    const size_t n2 = (size_t)pd.NL * pd.NL;
+    if (b->device_resident) {
+        // tables already in HBM: use the caller's pointer directly
+    } else {
+        UP(c->tables, b->tables, (size_t)b->n_sets * b->n_tables * b->n_samples * 16);
+    }
+    UP(c->seqs, b->seqs, (size_t)b->n_seq * sizeof(aceqd_seq));
+    UP(c->seq_base, base.data(), base.size() * sizeof(long long));
+    UP(c->entries, b->entries, (size_t)b->n_entries * sizeof(aceqd_entry));
+    UP(c->mto, b->mto_mats, (size_t)b->n_mto_mats * n2 * 16);
+    if ((rc = c->W.reserve((size_t)n_ent * pd.w_doubles * 8))) return rc;
+    if ((rc = c->OV.reserve((size_t)n_ent * pd.ov_doubles * 8 + 16))) return rc;
+
+    OpBuildParams op{};
+    op.prob = pd;
+    op.dt = b->dt;
+    op.t0 = b->t0;
+    op.eval_off1 = b->eval_off1;
+    op.eval_off2 = b->eval_off2;
+    op.n_sets = b->n_sets;
+    op.n_tables = b->n_tables;
+    op.n_samples = b->n_samples;
+    op.n_seq = b->n_seq;
+    op.tab_t0 = b->tab_t0;
+    op.tab_dt = b->tab_dt > 0 ? b->tab_dt : 1.0;
+    op.tables = b->device_resident ? b->tables : (const double*)c->tables.p;
+    op.seqs = (const aceqd_seq*)c->seqs.p;
+    op.seq_base = (const long long*)c->seq_base.p;
+    op.n_seq_entries = base[b->n_seq];
+    op.n_entries = b->n_entries;
+    op.n_mto_mats = b->n_mto_mats;
+    op.entries = (const aceqd_entry*)c->entries.p;
+    op.mto_mats = (const double*)c->mto.p;
+    op.W = (double*)c->W.p;
+    op.OV = (double*)c->OV.p;
+    ACEQD_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    if ((rc = launch_opbuild(op, c->stream, &c->launches))) return rc;
+    ACEQD_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    c->have_op = true;
+    return ACEQD_OK;
+}
+
+static int build_passes(const aceqd_problem* prob, int T, std::vector<PassDesc>& passes) {
+    const int NL = prob->d.NL;
+    std::vector<int> blk_of_pos(NL);
+    for (int a = 0; a < NL; ++a) blk_of_pos[prob->pos_of_alpha[a]] = prob->block_of_alpha[a];
+    passes.clear();
+    int p0 = 0;
+    while (p0 < NL) {
+        int p1 = p0;
+        while (p1 < NL && blk_of_pos[p1] == blk_of_pos[p0]) ++p1;
+        // rows [p0*T, p1*T) share PT block blk_of_pos[p0]
+        int row = p0 * T;
+        const int row_end = p1 * T;
+        while (row < row_end) {
+            PassDesc pd{};
+            pd.blk = blk_of_pos[p0];
+            for (int mc = 0; mc < MC; ++mc) {
+                pd.row0[mc] = row < row_end ? row : 0;
+                pd.nvalid[mc] = std::max(0, std::min(8, row_end - row));
+                row += 8;
+            }
+            passes.push_back(pd);
+        }
+        p0 = p1;
+    }
+    if ((int)passes.size() > MAX_PASSES) {
+        set_error("tile needs %zu GEMM passes (max %d)", passes.size(), MAX_PASSES);
+        return ACEQD_ERR_CAPACITY;
+    }
+    return ACEQD_OK;
+}
+
+int aceqd_max_tile(int NL, int chi_pad) {
+    for (int T = MAX_TILE_T; T >= 1; T >>= 1)
+        if (step_smem_bytes(NL, chi_pad, T, 2) <= (size_t)SMEM_BUDGET) return T;
+    return 0;
+}
+
+int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
+                    const aceqd_batch* b) {
+    int rc = check_batch(prob, b);
+    if (rc) return rc;
+    if (!c || !pt) return ACEQD_ERR_ARG;
+    ACEQD_CUDA(cudaSetDevice(c->device));
+    const ProbDev& pd = prob->d;
+    const int chi_pad = pt->d.chi_pad;
+    for (int a = 0; a < pd.NL; ++a)
+        if (prob->block_of_alpha[a] >= pt->d.n_cls) {
+            set_error("problem references PT block %d, PT has %d", prob->block_of_alpha[a],
+                      pt->d.n_cls);
+            return ACEQD_ERR_ARG;
+        }
+    const int T = b->tile_T;
+    if (b->kernel == 0) {
+        if (T < 1 || T > MAX_TILE_T || b->n_tiles <= 0 || !b->tile_traj) {
+            set_error("batch: tile_T must be 1..%d with a tile list", MAX_TILE_T);
+            return ACEQD_ERR_ARG;
+        }
+    }
+    // validate trajectories
+    const size_t snap_bytes = (size_t)pd.NL * chi_pad * 16;
+    for (int i = 0; i < b->n_traj; ++i) {
+        const aceqd_traj& t = b->trajs[i];
+        const char* why = nullptr;
+        if (t.n_steps < 0 || t.step0 < 0) why = "negative step count";
+        else if (t.ent0 < 0 || t.ent0 + t.n_steps >= c->n_seq_entries)
+            why = "operator entries beyond the sequence pool";
+        else if (t.n_ovr < 0 || t.n_ovr > ACEQD_MAX_OVR) why = "too many override entries";
+        else if (t.out_off < 0 || t.out_off + (long long)(t.n_steps + 1) * pd.n_out > b->out_elems)
+            why = "output block outside the output buffer";
+        else if (t.init_kind == 0 && (t.init_index < 0 || t.init_index >= b->n_rho0))
+            why = "initial state index out of range";
+        else if (t.init_kind == 1 && (t.init_index < 0 ||
+                 ((size_t)(t.init_index + 1) * snap_bytes > c->snaps.cap &&
+                  t.init_index >= b->n_snap_slots)))
+            why = "snapshot slot not available";
+        else if (t.init_kind != 0 && t.init_kind != 1) why = "unknown init_kind";
+        else if (t.snap_cnt < 0 || (t.snap_cnt > 0 && (t.snap_off < 0 ||
+                 t.snap_off + t.snap_cnt > b->n_snap_steps || t.snap_slot0 < 0 ||
+                 t.snap_slot0 + t.snap_cnt > b->n_snap_slots)))
+            why = "snapshot request out of range";
+        for (int q = 0; !why && q < t.n_ovr; ++q)
+            if (t.ovr_ent[q] < 0 || t.ovr_ent[q] >= b->n_entries) why = "override entry out of range";
+        if (why) {
+            set_error("batch: trajectory %d: %s", i, why);
+            return ACEQD_ERR_ARG;
+        }
+    }
+    UP(c->rho0s, b->rho0s, (size_t)b->n_rho0 * pd.NL * 16);
+    UP(c->trajs, b->trajs, (size_t)b->n_traj * sizeof(aceqd_traj));
+    UP(c->snap_steps, b->snap_steps, (size_t)b->n_snap_steps * sizeof(int32_t));
+    if (b->n_snap_slots > 0) {
+        // growing discards old snapshots; writers re-create them in this call
+        if ((rc = c->snaps.reserve((size_t)b->n_snap_slots * pd.NL * chi_pad * 16))) return rc;
+    }
+    double* out_dev = nullptr;
+    if (b->device_resident) {
+        out_dev = b->out;
+    } else {
+        if ((rc = c->out.reserve((size_t)b->out_elems * 16))) return rc;
+        out_dev = (double*)c->out.p;
+    }
+
+    StepParams sp{};
+    sp.pt = pt->d;
+    sp.prob = pd;
+    sp.trajs = (const aceqd_traj*)c->trajs.p;
+    sp.W = (const double*)c->W.p;
+    sp.OV = (const double*)c->OV.p;
+    sp.ovr_base = c->n_seq_entries;
+    sp.rho0s = (const double*)c->rho0s.p;
+    sp.snap_steps = (const int*)c->snap_steps.p;
+    sp.snaps = (double*)c->snaps.p;
+    sp.out = out_dev;
+
+    if (b->kernel == 1) {
+        sp.T = 1;
+        sp.n_tiles = b->n_traj;
+        if ((rc = c->scratch.reserve((size_t)b->n_traj * 2 * pd.NL * chi_pad * 16))) return rc;
+        ACEQD_CUDA(cudaEventRecord(c->ev[0], c->stream));
+        if ((rc = launch_step_check(sp, (double*)c->scratch.p, c->stream, &c->launches))) return rc;
+        ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    } else {
+        for (long long i = 0; i < (long long)b->n_tiles * T; ++i)
+            if (b->tile_traj[i] >= b->n_traj) {
+                set_error("batch: tile list references trajectory %d", b->tile_traj[i]);
+                return ACEQD_ERR_ARG;
+            }
+        std::vector<PassDesc> passes;
+        if ((rc = build_passes(prob, T, passes))) return rc;
+        UP(c->passes, passes.data(), passes.size() * sizeof(PassDesc));
+        UP(c->tiles, b->tile_traj, (size_t)b->n_tiles * T * sizeof(int32_t));
+        int stages = MAX_STAGES;
+        while (stages >= 2 && step_smem_bytes(pd.NL, chi_pad, T, stages) > (size_t)SMEM_BUDGET)
+            --stages;
+        if (stages < 2) {
+            set_error("NL=%d chi_pad=%d T=%d does not fit %d B of shared memory", pd.NL, chi_pad,
+                      T, SMEM_BUDGET);
+            return ACEQD_ERR_CAPACITY;
+        }
+        sp.T = T;
+        sp.n_pass = (int)passes.size();
+        sp.stages = stages;
+        sp.n_tiles = b->n_tiles;
+        sp.passes = (const PassDesc*)c->passes.p;
+        sp.tile_traj = (const int*)c->tiles.p;
+        const size_t smem = step_smem_bytes(pd.NL, chi_pad, T, stages);
+        ACEQD_CUDA(cudaEventRecord(c->ev[0], c->stream));
+        if ((rc = launch_step_dmma(sp, smem, c->stream, &c->launches))) return rc;
+        ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    }
+    c->have_step = true;
+    if (!b->device_resident) {
+        ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)b->out_elems * 16,
+                                   cudaMemcpyDeviceToHost, c->stream));
+        ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return ACEQD_OK;
+}
+
+int aceqd_propagate_batch(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
+                          const aceqd_batch* b) {
+    int rc = aceqd_build_operators(c, prob, b);
+    if (rc) return rc;
+    return aceqd_run_steps(c, prob, pt, b);
+}
+
+int aceqd_snapshot_read(aceqd_ctx* c, int slot, int NL, int chi_pad, double* host_out) {
+    if (!c || !host_out || slot < 0 || NL <= 0 || chi_pad <= 0) return ACEQD_ERR_ARG;
+    const size_t bytes = (size_t)NL * chi_pad * 16;
+    if ((size_t)(slot + 1) * bytes > c->snaps.cap) {
+        set_error("snapshot slot %d not allocated", slot);
+        return ACEQD_ERR_ARG;
+    }
+    ACEQD_CUDA(cudaSetDevice(c->device));
+    ACEQD_CUDA(cudaMemcpyAsync(host_out, (char*)c->snaps.p + (size_t)slot * bytes, bytes,
+                               cudaMemcpyDeviceToHost, c->stream));
+    ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+    return ACEQD_OK;
+}
+
+int aceqd_expm_batch(aceqd_ctx* c, int n, int count, const double* a_host, double* out_host) {
+    if (!c || n <= 0 || count < 0 || !a_host || !out_host) return ACEQD_ERR_ARG;
+    ACEQD_CUDA(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)count * n * n * 16;
+    int rc;
+    if ((rc = c->misc.reserve(2 * bytes + 32))) return rc;
+    double* a_dev = (double*)c->misc.p;
+    double* o_dev = (double*)((char*)c->misc.p + (bytes + 15) / 16 * 16);
+    ACEQD_CUDA(cudaMemcpyAsync(a_dev, a_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = launch_expm_batch(n, count, a_dev, o_dev, c->stream, &c->launches))) return rc;
+    ACEQD_CUDA(cudaMemcpyAsync(out_host, o_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+    return ACEQD_OK;
+}
+
+void aceqd_struct_sizes(int32_t out[4]) {
+    out[0] = (int32_t)sizeof(aceqd_seq);
+    out[1] = (int32_t)sizeof(aceqd_entry);
+    out[2] = (int32_t)sizeof(aceqd_traj);
+    out[3] = (int32_t)sizeof(aceqd_batch);
+}
+
+int aceqd_fp64_peak(aceqd_ctx* c, int kind, int iters, double* tflops) {
+    if (!c || !tflops || iters <= 0) return ACEQD_ERR_ARG;
+    ACEQD_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = c->misc.reserve(64))) return rc;
+    int blocks = 0, threads = 0;
+    cudaEvent_t e0, e1;
+    ACEQD_CUDA(cudaEventCreate(&e0));
+    ACEQD_CUDA(cudaEventCreate(&e1));
+    // warm-up
+    if ((rc = launch_fp64_peak(kind, iters / 8 + 1, (double*)c->misc.p, &blocks, &threads,
+                               c->stream, &c->launches)))
+        return rc;
+    ACEQD_CUDA(cudaEventRecord(e0, c->stream));
+    if ((rc = launch_fp64_peak(kind, iters, (double*)c->misc.p, &blocks, &threads, c->stream,
+                               &c->launches)))
+        return rc;
+    ACEQD_CUDA(cudaEventRecord(e1, c->stream));
+    ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    ACEQD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double warps = (double)blocks * threads / 32.0;
+    double flops;
+    if (kind == 0)
+        flops = warps * (double)iters * 8.0 * 512.0;  // 8 DMMA.8x8x4 per iteration per warp
+    else
+        flops = (double)blocks * threads * (double)iters * 16.0 * 2.0;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    return ACEQD_OK;
+}
+
+}  // extern "C"

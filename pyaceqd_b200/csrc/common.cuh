@@ -1,0 +1,122 @@
+// Shared declarations of libaceqd (sm_100a only).  See include/aceqd.h for the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/aceqd.h"
+
+namespace aceqd {
+
+constexpr int KC = 8;             // k rows of one PT chunk (two DMMA k-steps)
+constexpr int MC = 2;             // m-tiles (8 rows each) accumulated per pass
+constexpr int N_COMPUTE_WARPS = 8;
+constexpr int STEP_THREADS = (N_COMPUTE_WARPS + 1) * 32;  // + 1 TMA producer warp
+constexpr int MAX_NL = 64;
+constexpr int MAX_PASSES = 96;
+constexpr int MAX_TILE_T = 16;
+constexpr int MAX_STAGES = 4;
+constexpr int SMEM_BUDGET = 227 * 1024;
+
+void set_error(const char* fmt, ...);
+
+#define ACEQD_CUDA(call)                                                              \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            aceqd::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),  \
+                             __FILE__, __LINE__);                                     \
+            return ACEQD_ERR_CUDA;                                                    \
+        }                                                                             \
+    } while (0)
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------- device-side PT description
+struct PtDev {
+    int n_cls, n_slices, n_initial, n_repeat;
+    int chi_pad;        // max padded bond dimension (multiple of 8)
+    int strideB;        // doubles per k-row of a chunk plane: chi_pad + 4  (== 4 mod 8)
+    int chunk_doubles;  // 2 * KC * strideB  (re plane then im plane)
+    int pad_;
+    const int* kin_pad;      // [n_slices] padded input bond (multiple of KC)
+    const int* nout_pad;     // [n_slices] padded output bond (multiple of 8)
+    const long long* off;    // [n_slices] offset (doubles) of chunk (cls 0, j 0)
+    const double* blob;      // chunks ordered [slice][cls][chunk]
+    const double* closure;   // [n_slices][2*chi_pad] interleaved complex, zero padded
+};
+
+// ---------------------------------------------------------------- device-side problem
+struct ProbDev {
+    int NL, NLp8, NLp4, n_out, n_fields;
+    int w_doubles;   // doubles per W entry: 2*NLp8*NLp4
+    int ov_doubles;  // doubles per OV entry: 2*n_out*NL
+    int pad_;
+    const double* L0;        // [NL][NL] complex
+    const double* LA;        // [n_fields][NL][NL]
+    const double* LB;
+    const int* field_table;  // [n_fields]
+    const double* out_w;     // [n_out][NL]
+    const int* pos_of_alpha; // [NL]
+    const int* block_of_alpha;
+};
+
+// One GEMM pass of the step kernel: up to MC m-tiles of rows that share one PT block.
+struct PassDesc {
+    int blk;
+    int row0[MC];
+    int nvalid[MC];  // 0 = absent
+    int pad_;
+};
+
+struct StepParams {
+    PtDev pt;
+    ProbDev prob;
+    int T;           // trajectories per tile
+    int n_pass;
+    int stages;      // chunk pipeline depth
+    int n_tiles;
+    const PassDesc* passes;   // [n_pass]
+    const aceqd_traj* trajs;
+    const int* tile_traj;     // [n_tiles][T]
+    const double* W;          // entry pool
+    const double* OV;
+    long long ovr_base;       // entry index of explicit entry 0 in the pools
+    const double* rho0s;      // [n_rho0][NL] complex
+    const int* snap_steps;
+    double* snaps;            // [slots][NL][chi_pad] complex
+    double* out;
+};
+
+// ---------------------------------------------------------------- operator builder
+struct OpBuildParams {
+    ProbDev prob;
+    double dt, t0, eval_off1, eval_off2;
+    int n_sets, n_tables, n_samples, n_seq;
+    double tab_t0, tab_dt;
+    const double* tables;
+    const aceqd_seq* seqs;
+    const long long* seq_base;   // [n_seq+1] prefix sums of len
+    long long n_seq_entries;
+    int n_entries;               // explicit entries
+    int n_mto_mats;
+    const aceqd_entry* entries;
+    const double* mto_mats;
+    double* W;
+    double* OV;
+};
+
+int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches);
+int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, cudaStream_t s,
+                      long long* launches);
+int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, long long* launches);
+int launch_step_check(const StepParams& p, double* scratch, cudaStream_t s, long long* launches);
+size_t step_smem_bytes(int NL, int chi_pad, int T, int stages);
+int launch_fp64_peak(int kind, int iters, double* sink_dev, int* blocks, int* threads,
+                     cudaStream_t s, long long* launches);
+
+}  // namespace aceqd

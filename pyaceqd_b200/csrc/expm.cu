@@ -1,0 +1,354 @@
+// Batched Liouvillian assembly + matrix exponential (scaling and squaring, Taylor-Horner) and the
+// per-step operator builder (SURVEY 2.4 kernels K2/K3).  Replaces ACE's FreePropagator
+// (`fprop.update(t, dt); fprop.M`, pyaceqd/general_system/general_system.py:324-327) and the
+// apply_Operator bookkeeping of general_system.py:281-286.
+//
+// For every output row n of a trajectory the step kernel needs two small matrices:
+//     V_n  = S_before(t_n) * M2_{n-1}                    (second half step of the previous step)
+//     W_n  = M1_n * S_after(t_n) * V_n                   (first half step of the next step)
+//     OV_n = out_w * V_n                                  (output functionals pulled through V_n)
+// with M1_n = exp(L(t_n + off1*dt) dt/2), M2_{n-1} = exp(L(t_{n-1} + off2*dt) dt/2).  Closure and
+// system operators act on different indices, so rho(t_n) = V_n * (Y . q) and the next PT input is
+// X = W_n * Y, where Y is the bond state right after the previous PT slice.
+//
+// One thread group (32..256 threads) owns one entry; matrices live in shared memory.
+#include "common.cuh"
+
+namespace aceqd {
+
+namespace {
+
+constexpr int TAYLOR_M = 14;       // degree; with ||A||_1 <= 0.5 the remainder is < 3e-17
+constexpr double THETA = 0.5;
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ void cfma(double2& acc, double2 a, double2 b) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+
+template <int G>
+__device__ __forceinline__ void group_sync(int gid) {
+    if (G == 32)
+        __syncwarp();
+    else
+        asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(G) : "memory");
+}
+
+// C = scale * A*B (+ I)
+template <int G>
+__device__ void gmm(double2* C, const double2* A, const double2* B, int n, int tid, int gid,
+                    double scale, bool add_identity) {
+    const int n2 = n * n;
+    for (int e = tid; e < n2; e += G) {
+        const int i = e / n, j = e - i * n;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int k = 0; k < n; ++k) cfma(acc, A[i * n + k], B[k * n + j]);
+        acc.x *= scale;
+        acc.y *= scale;
+        if (add_identity && i == j) acc.x += 1.0;
+        C[e] = acc;
+    }
+    group_sync<G>(gid);
+}
+
+// exp(A) for the n x n matrix in `A` (destroyed).  Returns a pointer to the result, which is
+// one of P0 / P1.  `red` is a scratch of >= n doubles.
+template <int G>
+__device__ double2* expm_group(double2* A, double2* P0, double2* P1, double* red, int n, int tid,
+                               int gid) {
+    const int n2 = n * n;
+    for (int j = tid; j < n; j += G) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double2 v = A[i * n + j];
+            s += sqrt(v.x * v.x + v.y * v.y);
+        }
+        red[j] = s;
+    }
+    group_sync<G>(gid);
+    double nrm = 0.0;
+    for (int j = 0; j < n; ++j) nrm = fmax(nrm, red[j]);
+    int s = 0;
+    if (nrm > THETA) {
+        int ex;
+        frexp(nrm / THETA, &ex);  // nrm/THETA = m * 2^ex, m in [0.5, 1)
+        s = ex;
+        if (s > 60) s = 60;
+    }
+    const double sc = ldexp(1.0, -s);
+    group_sync<G>(gid);  // everyone has read `red`
+    for (int e = tid; e < n2; e += G) {
+        double2 v = A[e];
+        v.x *= sc;
+        v.y *= sc;
+        A[e] = v;
+        const int i = e / n, j = e - i * n;
+        // P = I + A/m
+        P0[e] = make_double2(v.x / TAYLOR_M + (i == j ? 1.0 : 0.0), v.y / TAYLOR_M);
+    }
+    group_sync<G>(gid);
+    double2* cur = P0;
+    double2* nxt = P1;
+    for (int j = TAYLOR_M - 1; j >= 1; --j) {
+        gmm<G>(nxt, A, cur, n, tid, gid, 1.0 / j, true);
+        double2* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    for (int q = 0; q < s; ++q) {
+        gmm<G>(nxt, cur, cur, n, tid, gid, 1.0, false);
+        double2* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    return cur;
+}
+
+__device__ __forceinline__ double2 sample_table(const double2* v, int n, double x) {
+    if (n <= 0) return make_double2(0.0, 0.0);
+    if (x <= 0.0) return v[0];
+    if (x >= (double)(n - 1)) return v[n - 1];
+    const int j = (int)floor(x);
+    const double w = x - j;
+    const double2 a = v[j], b = v[j + 1];
+    return make_double2((1.0 - w) * a.x + w * b.x, (1.0 - w) * a.y + w * b.y);
+}
+
+// A = (L0 + sum_k f_k LA_k + conj(f_k) LB_k) * delta   at time t, drive set `set`
+template <int G>
+__device__ void assemble(double2* A, const OpBuildParams& p, int set, double t, double delta,
+                         int tid, int gid) {
+    const int n = p.prob.NL, n2 = n * n;
+    const double2* L0 = reinterpret_cast<const double2*>(p.prob.L0);
+    const double2* LA = reinterpret_cast<const double2*>(p.prob.LA);
+    const double2* LB = reinterpret_cast<const double2*>(p.prob.LB);
+    const double2* tabs = reinterpret_cast<const double2*>(p.tables);
+    const double x = (t - p.tab_t0) / p.tab_dt;
+    for (int e = tid; e < n2; e += G) {
+        double2 acc = L0[e];
+        for (int k = 0; k < p.prob.n_fields; ++k) {
+            const int tb = p.prob.field_table[k];
+            if (tb < 0 || tb >= p.n_tables) continue;
+            const double2 f =
+                sample_table(tabs + ((size_t)set * p.n_tables + tb) * p.n_samples, p.n_samples, x);
+            cfma(acc, f, LA[(size_t)k * n2 + e]);
+            cfma(acc, make_double2(f.x, -f.y), LB[(size_t)k * n2 + e]);
+        }
+        A[e] = make_double2(acc.x * delta, acc.y * delta);
+    }
+    group_sync<G>(gid);
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) k_opbuild(OpBuildParams p) {
+    extern __shared__ double2 sm[];
+    const int n = p.prob.NL, n2 = n * n;
+    const int groups = blockDim.x / G;
+    const int gid = threadIdx.x / G, tid = threadIdx.x - gid * G;
+    const size_t per_group = (size_t)5 * n2 + MAX_NL;  // A, P0, P1, V, X + reduction scratch
+    double2* A = sm + gid * per_group;
+    double2* P0 = A + n2;
+    double2* P1 = P0 + n2;
+    double2* V = P1 + n2;
+    double2* X = V + n2;
+    double* red = reinterpret_cast<double*>(X + n2);
+
+    const long long total = p.n_seq_entries + p.n_entries;
+    const double half = 0.5 * p.dt;
+    for (long long e = (long long)blockIdx.x * groups + gid; e < total;
+         e += (long long)gridDim.x * groups) {
+        int set, step, sb = -1, sa = -1, has_prev;
+        if (e < p.n_seq_entries) {
+            int lo = 0, hi = p.n_seq;  // seq_base[lo] <= e < seq_base[hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (p.seq_base[mid] <= e) lo = mid; else hi = mid;
+            }
+            const aceqd_seq sq = p.seqs[lo];
+            const int i = (int)(e - p.seq_base[lo]);
+            set = sq.set;
+            step = sq.step0 + i;
+            has_prev = (i > 0) || sq.first_has_prev;
+        } else {
+            const aceqd_entry en = p.entries[e - p.n_seq_entries];
+            set = en.set; step = en.step; sb = en.sb; sa = en.sa; has_prev = en.has_prev;
+        }
+        const double t_n = p.t0 + (double)step * p.dt;
+        const double2* mto = reinterpret_cast<const double2*>(p.mto_mats);
+
+        // ---- V = Sb * M2_{n-1}
+        if (has_prev) {
+            assemble<G>(A, p, set, t_n - p.dt + p.eval_off2 * p.dt, half, tid, gid);
+            double2* M2 = expm_group<G>(A, P0, P1, red, n, tid, gid);
+            if (sb >= 0) {
+                gmm<G>(V, mto + (size_t)sb * n2, M2, n, tid, gid, 1.0, false);
+            } else {
+                for (int q = tid; q < n2; q += G) V[q] = M2[q];
+                group_sync<G>(gid);
+            }
+        } else {
+            for (int q = tid; q < n2; q += G) {
+                const int i = q / n, j = q - i * n;
+                V[q] = (sb >= 0) ? mto[(size_t)sb * n2 + q] : make_double2(i == j ? 1.0 : 0.0, 0.0);
+            }
+            group_sync<G>(gid);
+        }
+        // ---- OV = out_w * V
+        {
+            const double2* ow = reinterpret_cast<const double2*>(p.prob.out_w);
+            double2* ov = reinterpret_cast<double2*>(p.OV + (size_t)e * p.prob.ov_doubles);
+            const int cnt = p.prob.n_out * n;
+            for (int q = tid; q < cnt; q += G) {
+                const int j = q / n, a = q - j * n;
+                double2 acc = make_double2(0.0, 0.0);
+                for (int k = 0; k < n; ++k) cfma(acc, ow[j * n + k], V[k * n + a]);
+                ov[q] = acc;
+            }
+        }
+        // ---- X = Sa * V
+        const double2* Xp = V;
+        if (sa >= 0) {
+            gmm<G>(X, mto + (size_t)sa * n2, V, n, tid, gid, 1.0, false);
+            Xp = X;
+        }
+        // ---- W = M1_n * X   (zero padded to [NLp8][NLp4])
+        assemble<G>(A, p, set, t_n + p.eval_off1 * p.dt, half, tid, gid);
+        double2* M1 = expm_group<G>(A, P0, P1, red, n, tid, gid);
+        {
+            double2* w = reinterpret_cast<double2*>(p.W + (size_t)e * p.prob.w_doubles);
+            const int ld = p.prob.NLp4, cnt = p.prob.NLp8 * ld;
+            for (int q = tid; q < cnt; q += G) {
+                const int i = q / ld, j = q - i * ld;
+                double2 acc = make_double2(0.0, 0.0);
+                if (i < n && j < n)
+                    for (int k = 0; k < n; ++k) cfma(acc, M1[i * n + k], Xp[k * n + j]);
+                w[q] = acc;
+            }
+        }
+        group_sync<G>(gid);  // buffers are reused by the next entry
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) k_expm_batch(int n, int count, const double* a,
+                                                    double* out) {
+    extern __shared__ double2 sm[];
+    const int n2 = n * n;
+    const int groups = blockDim.x / G;
+    const int gid = threadIdx.x / G, tid = threadIdx.x - gid * G;
+    const size_t per_group = (size_t)3 * n2 + MAX_NL;
+    double2* A = sm + gid * per_group;
+    double2* P0 = A + n2;
+    double2* P1 = P0 + n2;
+    double* red = reinterpret_cast<double*>(P1 + n2);
+    for (int e = blockIdx.x * groups + gid; e < count; e += gridDim.x * groups) {
+        const double2* src = reinterpret_cast<const double2*>(a) + (size_t)e * n2;
+        for (int q = tid; q < n2; q += G) A[q] = src[q];
+        group_sync<G>(gid);
+        double2* R = expm_group<G>(A, P0, P1, red, n, tid, gid);
+        double2* dst = reinterpret_cast<double2*>(out) + (size_t)e * n2;
+        for (int q = tid; q < n2; q += G) dst[q] = R[q];
+        group_sync<G>(gid);
+    }
+}
+
+int pick_group(int n) {
+    if (n <= 8) return 32;
+    if (n <= 12) return 64;
+    if (n <= 20) return 128;
+    return 256;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024)
+        ACEQD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)bytes));
+    return ACEQD_OK;
+}
+
+}  // namespace
+
+int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches) {
+    const long long total = p.n_seq_entries + p.n_entries;
+    if (total <= 0) return ACEQD_OK;
+    const int n = p.prob.NL;
+    if (n > MAX_NL) {
+        set_error("NL=%d exceeds MAX_NL=%d", n, MAX_NL);
+        return ACEQD_ERR_CAPACITY;
+    }
+    const int G = pick_group(n);
+    const int groups = 256 / G;
+    const size_t smem = groups * ((size_t)5 * n * n + MAX_NL) * sizeof(double2);
+    if (smem > (size_t)SMEM_BUDGET) {
+        set_error("operator builder: NL=%d needs %zu B shared memory", n, smem);
+        return ACEQD_ERR_CAPACITY;
+    }
+    long long blocks = (total + groups - 1) / groups;
+    if (blocks > 148LL * 64) blocks = 148LL * 64;
+    int rc = ACEQD_OK;
+    switch (G) {
+        case 32:
+            if ((rc = set_smem(k_opbuild<32>, smem))) return rc;
+            k_opbuild<32><<<(int)blocks, 256, smem, s>>>(p);
+            break;
+        case 64:
+            if ((rc = set_smem(k_opbuild<64>, smem))) return rc;
+            k_opbuild<64><<<(int)blocks, 256, smem, s>>>(p);
+            break;
+        case 128:
+            if ((rc = set_smem(k_opbuild<128>, smem))) return rc;
+            k_opbuild<128><<<(int)blocks, 256, smem, s>>>(p);
+            break;
+        default:
+            if ((rc = set_smem(k_opbuild<256>, smem))) return rc;
+            k_opbuild<256><<<(int)blocks, 256, smem, s>>>(p);
+            break;
+    }
+    ++*launches;
+    ACEQD_CUDA(cudaGetLastError());
+    return ACEQD_OK;
+}
+
+int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, cudaStream_t s,
+                      long long* launches) {
+    if (count <= 0) return ACEQD_OK;
+    if (n > MAX_NL) {
+        set_error("n=%d exceeds MAX_NL=%d", n, MAX_NL);
+        return ACEQD_ERR_CAPACITY;
+    }
+    const int G = pick_group(n);
+    const int groups = 256 / G;
+    const size_t smem = groups * ((size_t)3 * n * n + MAX_NL) * sizeof(double2);
+    int blocks = (count + groups - 1) / groups;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    int rc = ACEQD_OK;
+    switch (G) {
+        case 32:
+            if ((rc = set_smem(k_expm_batch<32>, smem))) return rc;
+            k_expm_batch<32><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev);
+            break;
+        case 64:
+            if ((rc = set_smem(k_expm_batch<64>, smem))) return rc;
+            k_expm_batch<64><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev);
+            break;
+        case 128:
+            if ((rc = set_smem(k_expm_batch<128>, smem))) return rc;
+            k_expm_batch<128><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev);
+            break;
+        default:
+            if ((rc = set_smem(k_expm_batch<256>, smem))) return rc;
+            k_expm_batch<256><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev);
+            break;
+    }
+    ++*launches;
+    ACEQD_CUDA(cudaGetLastError());
+    return ACEQD_OK;
+}
+
+}  // namespace aceqd

@@ -1,0 +1,552 @@
+// The fused PT step kernel (SURVEY 2.4 kernel K1) for sm_100a.
+//
+// One persistent CTA owns a tile of T trajectories for their whole time evolution.  The bond
+// state of the tile ([T*NL rows] x [chi_pad] complex, split re/im planes) never leaves shared
+// memory; per absolute time step n the CTA does
+//   A  closure   r = Y . q_n ; outputs out = OV_n r ; optional snapshot of Y
+//   B  system    X = W_n Y          (DMMA, per trajectory, column-local -> no block barrier)
+//   C  PT slice  Y[alpha,:] = X[alpha,:] A_n[beta(alpha)]   (DMMA; PT chunks streamed L2 -> smem
+//                by a producer warp with cp.async.bulk + mbarrier full/empty pipeline)
+// Rows are stored alpha-major in coupling-class-sorted order (row = pos(alpha)*T + traj) so that
+// the 8 rows of a DMMA m-tile share one PT block.  Complex GEMM = 4 real DMMA.8x8x4 per tile.
+//
+// Replaces the inner loop of ACE's Simulation.run (pyaceqd/general_system/general_system.py:331
+// / the `ACE <param>` subprocess of :339-341) for a whole batch of trajectories.
+#include "common.cuh"
+
+namespace aceqd {
+
+namespace {
+
+struct SmemLayout {
+    size_t bar, traj, pass, pos, r, q, snapn, state, chunks, total;
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline SmemLayout make_layout(int NL, int chi_pad, int T, int stages) {
+    SmemLayout L;
+    const size_t R = (size_t)T * NL;
+    const size_t strideA = chi_pad + 4;
+    size_t o = 0;
+    L.bar = o;   o += 128;
+    L.traj = o;  o += align_up(sizeof(aceqd_traj) * T, 16);
+    L.pass = o;  o += align_up(sizeof(PassDesc) * MAX_PASSES, 16);
+    L.pos = o;   o += align_up(sizeof(int) * MAX_NL, 16);
+    L.snapn = o; o += align_up(sizeof(int) * MAX_TILE_T, 16);
+    L.r = o;     o += align_up(16 * R, 16);
+    L.q = o;     o += align_up(16 * (size_t)chi_pad, 16);
+    o = align_up(o, 128);
+    L.state = o; o += 2 * R * strideA * 8;
+    o = align_up(o, 128);
+    L.chunks = o; o += (size_t)stages * 2 * KC * strideA * 8;  // strideB == strideA
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                         uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void compute_bar() {  // the 8 compute warps only
+    asm volatile("bar.sync 1, %0;" ::"n"(N_COMPUTE_WARPS * 32) : "memory");
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ int slice_of(const PtDev& pt, int n) {
+    return n < pt.n_initial ? n : pt.n_initial + (n - pt.n_initial) % pt.n_repeat;
+}
+__device__ __forceinline__ long long entry_of(const aceqd_traj& t, int i, long long ovr_base) {
+    long long e = t.ent0 + i;
+    for (int q = 0; q < t.n_ovr; ++q)
+        if (t.ovr_step[q] == i) e = ovr_base + t.ovr_ent[q];
+    return e;
+}
+
+constexpr int KS_MAX = MAX_NL / 4;
+
+template <int NB>
+__global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_constant__ StepParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int T = p.T, NL = p.prob.NL, R = T * NL;
+    const int chi_pad = p.pt.chi_pad;
+    const int strideA = chi_pad + 4;
+    const int strideB = p.pt.strideB;
+    const int stages = p.stages;
+    const SmemLayout L = make_layout(NL, chi_pad, T, stages);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
+    aceqd_traj* trj = reinterpret_cast<aceqd_traj*>(smem_raw + L.traj);
+    PassDesc* passes = reinterpret_cast<PassDesc*>(smem_raw + L.pass);
+    int* pos = reinterpret_cast<int*>(smem_raw + L.pos);
+    int* snapn = reinterpret_cast<int*>(smem_raw + L.snapn);
+    double2* rbuf = reinterpret_cast<double2*>(smem_raw + L.r);
+    double2* qbuf = reinterpret_cast<double2*>(smem_raw + L.q);
+    double* Xre = reinterpret_cast<double*>(smem_raw + L.state);
+    double* Xim = Xre + (size_t)R * strideA;
+    double* chunks = reinterpret_cast<double*>(smem_raw + L.chunks);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
+
+    // ------------------------------------------------------------------ setup
+    for (int j = tid; j < T; j += blockDim.x) {
+        const int idx = p.tile_traj[(size_t)tile * T + j];
+        if (idx >= 0) {
+            trj[j] = p.trajs[idx];
+        } else {
+            aceqd_traj z;
+            memset(&z, 0, sizeof(z));
+            z.n_steps = -1;
+            trj[j] = z;
+        }
+        snapn[j] = 0;
+    }
+    for (int j = tid; j < p.n_pass; j += blockDim.x) passes[j] = p.passes[j];
+    for (int j = tid; j < NL; j += blockDim.x) pos[j] = p.prob.pos_of_alpha[j];
+    for (size_t e = tid; e < 2 * (size_t)R * strideA; e += blockDim.x) Xre[e] = 0.0;
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, N_COMPUTE_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    int n_begin = 0x7fffffff, n_end = -1;
+    for (int j = 0; j < T; ++j) {
+        if (trj[j].n_steps < 0) continue;
+        n_begin = min(n_begin, trj[j].step0);
+        n_end = max(n_end, trj[j].step0 + trj[j].n_steps);
+    }
+    if (n_end < 0) return;  // empty tile
+    // initial states (Y form)
+    for (int j = 0; j < T; ++j) {
+        if (trj[j].n_steps < 0) continue;
+        if (trj[j].init_kind == 0) {
+            const double2* r0 = reinterpret_cast<const double2*>(p.rho0s) + (size_t)trj[j].init_index * NL;
+            for (int a = tid; a < NL; a += blockDim.x) {
+                const int row = pos[a] * T + j;
+                Xre[(size_t)row * strideA] = r0[a].x;
+                Xim[(size_t)row * strideA] = r0[a].y;
+            }
+        } else {
+            const double2* sn = reinterpret_cast<const double2*>(p.snaps) +
+                                (size_t)trj[j].init_index * NL * chi_pad;
+            for (int e = tid; e < NL * chi_pad; e += blockDim.x) {
+                const int a = e / chi_pad, d = e - a * chi_pad;
+                const int row = pos[a] * T + j;
+                const double2 v = sn[e];
+                Xre[(size_t)row * strideA + d] = v.x;
+                Xim[(size_t)row * strideA + d] = v.y;
+            }
+        }
+    }
+    // closure of the slice before the first row (used by snapshot-started trajectories)
+    if (n_begin > 0) {
+        const double2* cl = reinterpret_cast<const double2*>(p.pt.closure) +
+                            (size_t)slice_of(p.pt, n_begin - 1) * chi_pad;
+        for (int d = tid; d < chi_pad; d += blockDim.x) qbuf[d] = cl[d];
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ producer warp
+    if (warp == N_COMPUTE_WARPS) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t bytes = (uint32_t)p.pt.chunk_doubles * 8u;
+            for (int n = n_begin; n < n_end; ++n) {
+                const int s = slice_of(p.pt, n);
+                const int nch = p.pt.kin_pad[s] / KC;
+                const double* sl = p.pt.blob + p.pt.off[s];
+                for (int ps = 0; ps < p.n_pass; ++ps) {
+                    const double* src = sl + (size_t)passes[ps].blk * nch * p.pt.chunk_doubles;
+                    for (int j = 0; j < nch; ++j) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+                        mbar_expect_tx(bar_full + 8 * stage, bytes);
+                        bulk_g2s(smem_u32(chunks + (size_t)stage * p.pt.chunk_doubles),
+                                 src + (size_t)j * p.pt.chunk_doubles, bytes, bar_full + 8 * stage);
+                        if (++stage == stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ------------------------------------------------------------------ compute warps
+    const int g = lane >> 2, tq = lane & 3;  // DMMA fragment coordinates
+    const int NT = chi_pad / 8;
+    const int n_out = p.prob.n_out;
+    const int NLp4 = p.prob.NLp4, MTU = p.prob.NLp8 / 8, KSU = NLp4 / 4;
+    int stage = 0;
+    uint32_t phase = 0;
+
+    for (int n = n_begin; n <= n_end; ++n) {
+        // ---------------- phase A: closure, outputs, snapshots
+        for (int row = warp; row < R; row += N_COMPUTE_WARPS) {
+            const int j = row % T;
+            const aceqd_traj& t = trj[j];
+            double2 acc = make_double2(0.0, 0.0);
+            if (t.n_steps >= 0 && n >= t.step0 && n <= t.step0 + t.n_steps) {
+                const double* xr = Xre + (size_t)row * strideA;
+                const double* xi = Xim + (size_t)row * strideA;
+                if (n == t.step0 && t.init_kind == 0) {
+                    if (lane == 0) acc = make_double2(xr[0], xi[0]);
+                } else {
+                    for (int d = lane; d < chi_pad; d += 32) {
+                        const double2 q = qbuf[d];
+                        const double a = xr[d], b = xi[d];
+                        acc.x += a * q.x - b * q.y;
+                        acc.y += a * q.y + b * q.x;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                }
+            }
+            if (lane == 0) rbuf[row] = acc;
+        }
+        compute_bar();
+        for (int it = tid; it < T * n_out; it += N_COMPUTE_WARPS * 32) {
+            const int j = it / n_out, o = it - j * n_out;
+            const aceqd_traj& t = trj[j];
+            if (t.n_steps < 0 || n < t.step0 || n > t.step0 + t.n_steps) continue;
+            const int i = n - t.step0;
+            const long long e = entry_of(t, i, p.ovr_base);
+            const double2* ov = reinterpret_cast<const double2*>(p.OV + (size_t)e * p.prob.ov_doubles) +
+                                (size_t)o * NL;
+            double2 acc = make_double2(0.0, 0.0);
+            for (int a = 0; a < NL; ++a) {
+                const double2 w = __ldg(ov + a);
+                const double2 r = rbuf[pos[a] * T + j];
+                acc.x += w.x * r.x - w.y * r.y;
+                acc.y += w.x * r.y + w.y * r.x;
+            }
+            reinterpret_cast<double2*>(p.out)[t.out_off + (long long)i * n_out + o] = acc;
+        }
+        for (int j = 0; j < T; ++j) {
+            const aceqd_traj& t = trj[j];
+            if (t.n_steps < 0 || snapn[j] >= t.snap_cnt) continue;
+            const int i = n - t.step0;
+            if (i < 0 || i > t.n_steps || p.snap_steps[t.snap_off + snapn[j]] != i) continue;
+            double2* dst = reinterpret_cast<double2*>(p.snaps) +
+                           (size_t)(t.snap_slot0 + snapn[j]) * NL * chi_pad;
+            for (int e = tid; e < NL * chi_pad; e += N_COMPUTE_WARPS * 32) {
+                const int a = e / chi_pad, d = e - a * chi_pad;
+                const size_t o = (size_t)(pos[a] * T + j) * strideA + d;
+                dst[e] = make_double2(Xre[o], Xim[o]);
+            }
+        }
+        if (n == n_end) break;
+        compute_bar();
+        if (tid < T) {  // advance snapshot cursors (read again only after later barriers)
+            const aceqd_traj& t = trj[tid];
+            const int i = n - t.step0;
+            if (t.n_steps >= 0 && snapn[tid] < t.snap_cnt && i >= 0 && i <= t.n_steps &&
+                p.snap_steps[t.snap_off + snapn[tid]] == i)
+                snapn[tid] += 1;
+        }
+
+        // ---------------- phase B: X = W_n Y   (items = (trajectory, n-tile), warp-local in place)
+        for (int item = warp; item < T * NT; item += N_COMPUTE_WARPS) {
+            const int j = item / NT, nt = item - j * NT;
+            const aceqd_traj& t = trj[j];
+            if (t.n_steps < 0 || n < t.step0 || n >= t.step0 + t.n_steps) continue;
+            const long long e = entry_of(t, n - t.step0, p.ovr_base);
+            const double2* Wp = reinterpret_cast<const double2*>(p.W + (size_t)e * p.prob.w_doubles);
+            double yre[KS_MAX], yim[KS_MAX];
+            const int col = 8 * nt + g;
+#pragma unroll
+            for (int ks = 0; ks < KS_MAX; ++ks) {
+                yre[ks] = 0.0;
+                yim[ks] = 0.0;
+                if (ks < KSU) {
+                    const int a = 4 * ks + tq;
+                    if (a < NL) {
+                        const size_t o = (size_t)(pos[a] * T + j) * strideA + col;
+                        yre[ks] = Xre[o];
+                        yim[ks] = Xim[o];
+                    }
+                }
+            }
+            __syncwarp();
+            for (int mt = 0; mt < MTU; ++mt) {
+                double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
+                const double2* wrow = Wp + (size_t)(8 * mt + g) * NLp4 + tq;
+#pragma unroll
+                for (int ks = 0; ks < KS_MAX; ++ks) {
+                    if (ks < KSU) {
+                        const double2 w = __ldg(wrow + 4 * ks);
+                        dmma(cr0, cr1, w.x, yre[ks]);
+                        dmma(cr0, cr1, -w.y, yim[ks]);
+                        dmma(ci0, ci1, w.x, yim[ks]);
+                        dmma(ci0, ci1, w.y, yre[ks]);
+                    }
+                }
+                const int a = 8 * mt + g;
+                if (a < NL) {
+                    const size_t o = (size_t)(pos[a] * T + j) * strideA + 8 * nt + 2 * tq;
+                    *reinterpret_cast<double2*>(Xre + o) = make_double2(cr0, cr1);
+                    *reinterpret_cast<double2*>(Xim + o) = make_double2(ci0, ci1);
+                }
+            }
+        }
+        compute_bar();
+
+        // ---------------- phase C: PT slice, Y = X A_n[beta]
+        const int s = slice_of(p.pt, n);
+        const int nch = p.pt.kin_pad[s] / KC;
+        const int nout = p.pt.nout_pad[s];
+        {   // stage the closure that phase A of the next row needs
+            const double2* cl = reinterpret_cast<const double2*>(p.pt.closure) + (size_t)s * chi_pad;
+            for (int d = tid; d < chi_pad; d += N_COMPUTE_WARPS * 32) qbuf[d] = cl[d];
+        }
+        for (int ps = 0; ps < p.n_pass; ++ps) {
+            const PassDesc pd = passes[ps];
+            double cre[MC][NB][2], cim[MC][NB][2];
+#pragma unroll
+            for (int mc = 0; mc < MC; ++mc)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    cre[mc][nb][0] = cre[mc][nb][1] = 0.0;
+                    cim[mc][nb][0] = cim[mc][nb][1] = 0.0;
+                }
+            const double* are[MC];
+            const double* aim[MC];
+            bool aval[MC];
+#pragma unroll
+            for (int mc = 0; mc < MC; ++mc) {
+                aval[mc] = g < pd.nvalid[mc];
+                const size_t o = (size_t)(pd.row0[mc] + (aval[mc] ? g : 0)) * strideA + tq;
+                are[mc] = Xre + o;
+                aim[mc] = Xim + o;
+            }
+            for (int jc = 0; jc < nch; ++jc) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                const double* bre = chunks + (size_t)stage * p.pt.chunk_doubles;
+                const double* bim = bre + KC * strideB;
+#pragma unroll
+                for (int ks = 0; ks < KC / 4; ++ks) {
+                    const int k = jc * KC + 4 * ks;
+                    double a_re[MC], a_im[MC];
+#pragma unroll
+                    for (int mc = 0; mc < MC; ++mc) {
+                        a_re[mc] = aval[mc] ? are[mc][k] : 0.0;
+                        a_im[mc] = aval[mc] ? aim[mc][k] : 0.0;
+                    }
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) {
+                        const int nt = warp + N_COMPUTE_WARPS * nb;
+                        if (8 * nt < nout) {
+                            const int bo = (4 * ks + tq) * strideB + 8 * nt + g;
+                            const double b_re = bre[bo], b_im = bim[bo];
+#pragma unroll
+                            for (int mc = 0; mc < MC; ++mc) {
+                                if (pd.nvalid[mc] > 0) {
+                                    dmma(cre[mc][nb][0], cre[mc][nb][1], a_re[mc], b_re);
+                                    dmma(cre[mc][nb][0], cre[mc][nb][1], -a_im[mc], b_im);
+                                    dmma(cim[mc][nb][0], cim[mc][nb][1], a_re[mc], b_im);
+                                    dmma(cim[mc][nb][0], cim[mc][nb][1], a_im[mc], b_re);
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+            compute_bar();  // every warp has finished reading this pass's X rows
+#pragma unroll
+            for (int mc = 0; mc < MC; ++mc) {
+                if (!aval[mc]) continue;
+                const int row = pd.row0[mc] + g;
+                const aceqd_traj& t = trj[row % T];
+                if (t.n_steps < 0 || n < t.step0 || n >= t.step0 + t.n_steps) continue;
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    const int nt = warp + N_COMPUTE_WARPS * nb;
+                    if (8 * nt < nout) {
+                        const size_t o = (size_t)row * strideA + 8 * nt + 2 * tq;
+                        *reinterpret_cast<double2*>(Xre + o) = make_double2(cre[mc][nb][0], cre[mc][nb][1]);
+                        *reinterpret_cast<double2*>(Xim + o) = make_double2(cim[mc][nb][0], cim[mc][nb][1]);
+                    }
+                }
+            }
+        }
+        compute_bar();
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// Plain-FMA check kernel (SURVEY 7.1 step 5 "v0"): one CTA per trajectory, state in global
+// memory, natural alpha order, no tensor cores, no pipeline.  Independent of the DMMA kernel's
+// tiling; used by the GPU parity tests to localise faults.  Same inputs, same outputs.
+__global__ void __launch_bounds__(256) k_step_check(const StepParams p, double* scratch) {
+    const int b = blockIdx.x;
+    const aceqd_traj t = p.trajs[b];
+    const int NL = p.prob.NL, chi_pad = p.pt.chi_pad, n_out = p.prob.n_out;
+    const int strideB = p.pt.strideB;
+    double2* Y = reinterpret_cast<double2*>(scratch) + (size_t)b * 2 * NL * chi_pad;
+    double2* X = Y + (size_t)NL * chi_pad;
+    __shared__ double2 r[MAX_NL];
+    const int tid = threadIdx.x;
+    const int tot = NL * chi_pad;
+    if (t.init_kind == 0) {
+        const double2* r0 = reinterpret_cast<const double2*>(p.rho0s) + (size_t)t.init_index * NL;
+        for (int e = tid; e < tot; e += blockDim.x) {
+            const int a = e / chi_pad, d = e - a * chi_pad;
+            Y[e] = d == 0 ? r0[a] : make_double2(0.0, 0.0);
+        }
+    } else {
+        const double2* sn = reinterpret_cast<const double2*>(p.snaps) + (size_t)t.init_index * tot;
+        for (int e = tid; e < tot; e += blockDim.x) Y[e] = sn[e];
+    }
+    __syncthreads();
+    int snapn = 0;
+    for (int i = 0; i <= t.n_steps; ++i) {
+        const int n = t.step0 + i;
+        const long long e_ = entry_of(t, i, p.ovr_base);
+        for (int a = tid; a < NL; a += blockDim.x) {
+            double2 acc = make_double2(0.0, 0.0);
+            if (i == 0 && t.init_kind == 0) {
+                acc = Y[(size_t)a * chi_pad];
+            } else {
+                const double2* q = reinterpret_cast<const double2*>(p.pt.closure) +
+                                   (size_t)slice_of(p.pt, n - 1) * chi_pad;
+                for (int d = 0; d < chi_pad; ++d) {
+                    const double2 y = Y[(size_t)a * chi_pad + d];
+                    acc.x += y.x * q[d].x - y.y * q[d].y;
+                    acc.y += y.x * q[d].y + y.y * q[d].x;
+                }
+            }
+            r[a] = acc;
+        }
+        __syncthreads();
+        for (int o = tid; o < n_out; o += blockDim.x) {
+            const double2* ov = reinterpret_cast<const double2*>(p.OV + (size_t)e_ * p.prob.ov_doubles) +
+                                (size_t)o * NL;
+            double2 acc = make_double2(0.0, 0.0);
+            for (int a = 0; a < NL; ++a) {
+                acc.x += ov[a].x * r[a].x - ov[a].y * r[a].y;
+                acc.y += ov[a].x * r[a].y + ov[a].y * r[a].x;
+            }
+            reinterpret_cast<double2*>(p.out)[t.out_off + (long long)i * n_out + o] = acc;
+        }
+        if (snapn < t.snap_cnt && p.snap_steps[t.snap_off + snapn] == i) {
+            double2* dst = reinterpret_cast<double2*>(p.snaps) + (size_t)(t.snap_slot0 + snapn) * tot;
+            for (int e = tid; e < tot; e += blockDim.x) dst[e] = Y[e];
+            ++snapn;
+        }
+        if (i == t.n_steps) break;
+        const double2* W = reinterpret_cast<const double2*>(p.W + (size_t)e_ * p.prob.w_doubles);
+        for (int e = tid; e < tot; e += blockDim.x) {
+            const int a = e / chi_pad, d = e - a * chi_pad;
+            double2 acc = make_double2(0.0, 0.0);
+            for (int k = 0; k < NL; ++k) {
+                const double2 w = W[(size_t)a * p.prob.NLp4 + k];
+                const double2 y = Y[(size_t)k * chi_pad + d];
+                acc.x += w.x * y.x - w.y * y.y;
+                acc.y += w.x * y.y + w.y * y.x;
+            }
+            X[e] = acc;
+        }
+        __syncthreads();
+        const int s = slice_of(p.pt, n);
+        const int nch = p.pt.kin_pad[s] / KC;
+        for (int e = tid; e < tot; e += blockDim.x) {
+            const int a = e / chi_pad, d2 = e - a * chi_pad;
+            const double* blk = p.pt.blob + p.pt.off[s] +
+                                (size_t)p.prob.block_of_alpha[a] * nch * p.pt.chunk_doubles;
+            double2 acc = make_double2(0.0, 0.0);
+            if (d2 < p.pt.nout_pad[s]) {
+                for (int d1 = 0; d1 < p.pt.kin_pad[s]; ++d1) {
+                    const double* ch = blk + (size_t)(d1 / KC) * p.pt.chunk_doubles;
+                    const double br = ch[(d1 % KC) * strideB + d2];
+                    const double bi = ch[KC * strideB + (d1 % KC) * strideB + d2];
+                    const double2 x = X[(size_t)a * chi_pad + d1];
+                    acc.x += x.x * br - x.y * bi;
+                    acc.y += x.x * bi + x.y * br;
+                }
+                Y[e] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+size_t step_smem_bytes(int NL, int chi_pad, int T, int stages) {
+    return make_layout(NL, chi_pad, T, stages).total;
+}
+
+int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, long long* launches) {
+    const int chi = p.pt.chi_pad;
+    if (chi > 256) {
+        set_error("chi_pad=%d exceeds the step kernel's 256 limit", chi);
+        return ACEQD_ERR_CAPACITY;
+    }
+    if (p.n_tiles <= 0) return ACEQD_OK;
+#define ACEQD_LAUNCH(NB)                                                                        \
+    do {                                                                                        \
+        ACEQD_CUDA(cudaFuncSetAttribute(k_step_dmma<NB>,                                        \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                        (int)smem_bytes));                                      \
+        k_step_dmma<NB><<<p.n_tiles, STEP_THREADS, smem_bytes, s>>>(p);                         \
+    } while (0)
+    if (chi <= 64) ACEQD_LAUNCH(1);
+    else if (chi <= 128) ACEQD_LAUNCH(2);
+    else ACEQD_LAUNCH(4);
+#undef ACEQD_LAUNCH
+    ++*launches;
+    ACEQD_CUDA(cudaGetLastError());
+    return ACEQD_OK;
+}
+
+int launch_step_check(const StepParams& p, double* scratch, cudaStream_t s, long long* launches) {
+    // n_tiles carries the trajectory count for this kernel
+    if (p.n_tiles <= 0) return ACEQD_OK;
+    k_step_check<<<p.n_tiles, 256, 0, s>>>(p, scratch);
+    ++*launches;
+    ACEQD_CUDA(cudaGetLastError());
+    return ACEQD_OK;
+}
+
+}  // namespace aceqd

@@ -1,0 +1,531 @@
+"""ctypes binding of libaceqd.so and the host-side batch planner.
+
+The planner turns a list of :class:`~pyaceqd_b200.jobs.Job` (one per ``system(...)`` call of the
+reference, e.g. the fan-out of ``pyaceqd/two_time/correlations.py:153-170``) into one
+``aceqd_batch``: drive tables, operator sequences, explicit MTO entries, trajectory descriptors
+and the tiling of trajectories onto persistent CTAs.  Jobs that share drive tables and start
+time are forked from one common trunk: the trunk is propagated once, the bond state
+is snapshotted at each job's first multi-time-operator step, and every job continues from its
+snapshot -- exact, because the full system x bond state is carried.
+
+There is no CPU fallback: importing works anywhere, but every compute call needs the CUDA
+library and a B200.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_longlong, c_void_p
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .jobs import FieldTable, Job
+from .problem import Problem
+from .process_tensor import ProcessTensor, trivial_pt
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libaceqd.so")
+MAX_OVR = 6
+N_SM = 148
+
+T_EVAL = {"half_mid": (0.25, 0.75), "step_mid": (0.5, 0.5), "start": (0.0, 0.5)}
+
+SEQ_DT = np.dtype([("set", "<i4"), ("step0", "<i4"), ("len", "<i4"), ("first_has_prev", "<i4")], align=True)
+ENTRY_DT = np.dtype([("set", "<i4"), ("step", "<i4"), ("sb", "<i4"), ("sa", "<i4"), ("has_prev", "<i4")],
+                    align=True)
+TRAJ_DT = np.dtype([("ent0", "<i8"), ("out_off", "<i8"), ("step0", "<i4"), ("n_steps", "<i4"),
+                    ("init_kind", "<i4"), ("init_index", "<i4"), ("n_ovr", "<i4"),
+                    ("ovr_step", "<i4", (MAX_OVR,)), ("ovr_ent", "<i4", (MAX_OVR,)),
+                    ("snap_off", "<i4"), ("snap_cnt", "<i4"), ("snap_slot0", "<i4"), ("pad_", "<i4")],
+                   align=True)
+
+
+class _Batch(ctypes.Structure):
+    _fields_ = [
+        ("dt", c_double), ("t0", c_double), ("eval_off1", c_double), ("eval_off2", c_double),
+        ("n_sets", c_int32), ("n_tables", c_int32), ("n_samples", c_int32),
+        ("tab_t0", c_double), ("tab_dt", c_double), ("tables", c_void_p),
+        ("n_seq", c_int32), ("seqs", c_void_p),
+        ("n_entries", c_int32), ("entries", c_void_p),
+        ("n_mto_mats", c_int32), ("mto_mats", c_void_p),
+        ("n_rho0", c_int32), ("rho0s", c_void_p),
+        ("n_traj", c_int32), ("trajs", c_void_p),
+        ("tile_T", c_int32), ("n_tiles", c_int32), ("tile_traj", c_void_p),
+        ("n_snap_steps", c_int32), ("snap_steps", c_void_p), ("n_snap_slots", c_int32),
+        ("out_elems", c_int64), ("out", c_void_p),
+        ("device_resident", c_int32), ("kernel", c_int32),
+    ]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib_handle = None
+
+
+def load_library():
+    """Load the in-tree CUDA library; fail loudly if it is missing (no fallback)."""
+    global _lib_handle
+    if _lib_handle is not None:
+        return _lib_handle
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(
+            f"{LIB_PATH} not found: build it with `python -m pyaceqd_b200.build` "
+            "(the engine has no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.aceqd_last_error.restype = c_char_p
+    lib.aceqd_version.restype = c_char_p
+    lib.aceqd_ctx_create.argtypes = [c_int, c_void_p, POINTER(c_void_p)]
+    lib.aceqd_ctx_destroy.argtypes = [c_void_p]
+    lib.aceqd_ctx_destroy.restype = None
+    lib.aceqd_ctx_sync.argtypes = [c_void_p]
+    lib.aceqd_launch_count.argtypes = [c_void_p]
+    lib.aceqd_launch_count.restype = c_longlong
+    lib.aceqd_last_timings.argtypes = [c_void_p, POINTER(c_float), POINTER(c_float)]
+    lib.aceqd_pt_create.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, POINTER(c_void_p)]
+    lib.aceqd_pt_destroy.argtypes = [c_void_p]
+    lib.aceqd_pt_destroy.restype = None
+    lib.aceqd_pt_chi_pad.argtypes = [c_void_p]
+    lib.aceqd_problem_create.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]
+    lib.aceqd_problem_destroy.argtypes = [c_void_p]
+    lib.aceqd_problem_destroy.restype = None
+    for name in ("aceqd_propagate_batch", "aceqd_run_steps"):
+        getattr(lib, name).argtypes = [c_void_p, c_void_p, c_void_p, POINTER(_Batch)]
+    lib.aceqd_build_operators.argtypes = [c_void_p, c_void_p, POINTER(_Batch)]
+    lib.aceqd_snapshot_read.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p]
+    lib.aceqd_expm_batch.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
+    lib.aceqd_max_tile.argtypes = [c_int, c_int]
+    lib.aceqd_fp64_peak.argtypes = [c_void_p, c_int, c_int, POINTER(c_double)]
+    lib.aceqd_struct_sizes.argtypes = [POINTER(c_int32)]
+    lib.aceqd_struct_sizes.restype = None
+    sizes = (c_int32 * 4)()
+    lib.aceqd_struct_sizes(sizes)
+    want = (SEQ_DT.itemsize, ENTRY_DT.itemsize, TRAJ_DT.itemsize, ctypes.sizeof(_Batch))
+    if tuple(sizes) != want:
+        raise EngineError(f"ABI mismatch between engine.py {want} and libaceqd.so {tuple(sizes)}")
+    _lib_handle = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load_library().aceqd_last_error().decode(errors="replace")
+        raise EngineError(f"{what} failed (status {rc}): {msg}")
+
+
+def _c128(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.complex128)
+
+
+def class_sorted_positions(block_of_alpha: np.ndarray) -> np.ndarray:
+    """Position of every Liouville index in PT-block-sorted order (stable)."""
+    order = np.argsort(block_of_alpha, kind="stable")
+    pos = np.empty_like(order)
+    pos[order] = np.arange(len(order))
+    return pos.astype(np.int32)
+
+
+def choose_tile(n_traj: int, rows_per_block: Sequence[int], t_max: int, n_sm: int = N_SM) -> int:
+    """Trajectories per persistent CTA: minimise waves x DMMA m-tiles per tile."""
+    best_t, best_cost = 1, None
+    t = 1
+    while t <= t_max:
+        tiles = -(-n_traj // t)
+        waves = -(-tiles // n_sm)
+        mtiles = sum(-(-(t * r) // 8) for r in rows_per_block)
+        cost = waves * mtiles
+        if best_cost is None or cost <= best_cost:  # ties -> larger tile (less L2 traffic)
+            best_t, best_cost = t, cost
+        t *= 2
+    return best_t
+
+
+@dataclass
+class _Plan:
+    """Host arrays of one aceqd_batch (kept alive for the duration of the call)."""
+    batch: _Batch
+    keep: list
+    out: np.ndarray
+    out_off: np.ndarray
+    n_rows: np.ndarray
+
+
+class Engine:
+    """One CUDA context (device + stream + workspace) with PT / problem handle caches."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.lib = load_library()
+        h = c_void_p()
+        _check(self.lib.aceqd_ctx_create(int(device), c_void_p(stream) if stream else None,
+                                         ctypes.byref(h)), "aceqd_ctx_create")
+        self.ctx = h
+        self.device = int(device)
+        self._pts: Dict[int, Tuple[c_void_p, ProcessTensor]] = {}
+        self._probs: Dict[Tuple[int, int], Tuple[c_void_p, Problem, np.ndarray]] = {}
+
+    # -------------------------------------------------------------- lifetime
+    def close(self):
+        if getattr(self, "ctx", None):
+            for h, _ in self._pts.values():
+                self.lib.aceqd_pt_destroy(h)
+            for h, _, _ in self._probs.values():
+                self.lib.aceqd_problem_destroy(h)
+            self._pts.clear()
+            self._probs.clear()
+            self.lib.aceqd_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -------------------------------------------------------------- handles
+    def pt_handle(self, pt: ProcessTensor) -> c_void_p:
+        key = id(pt)
+        if key in self._pts:
+            return self._pts[key][0]
+        ns = pt.n_slices
+        chi_in = np.asarray([s.shape[1] for s in pt.slices], dtype=np.int32)
+        chi_out = np.asarray([s.shape[2] for s in pt.slices], dtype=np.int32)
+        sl = [_c128(s) for s in pt.slices]
+        cl = [_c128(q) for q in pt.closures]
+        sp = (c_void_p * ns)(*[s.ctypes.data for s in sl])
+        cp = (c_void_p * ns)(*[q.ctypes.data for q in cl])
+        h = c_void_p()
+        _check(self.lib.aceqd_pt_create(self.ctx, pt.n_cls, ns, pt.n_initial, chi_in.ctypes.data,
+                                        chi_out.ctypes.data, sp, cp, ctypes.byref(h)), "aceqd_pt_create")
+        self._pts[key] = (h, pt)
+        return h
+
+    def problem_handle(self, prob: Problem, pt: ProcessTensor) -> Tuple[c_void_p, np.ndarray]:
+        key = (id(prob), id(pt))
+        if key in self._probs:
+            return self._probs[key][0], self._probs[key][2]
+        blk_of_cls = pt.block_of_class(prob.cls_keys)
+        blk_of_alpha = np.ascontiguousarray(blk_of_cls[np.asarray(prob.cls)], dtype=np.int32)
+        pos = np.ascontiguousarray(class_sorted_positions(blk_of_alpha), dtype=np.int32)
+        tab_index = {"x": 0, "y": 1, "rf": 2}
+        ft = np.asarray([tab_index[p] for p in prob.field_pol], dtype=np.int32)
+        L0, LA, LB, ow = _c128(prob.L0), _c128(prob.LA), _c128(prob.LB), _c128(prob.out_w)
+        h = c_void_p()
+        _check(self.lib.aceqd_problem_create(
+            self.ctx, prob.NL, prob.n_fields, prob.n_out, L0.ctypes.data,
+            LA.ctypes.data if prob.n_fields else None, LB.ctypes.data if prob.n_fields else None,
+            ft.ctypes.data if prob.n_fields else None, ow.ctypes.data if prob.n_out else None,
+            pos.ctypes.data, blk_of_alpha.ctypes.data, ctypes.byref(h)), "aceqd_problem_create")
+        self._probs[key] = (h, prob, blk_of_alpha)
+        return h, blk_of_alpha
+
+    # -------------------------------------------------------------- small services
+    def expm(self, mats: np.ndarray) -> np.ndarray:
+        """Batched matrix exponential on the device (the operator builder's kernel)."""
+        a = _c128(mats)
+        if a.ndim == 2:
+            a = a[None]
+        out = np.empty_like(a)
+        _check(self.lib.aceqd_expm_batch(self.ctx, a.shape[1], a.shape[0], a.ctypes.data,
+                                         out.ctypes.data), "aceqd_expm_batch")
+        return out
+
+    def fp64_peak(self, kind: str = "dmma", iters: int = 20000) -> float:
+        v = c_double()
+        _check(self.lib.aceqd_fp64_peak(self.ctx, 0 if kind == "dmma" else 1, iters, ctypes.byref(v)),
+               "aceqd_fp64_peak")
+        return v.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.aceqd_launch_count(self.ctx))
+
+    def last_timings(self) -> Tuple[float, float]:
+        a, b = c_float(), c_float()
+        _check(self.lib.aceqd_last_timings(self.ctx, ctypes.byref(a), ctypes.byref(b)), "aceqd_last_timings")
+        return a.value, b.value
+
+    def max_tile(self, NL: int, chi_pad: int) -> int:
+        return int(self.lib.aceqd_max_tile(NL, chi_pad))
+
+    def read_snapshot(self, slot: int, NL: int, chi_pad: int) -> np.ndarray:
+        out = np.empty((NL, chi_pad), dtype=np.complex128)
+        _check(self.lib.aceqd_snapshot_read(self.ctx, slot, NL, chi_pad, out.ctypes.data), "aceqd_snapshot_read")
+        return out
+
+    # -------------------------------------------------------------- planning
+    @staticmethod
+    def _tables_of(jobs: Sequence[Job]):
+        """Pack the jobs' drive tables into [n_sets, 3, n_samples]; identical table objects share
+        a set.  All tables of one batch must live on one sampling grid."""
+        set_of_job, sets, key_to_set = [], [], {}
+        grid = None
+        nmax = 1
+        for jb in jobs:
+            key = tuple(id(jb.tables.get(p)) if jb.tables.get(p) is not None else 0 for p in ("x", "y", "rf"))
+            if key not in key_to_set:
+                key_to_set[key] = len(sets)
+                sets.append(jb.tables)
+                for tb in jb.tables.values():
+                    if tb is None:
+                        continue
+                    g = (float(tb.t0), float(tb.dt))
+                    if grid is None:
+                        grid = g
+                    elif abs(grid[0] - g[0]) > 1e-12 or abs(grid[1] - g[1]) > 1e-15:
+                        raise ValueError("all drive tables of one batch must share t0 and dt")
+                    nmax = max(nmax, len(tb.values))
+            set_of_job.append(key_to_set[key])
+        if grid is None:
+            grid = (0.0, 1.0)
+        packed = np.zeros((len(sets), 3, nmax), dtype=np.complex128)
+        for s, tabs in enumerate(sets):
+            for k, pol in enumerate(("x", "y", "rf")):
+                tb = tabs.get(pol)
+                if tb is None or len(tb.values) == 0:
+                    continue
+                n = len(tb.values)
+                packed[s, k, :n] = tb.values
+                packed[s, k, n:] = tb.values[-1]  # end value held (oracle.sample_field)
+        return packed, np.asarray(set_of_job, dtype=np.int32), grid
+
+    def _mto_products(self, prob: Problem, job: Job, mats: list, cache: dict):
+        """Group a job's MTOs by step; returns {step: (sb_id, sa_id)} with matrix-pool ids."""
+        by_step: Dict[int, Tuple[list, list]] = {}
+        for m in job.mtos:
+            k = job.mto_step(m)
+            by_step.setdefault(k, ([], []))[0 if m.before else 1].append(m.superop)
+        out = {}
+        for k, (bef, aft) in by_step.items():
+            ids = []
+            for lst in (bef, aft):
+                if not lst:
+                    ids.append(-1)
+                    continue
+                prod = np.eye(prob.NL, dtype=complex)
+                for s in lst:  # file order: first listed acts first
+                    prod = s @ prod
+                key = prod.tobytes()
+                if key not in cache:
+                    cache[key] = len(mats)
+                    mats.append(_c128(prod))
+                ids.append(cache[key])
+            out[k] = (ids[0], ids[1])
+        return out
+
+    def plan(self, prob: Problem, pt: ProcessTensor, jobs: Sequence[Job], *, kernel: str = "dmma",
+             t_eval: str = "half_mid", fork: bool = True, tile_T: Optional[int] = None):
+        """Build the trunk batch (may be None) and the main batch for `jobs`."""
+        if not jobs:
+            raise ValueError("no jobs")
+        dt = float(jobs[0].dt)
+        for jb in jobs:
+            if abs(jb.dt - dt) > 1e-15:
+                raise ValueError("all jobs of one batch must share dt")
+            if len({jb.mto_step(m) for m in jb.mtos}) > MAX_OVR:
+                raise ValueError(f"more than {MAX_OVR} distinct multitime-operator times in one job")
+        packed, set_of_job, grid = self._tables_of(jobs)
+        chi_pad = -(-pt.chi_max // 8) * 8
+        NL, n_out = prob.NL, prob.n_out
+        off1, off2 = T_EVAL[t_eval]
+
+        # ---- absolute time origin: every job starts its own PT at its t_start (ACE: ta)
+        # jobs are grouped by (drive set, t_start); absolute step 0 of a group = its t_start
+        t0_ref = min(jb.t_start for jb in jobs)
+
+        mats: list = []
+        mcache: dict = {}
+        seqs, entries, trajs = [], [], []
+        trunk_seqs, trunk_trajs, snap_steps = [], [], []
+        n_slots = 0
+        groups: Dict[Tuple[int, float], List[int]] = {}
+        for i, jb in enumerate(jobs):
+            groups.setdefault((int(set_of_job[i]), round(jb.t_start / dt)), []).append(i)
+
+        out_off = np.zeros(len(jobs), dtype=np.int64)
+        n_rows = np.asarray([jb.n_steps + 1 for jb in jobs], dtype=np.int64)
+        out_off[1:] = np.cumsum(n_rows[:-1] * n_out)
+        out_elems = int(np.sum(n_rows * n_out))
+        copy_from_trunk = []  # (job, rows, trunk_job_index)
+
+        for (sset, _), members in groups.items():
+            # a separate time origin per group keeps `step` = steps since the group's t_start
+            t_start = jobs[members[0]].t_start
+            step_shift = int(round((t_start - t0_ref) / dt))  # table/time bookkeeping only
+            mto_maps = {i: self._mto_products(prob, jobs[i], mats, mcache) for i in members}
+            first = {i: (min(mto_maps[i]) if mto_maps[i] else None) for i in members}
+            use_fork = fork and len(members) > 1 and any(f is not None and f > 0 for f in first.values())
+            if use_fork:
+                fork_steps = sorted({f for f in first.values() if f is not None and f > 0})
+                trunk_len = max(max(fork_steps),
+                                max([jobs[i].n_steps for i in members if first[i] is None] + [0]))
+                q_trunk = len(trunk_seqs)
+                trunk_seqs.append((sset, step_shift, trunk_len + 1, 0))
+                slot_of_step = {f: n_slots + k for k, f in enumerate(fork_steps)}
+                trunk_trajs.append(dict(seq=q_trunk, off=0, step0=0, n_steps=trunk_len, init_kind=0,
+                                        init_index=0, ovr=[], snap=(len(snap_steps), len(fork_steps), n_slots),
+                                        shift=step_shift, members=members))
+                snap_steps.extend(fork_steps)
+                n_slots += len(fork_steps)
+                # main batch: one shared MTO-free sequence for the group, branches index into it
+                t_end_max = max(jobs[i].n_steps for i in members)
+                q_main = len(seqs)
+                seqs.append((sset, step_shift, t_end_max + 1, 0))
+                for i in members:
+                    jb = jobs[i]
+                    f = first[i]
+                    ovr = []
+                    for k, (sb, sa) in sorted(mto_maps[i].items()):
+                        ovr.append((k, len(entries)))
+                        entries.append((sset, step_shift + k, sb, sa, 1 if k > 0 else 0))
+                    if f is None or f == 0:
+                        trajs.append(dict(job=i, seq=q_main, off=0, step0=0, n_steps=jb.n_steps, init_kind=0,
+                                          init_index=0, ovr=ovr, row0=0))
+                    else:
+                        trajs.append(dict(job=i, seq=q_main, off=f, step0=f, n_steps=jb.n_steps - f,
+                                          init_kind=1, init_index=slot_of_step[f],
+                                          ovr=[(k - f, e) for k, e in ovr], row0=f))
+                        copy_from_trunk.append((i, f, len(trunk_trajs) - 1))
+            else:
+                for i in members:
+                    jb = jobs[i]
+                    q = len(seqs)
+                    seqs.append((sset, step_shift, jb.n_steps + 1, 0))
+                    ovr = []
+                    for k, (sb, sa) in sorted(mto_maps[i].items()):
+                        ovr.append((k, len(entries)))
+                        entries.append((sset, step_shift + k, sb, sa, 1 if k > 0 else 0))
+                    trajs.append(dict(job=i, seq=q, off=0, step0=0, n_steps=jb.n_steps, init_kind=0,
+                                      init_index=0, ovr=ovr, row0=0))
+
+        common = dict(prob=prob, pt=pt, dt=dt, t0=t0_ref, off=(off1, off2), packed=packed, grid=grid,
+                      mats=mats, chi_pad=chi_pad, kernel=kernel, tile_T=tile_T)
+        main = dict(seqs=seqs, entries=entries, trajs=trajs, snap_steps=[], n_slots=0)
+        trunk = None
+        if trunk_trajs:
+            trunk = dict(seqs=trunk_seqs, entries=[], trajs=trunk_trajs, snap_steps=snap_steps, n_slots=n_slots)
+        return common, trunk, main, (out_off, n_rows, out_elems, copy_from_trunk)
+
+    def _materialise(self, common, part, out_off_of_traj, out_elems, out_buf=None) -> _Plan:
+        prob, pt = common["prob"], common["pt"]
+        NL, n_out = prob.NL, prob.n_out
+        seqs = np.zeros(len(part["seqs"]), dtype=SEQ_DT)
+        for q, (sset, step0, ln, fhp) in enumerate(part["seqs"]):
+            seqs[q] = (sset, step0, ln, fhp)
+        seq_base = np.zeros(len(seqs) + 1, dtype=np.int64)
+        seq_base[1:] = np.cumsum(seqs["len"].astype(np.int64))
+        entries = np.zeros(len(part["entries"]), dtype=ENTRY_DT)
+        for e, tup in enumerate(part["entries"]):
+            entries[e] = tup
+        tr = part["trajs"]
+        trajs = np.zeros(len(tr), dtype=TRAJ_DT)
+        for b, t in enumerate(tr):
+            r = trajs[b]
+            r["ent0"] = seq_base[t["seq"]] + t["off"]
+            r["out_off"] = out_off_of_traj[b]
+            r["step0"] = t["step0"]
+            r["n_steps"] = t["n_steps"]
+            r["init_kind"] = t["init_kind"]
+            r["init_index"] = t["init_index"]
+            r["n_ovr"] = len(t["ovr"])
+            for k, (st, en) in enumerate(t["ovr"]):
+                r["ovr_step"][k] = st
+                r["ovr_ent"][k] = en
+            if "snap" in t:
+                r["snap_off"], r["snap_cnt"], r["snap_slot0"] = t["snap"]
+        # tiling: sort by (step0, n_steps) so that tiles are homogeneous in absolute time
+        order = np.lexsort((trajs["n_steps"], trajs["step0"]))
+        blk_of_alpha = self.problem_handle(prob, pt)[1]
+        rows_per_block = np.bincount(blk_of_alpha).tolist()
+        t_max = self.max_tile(NL, common["chi_pad"])
+        if t_max < 1:
+            raise EngineError(f"NL={NL}, chi={common['chi_pad']} does not fit the step kernel's shared memory")
+        T = common["tile_T"] or choose_tile(len(tr), [r for r in rows_per_block if r], t_max)
+        T = min(T, t_max)
+        n_tiles = -(-len(tr) // T)
+        tile_traj = np.full(n_tiles * T, -1, dtype=np.int32)
+        tile_traj[:len(tr)] = order
+        mats = _c128(np.asarray(common["mats"]).reshape(-1, NL, NL)) if common["mats"] else np.zeros((0, NL, NL), complex)
+        rho0 = _c128(prob.rho0).reshape(1, NL)
+        snap_steps = np.asarray(part["snap_steps"], dtype=np.int32)
+        out = out_buf if out_buf is not None else np.zeros(out_elems, dtype=np.complex128)
+        packed = common["packed"]
+        b = _Batch()
+        b.dt, b.t0 = common["dt"], common["t0"]
+        b.eval_off1, b.eval_off2 = common["off"]
+        b.n_sets, b.n_tables, b.n_samples = packed.shape
+        b.tab_t0, b.tab_dt = common["grid"]
+        b.tables = packed.ctypes.data
+        b.n_seq, b.seqs = len(seqs), seqs.ctypes.data
+        b.n_entries, b.entries = len(entries), (entries.ctypes.data if len(entries) else None)
+        b.n_mto_mats, b.mto_mats = len(mats), (mats.ctypes.data if len(mats) else None)
+        b.n_rho0, b.rho0s = 1, rho0.ctypes.data
+        b.n_traj, b.trajs = len(trajs), trajs.ctypes.data
+        b.tile_T, b.n_tiles, b.tile_traj = T, n_tiles, tile_traj.ctypes.data
+        b.n_snap_steps = len(snap_steps)
+        b.snap_steps = snap_steps.ctypes.data if len(snap_steps) else None
+        b.n_snap_slots = part["n_slots"]
+        b.out_elems, b.out = out_elems, out.ctypes.data
+        b.device_resident = 0
+        b.kernel = 0 if common["kernel"] == "dmma" else 1
+        return _Plan(batch=b, keep=[seqs, entries, trajs, tile_traj, mats, rho0, snap_steps, packed, out],
+                     out=out, out_off=np.asarray(out_off_of_traj), n_rows=trajs["n_steps"] + 1)
+
+    # -------------------------------------------------------------- running
+    def run_jobs(self, prob: Problem, pt: Optional[ProcessTensor], jobs: Sequence[Job], *,
+                 kernel: str = "dmma", t_eval: str = "half_mid", fork: bool = True,
+                 tile_T: Optional[int] = None) -> List[np.ndarray]:
+        """Propagate `jobs`; returns one ``[n_out, n_steps+1]`` complex array per job."""
+        if pt is None:
+            pt = self._trivial(prob)
+        hp, _ = self.problem_handle(prob, pt)
+        hpt = self.pt_handle(pt)
+        common, trunk, main, (out_off, n_rows, out_elems, copy_list) = self.plan(
+            prob, pt, jobs, kernel=kernel, t_eval=t_eval, fork=fork, tile_T=tile_T)
+        n_out = prob.n_out
+        trunk_out = None
+        if trunk is not None:
+            t_rows = np.asarray([t["n_steps"] + 1 for t in trunk["trajs"]], dtype=np.int64)
+            t_off = np.zeros(len(t_rows), dtype=np.int64)
+            t_off[1:] = np.cumsum(t_rows[:-1] * n_out)
+            tp = self._materialise(common, trunk, t_off, int(np.sum(t_rows * n_out)))
+            _check(self.lib.aceqd_propagate_batch(self.ctx, hp, hpt, ctypes.byref(tp.batch)),
+                   "aceqd_propagate_batch(trunk)")
+            trunk_out = (tp.out, t_off, t_rows)
+        # branch b writes its rows at the tail of its job's block
+        traj_out_off = [out_off[t["job"]] + t["row0"] * n_out for t in main["trajs"]]
+        mp = self._materialise(common, main, traj_out_off, out_elems)
+        _check(self.lib.aceqd_propagate_batch(self.ctx, hp, hpt, ctypes.byref(mp.batch)),
+               "aceqd_propagate_batch")
+        out = mp.out
+        for (job, f, ti) in copy_list:
+            src = trunk_out[0][trunk_out[1][ti]: trunk_out[1][ti] + f * n_out]
+            out[out_off[job]: out_off[job] + f * n_out] = src
+        res = []
+        for i in range(len(jobs)):
+            blk = out[out_off[i]: out_off[i] + n_rows[i] * n_out].reshape(n_rows[i], n_out)
+            res.append(np.ascontiguousarray(blk.T))
+        return res
+
+    def _trivial(self, prob: Problem) -> ProcessTensor:
+        key = ("trivial", len(prob.cls_keys))
+        if not hasattr(self, "_triv"):
+            self._triv = {}
+        if key not in self._triv:
+            self._triv[key] = trivial_pt(n_cls=len(prob.cls_keys))
+        return self._triv[key]
+
+
+_default_engines: Dict[int, Engine] = {}
+
+
+def default_engine(device: Optional[int] = None) -> Engine:
+    """Process-wide engine for `device` (default: LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _default_engines:
+        _default_engines[device] = Engine(device)
+    return _default_engines[device]

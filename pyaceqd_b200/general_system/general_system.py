@@ -1,0 +1,352 @@
+"""``system_ace_stream`` -- the drop-in boundary.
+
+Same signature, argument meaning, return layout and error behaviour as the reference's
+``pyaceqd/general_system/general_system.py:128-360``, but instead of writing an ACE parameter
+file + pulse files and spawning the ``ACE`` binary (``:227-343``) it builds a numeric
+:class:`~pyaceqd_b200.problem.Problem`, samples the drives exactly like the pulse files
+(grid ``np.arange(t_start, t_end, dt)`` ``:213``, 8 decimals ``:69-70``) and runs the CUDA engine
+in process.  Inside a :class:`~pyaceqd_b200.batch.BatchExecutor` the call is deferred so that a
+whole sweep becomes one GPU batch.
+"""
+from __future__ import annotations
+
+import os
+import threading
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+import pyaceqd_b200.constants as constants
+from pyaceqd_b200.jobs import FieldTable, Job
+from pyaceqd_b200.problem import Problem, build_problem
+from pyaceqd_b200.process_tensor import ProcessTensor
+
+hbar = constants.hbar  # meV*ps
+temp_dir = constants.temp_dir
+
+_capture = threading.local()          # set by BatchExecutor: deferred execution
+_problem_cache: Dict[tuple, Problem] = {}
+_pt_cache: Dict[str, ProcessTensor] = {}
+_table_cache: Dict[tuple, Dict[str, FieldTable]] = {}
+_cache_lock = threading.Lock()
+
+
+def sanity_checks(system_op, phonons, boson_op, initial, interaction_ops, verbose):
+    """Reference ``general_system.py:17-27`` (prints + exit on a missing boson operator)."""
+    if system_op is None and verbose:
+        print("System operator not supplied, assuming TLS")
+    if phonons and boson_op is None:
+        print("using phonons, but boson operator not specified")
+        exit(1)
+    if initial is None and verbose:
+        print("No initial state specified")
+    if interaction_ops is None and verbose:
+        print("No interaction hamiltonian ")
+
+
+def check_multitime(multitime_op, verbose):
+    """Normalise one multitime dict in place (reference ``general_system.py:29-53``)."""
+    if verbose:
+        print("multitime operator: {}".format(multitime_op))
+    if multitime_op is None:
+        return
+    if "operator" not in multitime_op or "time" not in multitime_op:
+        print("supply 'operator' and 'time' for multitime")
+        exit(0)
+    multitime_op.setdefault("applyFrom", "")       # "": A rho A^+
+    multitime_op.setdefault("applyBefore", "false")  # after `time`: visible at time+dt
+    if multitime_op["applyFrom"] not in ("_left", "_right", ""):
+        print(multitime_op)
+        print('give "_left" or "_right" or "" for multitime')
+        exit(0)
+
+
+def _quantise(v: np.ndarray) -> np.ndarray:
+    """The ``%.8f`` text round trip of the pulse files (``general_system.py:69-70``)."""
+    return np.round(np.real(v), 8) + 1j * np.round(np.imag(v), 8)
+
+
+def sample_pulses(t, pulses, abs_only=False) -> Tuple[np.ndarray, np.ndarray]:
+    """x / y drive samples, ``sum_p polar * p.get_total(t)`` (reference ``generate_pulsefiles``,
+    ``general_system.py:55-71``), quantised like the pulse file."""
+    px = np.zeros_like(t, dtype=complex)
+    py = np.zeros_like(t, dtype=complex)
+    for p in pulses:
+        f = p.get_total(t)
+        if abs_only:
+            f = np.abs(f)
+        px = px + p.polar_x * f
+        py = py + p.polar_y * f
+    return _quantise(px), _quantise(py)
+
+
+def sample_rf(t, pulses, firstonly=False):
+    """Rotating-frame tables (reference ``generate_rf_file``, ``general_system.py:73-102``): the rf
+    table is the instantaneous frequency of the first pulse; every carrier is shifted by the
+    first pulse's ``e_start`` and all chirps are zeroed before the x / y tables are regenerated."""
+    if len(pulses) > 1:
+        print("Warning: more than one pulse supplied, only the first one is used for rf")
+        print("Note that also, chirping more than the first pulse is not supported")
+    rf = _quantise(np.asarray(pulses[0].get_frequency(t), dtype=complex) * np.ones_like(t))
+    shifted = [p.copy() for p in pulses]
+    e0, _ = shifted[0].get_energy()
+    for p in shifted:
+        e, _ = p.get_energy()
+        p.set_energy(e - e0, 0)
+    px, py = sample_pulses(t, [shifted[0]] if firstonly else shifted)
+    return rf, px, py
+
+
+def read_pulse_file(path: str) -> FieldTable:
+    """ACE pulse-file reader: columns ``t Re Im`` (``general_system.py:69-70``), cached by mtime."""
+    key = ("file", os.path.abspath(path), os.path.getmtime(path))
+    with _cache_lock:
+        if key in _table_cache:
+            return _table_cache[key]["f"]
+    data = np.loadtxt(path, ndmin=2)
+    t = data[:, 0]
+    dt = float(t[1] - t[0]) if len(t) > 1 else 1.0
+    tab = FieldTable(float(t[0]), dt, data[:, 1] + 1j * data[:, 2])
+    with _cache_lock:
+        _table_cache[key] = {"f": tab}
+    return tab
+
+
+def read_result(data, n):
+    """``[t, Re o1, Im o1, ...]`` rows -> ``[(1+n), n_t]`` complex (reference ``:104-110``)."""
+    t = data[:, 0]
+    result = np.empty([1 + n, len(t)], dtype=complex)
+    result[0] = t
+    for i in range(n):
+        result[i + 1] = data[:, 2 * i + 1] + 1j * data[:, 2 * i + 2]
+    return result
+
+
+@dataclass
+class Request:
+    """One deferred ``system_ace_stream`` call."""
+    problem: Problem
+    pt: Optional[ProcessTensor]
+    job: Job
+    pulse_key: tuple          # identifies the drive (pulse objects / files) for table sharing
+    table_maker: object       # callable(t_end) -> tables dict, used when tables are unified
+    calc_dynmap: bool = False
+    result: Optional[np.ndarray] = None
+
+
+def _problem_for(**kw) -> Problem:
+    key = (tuple(kw.get("system_op") or ()), kw.get("boson_op"), kw.get("initial"),
+           tuple((o, float(r)) for o, r in (kw.get("lindblad_ops") or ())),
+           tuple((o, p) for o, p in (kw.get("interaction_ops") or ())),
+           tuple(kw.get("output_ops") or ()), kw.get("rf_op"),
+           None if kw.get("rho0") is None else np.asarray(kw["rho0"]).tobytes(), kw.get("dict_zero"))
+    with _cache_lock:
+        if key not in _problem_cache:
+            _problem_cache[key] = build_problem(
+                system_op=kw.get("system_op"), boson_op=kw.get("boson_op"), initial=kw.get("initial"),
+                lindblad_ops=kw.get("lindblad_ops"), interaction_ops=kw.get("interaction_ops"),
+                output_ops=kw.get("output_ops") or (), rf_op=kw.get("rf_op"), rho0=kw.get("rho0"),
+                dict_zero=10.0 ** (-int(kw.get("dict_zero") or 16)))
+        return _problem_cache[key]
+
+
+def resolve_pt(pt_file: str, *, boson_op, dt, t_mem, ae, temperature, threshold, factor_ah, use_infinite,
+               boson_e_max, J_file, verbose, problem: Problem) -> ProcessTensor:
+    """Load (or build and cache) the phonon PT named like the reference does (``:146-151``)."""
+    with _cache_lock:
+        if pt_file in _pt_cache:
+            return _pt_cache[pt_file]
+    if os.path.exists(pt_file):
+        pt = ProcessTensor.load(pt_file)
+        if verbose:
+            print("using pt_file " + pt_file)
+    else:
+        if os.path.exists(pt_file + "_initial"):
+            raise NotImplementedError(
+                "{}_initial is an ACE-format process tensor; its binary layout is undocumented "
+                "(SURVEY App. E, R2). Rebuild it with this engine (delete the ACE files).".format(pt_file))
+        print("{} not found. Calculating...".format(pt_file))
+        from pyaceqd_b200.pt_builder import build_qd_phonon_pt
+        if J_file is not None:
+            raise NotImplementedError("Boson_J_from_file is not supported by the PT builder yet")
+        pt = build_qd_phonon_pt(coupling_diag=problem.meta["coupling_diag"], dt=float(dt), t_mem=float(t_mem),
+                                a_e=float(ae), a_h=None if factor_ah is None else float(ae) / float(factor_ah),
+                                temperature=float(temperature), threshold=10.0 ** (-int(threshold)),
+                                e_max=float(boson_e_max), use_infinite=bool(use_infinite), verbose=verbose)
+        try:
+            pt.save(pt_file)
+        except OSError:
+            pass
+    with _cache_lock:
+        _pt_cache[pt_file] = pt
+    return pt
+
+
+def system_ace_stream(t_start, t_end, *pulses, dt=0.01, phonons=False, t_mem=20.48, ae=3.0, temperature=1,
+                      verbose=False, temp_dir=temp_dir, pt_file=None, suffix="", multitime_op=None,
+                      pulse_file_x=None, pulse_file_y=None, system_prefix="", threshold="10",
+                      threshold_ratio="0.3", buffer_blocksize="-1", dict_zero="16", precision="12",
+                      boson_e_max=7, system_op=None, boson_op=None, initial=None, lindblad_ops=None,
+                      interaction_ops=None, output_ops=[], prepare_only=False, LO_params=None,
+                      dressedstates=False, rf_op=None, rf_file=None, firstonly=False, J_to_file=None,
+                      J_file=None, factor_ah=None, use_infinite=False, print_H=False, calc_dynmap=False,
+                      rho0=None, get_M_t=None):
+    """In-process replacement of the ACE round trip; see the module docstring.
+
+    Returns ``ndarray[(1+len(output_ops)), n_t]`` complex with row 0 = time
+    (reference ``:343,360``); ``(result, dm[n_t, NL, NL])`` with ``calc_dynmap`` (``:358-359``);
+    the single-step propagator matrix with ``get_M_t`` (``:325-327``).
+    """
+    sanity_checks(system_op=system_op, phonons=phonons, boson_op=boson_op, initial=initial,
+                  interaction_ops=interaction_ops, verbose=verbose)
+    if multitime_op is not None:
+        if isinstance(multitime_op, dict):
+            multitime_op = [multitime_op]
+        for _mto in multitime_op:
+            check_multitime(multitime_op=_mto, verbose=verbose)
+    if LO_params is not None:
+        raise NotImplementedError("add_single_mode (LO_params) needs a non-diagonal environment; out of scope")
+    if dressedstates or print_H:
+        raise NotImplementedError("timedep_eigenstates / print_H are ACE diagnostics binaries; out of scope")
+    if prepare_only:
+        # the reference writes the param file and returns dummies (:292-296); nothing to prepare here
+        return [np.array([0, 0]) for _ in range(1 + len(output_ops))]
+
+    problem = _problem_for(system_op=system_op, boson_op=boson_op if phonons else None, initial=initial,
+                           lindblad_ops=lindblad_ops, interaction_ops=interaction_ops, output_ops=output_ops,
+                           rf_op=rf_op, rho0=rho0, dict_zero=dict_zero)
+
+    pt = None
+    if phonons:
+        if pt_file is None:
+            pt_file = "{}_{}nm_{}k_th{}_tmem{}_dt{}.ptr".format(system_prefix, ae, temperature, threshold, t_mem, dt)
+            if J_file is not None:
+                pt_file = "{}_{}_{}k_th{}_tmem{}_dt{}.ptr".format(system_prefix, os.path.splitext(J_file)[0],
+                                                                 temperature, threshold, t_mem, dt)
+            if use_infinite:
+                # the reference name omits ae (cache-collision hazard); keep ae in ours
+                pt_file = "{}_{}nm_{}k_th{}_dt{}.pt".format(system_prefix, ae, temperature, threshold, dt)
+        pt = resolve_pt(pt_file, boson_op=boson_op, dt=dt, t_mem=t_mem, ae=ae, temperature=temperature,
+                        threshold=threshold, factor_ah=factor_ah, use_infinite=use_infinite,
+                        boson_e_max=boson_e_max, J_file=J_file, verbose=verbose, problem=problem)
+
+    # ---- drive tables: the content of the pulse files
+    def make_tables(te):
+        t = np.arange(t_start, te, step=dt / 1)   # reference :213
+        tabs: Dict[str, FieldTable] = {}
+        if rf_op is not None and rf_file is None:
+            rf, px, py = sample_rf(t, pulses, firstonly=firstonly)
+            tabs["rf"] = FieldTable(float(t_start), float(dt), rf)
+            tabs["x"] = FieldTable(float(t_start), float(dt), px)
+            tabs["y"] = FieldTable(float(t_start), float(dt), py)
+            return tabs
+        if rf_op is not None:
+            tabs["rf"] = read_pulse_file(rf_file)
+        if pulse_file_x is not None:
+            tabs["x"] = read_pulse_file(pulse_file_x)
+            if pulse_file_y is not None:
+                tabs["y"] = read_pulse_file(pulse_file_y)
+        else:
+            px, py = sample_pulses(t, [pulses[0]] if firstonly else pulses)
+            tabs["x"] = FieldTable(float(t_start), float(dt), px)
+            tabs["y"] = FieldTable(float(t_start), float(dt), py)
+        return tabs
+
+    if interaction_ops is not None:
+        for _op in interaction_ops:
+            if _op[1] == "y" and pulse_file_x is not None and pulse_file_y is None:
+                print("Pulse file y not given")
+                exit(1)
+    pulse_key = (tuple(id(p) for p in pulses), pulse_file_x, pulse_file_y, rf_file, float(t_start), float(dt),
+                 bool(firstonly), rf_op)
+
+    if get_M_t is not None:
+        # fprop.update(t, dt); fprop.M  (:324-327): propagator of one full step starting at t
+        from pyaceqd_b200.engine import default_engine
+        job = Job(float(t_start), float(t_end), float(dt), tables=make_tables(t_end))
+        L = problem.L0.copy()
+        for k, pol in enumerate(problem.field_pol):
+            tab = job.tables.get(pol)
+            if tab is None:
+                continue
+            x = (get_M_t + 0.5 * dt - tab.t0) / tab.dt
+            f = np.interp(x, np.arange(len(tab.values)), tab.values.real) + \
+                1j * np.interp(x, np.arange(len(tab.values)), tab.values.imag)
+            L = L + f * problem.LA[k] + np.conj(f) * problem.LB[k]
+        return default_engine().expm(L * dt)[0]
+
+    job = Job(float(t_start), float(t_end), float(dt), tables=make_tables(t_end),
+              mtos=problem.parse_mtos(multitime_op))
+    req = Request(problem=problem, pt=pt, job=job, pulse_key=pulse_key, table_maker=make_tables,
+                  calc_dynmap=calc_dynmap)
+    sink = getattr(_capture, "sink", None)
+    if sink is not None and not calc_dynmap:
+        sink.append(req)
+        return req      # BatchExecutor resolves it
+    return run_requests([req])[0]
+
+
+def _finish(req: Request, out: np.ndarray):
+    res = np.empty((1 + out.shape[0], out.shape[1]), dtype=complex)
+    res[0] = req.job.times()
+    res[1:] = out
+    return res
+
+
+def run_requests(reqs: List[Request]):
+    """Execute deferred requests: one GPU batch per (problem, PT, dt) group."""
+    from pyaceqd_b200.engine import default_engine
+    eng = default_engine()
+    results = [None] * len(reqs)
+    groups: Dict[tuple, List[int]] = {}
+    for i, r in enumerate(reqs):
+        groups.setdefault((id(r.problem), id(r.pt), r.job.dt), []).append(i)
+    for (_, _, _), idx in groups.items():
+        prob, pt = reqs[idx[0]].problem, reqs[idx[0]].pt
+        # unify drive tables of requests that sample the same pulses from the same t_start
+        by_key: Dict[tuple, List[int]] = {}
+        for i in idx:
+            by_key.setdefault(reqs[i].pulse_key, []).append(i)
+        for key, members in by_key.items():
+            if len(members) > 1:
+                te = max(reqs[i].job.t_end for i in members)
+                tabs = reqs[members[0]].table_maker(te)
+                for i in members:
+                    reqs[i].job.tables = tabs
+        plain = [i for i in idx if not reqs[i].calc_dynmap]
+        if plain:
+            outs = eng.run_jobs(prob, pt, [reqs[i].job for i in plain])
+            for i, o in zip(plain, outs):
+                results[i] = _finish(reqs[i], o)
+        for i in idx:
+            if reqs[i].calc_dynmap:
+                results[i] = _run_dynmap(eng, reqs[i])
+    for r, res in zip(reqs, results):
+        r.result = res
+    return results
+
+
+def _run_dynmap(eng, req: Request):
+    """``DynamicalMap.E`` (reference ``:328-335``): propagate the NL unit vectors with identity
+    outputs in the same batch as the physical initial state."""
+    import copy
+    prob = req.problem
+    NL = prob.NL
+    res = _finish(req, eng.run_jobs(prob, req.pt, [req.job])[0])
+    E = np.empty((req.job.n_steps + 1, NL, NL), dtype=complex)
+    key = ("dynmap", id(prob))
+    with _cache_lock:
+        basis = _problem_cache.get(key)
+        if basis is None:
+            basis = []
+            for j in range(NL):
+                p = copy.copy(prob)
+                p.rho0 = np.zeros(NL, dtype=complex)
+                p.rho0[j] = 1.0
+                p.out_w = np.eye(NL, dtype=complex)
+                basis.append(p)
+            _problem_cache[key] = basis
+    for j, p in enumerate(basis):
+        E[:, :, j] = eng.run_jobs(p, req.pt, [req.job])[0].T
+    return res, E

@@ -1,0 +1,204 @@
+"""Host helpers that define the I/O contract of the engine: time grids, operator-string
+generators, density-matrix (de)composition, CSV export, concurrence.
+
+Public names and argument meaning follow the reference's ``pyaceqd/tools.py`` (cited per
+function); plotting helpers are out of scope.
+"""
+from __future__ import annotations
+
+import itertools
+import re
+
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------ grids
+def _merge_intervals(intervals):
+    """Merge sorted ``[start, end]`` intervals that overlap or touch (reference ``tools.py:9-26``;
+    cases pinned by ``pyaceqd/tests/test_merge_interval.py:5-23``).  Works in place and returns
+    the same list, like the reference."""
+    merged = []
+    for lo, hi in intervals:
+        if merged and lo <= merged[-1][1]:
+            merged[-1][1] = max(merged[-1][1], hi)
+        else:
+            merged.append([lo, hi])
+    intervals[:] = merged
+    return intervals
+
+
+def get_gaussian_t(t0, tend, *pulses, dt_max=1.0, dt_min=0.01, interval_per_step=0.05):
+    """Adaptive grid: a new point whenever the accumulated pulse area since the last point
+    reaches ``interval_per_step`` or ``dt_max`` has elapsed (reference ``tools.py:28-44``)."""
+    fine = np.arange(t0, tend, dt_min)
+    area = np.zeros(len(fine))
+    for p in pulses:
+        area = area + p.get_integral(fine)
+    n_max = int(dt_max / dt_min)
+    pts = [t0]
+    since, acc = 0, 0.0
+    for i in range(1, len(fine)):
+        acc += area[i] - area[i - 1]
+        since += 1
+        if acc >= interval_per_step or since == n_max:
+            pts.append(fine[i])
+            since, acc = 0, 0.0
+    return np.array(pts)
+
+
+def construct_t(t0, tend, dt_small=0.1, dt_big=1.0, dt_exp=None, *pulses, factor_tau=4, simple_exp=False,
+                gaussian_t=False, add_tend=True):
+    """Time axis with spacing ``dt_small`` within ``factor_tau*tau`` of every pulse centre and
+    ``dt_big`` elsewhere (reference ``tools.py:46-108``).  Note the positional ``dt_exp`` before
+    ``*pulses`` -- a reference quirk that callers rely on."""
+    if dt_exp is None:
+        dt_exp = dt_small
+    windows = []
+    for p in pulses:
+        if t0 < p.t0 < tend:
+            windows.append([p.t0 - factor_tau * p.tau, p.t0 + factor_tau * p.tau])
+        elif p.t0 > tend:
+            print("WARNING: tend is smaller than the end of a pulse")
+        elif p.t0 < t0:
+            print("WARNING: t0 is greater than the start of a pulse")
+    windows = _merge_intervals(sorted(windows))
+    if windows[0][0] < t0:
+        print("WARNING: t0 is greater than the start of the first pulse")
+    if windows[-1][1] > tend:
+        print("WARNING: tend is smaller than the end of the last pulse")
+    parts = [np.arange(t0, windows[0][0], dt_big)]
+    if simple_exp and len(windows) == 1 and windows[0][1] != 0:
+        lo, hi = windows[0]
+        if gaussian_t:
+            parts.append(get_gaussian_t(lo, hi, *pulses, dt_max=dt_big, dt_min=dt_small, interval_per_step=0.05))
+        else:
+            parts.append(np.arange(lo, hi, dt_small))
+        parts.append(np.round(np.exp(np.arange(np.log(hi), np.log(tend), dt_exp))))
+        parts.append(np.array([tend]))
+        return np.concatenate(parts)
+    for k, (lo, hi) in enumerate(windows):
+        if k > 0:
+            parts.append(np.arange(windows[k - 1][1], lo, dt_big))
+        parts.append(np.arange(lo, hi, dt_small))
+    parts.append(np.arange(windows[-1][1], tend, dt_big))
+    if add_tend:
+        parts.append(np.array([tend]))
+    return np.concatenate(parts)
+
+
+def round_to_dt(t, dt):
+    """Snap to multiples of ``dt`` and drop duplicates, keeping order (reference ``tools.py:110-118``)."""
+    snapped = np.round(np.asarray(t) / dt) * dt
+    _, first = np.unique(snapped, return_index=True)
+    return snapped[np.sort(first)]
+
+
+def simple_t_gaussian(t0, texp, tend, dt_small=0.1, dt_big=1.0, *pulses, decimals=2, exp_part=True, add_tend=True):
+    """Adaptive grid up to ``texp`` then exponential (or ``dt_big``) spacing (reference ``tools.py:120-135``)."""
+    parts = [get_gaussian_t(t0, texp, *pulses, dt_max=dt_big, dt_min=dt_small, interval_per_step=0.05)]
+    if exp_part:
+        parts.append(np.exp(np.arange(np.log(texp - t0), np.log(tend - t0), dt_small)) + t0)
+    else:
+        parts.append(np.arange(texp, tend, dt_big))
+    if add_tend:
+        parts.append(np.array([tend]))
+    return round_to_dt(np.concatenate(parts), dt_small)
+
+
+# ------------------------------------------------------------------------------------ I/O
+def export_csv(filename, *arg, precision=4, delimit=',', verbose=False):
+    """Write columns with fixed ``%.{precision}f`` formatting (reference ``tools.py:137-165``; the
+    ACE pulse-file format uses ``precision=8, delimit=' '``, ``general_system.py:69-70``)."""
+    fmt = ["%.{}f".format(precision)] * len(arg)
+    np.savetxt(filename, np.column_stack(arg), fmt=fmt, delimiter=delimit, newline="\n")
+    if verbose:
+        print("[i] csv saved to {}".format(filename))
+
+
+# ------------------------------------------------------------------------------------ density matrices
+def concurrence(rho):
+    """Wootters concurrence of a two-qubit density matrix (reference ``tools.py:167-172``)."""
+    flip = np.fliplr(np.diag([-1.0, 1.0, 1.0, -1.0]))
+    ev = np.real(np.linalg.eigvals(rho @ flip @ np.conjugate(rho) @ flip))
+    lam = np.sqrt(np.sort(ev))
+    return max(0.0, lam[-1] - np.sum(lam[:-1]))
+
+
+def serialize_dm(rho):
+    return np.concatenate((np.real(rho).flatten(), np.imag(rho).flatten()))
+
+
+def deserialize_dm(rho):
+    dim = int(np.sqrt(len(rho) / 2))
+    return rho[:dim ** 2].reshape(dim, dim) + 1j * rho[dim ** 2:].reshape(dim, dim)
+
+
+def compose_dm(outputs, dim=2):
+    """Assemble ``rho[t, j, k]`` from the upper-triangle outputs of :func:`output_ops_dm`
+    (reference ``tools.py:188-201``, layout pinned by ``tests/test_output_ops.py:26-41``):
+    output ``n`` (1-based, row 0 is time) fills ``rho[:, j, k]`` and its conjugate ``rho[:, k, j]``."""
+    outputs = np.asarray(outputs)
+    rho = np.zeros((len(outputs[0]), dim, dim), dtype=np.complex128)
+    iu, ku = np.triu_indices(dim)
+    for n, (j, k) in enumerate(zip(iu, ku), start=1):
+        rho[:, j, k] = outputs[n]
+        rho[:, k, j] = np.conjugate(outputs[n])
+    return np.real(outputs[0]), rho
+
+
+def generate_basis_states(dim):
+    """Product-basis index tuples, rightmost factor fastest (reference ``tools.py:203-211``)."""
+    return list(itertools.product(*[range(d) for d in dim]))
+
+
+def basis_states(dim):
+    if not isinstance(dim, list):
+        dim = [dim]
+    return ["|" + ",".join(str(i) for i in st) + "⟩" for st in generate_basis_states(dim)]
+
+
+def matrix_element_operators(basis_states, dim, readable=False):
+    """Operator strings ``|bra><ket|`` for every upper-triangle pair (reference ``tools.py:229-246``)."""
+    ops = []
+    for i, bra in enumerate(basis_states):
+        for ket in basis_states[i:]:
+            if readable:
+                ops.append(" ⊗ ".join(f"|{b}⟩⟨{k}|_{d}" for b, k, d in zip(bra, ket, dim)))
+            else:
+                ops.append(" otimes ".join(f"|{b}><{k}|_{d}" for b, k, d in zip(bra, ket, dim)))
+    return ops
+
+
+def output_ops_dm(dim=[2, 2], readable=False):
+    """Output operators whose expectation values give the full density matrix via
+    :func:`compose_dm` (reference ``tools.py:248-258``; strings pinned by
+    ``tests/test_output_ops.py:11-24,43-73``)."""
+    if not isinstance(dim, (list, tuple)):
+        dim = [dim]
+    return matrix_element_operators(generate_basis_states(dim), dim, readable=readable)
+
+
+def op_to_matrix(op):
+    """Matrix of a single ``|n><m|_dim`` string, optionally parenthesised (reference ``tools.py:260-304``)."""
+    dm = re.search(r"_(\d+)(?:\[.*\])?", op)
+    if not dm:
+        raise ValueError(f"Invalid dimension format in operator: {op}")
+    dim = int(dm.group(1))
+    m = re.match(r"[(]*\|(\d+)><(\d+)\|_[\d)]*", op)
+    if not m:
+        return None
+    ket, bra = int(m.group(1)), int(m.group(2))
+    if ket >= dim or bra >= dim:
+        raise ValueError(f"Index out of bounds: ket_idx={ket}, bra_idx={bra}, dim={dim}")
+    out = np.zeros((dim, dim), dtype=complex)
+    out[ket, bra] = 1.0
+    return out
+
+
+# ------------------------------------------------------------------------------------ units
+def nm_to_mev(lambda_light):
+    return 1239.84198 / lambda_light  # hc in eV*nm -> meV
+
+
+def mev_to_nm(energy_light):
+    return 1239.84198 / energy_light

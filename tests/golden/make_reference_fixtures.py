@@ -1,0 +1,76 @@
+"""Generate golden fixtures by IMPORTING the reference (run in the build container only;
+/root/reference does not exist on the GPU box).  matplotlib / ACEutils are absent here, so they
+are stubbed in sys.modules before import.  Output: reference_host.json.
+
+    python tests/golden/make_reference_fixtures.py
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+sys.path.insert(0, "/root/reference")
+for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.collections", "ACEutils"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+
+import pyaceqd.pulses as rp  # noqa: E402
+import pyaceqd.tools as rt  # noqa: E402
+
+out = {}
+# --- pulses (reference pulses.py): complex fields on a fixed grid
+t = np.linspace(-30.0, 60.0, 181)
+specs = {
+    "Pulse": ("Pulse", dict(tau=3, e_start=1.2, w_gain=0.05, t0=10, e0=2.0, phase=0.3, polar_x=0.6)),
+    "ChirpedPulse": ("ChirpedPulse", dict(tau_0=3, e_start=-2, alpha=20, t0=12, e0=5)),
+    "AsymmetricPulse": ("AsymmetricPulse", dict(tau1=2, tau2=6, e_start=0.5, t0=5, e0=1.5)),
+    "CWLaser": ("CWLaser", dict(e0=0.3, e_start=1)),
+    "SmoothRectangle": ("SmoothRectangle", dict(tau=20, e_start=0.2, t0=15, e0=0.4)),
+}
+out["pulse_t"] = t.tolist()
+out["pulses"] = {}
+for key, (cls, kw) in specs.items():
+    p = getattr(rp, cls)(**kw)
+    f = p.get_total(t)
+    out["pulses"][key] = dict(cls=cls, kw=kw, re=np.real(f).tolist(), im=np.imag(f).tolist(),
+                              freq=np.asarray(p.get_frequency(t), dtype=float).tolist() if cls != "CWLaser" else None,
+                              polar_y=float(p.polar_y))
+# --- tools: interval merging cases of tests/test_merge_interval.py:5-23
+cases = [[[-1, 1], [1, 2], [5, 8]], [[-1, 2], [1, 3], [4, 8]], [[-1, 3], [1, 3], [4, 8]],
+         [[-1, 1], [1, 3], [4, 8]], [[-1, 7], [1, 3], [4, 8]]]
+out["merge"] = [dict(inp=c, out=rt._merge_intervals([list(x) for x in c])) for c in cases]
+# --- construct_t grids of tests/test_merge_interval.py:25-33 (note the dt_exp positional quirk:
+#     the first pulse binds to dt_exp there; we call with dt_exp explicit AND in the quirky form)
+p1 = rp.ChirpedPulse(tau_0=1, e_start=0, t0=4)
+p2 = rp.ChirpedPulse(tau_0=1, e_start=0, t0=20)
+p3 = rp.ChirpedPulse(tau_0=1, e_start=0, t0=5)
+out["construct_t"] = {
+    "two_pulses": rt.construct_t(0, 80, 0.1, 1.0, None, p1, p2, simple_exp=False).tolist(),
+    "quirk_first_pulse_is_dt_exp": rt.construct_t(0, 80, 0.1, 1.0, p1, p2, simple_exp=False).tolist(),
+    "simple_exp": rt.construct_t(0, 80, 0.1, 1.0, 0.1, p1, p3, simple_exp=True).tolist(),
+    "gaussian_t": rt.construct_t(0, 80, 0.1, 1.0, 0.1, p1, simple_exp=True, gaussian_t=True).tolist(),
+}
+out["simple_t_gaussian"] = rt.simple_t_gaussian(0, 10, 80, 0.1, 1.0, p1).tolist()
+out["round_to_dt"] = rt.round_to_dt(np.array([0.04, 0.11, 0.12, 0.26, 0.31]), 0.1).tolist()
+# --- operator strings (tests/test_output_ops.py) and compose_dm
+out["output_ops_dm"] = {"2": rt.output_ops_dm(2), "6": rt.output_ops_dm(6), "2_1": rt.output_ops_dm((2, 1)),
+                        "2_2": rt.output_ops_dm([2, 2]), "2_2_2": rt.output_ops_dm([2, 2, 2])}
+rng = np.random.default_rng(5)
+data = rng.standard_normal((7, 4)) + 1j * rng.standard_normal((7, 4))
+tt, rho = rt.compose_dm(data, dim=3)
+out["compose_dm"] = dict(re=np.real(data).tolist(), im=np.imag(data).tolist(), t=tt.tolist(),
+                         rho_re=np.real(rho).tolist(), rho_im=np.imag(rho).tolist())
+r = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+r = r @ r.conj().T
+r /= np.trace(r)
+out["concurrence"] = dict(re=np.real(r).tolist(), im=np.imag(r).tolist(), value=float(rt.concurrence(r)))
+bell = np.zeros((4, 4), dtype=complex)
+bell[0, 0] = bell[3, 3] = bell[0, 3] = bell[3, 0] = 0.5
+out["concurrence_bell"] = float(rt.concurrence(bell))
+m = rt.op_to_matrix("(|1><0|_3)")
+out["op_to_matrix"] = np.real(m).tolist()
+
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_host.json"), "w") as fh:
+    json.dump(out, fh, default=lambda o: o.item() if hasattr(o, "item") else o.tolist())
+print("wrote reference_host.json")

@@ -1,0 +1,118 @@
+"""GPU parity: the CUDA path (through the C ABI, ctypes) against the CPU oracle on identical
+inputs.  Tolerance: 1e-10 absolute on every output (north star asks <= 1e-8 in FP64)."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import biexciton_problem, make_tables, sixls_problem, sweep_jobs, tls_problem
+from pyaceqd_b200.jobs import Job
+from pyaceqd_b200.problem import MTO
+from pyaceqd_b200.process_tensor import synthetic_growing_pt, synthetic_pt, trivial_pt
+from pyaceqd_b200.pulses import ChirpedPulse
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _compare(engine, prob, pt, jobs, kernel, **kw):
+    got = engine.run_jobs(prob, pt, jobs, kernel=kernel, **kw)
+    worst = 0.0
+    for g, jb in zip(got, jobs):
+        ref = oracle.propagate(prob, pt, jb)
+        assert g.shape == ref.shape
+        worst = max(worst, float(np.abs(g - ref).max()))
+    assert worst < TOL, f"max abs deviation {worst:.3e} (kernel={kernel})"
+    return worst
+
+
+def test_dmma_fragment_layout_via_expm(engine):
+    """Device expm (Taylor scaling-and-squaring) vs scipy Pade."""
+    from scipy.linalg import expm
+    rng = np.random.default_rng(0)
+    for n in (4, 9, 16, 25, 36):
+        a = (rng.standard_normal((7, n, n)) + 1j * rng.standard_normal((7, n, n))) * rng.uniform(0.01, 3.0, (7, 1, 1))
+        got = engine.expm(a)
+        for i in range(7):
+            ref = expm(a[i])
+            assert np.abs(got[i] - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("kernel", ["check", "dmma"])
+def test_tls_no_phonons(engine, kernel):
+    prob = tls_problem(phonons=False)
+    p = ChirpedPulse(tau_0=3, e_start=0, alpha=0, t0=12, e0=1)
+    jobs = [Job(0.0, 30.0, 0.1, tables=make_tables([p], 0.0, 30.0, 0.1))]
+    _compare(engine, prob, trivial_pt(len(prob.cls_keys)), jobs, kernel)
+
+
+@pytest.mark.parametrize("kernel", ["check", "dmma"])
+@pytest.mark.parametrize("chi", [8, 20, 64, 128])
+def test_tls_synthetic_pt_sweep(engine, kernel, chi):
+    prob = tls_problem()
+    pt = synthetic_pt(chi, len(prob.cls_keys), n_slices=2, kind="unitary", scale=0.999)
+    jobs = sweep_jobs(6, 7, t_end=4.0 if chi > 32 else 8.0)
+    _compare(engine, prob, pt, jobs, kernel)
+
+
+@pytest.mark.parametrize("kernel", ["check", "dmma"])
+def test_growing_pt_and_ragged_lengths(engine, kernel):
+    prob = tls_problem()
+    pt = synthetic_growing_pt(24, len(prob.cls_keys), n_initial=5, n_repeat=3)
+    p = ChirpedPulse(tau_0=1, e_start=0.5, alpha=0, t0=3, e0=2)
+    jobs = [Job(0.0, te, 0.1, tables=make_tables([p], 0.0, te, 0.1)) for te in (0.0, 0.1, 0.3, 1.0, 2.7, 5.0)]
+    _compare(engine, prob, pt, jobs, kernel)
+
+
+@pytest.mark.parametrize("kernel", ["check", "dmma"])
+def test_biexciton_mto_fork_equals_unforked_oracle(engine, kernel):
+    """G2-style grid: every job shares the drive, MTOs at t1_i; the engine forks
+    from one trunk, the oracle runs every trajectory from scratch."""
+    from pyaceqd_b200.opparser import parse_operator
+    prob = biexciton_problem(outputs=["|1><1|_4", "(|1><0|_4*|1><1|_4*|0><1|_4)", "|0><3|_4"])
+    pt = synthetic_pt(32, len(prob.cls_keys), n_slices=3, kind="unitary", scale=0.999)
+    dt, tau_max = 0.25, 3.0
+    p = ChirpedPulse(tau_0=1.0, e_start=-2.0, alpha=0, t0=3.0, e0=4.0, polar_x=0.8)
+    tabs = make_tables([p], 0.0, 12.0, dt)
+    a = parse_operator("|1><0|_4", 4)
+    c = parse_operator("|0><1|_4", 4)
+    jobs = []
+    for t1 in np.arange(0.0, 6.0, 0.75):
+        mtos = [MTO(prob.mto_superop(a, "_right"), float(t1), False),
+                MTO(prob.mto_superop(c, "_left"), float(t1), False)]
+        jobs.append(Job(0.0, float(t1 + tau_max), dt, tables=tabs, mtos=mtos))
+    w1 = _compare(engine, prob, pt, jobs, kernel, fork=True)
+    w2 = _compare(engine, prob, pt, jobs, kernel, fork=False)
+    assert max(w1, w2) < TOL
+
+
+@pytest.mark.parametrize("kernel", ["check", "dmma"])
+def test_mto_before_sandwich_and_multiple_times(engine, kernel):
+    from pyaceqd_b200.opparser import parse_operator
+    prob = tls_problem()
+    pt = synthetic_pt(16, len(prob.cls_keys), kind="unitary")
+    p = ChirpedPulse(tau_0=1.0, e_start=0.3, alpha=0, t0=2.0, e0=1.5)
+    tabs = make_tables([p], 0.0, 6.0, 0.1)
+    s = parse_operator("|0><1|_2", 2)
+    jobs = [Job(0.0, 6.0, 0.1, tables=tabs, mtos=[
+        MTO(prob.mto_superop(s, ""), 0.0, False), MTO(prob.mto_superop(s.conj().T, "_left"), 1.5, True),
+        MTO(prob.mto_superop(s, "_right"), 1.5, False), MTO(prob.mto_superop(s.conj().T, "_right"), 6.0, True)])]
+    _compare(engine, prob, pt, jobs, kernel)
+
+
+@pytest.mark.parametrize("kernel", ["check", "dmma"])
+def test_sixlevel_nl36(engine, kernel):
+    prob = sixls_problem()
+    pt = synthetic_pt(40, len(prob.cls_keys), kind="unitary")
+    p1 = ChirpedPulse(tau_0=1.0, e_start=-2.0, alpha=0, t0=3.0, e0=5.0, polar_x=0.7)
+    jobs = [Job(0.0, 2.0, 0.1, tables=make_tables([p1], 0.0, 2.0, 0.1)) for _ in range(3)]
+    _compare(engine, prob, pt, jobs, kernel)
+
+
+def test_tile_sizes_agree(engine):
+    prob = tls_problem()
+    pt = synthetic_pt(32, len(prob.cls_keys))
+    jobs = sweep_jobs(5, 5, t_end=3.0)
+    ref = engine.run_jobs(prob, pt, jobs, kernel="check")
+    for T in (1, 2, 4, 8, 16):
+        got = engine.run_jobs(prob, pt, jobs, kernel="dmma", tile_T=T)
+        assert max(np.abs(g - r).max() for g, r in zip(got, ref)) < 1e-12, T
