@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Benchmark of the PT-propagation hot path (BASELINE.json metric: trajectory-steps/sec at PT
+bond dimension chi).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One bench "step" = one pass of the hot path over one batch: the cfg2 pulse-area x detuning
+sweep of SURVEY 8d (two-level dot, synthetic PT of exact bond dimension chi, 64 x 64 = 4096
+pulses, 400 time steps of dt = 0.1 ps).  A trajectory-step = half step exp(L dt/2) -> PT slice
+-> half step -> closure/outputs for one trajectory.  Per rank the work is fixed (weak scaling):
+rank r sweeps its own detuning window; the only collective is the final all-gather of results.
+
+`value`  : whole-job trajectory-steps/s with drive tables and outputs resident in HBM
+           (operator builder + step kernel, CUDA events, max over ranks).
+`e2e`    : same metric through Engine.run_sweep -> aceqd_propagate_batch with HOST (pinned)
+           buffers: H2D of the drive tables and D2H of all outputs inside the timed region.
+`roofline`: step kernel only, algorithmic flops 8*NL*chi*(2*NL+chi) per trajectory-step
+            over its CUDA-event duration, against the FP64 DMMA peak measured by the
+           library's own register-resident micro-benchmark in this run (MEASURED_PEAKS.json has
+           no FP64 figure).
+`--impl reference`: the CPU restatement of the reference path (oracle/oracle_c.c, "port": the
+           reference's own implementation is the external ACE binary, absent here) on all host
+           threads, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HBAR = 0.6582119569
+METRIC = "trajectory-steps/sec at PT bond dim chi"
+UNIT = "trajectory-steps/s"
+
+
+def make_workload(chi, n_area, n_det, n_steps, dt, rank=0):
+    """cfg2 of SURVEY 8d: areas linspace(0,30,n_area) (units of pi), detunings
+    linspace(-5,5,n_det) meV (shifted by 10 meV per rank), Gaussian tau=5 ps at t0=20 ps."""
+    from pyaceqd_b200.problem import build_problem
+    from pyaceqd_b200.process_tensor import synthetic_pt
+    prob = build_problem(boson_op="1.000*|1><1|_2", initial="|0><0|_2", lindblad_ops=[["|0><1|_2", 0.01]],
+                         interaction_ops=[["|1><0|_2", "x"]],
+                         output_ops=["|0><0|_2", "|1><1|_2", "|0><1|_2", "|1><0|_2"])
+    pt = synthetic_pt(chi, len(prob.cls_keys), dt=dt, seed=1234)
+    t = dt * np.arange(n_steps)                       # pulse-file grid np.arange(t_start, t_end, dt)
+    areas = np.linspace(0.0, 30.0, n_area)
+    dets = np.linspace(-5.0, 5.0, n_det) + 10.0 * rank
+    tau, t0 = 5.0, 20.0
+    env = np.exp(-0.5 * ((t - t0) / tau) ** 2) / (np.sqrt(2 * np.pi) * tau)
+    f = (areas[:, None, None] * env[None, None, :]) * np.exp(-1j * (dets[None, :, None] / HBAR) * (t - t0)[None, None, :])
+    f = f.reshape(n_area * n_det, 1, n_steps)
+    f = np.round(f.real, 8) + 1j * np.round(f.imag, 8)   # %.8f pulse-file quantisation
+    return prob, pt, np.ascontiguousarray(f)
+
+
+def flops_per_step(NL, chi):
+    return 8.0 * NL * chi * (2 * NL + chi)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(c[0]))
+                mx = max(mx, float(c[1]))
+            except (ValueError, IndexError):
+                continue
+            for nme, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        # the median over samples under load (above the idle clock)
+        load = [x for x in sm if x > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_rate(prob, pt, tables, n_steps, dt, seconds=10.0, threads=0):
+    """Time the C oracle on a bounded sample of the same workload; returns (rate, sample str, cores)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_c
+    from pyaceqd_b200.jobs import FieldTable, Job
+    cores = oracle_c.max_threads() if threads <= 0 else threads
+
+    def run(n):
+        idx = np.linspace(0, tables.shape[0] - 1, n).astype(int)
+        jobs = [Job(0.0, n_steps * dt, dt, tables={"x": FieldTable(0.0, dt, tables[i, 0])}) for i in idx]
+        t = time.perf_counter()
+        oracle_c.propagate_sweep(prob, pt, jobs, n_threads=threads)
+        return time.perf_counter() - t
+
+    probe = max(cores, 8)
+    t_probe = run(probe)
+    n = int(min(tables.shape[0], max(probe, probe * seconds / max(t_probe, 1e-3))))
+    n = max(cores, n // cores * cores)
+    el = run(n)
+    return n * n_steps / el, f"{n} of {tables.shape[0]} trajectories x {n_steps} steps ({el:.1f} s)", cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chi", type=int, default=128)
+    ap.add_argument("--n-area", type=int, default=64)
+    ap.add_argument("--n-det", type=int, default=64)
+    ap.add_argument("--n-steps", type=int, default=400)
+    ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dt = 0.1
+    n_traj = args.n_area * args.n_det
+    config = {"workload": "cfg2: two-level QD + synthetic PT (seed 1234), %dx%d pulse-area x detuning sweep, "
+                          "%d steps of dt=0.1 ps" % (args.n_area, args.n_det, args.n_steps),
+              "chi": args.chi, "NL": 4, "n_traj_per_gpu": n_traj, "n_steps": args.n_steps,
+              "l2": "inputs larger than L2: %.2f GB of per-step operators rebuilt and streamed every pass"
+                    % (n_traj * (args.n_steps + 1) * (512 + 256) / 1e9)}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        prob, pt, tables = make_workload(args.chi, args.n_area, args.n_det, args.n_steps, dt)
+        vals = []
+        sample, cores = "", 0
+        for i in range(args.warmup + args.steps):
+            r, sample, cores = cpu_rate(prob, pt, tables, args.n_steps, dt,
+                                        seconds=max(2.0, 60.0 / (args.warmup + args.steps)))
+            if i >= args.warmup:
+                vals.append(r)
+        v = float(np.mean(vals))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": "CPU restatement (oracle/oracle_c.c), not ACE: the reference's own path is the external ACE binary"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    import torch.distributed as dist
+    from pyaceqd_b200.engine import Engine
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+    eng = Engine(local, stream=stream.cuda_stream)
+    prob, pt, tables_np = make_workload(args.chi, args.n_area, args.n_det, args.n_steps, dt, rank=rank)
+    n_out, NL = prob.n_out, prob.NL
+    tables_pin = eng.pinned_empty(tables_np.shape, np.complex128)
+    tables_pin[...] = tables_np
+    plan = eng.plan_sweep(prob, pt, n_traj, args.n_steps, dt, 0.0, n_traj, args.n_steps, (0.0, dt),
+                          tile_T=args.tile or None)
+    plan.batch.n_tables = 1
+    tables_dev = torch.from_numpy(tables_np).cuda()
+    out_dev = torch.empty((n_traj, args.n_steps + 1, n_out), dtype=torch.complex128, device="cuda")
+    gathered = torch.empty((world,) + tuple(out_dev.shape), dtype=torch.complex128, device="cuda") if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_pass():
+        eng.run_sweep_device(prob, pt, plan, tables_dev.data_ptr(), out_dev.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out_dev)
+
+    peak_dmma = eng.fp64_peak("dmma", 20000)
+    peak_dfma = eng.fp64_peak("dfma", 20000)
+
+    for _ in range(args.warmup):
+        one_pass()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    k_ms, op_ms = [], []
+    for _ in range(args.steps):
+        one_pass()
+    e1.record(stream)
+    barrier()
+    launches = eng.launch_count() - n0
+    ms_total = e0.elapsed_time(e1)
+    k_last, op_last = eng.last_timings()
+    # per-launch step-kernel durations: re-run K passes reading the library's own events
+    for _ in range(args.steps):
+        eng.run_sweep_device(prob, pt, plan, tables_dev.data_ptr(), out_dev.data_ptr())
+        a, b = eng.last_timings()
+        k_ms.append(a)
+        op_ms.append(b)
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total = float(tmax.item())
+    units = float(world) * n_traj * args.n_steps * args.steps
+    value = units / (ms_total * 1e-3)
+
+    # ---- end to end: host (pinned) buffers through the public API
+    eplan = eng.plan_sweep(prob, pt, n_traj, args.n_steps, dt, 0.0, n_traj, args.n_steps, (0.0, dt),
+                           tile_T=args.tile or None)
+    eplan.batch.n_tables = 1
+    for _ in range(2):
+        res = eng.run_sweep(prob, pt, tables_pin, (0.0, dt), 0.0, args.n_steps, dt, plan=eplan, copy=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = eng.run_sweep(prob, pt, tables_pin, (0.0, dt), 0.0, args.n_steps, dt, plan=eplan, copy=False)
+        final_x = float(res[-1, -1, 1].real)   # read a result on the host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = units / float(te.item())
+    # consistency of both legs (same inputs -> same numbers)
+    dev_host = out_dev.cpu().numpy()
+    leg_diff = float(np.abs(dev_host - res).max())
+
+    if rank == 0:
+        k_avg = float(np.mean(k_ms))
+        fl = flops_per_step(NL, args.chi) * n_traj * args.n_steps
+        achieved = fl / (k_avg * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tables_pin.nbytes),
+                    "d2h_bytes_per_step": int(res.nbytes), "ms_per_step": 1e3 * float(te.item()) / args.steps,
+                    "api": "Engine.run_sweep -> aceqd_propagate_batch (host pinned buffers)"},
+            "roofline": {"bound": "tensor", "kernel": "k_step_dmma", "achieved": achieved, "peak": peak_dmma,
+                         "unit": "TFLOP/s", "frac": achieved / peak_dmma, "traffic": None,
+                         "peak_source": "FP64 DMMA.8x8x4 register-resident micro-benchmark (aceqd_fp64_peak) measured in this run; "
+                                        "MEASURED_PEAKS.json holds no FP64 figure; nominal B200 FP64 ~40 TFLOP/s",
+                         "dfma_peak": peak_dfma, "kernel_ms": k_avg, "opbuild_ms": float(np.mean(op_ms)),
+                         "flops_per_trajectory_step": flops_per_step(NL, args.chi),
+                         "tile_T": int(plan.batch.tile_T), "n_tiles": int(plan.batch.n_tiles)},
+            "legs_max_abs_diff": leg_diff, "final_x_last_traj": final_x,
+        }
+        if not args.no_cpu and world == 1:
+            r, sample, cores = cpu_rate(prob, pt, tables_np, args.n_steps, dt, seconds=args.cpu_seconds)
+            line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                    "note": "CPU restatement (oracle/oracle_c.c, OpenMP), not ACE"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -180,6 +180,10 @@ int aceqd_snapshot_read(aceqd_ctx* ctx, int slot, int NL, int chi_pad, double* h
  * behind the operator builder.  Replaces `fprop.update(t, dt); fprop.M` (general_system.py:324-327). */
 int aceqd_expm_batch(aceqd_ctx* ctx, int n, int count, const double* a_host, double* out_host);
 
+/* Page-locked host memory for the end-to-end path (H2D of drive tables, D2H of outputs). */
+int aceqd_host_alloc(size_t bytes, void** out);
+void aceqd_host_free(void* p);
+
 /* sizeof() of aceqd_seq, aceqd_entry, aceqd_traj, aceqd_batch as compiled (binding self-check). */
 void aceqd_struct_sizes(int32_t out[4]);
 

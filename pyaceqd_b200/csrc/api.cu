@@ -640,6 +640,21 @@ int aceqd_expm_batch(aceqd_ctx* c, int n, int count, const double* a_host, doubl
     return ACEQD_OK;
 }
 
+int aceqd_host_alloc(size_t bytes, void** out) {
+    if (!out) return ACEQD_ERR_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return ACEQD_ERR_NOMEM;
+    }
+    return ACEQD_OK;
+}
+
+void aceqd_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 void aceqd_struct_sizes(int32_t out[4]) {
     out[0] = (int32_t)sizeof(aceqd_seq);
     out[1] = (int32_t)sizeof(aceqd_entry);

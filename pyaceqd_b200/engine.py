@@ -101,6 +101,9 @@ def load_library():
     lib.aceqd_expm_batch.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
     lib.aceqd_max_tile.argtypes = [c_int, c_int]
     lib.aceqd_fp64_peak.argtypes = [c_void_p, c_int, c_int, POINTER(c_double)]
+    lib.aceqd_host_alloc.argtypes = [ctypes.c_size_t, POINTER(c_void_p)]
+    lib.aceqd_host_free.argtypes = [c_void_p]
+    lib.aceqd_host_free.restype = None
     lib.aceqd_struct_sizes.argtypes = [POINTER(c_int32)]
     lib.aceqd_struct_sizes.restype = None
     sizes = (c_int32 * 4)()
@@ -165,6 +168,8 @@ class Engine:
                                          ctypes.byref(h)), "aceqd_ctx_create")
         self.ctx = h
         self.device = int(device)
+        self._pinned: list = []
+        self._out_pinned = None
         self._pts: Dict[int, Tuple[c_void_p, ProcessTensor]] = {}
         self._probs: Dict[Tuple[int, int], Tuple[c_void_p, Problem, np.ndarray]] = {}
 
@@ -177,6 +182,10 @@ class Engine:
                 self.lib.aceqd_problem_destroy(h)
             self._pts.clear()
             self._probs.clear()
+            self._out_pinned = None
+            for ptr in self._pinned:
+                self.lib.aceqd_host_free(ptr)
+            self._pinned = []
             self.lib.aceqd_ctx_destroy(self.ctx)
             self.ctx = None
 
@@ -255,6 +264,111 @@ class Engine:
         out = np.empty((NL, chi_pad), dtype=np.complex128)
         _check(self.lib.aceqd_snapshot_read(self.ctx, slot, NL, chi_pad, out.ctypes.data), "aceqd_snapshot_read")
         return out
+
+    # -------------------------------------------------------------- pinned host memory
+    def pinned_empty(self, shape, dtype=np.complex128) -> np.ndarray:
+        """Page-locked host array (owned by the engine; freed with it)."""
+        dt_ = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        ptr = c_void_p()
+        _check(self.lib.aceqd_host_alloc(max(1, n) * dt_.itemsize, ctypes.byref(ptr)), "aceqd_host_alloc")
+        self._pinned.append(ptr)
+        buf = (ctypes.c_char * (max(1, n) * dt_.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dt_, count=n).reshape(shape)
+
+    def _pinned_out(self, n_elems: int) -> np.ndarray:
+        if self._out_pinned is None or self._out_pinned.size < n_elems:
+            self._out_pinned = self.pinned_empty(int(n_elems * 1.1) + 16, np.complex128)
+        return self._out_pinned[:n_elems]
+
+    # -------------------------------------------------------------- uniform sweeps (vectorised)
+    def plan_sweep(self, prob: Problem, pt: ProcessTensor, n_traj: int, n_steps: int, dt: float,
+                   t_start: float, n_sets: int, n_samples: int, grid: Tuple[float, float], *,
+                   sets: Optional[np.ndarray] = None, kernel: str = "dmma", t_eval: str = "half_mid",
+                   tile_T: Optional[int] = None) -> "_Plan":
+        """Descriptors of a pulse-parameter sweep: `n_traj` MTO-free trajectories of equal length
+        starting at the PT origin (reference fan-out
+        ``two_level_system/rabi_rotations.py:172-198``).  Table / output pointers are filled in
+        by :meth:`run_sweep`."""
+        NL, n_out = prob.NL, prob.n_out
+        _, blk_of_alpha = self.problem_handle(prob, pt)
+        chi_pad = -(-pt.chi_max // 8) * 8
+        t_max = self.max_tile(NL, chi_pad)
+        if t_max < 1:
+            raise EngineError(f"NL={NL}, chi={chi_pad} does not fit the step kernel's shared memory")
+        rows_per_block = [r for r in np.bincount(blk_of_alpha).tolist() if r]
+        T = min(tile_T or choose_tile(n_traj, rows_per_block, t_max), t_max)
+        n_tiles = -(-n_traj // T)
+        sets = np.arange(n_traj, dtype=np.int32) if sets is None else np.asarray(sets, dtype=np.int32)
+        seqs = np.zeros(n_traj, dtype=SEQ_DT)
+        seqs["set"], seqs["step0"], seqs["len"] = sets, 0, n_steps + 1
+        trajs = np.zeros(n_traj, dtype=TRAJ_DT)
+        trajs["ent0"] = np.arange(n_traj, dtype=np.int64) * (n_steps + 1)
+        trajs["out_off"] = np.arange(n_traj, dtype=np.int64) * (n_steps + 1) * n_out
+        trajs["n_steps"] = n_steps
+        tile_traj = np.full(n_tiles * T, -1, dtype=np.int32)
+        tile_traj[:n_traj] = np.arange(n_traj, dtype=np.int32)
+        rho0 = _c128(prob.rho0).reshape(1, NL)
+        off1, off2 = T_EVAL[t_eval]
+        b = _Batch()
+        b.dt, b.t0, b.eval_off1, b.eval_off2 = float(dt), float(t_start), off1, off2
+        b.n_sets, b.n_tables, b.n_samples = int(n_sets), 3, int(n_samples)
+        b.tab_t0, b.tab_dt = float(grid[0]), float(grid[1])
+        b.n_seq, b.seqs = n_traj, seqs.ctypes.data
+        b.n_entries, b.entries, b.n_mto_mats, b.mto_mats = 0, None, 0, None
+        b.n_rho0, b.rho0s = 1, rho0.ctypes.data
+        b.n_traj, b.trajs = n_traj, trajs.ctypes.data
+        b.tile_T, b.n_tiles, b.tile_traj = T, n_tiles, tile_traj.ctypes.data
+        b.n_snap_steps, b.snap_steps, b.n_snap_slots = 0, None, 0
+        b.out_elems = int(n_traj) * (n_steps + 1) * n_out
+        b.kernel = 0 if kernel == "dmma" else 1
+        return _Plan(batch=b, keep=[seqs, trajs, tile_traj, rho0], out=None,
+                     out_off=trajs["out_off"], n_rows=trajs["n_steps"] + 1)
+
+    def run_sweep(self, prob: Problem, pt: Optional[ProcessTensor], tables: np.ndarray,
+                  grid: Tuple[float, float], t_start: float, n_steps: int, dt: float, *,
+                  plan: Optional["_Plan"] = None, copy: bool = True, kernel: str = "dmma",
+                  t_eval: str = "half_mid", tile_T: Optional[int] = None) -> np.ndarray:
+        """End-to-end sweep through the C ABI with HOST buffers: `tables[n_traj, 3, n_samples]`
+        (x, y, rf drive samples of every trajectory; ideally :meth:`pinned_empty` memory) is
+        copied to the device, the operators are built, the trajectories propagated and the
+        outputs copied back.  Returns ``out[n_traj, n_steps+1, n_out]`` (a view of an
+        engine-owned pinned buffer, valid until the next call, if ``copy=False``)."""
+        if pt is None:
+            pt = self._trivial(prob)
+        hp, _ = self.problem_handle(prob, pt)
+        hpt = self.pt_handle(pt)
+        tables = np.ascontiguousarray(tables, dtype=np.complex128)
+        n_traj, n_tab, n_samples = tables.shape
+        if not 1 <= n_tab <= 3:
+            raise ValueError("tables must be [n_traj, n_tab<=3 (x, y, rf), n_samples]")
+        if plan is None:
+            plan = self.plan_sweep(prob, pt, n_traj, n_steps, dt, t_start, n_traj, n_samples, grid,
+                                   kernel=kernel, t_eval=t_eval, tile_T=tile_T)
+        out = self._pinned_out(plan.batch.out_elems)
+        plan.batch.tables = tables.ctypes.data
+        plan.batch.n_tables = n_tab
+        plan.batch.out = out.ctypes.data
+        plan.batch.device_resident = 0
+        _check(self.lib.aceqd_propagate_batch(self.ctx, hp, hpt, ctypes.byref(plan.batch)),
+               "aceqd_propagate_batch")
+        res = out.reshape(n_traj, n_steps + 1, prob.n_out)
+        return res.copy() if copy else res
+
+    def run_sweep_device(self, prob: Problem, pt: ProcessTensor, plan: "_Plan", tables_ptr: int,
+                         out_ptr: int) -> None:
+        """HBM-resident leg: drive tables and outputs are device pointers; asynchronous on the
+        engine's stream."""
+        hp, _ = self.problem_handle(prob, pt)
+        hpt = self.pt_handle(pt)
+        plan.batch.tables = tables_ptr
+        plan.batch.out = out_ptr
+        plan.batch.device_resident = 1
+        _check(self.lib.aceqd_propagate_batch(self.ctx, hp, hpt, ctypes.byref(plan.batch)),
+               "aceqd_propagate_batch(device)")
+
+    def sync(self):
+        _check(self.lib.aceqd_ctx_sync(self.ctx), "aceqd_ctx_sync")
 
     # -------------------------------------------------------------- planning
     @staticmethod
