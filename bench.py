@@ -72,6 +72,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
@@ -84,14 +85,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if self.t_begin is not None and not (self.t_begin <= ts <= (self.t_end or ts) + 0.15):
+                continue
             c = [x.strip() for x in r.split(",")]
             try:
                 sm.append(float(c[0]))
@@ -185,7 +188,11 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: handle 0 would make the library create its own stream and the
+    # torch events below would not see the kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng = Engine(local, stream=stream.cuda_stream)
     prob, pt, tables_np = make_workload(args.chi, args.n_area, args.n_det, args.n_steps, dt, rank=rank)
     n_out, NL = prob.n_out, prob.NL
@@ -211,12 +218,28 @@ def main():
     peak_dmma = eng.fp64_peak("dmma", 20000)
     peak_dfma = eng.fp64_peak("dfma", 20000)
 
-    for _ in range(args.warmup):
-        one_pass()
-    barrier()
-    sampler = ClockSampler(local)
+    dbg = os.environ.get("BENCH_DEBUG")
+    tdbg = time.perf_counter()
+
+    def mark(msg):
+        nonlocal tdbg
+        if dbg and rank == 0:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            sys.stderr.write("[bench] %-28s %.1f ms\n" % (msg, 1e3 * (now - tdbg)))
+            tdbg = now
+
+    mark("setup")
+    sampler = ClockSampler(local)   # started before warm-up: the first nvidia-smi start on a box can stall
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)
+    mark("sampler start")
+    for _ in range(args.warmup):
+        one_pass()
+        mark("warmup pass")
+    barrier()
+    sampler.t_begin = time.perf_counter()
     n0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -225,6 +248,8 @@ def main():
         one_pass()
     e1.record(stream)
     barrier()
+    sampler.t_end = time.perf_counter()
+    mark("timed passes")
     launches = eng.launch_count() - n0
     ms_total = e0.elapsed_time(e1)
     k_last, op_last = eng.last_timings()

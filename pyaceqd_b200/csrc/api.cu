@@ -478,7 +478,7 @@ static int build_passes(const aceqd_problem* prob, int T, std::vector<PassDesc>&
 
 int aceqd_max_tile(int NL, int chi_pad) {
     for (int T = MAX_TILE_T; T >= 1; T >>= 1)
-        if (step_smem_bytes(NL, chi_pad, T, 2) <= (size_t)SMEM_BUDGET) return T;
+        if (step_smem_bytes(NL, chi_pad, T, 2, 0) <= (size_t)SMEM_BUDGET) return T;
     return 0;
 }
 
@@ -576,9 +576,20 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
         if ((rc = build_passes(prob, T, passes))) return rc;
         UP(c->passes, passes.data(), passes.size() * sizeof(PassDesc));
         UP(c->tiles, b->tile_traj, (size_t)b->n_tiles * T * sizeof(int32_t));
-        int stages = MAX_STAGES;
-        while (stages >= 2 && step_smem_bytes(pd.NL, chi_pad, T, stages) > (size_t)SMEM_BUDGET)
-            --stages;
+        // prefer staging the per-row operators in shared memory (hides their DRAM latency) if at
+        // least 3 chunk stages still fit; otherwise read them from global memory
+        const int wov_full = pd.w_doubles + pd.ov_doubles;
+        int stages = 0, wov = 0;
+        for (int cand_wov : {wov_full, 0}) {
+            const int min_stages = cand_wov ? 3 : 2;
+            for (int st = MAX_STAGES; st >= min_stages; --st)
+                if (step_smem_bytes(pd.NL, chi_pad, T, st, cand_wov) <= (size_t)SMEM_BUDGET) {
+                    stages = st;
+                    wov = cand_wov;
+                    break;
+                }
+            if (stages) break;
+        }
         if (stages < 2) {
             set_error("NL=%d chi_pad=%d T=%d does not fit %d B of shared memory", pd.NL, chi_pad,
                       T, SMEM_BUDGET);
@@ -587,10 +598,11 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
         sp.T = T;
         sp.n_pass = (int)passes.size();
         sp.stages = stages;
+        sp.wov_doubles = wov;
         sp.n_tiles = b->n_tiles;
         sp.passes = (const PassDesc*)c->passes.p;
         sp.tile_traj = (const int*)c->tiles.p;
-        const size_t smem = step_smem_bytes(pd.NL, chi_pad, T, stages);
+        const size_t smem = step_smem_bytes(pd.NL, chi_pad, T, stages, wov);
         ACEQD_CUDA(cudaEventRecord(c->ev[0], c->stream));
         if ((rc = launch_step_dmma(sp, smem, c->stream, &c->launches))) return rc;
         ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));

@@ -79,6 +79,7 @@ struct StepParams {
     int T;           // trajectories per tile
     int n_pass;
     int stages;      // chunk pipeline depth
+    int wov_doubles; // per-trajectory smem staging of W|OV (0: read operators from global)
     int n_tiles;
     const PassDesc* passes;   // [n_pass]
     const aceqd_traj* trajs;
@@ -115,7 +116,7 @@ int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, cu
                       long long* launches);
 int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, long long* launches);
 int launch_step_check(const StepParams& p, double* scratch, cudaStream_t s, long long* launches);
-size_t step_smem_bytes(int NL, int chi_pad, int T, int stages);
+size_t step_smem_bytes(int NL, int chi_pad, int T, int stages, int wov_doubles);
 int launch_fp64_peak(int kind, int iters, double* sink_dev, int* blocks, int* threads,
                      cudaStream_t s, long long* launches);
 

@@ -19,12 +19,16 @@ namespace aceqd {
 namespace {
 
 struct SmemLayout {
-    size_t bar, traj, pass, pos, r, q, snapn, state, chunks, total;
+    size_t bar, traj, pass, pos, r, q, snapn, wov, state, chunks, total;
+    size_t plane;  // doubles per state plane
 };
+
+constexpr int SKEW = 4;  // extra doubles after every alpha block of T rows (bank skew for phase B)
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline SmemLayout make_layout(int NL, int chi_pad, int T, int stages) {
+__host__ __device__ inline SmemLayout make_layout(int NL, int chi_pad, int T, int stages,
+                                                  int wov_doubles) {
     SmemLayout L;
     const size_t R = (size_t)T * NL;
     const size_t strideA = chi_pad + 4;
@@ -37,7 +41,10 @@ __host__ __device__ inline SmemLayout make_layout(int NL, int chi_pad, int T, in
     L.r = o;     o += align_up(16 * R, 16);
     L.q = o;     o += align_up(16 * (size_t)chi_pad, 16);
     o = align_up(o, 128);
-    L.state = o; o += 2 * R * strideA * 8;
+    L.wov = o;   o += (size_t)2 * T * wov_doubles * 8;   // double-buffered W|OV of the tile (0 = global mode)
+    o = align_up(o, 128);
+    L.plane = R * strideA + (size_t)NL * SKEW;
+    L.state = o; o += 2 * L.plane * 8;
     o = align_up(o, 128);
     L.chunks = o; o += (size_t)stages * 2 * KC * strideA * 8;  // strideB == strideA
     L.total = o;
@@ -80,9 +87,9 @@ __device__ __forceinline__ void compute_bar() {  // the 8 compute warps only
     asm volatile("bar.sync 1, %0;" ::"n"(N_COMPUTE_WARPS * 32) : "memory");
 }
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
 }
 __device__ __forceinline__ int slice_of(const PtDev& pt, int n) {
     return n < pt.n_initial ? n : pt.n_initial + (n - pt.n_initial) % pt.n_repeat;
@@ -94,9 +101,9 @@ __device__ __forceinline__ long long entry_of(const aceqd_traj& t, int i, long l
     return e;
 }
 
-constexpr int KS_MAX = MAX_NL / 4;
-
-template <int NB>
+// NB   = n-tiles (8 bond columns) per compute warp; KSU_T = compile-time bound on the number of
+// DMMA k-steps of the system-operator product (ceil(NL/4) <= KSU_T).
+template <int NB, int KSU_T>
 __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int T = p.T, NL = p.prob.NL, R = T * NL;
@@ -104,7 +111,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     const int strideA = chi_pad + 4;
     const int strideB = p.pt.strideB;
     const int stages = p.stages;
-    const SmemLayout L = make_layout(NL, chi_pad, T, stages);
+    const int wov = p.wov_doubles;          // 0: operators are read from global memory
+    const bool wsm = wov > 0;
+    const SmemLayout L = make_layout(NL, chi_pad, T, stages, wov);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
     aceqd_traj* trj = reinterpret_cast<aceqd_traj*>(smem_raw + L.traj);
     PassDesc* passes = reinterpret_cast<PassDesc*>(smem_raw + L.pass);
@@ -112,13 +121,18 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     int* snapn = reinterpret_cast<int*>(smem_raw + L.snapn);
     double2* rbuf = reinterpret_cast<double2*>(smem_raw + L.r);
     double2* qbuf = reinterpret_cast<double2*>(smem_raw + L.q);
+    double* Wst = reinterpret_cast<double*>(smem_raw + L.wov);
     double* Xre = reinterpret_cast<double*>(smem_raw + L.state);
-    double* Xim = Xre + (size_t)R * strideA;
+    double* Xim = Xre + L.plane;
     double* chunks = reinterpret_cast<double*>(smem_raw + L.chunks);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x;
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
+    const uint32_t bar_wfull = smem_u32(bars + 2 * MAX_STAGES), bar_wempty = smem_u32(bars + 2 * MAX_STAGES + 2);
+    // offset (doubles) of state row (pos, j) inside a plane; rows are alpha-major with a skew
+    auto rowoff = [&](int ps, int j) -> size_t { return (size_t)(ps * T + j) * strideA + (size_t)ps * SKEW; };
+    auto rowoff_r = [&](int row) -> size_t { return (size_t)row * strideA + (size_t)(row / T) * SKEW; };
 
     // ------------------------------------------------------------------ setup
     for (int j = tid; j < T; j += blockDim.x) {
@@ -135,11 +149,15 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     }
     for (int j = tid; j < p.n_pass; j += blockDim.x) passes[j] = p.passes[j];
     for (int j = tid; j < NL; j += blockDim.x) pos[j] = p.prob.pos_of_alpha[j];
-    for (size_t e = tid; e < 2 * (size_t)R * strideA; e += blockDim.x) Xre[e] = 0.0;
+    for (size_t e = tid; e < 2 * L.plane; e += blockDim.x) Xre[e] = 0.0;
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, N_COMPUTE_WARPS);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_wfull + 8 * s, 1);
+            mbar_init(bar_wempty + 8 * s, N_COMPUTE_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -158,19 +176,19 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         if (trj[j].init_kind == 0) {
             const double2* r0 = reinterpret_cast<const double2*>(p.rho0s) + (size_t)trj[j].init_index * NL;
             for (int a = tid; a < NL; a += blockDim.x) {
-                const int row = pos[a] * T + j;
-                Xre[(size_t)row * strideA] = r0[a].x;
-                Xim[(size_t)row * strideA] = r0[a].y;
+                const size_t o = rowoff(pos[a], j);
+                Xre[o] = r0[a].x;
+                Xim[o] = r0[a].y;
             }
         } else {
             const double2* sn = reinterpret_cast<const double2*>(p.snaps) +
                                 (size_t)trj[j].init_index * NL * chi_pad;
             for (int e = tid; e < NL * chi_pad; e += blockDim.x) {
                 const int a = e / chi_pad, d = e - a * chi_pad;
-                const int row = pos[a] * T + j;
+                const size_t o = rowoff(pos[a], j) + d;
                 const double2 v = sn[e];
-                Xre[(size_t)row * strideA + d] = v.x;
-                Xim[(size_t)row * strideA + d] = v.y;
+                Xre[o] = v.x;
+                Xim[o] = v.y;
             }
         }
     }
@@ -186,9 +204,33 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     if (warp == N_COMPUTE_WARPS) {
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, wph0 = 0u, wph1 = 0u;
             const uint32_t bytes = (uint32_t)p.pt.chunk_doubles * 8u;
+            const uint32_t w_bytes = (uint32_t)p.prob.w_doubles * 8u, ov_bytes = (uint32_t)p.prob.ov_doubles * 8u;
+            // stage the per-row operators W_n | OV_n of every active trajectory into buffer n & 1
+            auto issue_wov = [&](int n) {
+                const int buf = n & 1;
+                mbar_wait(bar_wempty + 8 * buf, (buf ? wph1 : wph0) ^ 1u);
+                if (buf) wph1 ^= 1u; else wph0 ^= 1u;
+                uint32_t total = 0;
+                for (int j = 0; j < T; ++j) {
+                    const aceqd_traj& t = trj[j];
+                    if (t.n_steps >= 0 && n >= t.step0 && n <= t.step0 + t.n_steps) total += w_bytes + ov_bytes;
+                }
+                mbar_expect_tx(bar_wfull + 8 * buf, total);
+                for (int j = 0; j < T; ++j) {
+                    const aceqd_traj& t = trj[j];
+                    if (t.n_steps < 0 || n < t.step0 || n > t.step0 + t.n_steps) continue;
+                    const long long e = entry_of(t, n - t.step0, p.ovr_base);
+                    double* dst = Wst + (size_t)(buf * T + j) * wov;
+                    bulk_g2s(smem_u32(dst), p.W + (size_t)e * p.prob.w_doubles, w_bytes, bar_wfull + 8 * buf);
+                    bulk_g2s(smem_u32(dst + p.prob.w_doubles), p.OV + (size_t)e * p.prob.ov_doubles, ov_bytes,
+                             bar_wfull + 8 * buf);
+                }
+            };
+            if (wsm) issue_wov(n_begin);
             for (int n = n_begin; n < n_end; ++n) {
+                if (wsm) issue_wov(n + 1);
                 const int s = slice_of(p.pt, n);
                 const int nch = p.pt.kin_pad[s] / KC;
                 const double* sl = p.pt.blob + p.pt.off[s];
@@ -213,17 +255,18 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     const int n_out = p.prob.n_out;
     const int NLp4 = p.prob.NLp4, MTU = p.prob.NLp8 / 8, KSU = NLp4 / 4;
     int stage = 0;
-    uint32_t phase = 0;
+    uint32_t phase = 0, wph0 = 0u, wph1 = 0u;
 
     for (int n = n_begin; n <= n_end; ++n) {
+        const int buf = n & 1;
         // ---------------- phase A: closure, outputs, snapshots
         for (int row = warp; row < R; row += N_COMPUTE_WARPS) {
             const int j = row % T;
             const aceqd_traj& t = trj[j];
             double2 acc = make_double2(0.0, 0.0);
             if (t.n_steps >= 0 && n >= t.step0 && n <= t.step0 + t.n_steps) {
-                const double* xr = Xre + (size_t)row * strideA;
-                const double* xi = Xim + (size_t)row * strideA;
+                const double* xr = Xre + rowoff_r(row);
+                const double* xi = Xim + rowoff_r(row);
                 if (n == t.step0 && t.init_kind == 0) {
                     if (lane == 0) acc = make_double2(xr[0], xi[0]);
                 } else {
@@ -242,21 +285,33 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             }
             if (lane == 0) rbuf[row] = acc;
         }
+        if (wsm) mbar_wait(bar_wfull + 8 * buf, buf ? wph1 : wph0);
         compute_bar();
         for (int it = tid; it < T * n_out; it += N_COMPUTE_WARPS * 32) {
             const int j = it / n_out, o = it - j * n_out;
             const aceqd_traj& t = trj[j];
             if (t.n_steps < 0 || n < t.step0 || n > t.step0 + t.n_steps) continue;
             const int i = n - t.step0;
-            const long long e = entry_of(t, i, p.ovr_base);
-            const double2* ov = reinterpret_cast<const double2*>(p.OV + (size_t)e * p.prob.ov_doubles) +
-                                (size_t)o * NL;
             double2 acc = make_double2(0.0, 0.0);
-            for (int a = 0; a < NL; ++a) {
-                const double2 w = __ldg(ov + a);
-                const double2 r = rbuf[pos[a] * T + j];
-                acc.x += w.x * r.x - w.y * r.y;
-                acc.y += w.x * r.y + w.y * r.x;
+            if (wsm) {
+                const double2* ov = reinterpret_cast<const double2*>(Wst + (size_t)(buf * T + j) * wov +
+                                                                     p.prob.w_doubles) + (size_t)o * NL;
+                for (int a = 0; a < NL; ++a) {
+                    const double2 w = ov[a];
+                    const double2 r = rbuf[pos[a] * T + j];
+                    acc.x += w.x * r.x - w.y * r.y;
+                    acc.y += w.x * r.y + w.y * r.x;
+                }
+            } else {
+                const long long e = entry_of(t, i, p.ovr_base);
+                const double2* ov = reinterpret_cast<const double2*>(p.OV + (size_t)e * p.prob.ov_doubles) +
+                                    (size_t)o * NL;
+                for (int a = 0; a < NL; ++a) {
+                    const double2 w = __ldg(ov + a);
+                    const double2 r = rbuf[pos[a] * T + j];
+                    acc.x += w.x * r.x - w.y * r.y;
+                    acc.y += w.x * r.y + w.y * r.x;
+                }
             }
             reinterpret_cast<double2*>(p.out)[t.out_off + (long long)i * n_out + o] = acc;
         }
@@ -269,7 +324,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                            (size_t)(t.snap_slot0 + snapn[j]) * NL * chi_pad;
             for (int e = tid; e < NL * chi_pad; e += N_COMPUTE_WARPS * 32) {
                 const int a = e / chi_pad, d = e - a * chi_pad;
-                const size_t o = (size_t)(pos[a] * T + j) * strideA + d;
+                const size_t o = rowoff(pos[a], j) + d;
                 dst[e] = make_double2(Xre[o], Xim[o]);
             }
         }
@@ -288,21 +343,24 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             const int j = item / NT, nt = item - j * NT;
             const aceqd_traj& t = trj[j];
             if (t.n_steps < 0 || n < t.step0 || n >= t.step0 + t.n_steps) continue;
-            const long long e = entry_of(t, n - t.step0, p.ovr_base);
-            const double2* Wp = reinterpret_cast<const double2*>(p.W + (size_t)e * p.prob.w_doubles);
-            double yre[KS_MAX], yim[KS_MAX];
+            const double2* Wp;
+            if (wsm) {
+                Wp = reinterpret_cast<const double2*>(Wst + (size_t)(buf * T + j) * wov);
+            } else {
+                const long long e = entry_of(t, n - t.step0, p.ovr_base);
+                Wp = reinterpret_cast<const double2*>(p.W + (size_t)e * p.prob.w_doubles);
+            }
+            double yre[KSU_T], yim[KSU_T];
             const int col = 8 * nt + g;
 #pragma unroll
-            for (int ks = 0; ks < KS_MAX; ++ks) {
+            for (int ks = 0; ks < KSU_T; ++ks) {
                 yre[ks] = 0.0;
                 yim[ks] = 0.0;
-                if (ks < KSU) {
-                    const int a = 4 * ks + tq;
-                    if (a < NL) {
-                        const size_t o = (size_t)(pos[a] * T + j) * strideA + col;
-                        yre[ks] = Xre[o];
-                        yim[ks] = Xim[o];
-                    }
+                const int a = 4 * ks + tq;
+                if (ks < KSU && a < NL) {
+                    const size_t o = rowoff(pos[a], j) + col;
+                    yre[ks] = Xre[o];
+                    yim[ks] = Xim[o];
                 }
             }
             __syncwarp();
@@ -310,22 +368,27 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
                 const double2* wrow = Wp + (size_t)(8 * mt + g) * NLp4 + tq;
 #pragma unroll
-                for (int ks = 0; ks < KS_MAX; ++ks) {
+                for (int ks = 0; ks < KSU_T; ++ks) {
                     if (ks < KSU) {
-                        const double2 w = __ldg(wrow + 4 * ks);
+                        const double2 w = wsm ? wrow[4 * ks] : __ldg(wrow + 4 * ks);
                         dmma(cr0, cr1, w.x, yre[ks]);
-                        dmma(cr0, cr1, -w.y, yim[ks]);
                         dmma(ci0, ci1, w.x, yim[ks]);
+                        dmma(cr0, cr1, -w.y, yim[ks]);
                         dmma(ci0, ci1, w.y, yre[ks]);
                     }
                 }
                 const int a = 8 * mt + g;
                 if (a < NL) {
-                    const size_t o = (size_t)(pos[a] * T + j) * strideA + 8 * nt + 2 * tq;
+                    const size_t o = rowoff(pos[a], j) + 8 * nt + 2 * tq;
                     *reinterpret_cast<double2*>(Xre + o) = make_double2(cr0, cr1);
                     *reinterpret_cast<double2*>(Xim + o) = make_double2(ci0, ci1);
                 }
             }
+        }
+        if (wsm) {  // this row's operators are consumed: hand the buffer back to the producer
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_wempty + 8 * buf);
+            if (buf) wph1 ^= 1u; else wph0 ^= 1u;
         }
         compute_bar();
 
@@ -337,6 +400,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             const double2* cl = reinterpret_cast<const double2*>(p.pt.closure) + (size_t)s * chi_pad;
             for (int d = tid; d < chi_pad; d += N_COMPUTE_WARPS * 32) qbuf[d] = cl[d];
         }
+        bool nbv[NB];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) nbv[nb] = 8 * (warp + N_COMPUTE_WARPS * nb) < nout;
         for (int ps = 0; ps < p.n_pass; ++ps) {
             const PassDesc pd = passes[ps];
             double cre[MC][NB][2], cim[MC][NB][2];
@@ -349,11 +415,12 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 }
             const double* are[MC];
             const double* aim[MC];
-            bool aval[MC];
+            bool aval[MC], mcv[MC];
 #pragma unroll
             for (int mc = 0; mc < MC; ++mc) {
                 aval[mc] = g < pd.nvalid[mc];
-                const size_t o = (size_t)(pd.row0[mc] + (aval[mc] ? g : 0)) * strideA + tq;
+                mcv[mc] = pd.nvalid[mc] > 0;
+                const size_t o = rowoff_r(pd.row0[mc] + (aval[mc] ? g : 0)) + tq;
                 are[mc] = Xre + o;
                 aim[mc] = Xim + o;
             }
@@ -364,7 +431,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
 #pragma unroll
                 for (int ks = 0; ks < KC / 4; ++ks) {
                     const int k = jc * KC + 4 * ks;
-                    double a_re[MC], a_im[MC];
+                    double a_re[MC], a_im[MC], b_re[NB], b_im[NB];
 #pragma unroll
                     for (int mc = 0; mc < MC; ++mc) {
                         a_re[mc] = aval[mc] ? are[mc][k] : 0.0;
@@ -372,21 +439,27 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                     }
 #pragma unroll
                     for (int nb = 0; nb < NB; ++nb) {
-                        const int nt = warp + N_COMPUTE_WARPS * nb;
-                        if (8 * nt < nout) {
-                            const int bo = (4 * ks + tq) * strideB + 8 * nt + g;
-                            const double b_re = bre[bo], b_im = bim[bo];
-#pragma unroll
-                            for (int mc = 0; mc < MC; ++mc) {
-                                if (pd.nvalid[mc] > 0) {
-                                    dmma(cre[mc][nb][0], cre[mc][nb][1], a_re[mc], b_re);
-                                    dmma(cre[mc][nb][0], cre[mc][nb][1], -a_im[mc], b_im);
-                                    dmma(cim[mc][nb][0], cim[mc][nb][1], a_re[mc], b_im);
-                                    dmma(cim[mc][nb][0], cim[mc][nb][1], a_im[mc], b_re);
-                                }
-                            }
-                        }
+                        const int bo = (4 * ks + tq) * strideB + 8 * (warp + N_COMPUTE_WARPS * nb) + g;
+                        b_re[nb] = nbv[nb] ? bre[bo] : 0.0;
+                        b_im[nb] = nbv[nb] ? bim[bo] : 0.0;
                     }
+                    // two sweeps so that consecutive DMMAs never share an accumulator
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                        for (int mc = 0; mc < MC; ++mc)
+                            if (nbv[nb] && mcv[mc]) {
+                                dmma(cre[mc][nb][0], cre[mc][nb][1], a_re[mc], b_re[nb]);
+                                dmma(cim[mc][nb][0], cim[mc][nb][1], a_re[mc], b_im[nb]);
+                            }
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                        for (int mc = 0; mc < MC; ++mc)
+                            if (nbv[nb] && mcv[mc]) {
+                                dmma(cre[mc][nb][0], cre[mc][nb][1], -a_im[mc], b_im[nb]);
+                                dmma(cim[mc][nb][0], cim[mc][nb][1], a_im[mc], b_re[nb]);
+                            }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
@@ -401,9 +474,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 if (t.n_steps < 0 || n < t.step0 || n >= t.step0 + t.n_steps) continue;
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) {
-                    const int nt = warp + N_COMPUTE_WARPS * nb;
-                    if (8 * nt < nout) {
-                        const size_t o = (size_t)row * strideA + 8 * nt + 2 * tq;
+                    if (nbv[nb]) {
+                        const size_t o = rowoff_r(row) + 8 * (warp + N_COMPUTE_WARPS * nb) + 2 * tq;
                         *reinterpret_cast<double2*>(Xre + o) = make_double2(cre[mc][nb][0], cre[mc][nb][1]);
                         *reinterpret_cast<double2*>(Xim + o) = make_double2(cim[mc][nb][0], cim[mc][nb][1]);
                     }
@@ -513,8 +585,26 @@ __global__ void __launch_bounds__(256) k_step_check(const StepParams p, double* 
 
 }  // namespace
 
-size_t step_smem_bytes(int NL, int chi_pad, int T, int stages) {
-    return make_layout(NL, chi_pad, T, stages).total;
+size_t step_smem_bytes(int NL, int chi_pad, int T, int stages, int wov_doubles) {
+    return make_layout(NL, chi_pad, T, stages, wov_doubles).total;
+}
+
+template <int NB>
+static int launch_nb(const StepParams& p, size_t smem_bytes, cudaStream_t s) {
+    const int ksu = p.prob.NLp4 / 4;
+#define ACEQD_LAUNCH(KS)                                                                        \
+    do {                                                                                        \
+        ACEQD_CUDA(cudaFuncSetAttribute(k_step_dmma<NB, KS>,                                    \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                        (int)smem_bytes));                                      \
+        k_step_dmma<NB, KS><<<p.n_tiles, STEP_THREADS, smem_bytes, s>>>(p);                     \
+    } while (0)
+    if (ksu <= 1) ACEQD_LAUNCH(1);
+    else if (ksu <= 4) ACEQD_LAUNCH(4);
+    else if (ksu <= 9) ACEQD_LAUNCH(9);
+    else ACEQD_LAUNCH(16);
+#undef ACEQD_LAUNCH
+    return ACEQD_OK;
 }
 
 int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, long long* launches) {
@@ -524,17 +614,11 @@ int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, lon
         return ACEQD_ERR_CAPACITY;
     }
     if (p.n_tiles <= 0) return ACEQD_OK;
-#define ACEQD_LAUNCH(NB)                                                                        \
-    do {                                                                                        \
-        ACEQD_CUDA(cudaFuncSetAttribute(k_step_dmma<NB>,                                        \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                        (int)smem_bytes));                                      \
-        k_step_dmma<NB><<<p.n_tiles, STEP_THREADS, smem_bytes, s>>>(p);                         \
-    } while (0)
-    if (chi <= 64) ACEQD_LAUNCH(1);
-    else if (chi <= 128) ACEQD_LAUNCH(2);
-    else ACEQD_LAUNCH(4);
-#undef ACEQD_LAUNCH
+    int rc;
+    if (chi <= 64) rc = launch_nb<1>(p, smem_bytes, s);
+    else if (chi <= 128) rc = launch_nb<2>(p, smem_bytes, s);
+    else rc = launch_nb<4>(p, smem_bytes, s);
+    if (rc) return rc;
     ++*launches;
     ACEQD_CUDA(cudaGetLastError());
     return ACEQD_OK;
