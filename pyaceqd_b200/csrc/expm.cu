@@ -18,8 +18,11 @@ namespace aceqd {
 
 namespace {
 
-constexpr int TAYLOR_M = 14;       // degree; with ||A||_1 <= 0.5 the remainder is < 3e-17
-constexpr double THETA = 0.5;
+// exp(A) by scaling and squaring around a degree-12 Taylor polynomial evaluated in
+// Paterson-Stockmeyer form (5 matrix products): with ||A/2^s||_1 <= THETA = 0.25 the truncation
+// error 0.25^13/13! = 2.4e-18 is below double rounding.
+constexpr double THETA = 0.25;
+constexpr int EXPM_BUFS = 6;       // A, A2, A3, A4, P0, P1
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -33,7 +36,9 @@ __device__ __forceinline__ void cfma(double2& acc, double2 a, double2 b) {
 
 template <int G>
 __device__ __forceinline__ void group_sync(int gid) {
-    if (G == 32)
+    if (G == 16)
+        __syncwarp(0xFFFFu << ((gid & 1) * 16));
+    else if (G == 32)
         __syncwarp();
     else
         asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(G) : "memory");
@@ -56,12 +61,30 @@ __device__ void gmm(double2* C, const double2* A, const double2* B, int n, int t
     group_sync<G>(gid);
 }
 
-// exp(A) for the n x n matrix in `A` (destroyed).  Returns a pointer to the result, which is
-// one of P0 / P1.  `red` is a scratch of >= n doubles.
+// C = A*B + (c0 I + c1 X1 + c2 X2 + c3 X3)   (any Xi may be null)
 template <int G>
-__device__ double2* expm_group(double2* A, double2* P0, double2* P1, double* red, int n, int tid,
-                               int gid) {
+__device__ void gmm_poly(double2* C, const double2* A, const double2* B, int n, int tid, int gid,
+                         double c0, double c1, const double2* X1, double c2, const double2* X2,
+                         double c3, const double2* X3) {
     const int n2 = n * n;
+    for (int e = tid; e < n2; e += G) {
+        const int i = e / n, j = e - i * n;
+        double2 acc = make_double2(i == j ? c0 : 0.0, 0.0);
+        if (X1) { acc.x = fma(c1, X1[e].x, acc.x); acc.y = fma(c1, X1[e].y, acc.y); }
+        if (X2) { acc.x = fma(c2, X2[e].x, acc.x); acc.y = fma(c2, X2[e].y, acc.y); }
+        if (X3) { acc.x = fma(c3, X3[e].x, acc.x); acc.y = fma(c3, X3[e].y, acc.y); }
+        for (int k = 0; k < n; ++k) cfma(acc, A[i * n + k], B[k * n + j]);
+        C[e] = acc;
+    }
+    group_sync<G>(gid);
+}
+
+// exp(A) for the n x n matrix in buf[0..n2) (destroyed).  `buf` holds EXPM_BUFS matrices; the
+// result pointer is one of them.  `red` is a scratch of >= n doubles.
+template <int G>
+__device__ double2* expm_group(double2* buf, double* red, int n, int tid, int gid) {
+    const int n2 = n * n;
+    double2 *A = buf, *A2 = A + n2, *A3 = A2 + n2, *A4 = A3 + n2, *P0 = A4 + n2, *P1 = P0 + n2;
     for (int j = tid; j < n; j += G) {
         double s = 0.0;
         for (int i = 0; i < n; ++i) {
@@ -77,31 +100,37 @@ __device__ double2* expm_group(double2* A, double2* P0, double2* P1, double* red
     if (nrm > THETA) {
         int ex;
         frexp(nrm / THETA, &ex);  // nrm/THETA = m * 2^ex, m in [0.5, 1)
-        s = ex;
-        if (s > 60) s = 60;
+        s = ex > 60 ? 60 : ex;
     }
     const double sc = ldexp(1.0, -s);
     group_sync<G>(gid);  // everyone has read `red`
     for (int e = tid; e < n2; e += G) {
         double2 v = A[e];
-        v.x *= sc;
-        v.y *= sc;
-        A[e] = v;
-        const int i = e / n, j = e - i * n;
-        // P = I + A/m
-        P0[e] = make_double2(v.x / TAYLOR_M + (i == j ? 1.0 : 0.0), v.y / TAYLOR_M);
+        A[e] = make_double2(v.x * sc, v.y * sc);
     }
     group_sync<G>(gid);
+    constexpr double c2 = 1.0 / 2, c3 = 1.0 / 6, c4 = 1.0 / 24, c5 = 1.0 / 120, c6 = 1.0 / 720,
+                     c7 = 1.0 / 5040, c8 = 1.0 / 40320, c9 = 1.0 / 362880, c10 = 1.0 / 3628800,
+                     c11 = 1.0 / 39916800, c12 = 1.0 / 479001600;
+    gmm_poly<G>(A2, A, A, n, tid, gid, 0.0, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
+    gmm_poly<G>(A3, A2, A, n, tid, gid, 0.0, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
+    // P0 = c8 I + c9 A + c10 A2 + c11 A3 + c12 A4 ,  A4 = A2*A2  (one product gives both)
+    gmm_poly<G>(A4, A2, A2, n, tid, gid, 0.0, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
+    for (int e = tid; e < n2; e += G) {
+        const int i = e / n, j = e - i * n;
+        double2 v = make_double2(i == j ? c8 : 0.0, 0.0);
+        v.x += c9 * A[e].x + c10 * A2[e].x + c11 * A3[e].x + c12 * A4[e].x;
+        v.y += c9 * A[e].y + c10 * A2[e].y + c11 * A3[e].y + c12 * A4[e].y;
+        P0[e] = v;
+    }
+    group_sync<G>(gid);
+    // P1 = (c4 I + c5 A + c6 A2 + c7 A3) + A4 P0 ;  P0 = (I + A + c2 A2 + c3 A3) + A4 P1
+    gmm_poly<G>(P1, A4, P0, n, tid, gid, c4, c5, A, c6, A2, c7, A3);
+    gmm_poly<G>(P0, A4, P1, n, tid, gid, 1.0, 1.0, A, c2, A2, c3, A3);
     double2* cur = P0;
     double2* nxt = P1;
-    for (int j = TAYLOR_M - 1; j >= 1; --j) {
-        gmm<G>(nxt, A, cur, n, tid, gid, 1.0 / j, true);
-        double2* t = cur;
-        cur = nxt;
-        nxt = t;
-    }
     for (int q = 0; q < s; ++q) {
-        gmm<G>(nxt, cur, cur, n, tid, gid, 1.0, false);
+        gmm_poly<G>(nxt, cur, cur, n, tid, gid, 0.0, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
         double2* t = cur;
         cur = nxt;
         nxt = t;
@@ -150,11 +179,9 @@ __global__ void __launch_bounds__(256) k_opbuild(OpBuildParams p) {
     const int n = p.prob.NL, n2 = n * n;
     const int groups = blockDim.x / G;
     const int gid = threadIdx.x / G, tid = threadIdx.x - gid * G;
-    const size_t per_group = (size_t)5 * n2 + MAX_NL;  // A, P0, P1, V, X + reduction scratch
+    const size_t per_group = (size_t)(EXPM_BUFS + 2) * n2 + MAX_NL;  // expm buffers, V, X + scratch
     double2* A = sm + gid * per_group;
-    double2* P0 = A + n2;
-    double2* P1 = P0 + n2;
-    double2* V = P1 + n2;
+    double2* V = A + (size_t)EXPM_BUFS * n2;
     double2* X = V + n2;
     double* red = reinterpret_cast<double*>(X + n2);
 
@@ -184,7 +211,7 @@ __global__ void __launch_bounds__(256) k_opbuild(OpBuildParams p) {
         // ---- V = Sb * M2_{n-1}
         if (has_prev) {
             assemble<G>(A, p, set, t_n - p.dt + p.eval_off2 * p.dt, half, tid, gid);
-            double2* M2 = expm_group<G>(A, P0, P1, red, n, tid, gid);
+            double2* M2 = expm_group<G>(A, red, n, tid, gid);
             if (sb >= 0) {
                 gmm<G>(V, mto + (size_t)sb * n2, M2, n, tid, gid, 1.0, false);
             } else {
@@ -218,7 +245,7 @@ __global__ void __launch_bounds__(256) k_opbuild(OpBuildParams p) {
         }
         // ---- W = M1_n * X   (zero padded to [NLp8][NLp4])
         assemble<G>(A, p, set, t_n + p.eval_off1 * p.dt, half, tid, gid);
-        double2* M1 = expm_group<G>(A, P0, P1, red, n, tid, gid);
+        double2* M1 = expm_group<G>(A, red, n, tid, gid);
         {
             double2* w = reinterpret_cast<double2*>(p.W + (size_t)e * p.prob.w_doubles);
             const int ld = p.prob.NLp4, cnt = p.prob.NLp8 * ld;
@@ -241,16 +268,14 @@ __global__ void __launch_bounds__(256) k_expm_batch(int n, int count, const doub
     const int n2 = n * n;
     const int groups = blockDim.x / G;
     const int gid = threadIdx.x / G, tid = threadIdx.x - gid * G;
-    const size_t per_group = (size_t)3 * n2 + MAX_NL;
+    const size_t per_group = (size_t)EXPM_BUFS * n2 + MAX_NL;
     double2* A = sm + gid * per_group;
-    double2* P0 = A + n2;
-    double2* P1 = P0 + n2;
-    double* red = reinterpret_cast<double*>(P1 + n2);
+    double* red = reinterpret_cast<double*>(A + (size_t)EXPM_BUFS * n2);
     for (int e = blockIdx.x * groups + gid; e < count; e += gridDim.x * groups) {
         const double2* src = reinterpret_cast<const double2*>(a) + (size_t)e * n2;
         for (int q = tid; q < n2; q += G) A[q] = src[q];
         group_sync<G>(gid);
-        double2* R = expm_group<G>(A, P0, P1, red, n, tid, gid);
+        double2* R = expm_group<G>(A, red, n, tid, gid);
         double2* dst = reinterpret_cast<double2*>(out) + (size_t)e * n2;
         for (int q = tid; q < n2; q += G) dst[q] = R[q];
         group_sync<G>(gid);
@@ -258,6 +283,7 @@ __global__ void __launch_bounds__(256) k_expm_batch(int n, int count, const doub
 }
 
 int pick_group(int n) {
+    if (n <= 4) return 16;
     if (n <= 8) return 32;
     if (n <= 12) return 64;
     if (n <= 20) return 128;
@@ -284,7 +310,7 @@ int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches) 
     }
     const int G = pick_group(n);
     const int groups = 256 / G;
-    const size_t smem = groups * ((size_t)5 * n * n + MAX_NL) * sizeof(double2);
+    const size_t smem = groups * ((size_t)(EXPM_BUFS + 2) * n * n + MAX_NL) * sizeof(double2);
     if (smem > (size_t)SMEM_BUDGET) {
         set_error("operator builder: NL=%d needs %zu B shared memory", n, smem);
         return ACEQD_ERR_CAPACITY;
@@ -293,6 +319,10 @@ int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches) 
     if (blocks > 148LL * 64) blocks = 148LL * 64;
     int rc = ACEQD_OK;
     switch (G) {
+        case 16:
+            if ((rc = set_smem(k_opbuild<16>, smem))) return rc;
+            k_opbuild<16><<<(int)blocks, 256, smem, s>>>(p);
+            break;
         case 32:
             if ((rc = set_smem(k_opbuild<32>, smem))) return rc;
             k_opbuild<32><<<(int)blocks, 256, smem, s>>>(p);
@@ -324,11 +354,15 @@ int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, cu
     }
     const int G = pick_group(n);
     const int groups = 256 / G;
-    const size_t smem = groups * ((size_t)3 * n * n + MAX_NL) * sizeof(double2);
+    const size_t smem = groups * ((size_t)EXPM_BUFS * n * n + MAX_NL) * sizeof(double2);
     int blocks = (count + groups - 1) / groups;
     if (blocks > 148 * 64) blocks = 148 * 64;
     int rc = ACEQD_OK;
     switch (G) {
+        case 16:
+            if ((rc = set_smem(k_expm_batch<16>, smem))) return rc;
+            k_expm_batch<16><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev);
+            break;
         case 32:
             if ((rc = set_smem(k_expm_batch<32>, smem))) return rc;
             k_expm_batch<32><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev);

@@ -19,10 +19,11 @@ namespace aceqd {
 namespace {
 
 struct SmemLayout {
-    size_t bar, traj, pass, pos, r, q, snapn, wov, state, chunks, total;
+    size_t bar, traj, pass, pos, r, q, snapn, meta, wov, state, chunks, total;
     size_t plane;  // doubles per state plane
 };
 
+constexpr int META_SLICES = 256;  // kin/nout of this many slices are cached in shared memory
 constexpr int SKEW = 4;  // extra doubles after every alpha block of T rows (bank skew for phase B)
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -38,7 +39,8 @@ __host__ __device__ inline SmemLayout make_layout(int NL, int chi_pad, int T, in
     L.pass = o;  o += align_up(sizeof(PassDesc) * MAX_PASSES, 16);
     L.pos = o;   o += align_up(sizeof(int) * MAX_NL, 16);
     L.snapn = o; o += align_up(sizeof(int) * MAX_TILE_T, 16);
-    L.r = o;     o += align_up(16 * R, 16);
+    L.r = o;     o += align_up(16 * R * N_COMPUTE_WARPS, 16);   // per-warp partial closures
+    L.meta = o;  o += align_up(sizeof(int) * 2 * META_SLICES, 16);
     L.q = o;     o += align_up(16 * (size_t)chi_pad, 16);
     o = align_up(o, 128);
     L.wov = o;   o += (size_t)2 * T * wov_doubles * 8;   // double-buffered W|OV of the tile (0 = global mode)
@@ -119,8 +121,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     PassDesc* passes = reinterpret_cast<PassDesc*>(smem_raw + L.pass);
     int* pos = reinterpret_cast<int*>(smem_raw + L.pos);
     int* snapn = reinterpret_cast<int*>(smem_raw + L.snapn);
-    double2* rbuf = reinterpret_cast<double2*>(smem_raw + L.r);
+    double2* rpart = reinterpret_cast<double2*>(smem_raw + L.r);   // [warp][row]
     double2* qbuf = reinterpret_cast<double2*>(smem_raw + L.q);
+    int* smeta = reinterpret_cast<int*>(smem_raw + L.meta);
     double* Wst = reinterpret_cast<double*>(smem_raw + L.wov);
     double* Xre = reinterpret_cast<double*>(smem_raw + L.state);
     double* Xim = Xre + L.plane;
@@ -149,6 +152,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     }
     for (int j = tid; j < p.n_pass; j += blockDim.x) passes[j] = p.passes[j];
     for (int j = tid; j < NL; j += blockDim.x) pos[j] = p.prob.pos_of_alpha[j];
+    for (int j = tid; j < min(p.pt.n_slices, META_SLICES); j += blockDim.x) {
+        smeta[2 * j] = p.pt.kin_pad[j];
+        smeta[2 * j + 1] = p.pt.nout_pad[j];
+    }
     for (size_t e = tid; e < 2 * L.plane; e += blockDim.x) Xre[e] = 0.0;
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             for (int n = n_begin; n < n_end; ++n) {
                 if (wsm) issue_wov(n + 1);
                 const int s = slice_of(p.pt, n);
-                const int nch = p.pt.kin_pad[s] / KC;
+                const int nch = (s < META_SLICES ? smeta[2 * s] : p.pt.kin_pad[s]) / KC;
                 const double* sl = p.pt.blob + p.pt.off[s];
                 for (int ps = 0; ps < p.n_pass; ++ps) {
                     const double* src = sl + (size_t)passes[ps].blk * nch * p.pt.chunk_doubles;
@@ -259,15 +266,26 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
 
     for (int n = n_begin; n <= n_end; ++n) {
         const int buf = n & 1;
-        // ---------------- phase A: closure, outputs, snapshots
-        for (int row = warp; row < R; row += N_COMPUTE_WARPS) {
-            const int j = row % T;
+        // ---------------- phase A: outputs (closure partials come from the previous GEMM epilogue)
+        // rows of trajectories that START at this row have no partials yet: generic closure pass
+        bool any_start = false, any_snap = false;
+        for (int j = 0; j < T; ++j) {
             const aceqd_traj& t = trj[j];
-            double2 acc = make_double2(0.0, 0.0);
-            if (t.n_steps >= 0 && n >= t.step0 && n <= t.step0 + t.n_steps) {
+            if (t.n_steps < 0) continue;
+            any_start |= (n == t.step0);
+            const int i = n - t.step0;
+            any_snap |= (snapn[j] < t.snap_cnt && i >= 0 && i <= t.n_steps &&
+                         p.snap_steps[t.snap_off + snapn[j]] == i);
+        }
+        if (any_start) {
+            for (int row = warp; row < R; row += N_COMPUTE_WARPS) {
+                const int j = row % T;
+                const aceqd_traj& t = trj[j];
+                if (t.n_steps < 0 || n != t.step0) continue;
+                double2 acc = make_double2(0.0, 0.0);
                 const double* xr = Xre + rowoff_r(row);
                 const double* xi = Xim + rowoff_r(row);
-                if (n == t.step0 && t.init_kind == 0) {
+                if (t.init_kind == 0) {
                     if (lane == 0) acc = make_double2(xr[0], xi[0]);
                 } else {
                     for (int d = lane; d < chi_pad; d += 32) {
@@ -282,107 +300,173 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
                     acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
                 }
+                if (lane < N_COMPUTE_WARPS) rpart[lane * R + row] = lane == 0 ? acc : make_double2(0.0, 0.0);
             }
-            if (lane == 0) rbuf[row] = acc;
+            compute_bar();
         }
         if (wsm) mbar_wait(bar_wfull + 8 * buf, buf ? wph1 : wph0);
-        compute_bar();
         for (int it = tid; it < T * n_out; it += N_COMPUTE_WARPS * 32) {
             const int j = it / n_out, o = it - j * n_out;
             const aceqd_traj& t = trj[j];
             if (t.n_steps < 0 || n < t.step0 || n > t.step0 + t.n_steps) continue;
             const int i = n - t.step0;
-            double2 acc = make_double2(0.0, 0.0);
+            const double2* ov;
             if (wsm) {
-                const double2* ov = reinterpret_cast<const double2*>(Wst + (size_t)(buf * T + j) * wov +
-                                                                     p.prob.w_doubles) + (size_t)o * NL;
-                for (int a = 0; a < NL; ++a) {
-                    const double2 w = ov[a];
-                    const double2 r = rbuf[pos[a] * T + j];
-                    acc.x += w.x * r.x - w.y * r.y;
-                    acc.y += w.x * r.y + w.y * r.x;
-                }
+                ov = reinterpret_cast<const double2*>(Wst + (size_t)(buf * T + j) * wov + p.prob.w_doubles) +
+                     (size_t)o * NL;
             } else {
                 const long long e = entry_of(t, i, p.ovr_base);
-                const double2* ov = reinterpret_cast<const double2*>(p.OV + (size_t)e * p.prob.ov_doubles) +
-                                    (size_t)o * NL;
-                for (int a = 0; a < NL; ++a) {
-                    const double2 w = __ldg(ov + a);
-                    const double2 r = rbuf[pos[a] * T + j];
-                    acc.x += w.x * r.x - w.y * r.y;
-                    acc.y += w.x * r.y + w.y * r.x;
+                ov = reinterpret_cast<const double2*>(p.OV + (size_t)e * p.prob.ov_doubles) + (size_t)o * NL;
+            }
+            double2 acc = make_double2(0.0, 0.0);
+            for (int a = 0; a < NL; ++a) {
+                const double2 w = ov[a];
+                const int row = pos[a] * T + j;
+                double2 r = rpart[row];
+#pragma unroll
+                for (int w8 = 1; w8 < N_COMPUTE_WARPS; ++w8) {
+                    const double2 r2 = rpart[w8 * R + row];
+                    r.x += r2.x;
+                    r.y += r2.y;
                 }
+                acc.x += w.x * r.x - w.y * r.y;
+                acc.y += w.x * r.y + w.y * r.x;
             }
             reinterpret_cast<double2*>(p.out)[t.out_off + (long long)i * n_out + o] = acc;
         }
-        for (int j = 0; j < T; ++j) {
-            const aceqd_traj& t = trj[j];
-            if (t.n_steps < 0 || snapn[j] >= t.snap_cnt) continue;
-            const int i = n - t.step0;
-            if (i < 0 || i > t.n_steps || p.snap_steps[t.snap_off + snapn[j]] != i) continue;
-            double2* dst = reinterpret_cast<double2*>(p.snaps) +
-                           (size_t)(t.snap_slot0 + snapn[j]) * NL * chi_pad;
-            for (int e = tid; e < NL * chi_pad; e += N_COMPUTE_WARPS * 32) {
-                const int a = e / chi_pad, d = e - a * chi_pad;
-                const size_t o = rowoff(pos[a], j) + d;
-                dst[e] = make_double2(Xre[o], Xim[o]);
+        if (any_snap) {
+            for (int j = 0; j < T; ++j) {
+                const aceqd_traj& t = trj[j];
+                if (t.n_steps < 0 || snapn[j] >= t.snap_cnt) continue;
+                const int i = n - t.step0;
+                if (i < 0 || i > t.n_steps || p.snap_steps[t.snap_off + snapn[j]] != i) continue;
+                double2* dst = reinterpret_cast<double2*>(p.snaps) +
+                               (size_t)(t.snap_slot0 + snapn[j]) * NL * chi_pad;
+                for (int e = tid; e < NL * chi_pad; e += N_COMPUTE_WARPS * 32) {
+                    const int a = e / chi_pad, d = e - a * chi_pad;
+                    const size_t o = rowoff(pos[a], j) + d;
+                    dst[e] = make_double2(Xre[o], Xim[o]);
+                }
             }
         }
         if (n == n_end) break;
-        compute_bar();
-        if (tid < T) {  // advance snapshot cursors (read again only after later barriers)
-            const aceqd_traj& t = trj[tid];
-            const int i = n - t.step0;
-            if (t.n_steps >= 0 && snapn[tid] < t.snap_cnt && i >= 0 && i <= t.n_steps &&
-                p.snap_steps[t.snap_off + snapn[tid]] == i)
-                snapn[tid] += 1;
+        if (any_snap) {
+            compute_bar();   // snapshot reads of the state precede phase B's in-place update
+            if (tid < T) {   // advance snapshot cursors (read again only after later barriers)
+                const aceqd_traj& t = trj[tid];
+                const int i = n - t.step0;
+                if (t.n_steps >= 0 && snapn[tid] < t.snap_cnt && i >= 0 && i <= t.n_steps &&
+                    p.snap_steps[t.snap_off + snapn[tid]] == i)
+                    snapn[tid] += 1;
+            }
         }
 
-        // ---------------- phase B: X = W_n Y   (items = (trajectory, n-tile), warp-local in place)
-        for (int item = warp; item < T * NT; item += N_COMPUTE_WARPS) {
-            const int j = item / NT, nt = item - j * NT;
-            const aceqd_traj& t = trj[j];
-            if (t.n_steps < 0 || n < t.step0 || n >= t.step0 + t.n_steps) continue;
-            const double2* Wp;
-            if (wsm) {
-                Wp = reinterpret_cast<const double2*>(Wst + (size_t)(buf * T + j) * wov);
-            } else {
-                const long long e = entry_of(t, n - t.step0, p.ovr_base);
-                Wp = reinterpret_cast<const double2*>(p.W + (size_t)e * p.prob.w_doubles);
-            }
-            double yre[KSU_T], yim[KSU_T];
-            const int col = 8 * nt + g;
+        // ---------------- phase B: X = W_n Y.  Warp w owns bond columns of its n-tiles for every
+        // trajectory (column-local, in place, no block barrier); JU trajectories x NBB n-tiles are
+        // kept in flight for instruction-level parallelism (bounded by the register budget).
+        constexpr int NBB = (KSU_T * NB <= 8) ? NB : 1;
+        constexpr int JU_ = 8 / (KSU_T * NBB);
+        constexpr int JU = JU_ < 1 ? 1 : (JU_ > 4 ? 4 : JU_);
+        for (int j0 = 0; j0 < T; j0 += JU) {
+            bool act[JU];
+            const double2* Wp[JU];
+            bool any = false;
 #pragma unroll
-            for (int ks = 0; ks < KSU_T; ++ks) {
-                yre[ks] = 0.0;
-                yim[ks] = 0.0;
-                const int a = 4 * ks + tq;
-                if (ks < KSU && a < NL) {
-                    const size_t o = rowoff(pos[a], j) + col;
-                    yre[ks] = Xre[o];
-                    yim[ks] = Xim[o];
-                }
-            }
-            __syncwarp();
-            for (int mt = 0; mt < MTU; ++mt) {
-                double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
-                const double2* wrow = Wp + (size_t)(8 * mt + g) * NLp4 + tq;
-#pragma unroll
-                for (int ks = 0; ks < KSU_T; ++ks) {
-                    if (ks < KSU) {
-                        const double2 w = wsm ? wrow[4 * ks] : __ldg(wrow + 4 * ks);
-                        dmma(cr0, cr1, w.x, yre[ks]);
-                        dmma(ci0, ci1, w.x, yim[ks]);
-                        dmma(cr0, cr1, -w.y, yim[ks]);
-                        dmma(ci0, ci1, w.y, yre[ks]);
+            for (int jj = 0; jj < JU; ++jj) {
+                const int j = j0 + jj;
+                act[jj] = false;
+                Wp[jj] = nullptr;
+                if (j < T) {
+                    const aceqd_traj& t = trj[j];
+                    act[jj] = t.n_steps >= 0 && n >= t.step0 && n < t.step0 + t.n_steps;
+                    if (act[jj]) {
+                        if (wsm) {
+                            Wp[jj] = reinterpret_cast<const double2*>(Wst + (size_t)(buf * T + j) * wov);
+                        } else {
+                            const long long e = entry_of(t, n - t.step0, p.ovr_base);
+                            Wp[jj] = reinterpret_cast<const double2*>(p.W + (size_t)e * p.prob.w_doubles);
+                        }
                     }
                 }
-                const int a = 8 * mt + g;
-                if (a < NL) {
-                    const size_t o = rowoff(pos[a], j) + 8 * nt + 2 * tq;
-                    *reinterpret_cast<double2*>(Xre + o) = make_double2(cr0, cr1);
-                    *reinterpret_cast<double2*>(Xim + o) = make_double2(ci0, ci1);
+                any |= act[jj];
+            }
+            if (!any) continue;
+            for (int nb0 = 0; nb0 < NB; nb0 += NBB) {
+                bool nbB[NBB];
+                int ncol[NBB];
+#pragma unroll
+                for (int nb = 0; nb < NBB; ++nb) {
+                    const int nt = warp + N_COMPUTE_WARPS * (nb0 + nb);
+                    nbB[nb] = nt < NT;
+                    ncol[nb] = 8 * nt;
                 }
+                double yre[JU][NBB][KSU_T], yim[JU][NBB][KSU_T];
+#pragma unroll
+                for (int jj = 0; jj < JU; ++jj)
+#pragma unroll
+                    for (int ks = 0; ks < KSU_T; ++ks) {
+                        const int a = 4 * ks + tq;
+                        const bool ld = act[jj] && ks < KSU && a < NL;
+                        const size_t o = ld ? rowoff(pos[a], j0 + jj) + g : 0;
+#pragma unroll
+                        for (int nb = 0; nb < NBB; ++nb) {
+                            const bool l2 = ld && nbB[nb];
+                            yre[jj][nb][ks] = l2 ? Xre[o + ncol[nb]] : 0.0;
+                            yim[jj][nb][ks] = l2 ? Xim[o + ncol[nb]] : 0.0;
+                        }
+                    }
+                __syncwarp();
+                for (int mt = 0; mt < MTU; ++mt) {
+                    double cr[JU][NBB][2], ci[JU][NBB][2];
+#pragma unroll
+                    for (int jj = 0; jj < JU; ++jj)
+#pragma unroll
+                        for (int nb = 0; nb < NBB; ++nb)
+                            cr[jj][nb][0] = cr[jj][nb][1] = ci[jj][nb][0] = ci[jj][nb][1] = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < KSU_T; ++ks) {
+                        if (ks < KSU) {
+                            double2 w[JU];
+#pragma unroll
+                            for (int jj = 0; jj < JU; ++jj) {
+                                w[jj] = make_double2(0.0, 0.0);
+                                if (act[jj]) {
+                                    const double2* wp = Wp[jj] + (size_t)(8 * mt + g) * NLp4 + tq + 4 * ks;
+                                    w[jj] = wsm ? *wp : __ldg(wp);
+                                }
+                            }
+#pragma unroll
+                            for (int jj = 0; jj < JU; ++jj)
+#pragma unroll
+                                for (int nb = 0; nb < NBB; ++nb)
+                                    if (act[jj] && nbB[nb]) {
+                                        dmma(cr[jj][nb][0], cr[jj][nb][1], w[jj].x, yre[jj][nb][ks]);
+                                        dmma(ci[jj][nb][0], ci[jj][nb][1], w[jj].x, yim[jj][nb][ks]);
+                                    }
+#pragma unroll
+                            for (int jj = 0; jj < JU; ++jj)
+#pragma unroll
+                                for (int nb = 0; nb < NBB; ++nb)
+                                    if (act[jj] && nbB[nb]) {
+                                        dmma(cr[jj][nb][0], cr[jj][nb][1], -w[jj].y, yim[jj][nb][ks]);
+                                        dmma(ci[jj][nb][0], ci[jj][nb][1], w[jj].y, yre[jj][nb][ks]);
+                                    }
+                        }
+                    }
+                    const int a = 8 * mt + g;
+                    if (a < NL) {
+#pragma unroll
+                        for (int jj = 0; jj < JU; ++jj)
+#pragma unroll
+                            for (int nb = 0; nb < NBB; ++nb)
+                                if (act[jj] && nbB[nb]) {
+                                    const size_t o = rowoff(pos[a], j0 + jj) + ncol[nb] + 2 * tq;
+                                    *reinterpret_cast<double2*>(Xre + o) = make_double2(cr[jj][nb][0], cr[jj][nb][1]);
+                                    *reinterpret_cast<double2*>(Xim + o) = make_double2(ci[jj][nb][0], ci[jj][nb][1]);
+                                }
+                    }
+                }
+                __syncwarp();
             }
         }
         if (wsm) {  // this row's operators are consumed: hand the buffer back to the producer
@@ -394,9 +478,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
 
         // ---------------- phase C: PT slice, Y = X A_n[beta]
         const int s = slice_of(p.pt, n);
-        const int nch = p.pt.kin_pad[s] / KC;
-        const int nout = p.pt.nout_pad[s];
-        {   // stage the closure that phase A of the next row needs
+        const int nch = (s < META_SLICES ? smeta[2 * s] : p.pt.kin_pad[s]) / KC;
+        const int nout = s < META_SLICES ? smeta[2 * s + 1] : p.pt.nout_pad[s];
+        {   // stage the closure of this slice: consumed by the GEMM epilogue below
             const double2* cl = reinterpret_cast<const double2*>(p.pt.closure) + (size_t)s * chi_pad;
             for (int d = tid; d < chi_pad; d += N_COMPUTE_WARPS * 32) qbuf[d] = cl[d];
         }
@@ -468,18 +552,31 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             compute_bar();  // every warp has finished reading this pass's X rows
 #pragma unroll
             for (int mc = 0; mc < MC; ++mc) {
-                if (!aval[mc]) continue;
-                const int row = pd.row0[mc] + g;
+                if (!mcv[mc]) continue;   // warp-uniform
+                const int row = pd.row0[mc] + (aval[mc] ? g : 0);
                 const aceqd_traj& t = trj[row % T];
-                if (t.n_steps < 0 || n < t.step0 || n >= t.step0 + t.n_steps) continue;
+                const bool wr = aval[mc] && t.n_steps >= 0 && n >= t.step0 && n < t.step0 + t.n_steps;
+                // closure partial of this warp's columns: r[row] += sum_col Y[row, col] q[col]
+                double pr = 0.0, pi = 0.0;
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) {
                     if (nbv[nb]) {
-                        const size_t o = rowoff_r(row) + 8 * (warp + N_COMPUTE_WARPS * nb) + 2 * tq;
-                        *reinterpret_cast<double2*>(Xre + o) = make_double2(cre[mc][nb][0], cre[mc][nb][1]);
-                        *reinterpret_cast<double2*>(Xim + o) = make_double2(cim[mc][nb][0], cim[mc][nb][1]);
+                        const int c0 = 8 * (warp + N_COMPUTE_WARPS * nb) + 2 * tq;
+                        const double2 q0 = qbuf[c0], q1 = qbuf[c0 + 1];
+                        pr += cre[mc][nb][0] * q0.x - cim[mc][nb][0] * q0.y + cre[mc][nb][1] * q1.x - cim[mc][nb][1] * q1.y;
+                        pi += cre[mc][nb][0] * q0.y + cim[mc][nb][0] * q0.x + cre[mc][nb][1] * q1.y + cim[mc][nb][1] * q1.x;
+                        if (wr) {
+                            const size_t o = rowoff_r(row) + c0;
+                            *reinterpret_cast<double2*>(Xre + o) = make_double2(cre[mc][nb][0], cre[mc][nb][1]);
+                            *reinterpret_cast<double2*>(Xim + o) = make_double2(cim[mc][nb][0], cim[mc][nb][1]);
+                        }
                     }
                 }
+                pr += __shfl_xor_sync(0xffffffffu, pr, 1);
+                pi += __shfl_xor_sync(0xffffffffu, pi, 1);
+                pr += __shfl_xor_sync(0xffffffffu, pr, 2);
+                pi += __shfl_xor_sync(0xffffffffu, pi, 2);
+                if (wr && tq == 0) rpart[warp * R + row] = make_double2(pr, pi);
             }
         }
         compute_bar();

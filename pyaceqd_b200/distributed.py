@@ -1,0 +1,103 @@
+"""Multi-GPU plumbing: independent trajectories shard across ranks, one final gather.
+
+The reference runs every trajectory as an independent ACE process behind a thread pool
+(SURVEY 2.3), so the batch axis shards trivially: contiguous, step-count-balanced
+blocks per rank, the PT and problem replicated per GPU, and a single collective at the end --
+an all-gather of the per-rank result blocks over NCCL/NVLink (gloo in the CPU tests).  There is
+no per-step communication.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def balanced_blocks(costs: Sequence[float], world: int) -> List[Tuple[int, int]]:
+    """Split indices 0..n-1 into `world` contiguous blocks of nearly equal total cost.
+
+    `costs[i]` is the step count of trajectory i (``tend_i`` varies across a G(t,tau) sweep,
+    reference ``two_time/correlations.py:156``).  Returns ``[(start, stop)] * world``.
+    """
+    c = np.asarray(costs, dtype=float)
+    n = len(c)
+    if world <= 0:
+        raise ValueError("world must be positive")
+    cum = np.concatenate([[0.0], np.cumsum(c)])
+    total = cum[-1]
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        k = int(np.searchsorted(cum, target, side="left"))
+        # pick the boundary closest to the target
+        if k > 0 and abs(cum[k - 1] - target) <= abs(cum[min(k, n)] - target):
+            k -= 1
+        bounds.append(min(max(k, bounds[-1]), n))
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def shard(items: Sequence, rank: int, world: int, costs: Optional[Sequence[float]] = None):
+    """This rank's contiguous slice of `items` (and its (start, stop))."""
+    if costs is None:
+        costs = [1.0] * len(items)
+    a, b = balanced_blocks(costs, world)[rank]
+    return items[a:b], (a, b)
+
+
+def all_gather_blocks(local: np.ndarray, counts: Sequence[int], device=None, group=None) -> np.ndarray:
+    """All-gather ragged per-rank blocks (rank r contributes ``counts[r]`` rows of `local`'s
+    row shape); returns the concatenation on every rank.  complex128 travels as float64 pairs.
+    Uses the default process group's backend: NCCL with CUDA tensors, gloo on the CPU."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if len(counts) != world or counts[rank] != local.shape[0]:
+        raise ValueError("counts must list every rank's row count")
+    row_shape = local.shape[1:]
+    row_elems = int(np.prod(row_shape)) if row_shape else 1
+    is_c = np.iscomplexobj(local)
+    flat = np.ascontiguousarray(local).reshape(local.shape[0], row_elems)
+    if is_c:
+        flat = flat.view(np.float64)
+    width = flat.shape[1] if flat.ndim == 2 and flat.shape[0] else row_elems * (2 if is_c else 1)
+    cmax = max(counts) if counts else 0
+    send = torch.zeros((cmax, width), dtype=torch.float64, device=device)
+    if local.shape[0]:
+        send[:local.shape[0]] = torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float64)).to(send.device)
+    recv = torch.empty((world * cmax, width), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    host = recv.cpu().numpy().reshape(world, cmax, width)
+    parts = [host[r, :counts[r]] for r in range(world)]
+    out = np.concatenate(parts, axis=0) if parts else np.zeros((0, width))
+    if is_c:
+        out = np.ascontiguousarray(out).view(np.complex128)
+    return out.reshape((out.shape[0],) + tuple(row_shape))
+
+
+def run_jobs_sharded(engine, prob, pt, jobs, device=None, group=None, **kw) -> List[np.ndarray]:
+    """Propagate this rank's share of `jobs` and all-gather the results (every rank returns the
+    full list, like ``wait(futures)`` in the reference).  Requires an initialised process group;
+    with world size 1 it is `engine.run_jobs`."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return engine.run_jobs(prob, pt, jobs, **kw)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    costs = [max(1, j.n_steps) for j in jobs]
+    blocks = balanced_blocks(costs, world)
+    a, b = blocks[rank]
+    mine = engine.run_jobs(prob, pt, jobs[a:b], **kw) if b > a else []
+    n_out = prob.n_out
+    rows = [j.n_steps + 1 for j in jobs]
+    # pack ragged [n_out, rows_i] results into one [sum rows, n_out] block per rank
+    local = (np.concatenate([m.T for m in mine], axis=0) if mine else np.zeros((0, n_out), complex))
+    counts = [int(sum(rows[x:y])) for (x, y) in blocks]
+    full = all_gather_blocks(np.ascontiguousarray(local), counts, device=device, group=group)
+    out, off = [], 0
+    for r in rows:
+        out.append(np.ascontiguousarray(full[off:off + r].T))
+        off += r
+    return out
