@@ -8,3 +8,7 @@ hbar = 0.6582119569  # meV*ps  (reference: pyaceqd/constants.py:1)
 kB = 0.0861733326  # meV/K
 pybind_path = ""
 temp_dir = ""
+# "_right" multi-time operators: False = rho -> rho A with A as given (the reference author's own
+# restatement, two_time/propagate_tau.f90:91-92); True = rho -> rho A^T (the transposition the
+# legacy comment at four_level_system/dark_model.py:267-268 attributes to ACE).  SURVEY App. C.3.
+mto_right_transposed = False

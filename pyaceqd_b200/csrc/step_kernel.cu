@@ -103,6 +103,58 @@ __device__ __forceinline__ long long entry_of(const aceqd_traj& t, int i, long l
     return e;
 }
 
+// Main loop of one GEMM pass: MCV (<= MC) m-tiles x NB n-tiles of this warp over all k-chunks of
+// one PT block.  ALLNB: every n-tile of the warp is inside the slice (no predicates at all).
+template <int NB, int MCV, bool ALLNB>
+__device__ __forceinline__ void gemm_pass(double (&cre)[MC][NB][2], double (&cim)[MC][NB][2],
+                                          const double* const (&are)[MC], const double* const (&aim)[MC],
+                                          const bool (&aval)[MC], const bool (&nbv)[NB],
+                                          const double* chunks, int chunk_doubles, int strideB, int nch,
+                                          int warp, int g, int tq, uint32_t bar_full, uint32_t bar_empty,
+                                          int& stage, uint32_t& phase, int stages, int lane) {
+    for (int jc = 0; jc < nch; ++jc) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        const double* bre = chunks + (size_t)stage * chunk_doubles;
+        const double* bim = bre + KC * strideB;
+#pragma unroll
+        for (int ks = 0; ks < KC / 4; ++ks) {
+            const int k = jc * KC + 4 * ks;
+            double a_re[MCV], a_im[MCV], b_re[NB], b_im[NB];
+#pragma unroll
+            for (int mc = 0; mc < MCV; ++mc) {
+                a_re[mc] = aval[mc] ? are[mc][k] : 0.0;
+                a_im[mc] = aval[mc] ? aim[mc][k] : 0.0;
+            }
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                const int bo = (4 * ks + tq) * strideB + 8 * (warp + N_COMPUTE_WARPS * nb) + g;
+                b_re[nb] = (ALLNB || nbv[nb]) ? bre[bo] : 0.0;
+                b_im[nb] = (ALLNB || nbv[nb]) ? bim[bo] : 0.0;
+            }
+            // two sweeps so that consecutive DMMAs never share an accumulator
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                for (int mc = 0; mc < MCV; ++mc)
+                    if (ALLNB || nbv[nb]) {
+                        dmma(cre[mc][nb][0], cre[mc][nb][1], a_re[mc], b_re[nb]);
+                        dmma(cim[mc][nb][0], cim[mc][nb][1], a_re[mc], b_im[nb]);
+                    }
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                for (int mc = 0; mc < MCV; ++mc)
+                    if (ALLNB || nbv[nb]) {
+                        dmma(cre[mc][nb][0], cre[mc][nb][1], -a_im[mc], b_im[nb]);
+                        dmma(cim[mc][nb][0], cim[mc][nb][1], a_im[mc], b_re[nb]);
+                    }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+    }
+}
+
 // NB   = n-tiles (8 bond columns) per compute warp; KSU_T = compile-time bound on the number of
 // DMMA k-steps of the system-operator product (ceil(NL/4) <= KSU_T).
 template <int NB, int KSU_T>
@@ -508,47 +560,33 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 are[mc] = Xre + o;
                 aim[mc] = Xim + o;
             }
-            for (int jc = 0; jc < nch; ++jc) {
-                mbar_wait(bar_full + 8 * stage, phase);
-                const double* bre = chunks + (size_t)stage * p.pt.chunk_doubles;
-                const double* bim = bre + KC * strideB;
+            // warp-uniform dispatch to a main loop without predicated-off DMMAs (a nullified
+            // DMMA.8x8x4 still occupies the tensor pipe: profiles/r01f_cfg3_step_kernel_ncu.txt)
+            const int mcn = mcv[MC - 1] ? MC : 1;
+            bool allnb = true, anynb = false;
 #pragma unroll
-                for (int ks = 0; ks < KC / 4; ++ks) {
-                    const int k = jc * KC + 4 * ks;
-                    double a_re[MC], a_im[MC], b_re[NB], b_im[NB];
-#pragma unroll
-                    for (int mc = 0; mc < MC; ++mc) {
-                        a_re[mc] = aval[mc] ? are[mc][k] : 0.0;
-                        a_im[mc] = aval[mc] ? aim[mc][k] : 0.0;
-                    }
-#pragma unroll
-                    for (int nb = 0; nb < NB; ++nb) {
-                        const int bo = (4 * ks + tq) * strideB + 8 * (warp + N_COMPUTE_WARPS * nb) + g;
-                        b_re[nb] = nbv[nb] ? bre[bo] : 0.0;
-                        b_im[nb] = nbv[nb] ? bim[bo] : 0.0;
-                    }
-                    // two sweeps so that consecutive DMMAs never share an accumulator
-#pragma unroll
-                    for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-                        for (int mc = 0; mc < MC; ++mc)
-                            if (nbv[nb] && mcv[mc]) {
-                                dmma(cre[mc][nb][0], cre[mc][nb][1], a_re[mc], b_re[nb]);
-                                dmma(cim[mc][nb][0], cim[mc][nb][1], a_re[mc], b_im[nb]);
-                            }
-#pragma unroll
-                    for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-                        for (int mc = 0; mc < MC; ++mc)
-                            if (nbv[nb] && mcv[mc]) {
-                                dmma(cre[mc][nb][0], cre[mc][nb][1], -a_im[mc], b_im[nb]);
-                                dmma(cim[mc][nb][0], cim[mc][nb][1], a_im[mc], b_re[nb]);
-                            }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
-                if (++stage == stages) { stage = 0; phase ^= 1u; }
+            for (int nb = 0; nb < NB; ++nb) {
+                allnb &= nbv[nb];
+                anynb |= nbv[nb];
             }
+            if (!anynb) {  // this warp owns no bond column of the slice: keep the pipeline moving only
+                for (int jc = 0; jc < nch; ++jc) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
+            } else if (allnb && mcn == MC)
+                gemm_pass<NB, MC, true>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
+                                        warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
+            else if (allnb)
+                gemm_pass<NB, 1, true>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
+                                       warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
+            else if (mcn == MC)
+                gemm_pass<NB, MC, false>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
+                                         warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
+            else
+                gemm_pass<NB, 1, false>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
+                                        warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
             compute_bar();  // every warp has finished reading this pass's X rows
 #pragma unroll
             for (int mc = 0; mc < MC; ++mc) {

@@ -172,6 +172,8 @@ class Engine:
         self._out_pinned = None
         self._pts: Dict[int, Tuple[c_void_p, ProcessTensor]] = {}
         self._probs: Dict[Tuple[int, int], Tuple[c_void_p, Problem, np.ndarray]] = {}
+        self.record_timings = False      # bench: log device times of every run_jobs launch
+        self.timing_log: List[dict] = []
 
     # -------------------------------------------------------------- lifetime
     def close(self):
@@ -608,12 +610,14 @@ class Engine:
             tp = self._materialise(common, trunk, t_off, int(np.sum(t_rows * n_out)))
             _check(self.lib.aceqd_propagate_batch(self.ctx, hp, hpt, ctypes.byref(tp.batch)),
                    "aceqd_propagate_batch(trunk)")
+            self._log_launch("trunk", prob, common["chi_pad"], tp)
             trunk_out = (tp.out, t_off, t_rows)
         # branch b writes its rows at the tail of its job's block
         traj_out_off = [out_off[t["job"]] + t["row0"] * n_out for t in main["trajs"]]
         mp = self._materialise(common, main, traj_out_off, out_elems)
         _check(self.lib.aceqd_propagate_batch(self.ctx, hp, hpt, ctypes.byref(mp.batch)),
                "aceqd_propagate_batch")
+        self._log_launch("main", prob, common["chi_pad"], mp)
         out = mp.out
         for (job, f, ti) in copy_list:
             src = trunk_out[0][trunk_out[1][ti]: trunk_out[1][ti] + f * n_out]
@@ -623,6 +627,15 @@ class Engine:
             blk = out[out_off[i]: out_off[i] + n_rows[i] * n_out].reshape(n_rows[i], n_out)
             res.append(np.ascontiguousarray(blk.T))
         return res
+
+    def _log_launch(self, kind: str, prob: Problem, chi_pad: int, plan: "_Plan"):
+        if not self.record_timings:
+            return
+        step_ms, op_ms = self.last_timings()
+        self.timing_log.append(dict(kind=kind, step_ms=step_ms, opbuild_ms=op_ms, NL=prob.NL, chi_pad=chi_pad,
+                                    n_traj=int(plan.batch.n_traj), tile_T=int(plan.batch.tile_T),
+                                    n_tiles=int(plan.batch.n_tiles),
+                                    traj_steps=int(np.sum(np.asarray(plan.n_rows) - 1))))
 
     def _trivial(self, prob: Problem) -> ProcessTensor:
         key = ("trivial", len(prob.cls_keys))

@@ -107,16 +107,21 @@ class Problem:
             L += f * self.LA[k] + np.conj(f) * self.LB[k]
         return L
 
-    def mto_superop(self, op: np.ndarray, apply_from: str) -> np.ndarray:
+    def mto_superop(self, op: np.ndarray, apply_from: str, right_transposed: Optional[bool] = None) -> np.ndarray:
+        """``right_transposed`` switches the ``_right`` convention to ``rho -> rho A^T`` (the
+        index-order ambiguity of SURVEY App. C.3 / ``dark_model.py:267-268``); default from
+        ``constants.mto_right_transposed`` (False: A as given, like ``propagate_tau.f90:91-92``)."""
+        if right_transposed is None:
+            right_transposed = bool(getattr(constants, "mto_right_transposed", False))
         if apply_from == "_left":
             return liouville_left(op)
         if apply_from == "_right":
-            return liouville_right(op)
+            return liouville_right(op.T if right_transposed else op)
         if apply_from == "":
             return liouville_sandwich(op)
         raise ValueError('give "_left" or "_right" or "" for multitime')
 
-    def parse_mtos(self, multitime_op) -> List[MTO]:
+    def parse_mtos(self, multitime_op, right_transposed: Optional[bool] = None) -> List[MTO]:
         """Normalise the reference's ``multitime_op`` argument (dict or list of dicts)."""
         if multitime_op is None:
             return []
@@ -128,7 +133,7 @@ class Problem:
                 raise ValueError("supply 'operator' and 'time' for multitime")
             a = parse_operator(m["operator"], self.N)
             before = str(m.get("applyBefore", "false")).strip().lower() == "true"
-            out.append(MTO(self.mto_superop(a, m.get("applyFrom", "")), float(m["time"]), before))
+            out.append(MTO(self.mto_superop(a, m.get("applyFrom", ""), right_transposed), float(m["time"]), before))
         return out
 
 
