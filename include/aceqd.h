@@ -101,7 +101,8 @@ typedef struct {
 /* One trajectory = one `system(t_start, t_end, ...)` call of the reference. */
 typedef struct {
     int64_t ent0;     /* operator entry of its local step 0: seq_base[seq] + offset            */
-    int64_t out_off;  /* offset (complex elements) of its output block [n_steps+1][n_out]      */
+    int64_t out_off;  /* offset (complex elements) of its output block                         */
+                      /*   [n_steps+1-out_from][n_out]: rows out_from..n_steps                 */
     int32_t step0;    /* absolute step index of local step 0 (selects PT slices)               */
     int32_t n_steps;
     int32_t init_kind;  /* 0: rho0s[init_index] in bond column 0; 1: snapshot slot init_index  */
@@ -112,7 +113,8 @@ typedef struct {
     int32_t snap_off;   /* offset into snap_steps of this trajectory's snapshot requests       */
     int32_t snap_cnt;
     int32_t snap_slot0; /* snapshot j goes to slot snap_slot0 + j                              */
-    int32_t pad_;
+    int32_t out_from;   /* first local row that is written out (consumers index results from   */
+                        /* the END: two_time/correlations.py:182-183), 0 = every row            */
 } aceqd_traj;
 
 /*

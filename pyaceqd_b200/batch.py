@@ -39,8 +39,12 @@ class BatchFuture:
 class BatchExecutor:
     """Drop-in for ``concurrent.futures.ThreadPoolExecutor`` around ``system(...)`` calls."""
 
-    def __init__(self, max_workers=None, **_ignored):
+    def __init__(self, max_workers=None, tail_rows=0, **_ignored):
+        """``tail_rows`` > 0: every deferred job returns only its last ``tail_rows`` output rows
+        (the workflows index results from the end, e.g. ``res[1][-n_tau:]``
+        ``two_time/correlations.py:182-183``), which bounds the device->host volume of a sweep."""
         self.max_workers = max_workers
+        self.tail_rows = int(tail_rows or 0)
         self._requests = []     # (Request | immediate result, post-processing)
         self._results: list = []
         self._futures: List[BatchFuture] = []
@@ -57,6 +61,13 @@ class BatchExecutor:
     def shutdown(self, wait=True):
         self.flush()
 
+    def submit_tail(self, tail_rows, fn, *args, **kwargs) -> BatchFuture:
+        """``submit`` with a per-job tail length."""
+        fut = self.submit(fn, *args, **kwargs)
+        if self._requests and self._requests[-1][0] == fut._index:
+            self._requests[-1][1].job.tail_rows = int(tail_rows or 0)
+        return fut
+
     def submit(self, fn, *args, **kwargs) -> BatchFuture:
         sink: list = []
         prev = getattr(_gs._capture, "sink", None)
@@ -72,6 +83,7 @@ class BatchExecutor:
         # wrapped by post-processing that cannot run on a placeholder -> only plain pass-through
         # adapters are deferred; anything else has already been computed eagerly.
         if isinstance(ret, _gs.Request):
+            ret.job.tail_rows = self.tail_rows
             self._requests.append((len(self._results) - 1, ret))
         else:
             if sink:  # adapter post-processed a placeholder: run it again eagerly

@@ -512,7 +512,9 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
         else if (t.ent0 < 0 || t.ent0 + t.n_steps >= c->n_seq_entries)
             why = "operator entries beyond the sequence pool";
         else if (t.n_ovr < 0 || t.n_ovr > ACEQD_MAX_OVR) why = "too many override entries";
-        else if (t.out_off < 0 || t.out_off + (long long)(t.n_steps + 1) * pd.n_out > b->out_elems)
+        else if (t.out_from < 0 || t.out_from > t.n_steps + 1) why = "out_from outside the trajectory";
+        else if (t.out_off < 0 ||
+                 t.out_off + (long long)(t.n_steps + 1 - t.out_from) * pd.n_out > b->out_elems)
             why = "output block outside the output buffer";
         else if (t.init_kind == 0 && (t.init_index < 0 || t.init_index >= b->n_rho0))
             why = "initial state index out of range";

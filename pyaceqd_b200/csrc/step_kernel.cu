@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         for (int it = tid; it < T * n_out; it += N_COMPUTE_WARPS * 32) {
             const int j = it / n_out, o = it - j * n_out;
             const aceqd_traj& t = trj[j];
-            if (t.n_steps < 0 || n < t.step0 || n > t.step0 + t.n_steps) continue;
+            if (t.n_steps < 0 || n < t.step0 + t.out_from || n > t.step0 + t.n_steps) continue;
             const int i = n - t.step0;
             const double2* ov;
             if (wsm) {
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 acc.x += w.x * r.x - w.y * r.y;
                 acc.y += w.x * r.y + w.y * r.x;
             }
-            reinterpret_cast<double2*>(p.out)[t.out_off + (long long)i * n_out + o] = acc;
+            reinterpret_cast<double2*>(p.out)[t.out_off + (long long)(i - t.out_from) * n_out + o] = acc;
         }
         if (any_snap) {
             for (int j = 0; j < T; ++j) {
@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(256) k_step_check(const StepParams p, double* 
             r[a] = acc;
         }
         __syncthreads();
-        for (int o = tid; o < n_out; o += blockDim.x) {
+        for (int o = tid; o < n_out && i >= t.out_from; o += blockDim.x) {
             const double2* ov = reinterpret_cast<const double2*>(p.OV + (size_t)e_ * p.prob.ov_doubles) +
                                 (size_t)o * NL;
             double2 acc = make_double2(0.0, 0.0);
@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(256) k_step_check(const StepParams p, double* 
                 acc.x += ov[a].x * r[a].x - ov[a].y * r[a].y;
                 acc.y += ov[a].x * r[a].y + ov[a].y * r[a].x;
             }
-            reinterpret_cast<double2*>(p.out)[t.out_off + (long long)i * n_out + o] = acc;
+            reinterpret_cast<double2*>(p.out)[t.out_off + (long long)(i - t.out_from) * n_out + o] = acc;
         }
         if (snapn < t.snap_cnt && p.snap_steps[t.snap_off + snapn] == i) {
             double2* dst = reinterpret_cast<double2*>(p.snaps) + (size_t)(t.snap_slot0 + snapn) * tot;

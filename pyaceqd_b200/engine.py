@@ -38,7 +38,7 @@ ENTRY_DT = np.dtype([("set", "<i4"), ("step", "<i4"), ("sb", "<i4"), ("sa", "<i4
 TRAJ_DT = np.dtype([("ent0", "<i8"), ("out_off", "<i8"), ("step0", "<i4"), ("n_steps", "<i4"),
                     ("init_kind", "<i4"), ("init_index", "<i4"), ("n_ovr", "<i4"),
                     ("ovr_step", "<i4", (MAX_OVR,)), ("ovr_ent", "<i4", (MAX_OVR,)),
-                    ("snap_off", "<i4"), ("snap_cnt", "<i4"), ("snap_slot0", "<i4"), ("pad_", "<i4")],
+                    ("snap_off", "<i4"), ("snap_cnt", "<i4"), ("snap_slot0", "<i4"), ("out_from", "<i4")],
                    align=True)
 
 
@@ -421,6 +421,10 @@ class Engine:
                 if not lst:
                     ids.append(-1)
                     continue
+                idkey = tuple(id(s) for s in lst)   # superoperators are cached objects (Problem.parse_mtos)
+                if idkey in cache:
+                    ids.append(cache[idkey][0])
+                    continue
                 prod = np.eye(prob.NL, dtype=complex)
                 for s in lst:  # file order: first listed acts first
                     prod = s @ prod
@@ -428,6 +432,7 @@ class Engine:
                 if key not in cache:
                     cache[key] = len(mats)
                     mats.append(_c128(prod))
+                cache[idkey] = (cache[key], lst)   # keeps the operands alive so the ids stay unique
                 ids.append(cache[key])
             out[k] = (ids[0], ids[1])
         return out
@@ -462,7 +467,10 @@ class Engine:
             groups.setdefault((int(set_of_job[i]), round(jb.t_start / dt)), []).append(i)
 
         out_off = np.zeros(len(jobs), dtype=np.int64)
-        n_rows = np.asarray([jb.n_steps + 1 for jb in jobs], dtype=np.int64)
+        # only the last `tail_rows` output rows of a job are kept (consumers index from the end)
+        n_rows = np.asarray([min(jb.n_steps + 1, jb.tail_rows) if jb.tail_rows else jb.n_steps + 1
+                             for jb in jobs], dtype=np.int64)
+        g0 = np.asarray([jb.n_steps + 1 for jb in jobs], dtype=np.int64) - n_rows   # first global row kept
         out_off[1:] = np.cumsum(n_rows[:-1] * n_out)
         out_elems = int(np.sum(n_rows * n_out))
         copy_from_trunk = []  # (job, rows, trunk_job_index)
@@ -499,12 +507,16 @@ class Engine:
                         entries.append((sset, step_shift + k, sb, sa, 1 if k > 0 else 0))
                     if f is None or f == 0:
                         trajs.append(dict(job=i, seq=q_main, off=0, step0=0, n_steps=jb.n_steps, init_kind=0,
-                                          init_index=0, ovr=ovr, row0=0))
-                    else:
+                                          init_index=0, ovr=ovr, row0=0, out_from=int(g0[i])))
+                    elif g0[i] >= f:     # every kept row lies on the branch
                         trajs.append(dict(job=i, seq=q_main, off=f, step0=f, n_steps=jb.n_steps - f,
                                           init_kind=1, init_index=slot_of_step[f],
-                                          ovr=[(k - f, e) for k, e in ovr], row0=f))
-                        copy_from_trunk.append((i, f, len(trunk_trajs) - 1))
+                                          ovr=[(k - f, e) for k, e in ovr], row0=0, out_from=int(g0[i] - f)))
+                    else:                # rows g0..f-1 come from the trunk
+                        trajs.append(dict(job=i, seq=q_main, off=f, step0=f, n_steps=jb.n_steps - f,
+                                          init_kind=1, init_index=slot_of_step[f],
+                                          ovr=[(k - f, e) for k, e in ovr], row0=int(f - g0[i]), out_from=0))
+                        copy_from_trunk.append((i, int(f - g0[i]), len(trunk_trajs) - 1, int(g0[i])))
             else:
                 for i in members:
                     jb = jobs[i]
@@ -515,7 +527,7 @@ class Engine:
                         ovr.append((k, len(entries)))
                         entries.append((sset, step_shift + k, sb, sa, 1 if k > 0 else 0))
                     trajs.append(dict(job=i, seq=q, off=0, step0=0, n_steps=jb.n_steps, init_kind=0,
-                                      init_index=0, ovr=ovr, row0=0))
+                                      init_index=0, ovr=ovr, row0=0, out_from=int(g0[i])))
 
         common = dict(prob=prob, pt=pt, dt=dt, t0=t0_ref, off=(off1, off2), packed=packed, grid=grid,
                       mats=mats, chi_pad=chi_pad, kernel=kernel, tile_T=tile_T)
@@ -550,6 +562,7 @@ class Engine:
             for k, (st, en) in enumerate(t["ovr"]):
                 r["ovr_step"][k] = st
                 r["ovr_ent"][k] = en
+            r["out_from"] = t.get("out_from", 0)
             if "snap" in t:
                 r["snap_off"], r["snap_cnt"], r["snap_slot0"] = t["snap"]
         # tiling: sort by (step0, n_steps) so that tiles are homogeneous in absolute time
@@ -619,9 +632,9 @@ class Engine:
                "aceqd_propagate_batch")
         self._log_launch("main", prob, common["chi_pad"], mp)
         out = mp.out
-        for (job, f, ti) in copy_list:
-            src = trunk_out[0][trunk_out[1][ti]: trunk_out[1][ti] + f * n_out]
-            out[out_off[job]: out_off[job] + f * n_out] = src
+        for (job, n_copy, ti, row_first) in copy_list:
+            a = trunk_out[1][ti] + row_first * n_out
+            out[out_off[job]: out_off[job] + n_copy * n_out] = trunk_out[0][a: a + n_copy * n_out]
         res = []
         for i in range(len(jobs)):
             blk = out[out_off[i]: out_off[i] + n_rows[i] * n_out].reshape(n_rows[i], n_out)

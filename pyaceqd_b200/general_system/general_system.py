@@ -276,11 +276,13 @@ def system_ace_stream(t_start, t_end, *pulses, dt=0.01, phonons=False, t_mem=20.
             L = L + f * problem.LA[k] + np.conj(f) * problem.LB[k]
         return default_engine().expm(L * dt)[0]
 
-    job = Job(float(t_start), float(t_end), float(dt), tables=make_tables(t_end),
+    sink = getattr(_capture, "sink", None)
+    # deferred calls sample their drives once per sweep in run_requests (shared, longest window)
+    job = Job(float(t_start), float(t_end), float(dt),
+              tables={} if (sink is not None and not calc_dynmap) else make_tables(t_end),
               mtos=problem.parse_mtos(multitime_op))
     req = Request(problem=problem, pt=pt, job=job, pulse_key=pulse_key, table_maker=make_tables,
                   calc_dynmap=calc_dynmap)
-    sink = getattr(_capture, "sink", None)
     if sink is not None and not calc_dynmap:
         sink.append(req)
         return req      # BatchExecutor resolves it
@@ -289,7 +291,7 @@ def system_ace_stream(t_start, t_end, *pulses, dt=0.01, phonons=False, t_mem=20.
 
 def _finish(req: Request, out: np.ndarray):
     res = np.empty((1 + out.shape[0], out.shape[1]), dtype=complex)
-    res[0] = req.job.times()
+    res[0] = req.job.times()[-out.shape[1]:]   # deferred jobs may keep only their last rows
     res[1:] = out
     return res
 
@@ -309,7 +311,7 @@ def run_requests(reqs: List[Request]):
         for i in idx:
             by_key.setdefault(reqs[i].pulse_key, []).append(i)
         for key, members in by_key.items():
-            if len(members) > 1:
+            if len(members) > 1 or not reqs[members[0]].job.tables:
                 te = max(reqs[i].job.t_end for i in members)
                 tabs = reqs[members[0]].table_maker(te)
                 for i in members:

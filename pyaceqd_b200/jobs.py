@@ -33,6 +33,7 @@ class Job:
     dt: float
     tables: Dict[str, FieldTable] = field(default_factory=dict)  # "x", "y", "rf"
     mtos: List[MTO] = field(default_factory=list)
+    tail_rows: int = 0   # > 0: only the last `tail_rows` output rows are needed (0 = all)
 
     @property
     def n_steps(self) -> int:

@@ -128,12 +128,18 @@ class Problem:
         if isinstance(multitime_op, dict):
             multitime_op = [multitime_op]
         out = []
+        cache = self.meta.setdefault("_mto_cache", {})   # sweeps re-issue the same operators per job
         for m in multitime_op:
             if "operator" not in m or "time" not in m:
                 raise ValueError("supply 'operator' and 'time' for multitime")
-            a = parse_operator(m["operator"], self.N)
+            key = (m["operator"], m.get("applyFrom", ""), right_transposed,
+                   bool(getattr(constants, "mto_right_transposed", False)))
+            sup = cache.get(key)
+            if sup is None:
+                a = parse_operator(m["operator"], self.N)
+                sup = cache[key] = self.mto_superop(a, m.get("applyFrom", ""), right_transposed)
             before = str(m.get("applyBefore", "false")).strip().lower() == "true"
-            out.append(MTO(self.mto_superop(a, m.get("applyFrom", ""), right_transposed), float(m["time"]), before))
+            out.append(MTO(sup, float(m["time"]), before))
         return out
 
 

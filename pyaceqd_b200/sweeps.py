@@ -1,0 +1,70 @@
+"""Shared machinery of the batch issuers.
+
+Every (t, tau) workflow of the reference is one of two sweep shapes, written out many times
+with a ``ThreadPoolExecutor`` of ACE subprocesses:
+
+* **tail sweep** -- one job per ``t1``: multi-time operators moved to ``t1`` (+ offsets), the
+  last rows of one output give the ``tau > 0`` axis and one row of a second output the
+  ``tau = 0`` element (``two_time/correlations.py:153-184``, ``two_time/G1.py:66-89``,
+  ``pol_entanglement/G2.py:189-204,488-530``, ``timebin/twophoton_new.py:215-262``);
+* **triangular sweep** -- one job per pair ``t1 <= t2`` with three operators and only the very
+  last output value kept (``timebin/twophoton_new.py:515-557``).
+
+Here each sweep is ONE deferred GPU batch (:class:`~pyaceqd_b200.batch.BatchExecutor`): jobs that
+share the drive are forked from a common trunk and only the rows a consumer reads are copied back.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from pyaceqd_b200.batch import BatchExecutor, wait
+import pyaceqd_b200.constants as constants
+
+
+def at_time(mto: dict, time: float) -> dict:
+    """Copy of a multitime dict with its ``time`` set (callers must not share dicts between jobs)."""
+    m = dict(mto)
+    m["time"] = time
+    return m
+
+
+def run_sweep(system, jobs: Sequence[dict], *pulses, options: Optional[dict] = None, workers=None) -> List:
+    """Submit ``system(t0, tend, *pulses, multitime_op=..., output_ops=..., suffix=i, **options)`` for
+    every job spec ``{"t0", "tend", "mtos", "output_ops", "tail"}`` in one batch; return results."""
+    opts = dict(options or {})
+    with BatchExecutor(max_workers=workers) as ex:
+        futs = []
+        for i, jb in enumerate(jobs):
+            kw = dict(opts)
+            if jb.get("output_ops") is not None:
+                kw["output_ops"] = jb["output_ops"]
+            futs.append(ex.submit_tail(jb.get("tail", 0), system, jb.get("t0", 0), jb["tend"], *pulses,
+                                       multitime_op=jb["mtos"], suffix=i, **kw))
+        wait(futs)
+    return [f.result() for f in futs]
+
+
+def tail_series(res, n_after: int, i_tau: int = 1, i_zero: int = 2) -> np.ndarray:
+    """``[G(tau=0), G(tau_1), ..., G(tau_n)]`` from one job result: the ``n_after`` last rows of output
+    ``i_tau`` and, for ``tau = 0``, the row just before them of output ``i_zero`` -- the full
+    operator product evaluated at the MTO time."""
+    col = np.empty(n_after + 1, dtype=complex)
+    col[0] = res[i_zero][-(n_after + 1)]
+    if n_after > 0:
+        col[1:] = res[i_tau][-n_after:]
+    return col
+
+
+def symmetrised_spectrum(t_axis, tau_axis, g1, hbar: float = constants.hbar):
+    """Emission spectrum from ``G1(t, tau)``: extend to negative ``tau`` by conjugation, FFT along
+    ``tau`` for every ``t``, integrate over ``t`` (``two_time/G1.py:101-110``,
+    ``pol_entanglement/G2.py:225-241``).  Returns ``(energies, spectrum, spectra[t, E])``."""
+    n = len(tau_axis)
+    dtau = abs(tau_axis[1] - tau_axis[0])
+    energies = np.fft.fftshift(-2 * np.pi * hbar * np.fft.fftfreq(2 * n - 1, d=dtau))
+    sym = np.concatenate([g1[:, ::-1], np.conj(g1[:, 1:])], axis=1)
+    spectra = np.fft.fftshift(np.fft.fft(sym, axis=1), axes=1)
+    spectrum = np.real(np.trapezoid(spectra, t_axis, axis=0))
+    return energies, spectrum, spectra

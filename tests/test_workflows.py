@@ -1,0 +1,234 @@
+"""Batch issuers: two_time.G1, pol_entanglement.G2, timebin, rabi / tpe sweeps.
+
+CPU tests run the workflows on the oracle backend (host logic: job construction, tail indexing,
+integration, density-matrix assembly).  GPU tests run the SAME scenarios on the CUDA engine and
+compare every returned array with the oracle-backend result (workflow-level parity, <= 1e-10)."""
+import numpy as np
+import pytest
+
+from oracle_backend import oracle_backend
+from pyaceqd_b200.pulses import ChirpedPulse
+
+TOL = 1e-10
+
+
+# ------------------------------------------------------------------------------------ scenarios
+def scenario_g1(tmp):
+    from pyaceqd_b200.two_time.G1 import G1_twols
+    p = ChirpedPulse(tau_0=1.0, e_start=0.3, alpha=0, t0=3.0, e0=2.0)
+    t, tau, g1 = G1_twols(0, 4, 0, 3, 0.5, 0.1, p, gamma_e=0.05, temp_dir=tmp)
+    return {"t": t, "tau": tau, "g1": g1}
+
+
+def _polent(tmp):
+    from pyaceqd_b200.four_level_system.linear import biexciton
+    from pyaceqd_b200.pol_entanglement.G2 import PolarizatzionEntanglement
+    p = ChirpedPulse(tau_0=1.0, e_start=-2.0, alpha=0, t0=3.0, e0=5.0, polar_x=np.sqrt(0.5))
+    opts = {"lindblad": True, "gamma_e": 0.1, "delta_b": 4.0, "delta_xy": 0.2, "phonons": False, "temp_dir": tmp}
+    return PolarizatzionEntanglement(biexciton, "|0><1|_4 + |1><3|_4", "|0><2|_4 + |2><3|_4",
+                                     "|1><0|_4 + |3><1|_4", "|2><0|_4 + |3><2|_4", p, dt=0.25, tend=10,
+                                     regular_grid=True, dt_small=2.5, options=opts)
+
+
+def scenario_polent(tmp):
+    pe = _polent(tmp)
+    t1, g2_t, g2 = pe.G2_reuse(pe.axdag, [pe.axdag + " * " + pe.ax, pe.aydag + " * " + pe.ay], pe.ax)
+    _, g2_single_t, g2_single = pe.G2(pe.axdag, pe.aydag, pe.ay, pe.ax)
+    conc, rho = pe.calc_densitymatrix_reuse(return_rho=True)
+    t, c_t, rho_t, norm, rho_int, c_int = pe.calc_timedependent_rho(skip=2)
+    _, tau, g1 = pe.G1(pe.ax, pe.axdag)
+    return {"t1": t1, "g2_t": g2_t, "g2": g2, "g2_single_t": g2_single_t, "g2_single": g2_single, "conc": conc,
+            "rho": rho, "c_t": c_t, "rho_t": rho_t, "c_int": c_int, "g1": g1}
+
+
+def _timebin(tmp):
+    from pyaceqd_b200.four_level_system.linear import biexciton
+    from pyaceqd_b200.timebin.twophoton_new import TwoPhotonTimebinNew
+    tb = 4.0
+    p1 = ChirpedPulse(tau_0=0.25, e_start=-2.0, alpha=0, t0=1.5, e0=4.0)
+    p2 = ChirpedPulse(tau_0=0.25, e_start=-2.0, alpha=0, t0=1.5 + tb, e0=4.0)
+    opts = {"lindblad": True, "gamma_e": 0.5, "delta_b": 4.0, "phonons": False, "temp_dir": tmp}
+    return TwoPhotonTimebinNew(biexciton, "|0><1|_4", "|1><0|_4", "|1><3|_4", "|3><1|_4", p1, p2, dt=0.25, dim=4,
+                               tb=tb, dt_small=0.5, n_tbig=2, simple_exp=False, options=opts)
+
+
+def scenario_timebin(tmp):
+    tbn = _timebin(tmp)
+    conc, rho = tbn.calc_densitymatrix()
+    t1, g2, tot, grid = tbn.four_time([tbn.sigma_x, tbn.sigma_x + "*" + tbn.sigma_b],
+                                      {"operator": tbn.sigma_bdag, "applyFrom": "_right", "applyBefore": "false"},
+                                      {"operator": tbn.sigma_xdag, "applyFrom": "_right", "applyBefore": "false"},
+                                      {"operator": tbn.sigma_b, "applyFrom": "_left", "applyBefore": "false"})
+    return {"t1": t1, "conc": conc, "rho": rho, "four_time": grid, "g2": g2, "tot": tot}
+
+
+def scenario_onephoton(tmp):
+    from pyaceqd_b200.timebin.onephoton import OnePhotonTimebin
+    from pyaceqd_b200.two_level_system.tls import tls
+    tb = 4.0
+    pulses = [ChirpedPulse(tau_0=0.25, e_start=0, alpha=0, t0=1.5 + k * tb, e0=0.5) for k in range(2)]
+    # gaussian_t: the default grid path binds the first pulse to construct_t's dt_exp
+    one = OnePhotonTimebin(tls, "|0><1|_2", *pulses, dt=0.1, tb=tb, simple_exp=False, gaussian_t=3.0,
+                           options={"lindblad": True, "gamma_e": 0.8, "phonons": False, "temp_dir": tmp})
+    ee, ll, el, norm = one.calc_densitymatrix()
+    return {"ee": ee, "ll": ll, "el": el, "norm": norm}
+
+
+def scenario_rabi(tmp):
+    from pyaceqd_b200.four_level_system.tpe_rotations import TPERotations
+    from pyaceqd_b200.two_level_system.rabi_rotations import RabiRotations
+    rr = RabiRotations(dt=0.1, tau=1.0, area_max=4, n_area=9, temp_dir=tmp)
+    areas, final = rr.get_rabi_rotations(integrate=False, path=tmp)
+    tp = TPERotations(dt=0.25, tau=1.0, area_max=6, n_area=4, gamma_e=0.5)
+    a2, xyb = tp.get_rabi_rotations(detuning=-2.0, integrate=True, path=tmp + "i_")
+    return {"areas": areas, "final": final, "tpe": xyb}
+
+
+SCENARIOS = {"g1": scenario_g1, "polent": scenario_polent, "timebin": scenario_timebin,
+             "onephoton": scenario_onephoton, "rabi": scenario_rabi}
+
+
+def _run_oracle(name, tmp_path):
+    with oracle_backend() as eng:
+        out = SCENARIOS[name](str(tmp_path) + "/o_")
+    return out, eng
+
+
+# ------------------------------------------------------------------------------------ CPU: host logic
+def test_g1_layout_and_tau0(tmp_path):
+    out, eng = _run_oracle("g1", tmp_path)
+    assert out["g1"].shape == (len(out["t"]), 31) and np.allclose(out["tau"], np.linspace(0, 3, 31))
+    assert len(eng.calls) == 1 and eng.calls[0][0] == len(out["t"])          # ONE batch for the sweep
+    assert np.abs(out["g1"][:, 0].imag).max() < 1e-14 and out["g1"][:, 0].real.min() > -1e-12   # G1(t,0) = x(t)
+    # |G1(t,tau)|^2 <= x(t) x(t+tau) (Cauchy-Schwarz); spot check the weaker |G1| <= 1
+    assert np.abs(out["g1"]).max() <= 1.0
+
+
+def test_polent_reuse_equals_single_and_assembly(tmp_path):
+    out, eng = _run_oracle("polent", tmp_path)
+    assert np.allclose(out["t1"], [0, 2.5, 5.0, 7.5, 10.0])
+    # component 1 of the reuse sweep == the stand-alone G2 with the same four operators
+    assert np.abs(out["g2_t"][1] - out["g2_single_t"]).max() < 1e-13
+    assert abs(out["g2"][1] - out["g2_single"]) < 1e-13
+    rho = out["rho"]
+    assert np.abs(rho - rho.conj().T).max() < 1e-14 and np.all(np.diag(rho).real >= 0)
+    assert 0.0 <= out["conc"] <= 1.0 + 1e-12 and 0.0 <= out["c_int"] <= 1.0 + 1e-12
+    assert out["rho_t"].shape == (3, 4, 4) and out["g1"].shape == (5, 41)
+
+
+def test_integrate_timedep_g2_matches_reference_loops():
+    """Vectorised G2(t) = int_0^t dt' int_0^{t-t'} dtau G2(t',tau) against the reference's triple loop
+    (pol_entanglement/G2.py:552-606), restated here."""
+    from pyaceqd_b200.pol_entanglement.G2 import PolarizatzionEntanglement
+    rng = np.random.default_rng(3)
+    t1 = np.array([0, 0.5, 1.0, 2.0, 2.5, 4.0])
+    t2 = np.linspace(0, 4, 17)
+    full = rng.standard_normal((3, len(t1), len(t2))) + 1j * rng.standard_normal((3, len(t1), len(t2)))
+    _, got = PolarizatzionEntanglement.integrate_timedep_G2(None, t1, t2, full)
+    want = np.zeros((3, len(t1)), dtype=complex)
+    for i in range(len(t1)):
+        inner = np.zeros((3, i + 1), dtype=complex)
+        for j in range(i + 1):
+            idx = t2 <= t1[i] - t1[j]
+            inner[:, j] = np.trapezoid(full[:, j, idx], t2[idx])
+        want[:, i] = np.trapezoid(inner, t1[:i + 1])
+    assert np.abs(got - want).max() < 1e-13
+    _, g_tau = PolarizatzionEntanglement.integrate_g2_tau(None, t1, t2, full)
+    assert np.abs(g_tau[1, 4] - np.trapezoid(full[1, :, 4], t1)) < 1e-14
+
+
+def test_symmetrised_spectrum_matches_loops():
+    from pyaceqd_b200.sweeps import symmetrised_spectrum
+    rng = np.random.default_rng(5)
+    t, tau = np.array([0, 1.0, 1.5, 3.0]), np.linspace(0, 2, 9)
+    g1 = rng.standard_normal((4, 9)) + 1j * rng.standard_normal((4, 9))
+    e, spec, spectra = symmetrised_spectrum(t, tau, g1, 0.6582119569)
+    sym = np.empty((4, 17), dtype=complex)
+    sym[:, :9] = g1[:, ::-1]
+    sym[:, -8:] = np.conj(g1[:, 1:])
+    want = np.array([np.fft.fftshift(np.fft.fft(sym[j])) for j in range(4)])
+    assert np.abs(spectra - want).max() < 1e-12
+    assert np.abs(spec - np.real(np.trapezoid(want.T, t))).max() < 1e-12
+    assert len(e) == 17 and np.all(np.diff(e) < 0)      # energies = -2 pi hbar f, shifted
+
+
+def test_timebin_density_matrix_structure(tmp_path):
+    out, eng = _run_oracle("timebin", tmp_path)
+    rho, n = out["rho"], len(out["t1"])
+    assert np.abs(rho - rho.conj().T).max() < 1e-14
+    assert np.all(np.diag(rho).real > 0) and 0.0 <= out["conc"] <= 1.0 + 1e-12
+    # identical pulses in both bins -> similar early/late populations (decay is not complete within tb here)
+    assert abs(rho[0, 0] - rho[3, 3]) < 0.25 * abs(rho[0, 0])
+    # triangular sweeps are issued as few large batches, not one per t1
+    assert max(c[0] for c in eng.calls) == n * (n + 1) // 2
+    assert np.allclose(np.tril(out["four_time"], -1), 0)
+
+
+def test_onephoton_and_area_sweeps(tmp_path):
+    out, _ = _run_oracle("onephoton", tmp_path)
+    assert 0 < out["ee"] < out["ll"] < 2 * out["ee"]      # late bin also collects the early bin's leftover
+    assert 0 < out["el"] <= np.sqrt(out["ee"] * out["ll"]) + 1e-9    # |rho_el| <= sqrt(rho_ee rho_ll) (gamma_e units)
+    out, eng = _run_oracle("rabi", tmp_path)
+    assert np.abs(out["final"] - np.sin(np.pi * out["areas"] / 2) ** 2).max() < 2e-3    # Rabi rotations
+    assert out["tpe"].shape == (3, 4) and np.all(out["tpe"] >= -1e-12)
+    assert [c[0] for c in eng.calls] == [9, 4]
+
+
+def test_planner_tail_rows_and_fork_bookkeeping():
+    """Engine.plan with tail_rows: rows kept, out_from, trunk copies (no GPU needed)."""
+    from helpers import make_tables, tls_problem
+    from pyaceqd_b200.engine import Engine
+    from pyaceqd_b200.jobs import Job
+    from pyaceqd_b200.process_tensor import trivial_pt
+    prob = tls_problem(phonons=False)
+    p = ChirpedPulse(tau_0=1.0, e_start=0, alpha=0, t0=2.0, e0=1.0)
+    tabs = make_tables([p], 0.0, 6.0, 0.1)
+    mto = lambda t: prob.parse_mtos([{"operator": "|0><1|_2", "applyFrom": "_left", "time": t}])
+    jobs = [Job(0.0, 4.0, 0.1, tables=tabs, mtos=mto(1.0), tail_rows=11),     # tail entirely on the branch
+            Job(0.0, 4.0, 0.1, tables=tabs, mtos=mto(3.5), tail_rows=11),     # tail reaches back into the trunk
+            Job(0.0, 5.0, 0.1, tables=tabs, mtos=mto(2.0))]                   # all rows
+    eng = Engine.__new__(Engine)
+    common, trunk, main, (out_off, n_rows, out_elems, copies) = Engine.plan(eng, prob, trivial_pt(1), jobs)
+    assert n_rows.tolist() == [11, 11, 51] and out_elems == (11 + 11 + 51) * prob.n_out
+    tj = {t["job"]: t for t in main["trajs"]}
+    assert (tj[0]["step0"], tj[0]["out_from"], tj[0]["row0"]) == (10, 20, 0)     # rows 30..40, branch starts at 10
+    assert (tj[1]["step0"], tj[1]["out_from"], tj[1]["row0"]) == (35, 0, 5)      # rows 30..34 from the trunk
+    assert (tj[2]["step0"], tj[2]["out_from"], tj[2]["row0"]) == (20, 0, 20)
+    assert sorted((c[0], c[1], c[3]) for c in copies) == [(1, 5, 30), (2, 20, 0)]
+    assert trunk["snap_steps"] == [10, 20, 35] and trunk["trajs"][0]["n_steps"] == 35
+
+
+# ------------------------------------------------------------------------------------ GPU: workflow parity
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_workflow_gpu_equals_oracle_backend(name, tmp_path):
+    want, _ = _run_oracle(name, tmp_path)
+    got = SCENARIOS[name](str(tmp_path) + "/g_")
+    assert sorted(got) == sorted(want)
+    for k in want:
+        d = np.abs(np.asarray(got[k]) - np.asarray(want[k])).max()
+        assert d < TOL, (name, k, d)
+
+
+@pytest.mark.gpu
+def test_tail_rows_equal_tail_of_full_run():
+    from helpers import make_tables, tls_problem
+    from pyaceqd_b200.engine import default_engine
+    from pyaceqd_b200.jobs import Job
+    from pyaceqd_b200.process_tensor import synthetic_pt
+    prob = tls_problem()
+    pt = synthetic_pt(24, len(prob.cls_keys), kind="unitary", scale=0.999)
+    p = ChirpedPulse(tau_0=1.0, e_start=0.5, alpha=0, t0=2.0, e0=3.0)
+    tabs = make_tables([p], 0.0, 6.0, 0.1)
+    mto = lambda t: prob.parse_mtos([{"operator": "|0><1|_2", "applyFrom": "_left", "time": t}])
+    mk = lambda tail: [Job(0.0, 4.0, 0.1, tables=tabs, mtos=mto(1.0), tail_rows=tail),
+                       Job(0.0, 4.0, 0.1, tables=tabs, mtos=mto(3.5), tail_rows=tail),
+                       Job(0.0, 5.0, 0.1, tables=tabs, mtos=mto(2.0), tail_rows=tail),
+                       Job(0.0, 3.0, 0.1, tables=tabs, tail_rows=tail)]
+    eng = default_engine(0)
+    full = eng.run_jobs(prob, pt, mk(0))
+    for kernel in ("dmma", "check"):
+        for fork in (True, False):
+            tails = eng.run_jobs(prob, pt, mk(11), kernel=kernel, fork=fork)
+            for f, t in zip(full, tails):
+                assert t.shape[1] == 11 and np.abs(f[:, -11:] - t).max() < 1e-12
