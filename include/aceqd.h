@@ -182,6 +182,32 @@ int aceqd_snapshot_read(aceqd_ctx* ctx, int slot, int NL, int chi_pad, double* h
  * behind the operator builder.  Replaces `fprop.update(t, dt); fprop.M` (general_system.py:324-327). */
 int aceqd_expm_batch(aceqd_ctx* ctx, int n, int count, const double* a_host, double* out_host);
 
+/*
+ * Time-local dynamical-map chains.  Replaces the reference's f2py/OpenMP/BLAS modules
+ * `propagate_tau_module` (pyaceqd/two_time/propagate_tau.f90:3-536) and `timebin_tl`
+ * (pyaceqd/timebin/timebin_tl.f90:23-397), which push Liouville vectors through chains of
+ * NL x NL matrices (zgemv) with operator insertions and traces.  A chain is a program of
+ * segments over one matrix pool `mats[n_mats][NL][NL]` (time-local maps, binary powers of the
+ * stationary map, operator superoperators): segment (start, count, stride) applies
+ * mats[start], mats[start+stride], ... (count matrices, stride 0 or 1) in order; after every step of a segment with emit != 0 the functionals
+ * w[n_w][NL] of the vector are appended to the chain's output row.
+ *   v0      [n_chains][NL]   start vectors        seg_off [n_chains+1] first segment of each chain
+ *   out     [n_chains][n_emit_max][n_w] (may be NULL)   final_v [n_chains][NL] (may be NULL)
+ * All pointers are host pointers; copies happen inside the call.
+ */
+typedef struct {
+    int32_t start;  /* first matrix of the segment                                             */
+    int32_t count;  /* consecutive matrices applied                                            */
+    int32_t emit;   /* != 0: emit the output functionals after each step                       */
+    int32_t stride; /* 1: consecutive matrices; 0: mats[start] applied `count` times            */
+} aceqd_tlseg;
+
+int aceqd_tlmap_run(aceqd_ctx* ctx, int NL, int n_mats, const double* mats, int n_chains,
+                    const double* v0, const int64_t* seg_off, int64_t n_segs, const aceqd_tlseg* segs,
+                    int n_w, const double* w, int n_emit_max, double* out, double* final_v);
+/* Device time (ms) of the last aceqd_tlmap_run kernel. */
+int aceqd_tlmap_last_ms(aceqd_ctx* ctx, float* ms);
+
 /* Page-locked host memory for the end-to-end path (H2D of drive tables, D2H of outputs). */
 int aceqd_host_alloc(size_t bytes, void** out);
 void aceqd_host_free(void* p);

@@ -12,3 +12,6 @@ temp_dir = ""
 # restatement, two_time/propagate_tau.f90:91-92); True = rho -> rho A^T (the transposition the
 # legacy comment at four_level_system/dark_model.py:267-268 attributes to ACE).  SURVEY App. C.3.
 mto_right_transposed = False
+# DynamicalMap.E layout: the reference's consumers treat dm[0] as E_{t1,t0} (tools.py:470-479), so the
+# identity at t0 is not returned by default.
+dynmap_includes_t0 = False

@@ -55,10 +55,10 @@ struct aceqd_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     long long launches = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // step start/stop, opbuild start/stop
-    bool have_step = false, have_op = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // step, opbuild, tlmap start/stop
+    bool have_step = false, have_op = false, have_tl = false;
     DevBuf W, OV, tables, seqs, seq_base, entries, mto, rho0s, trajs, tiles, snap_steps, snaps,
-        out, passes, scratch, misc;
+        out, passes, scratch, misc, tl_pool, tl_v0, tl_segoff, tl_segs, tl_w, tl_out, tl_final;
     // layout of the operators currently in the workspace
     long long n_seq_entries = 0;
 };
@@ -126,7 +126,8 @@ void aceqd_ctx_destroy(aceqd_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->W, &c->OV, &c->tables, &c->seqs, &c->seq_base, &c->entries, &c->mto,
                       &c->rho0s, &c->trajs, &c->tiles, &c->snap_steps, &c->snaps, &c->out,
-                      &c->passes, &c->scratch, &c->misc})
+                      &c->passes, &c->scratch, &c->misc, &c->tl_pool, &c->tl_v0, &c->tl_segoff,
+                      &c->tl_segs, &c->tl_w, &c->tl_out, &c->tl_final})
         b->release();
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -651,6 +652,69 @@ int aceqd_expm_batch(aceqd_ctx* c, int n, int count, const double* a_host, doubl
     if ((rc = launch_expm_batch(n, count, a_dev, o_dev, c->stream, &c->launches))) return rc;
     ACEQD_CUDA(cudaMemcpyAsync(out_host, o_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
     ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+    return ACEQD_OK;
+}
+
+int aceqd_tlmap_run(aceqd_ctx* c, int NL, int n_mats, const double* mats, int n_chains,
+                    const double* v0, const int64_t* seg_off, int64_t n_segs, const aceqd_tlseg* segs,
+                    int n_w, const double* w, int n_emit_max, double* out, double* final_v) {
+    if (!c || NL <= 0 || n_mats <= 0 || !mats || n_chains < 0 || !v0 || !seg_off || n_segs < 0 ||
+        (n_segs && !segs) || n_w < 0 || (n_w && !w) || n_emit_max < 0 || (!out && !final_v)) {
+        set_error("aceqd_tlmap_run: invalid argument");
+        return ACEQD_ERR_ARG;
+    }
+    if (n_chains == 0) return ACEQD_OK;
+    if (seg_off[0] != 0 || seg_off[n_chains] != n_segs) {
+        set_error("aceqd_tlmap_run: seg_off must run from 0 to n_segs");
+        return ACEQD_ERR_ARG;
+    }
+    for (int i = 0; i < n_chains; ++i)
+        if (seg_off[i + 1] < seg_off[i]) {
+            set_error("aceqd_tlmap_run: seg_off not monotone at chain %d", i);
+            return ACEQD_ERR_ARG;
+        }
+    for (int64_t s = 0; s < n_segs; ++s)
+        if (segs[s].start < 0 || segs[s].count < 0 || segs[s].stride < 0 || segs[s].stride > 1 ||
+            (long long)segs[s].start + (long long)(segs[s].count > 0 ? segs[s].count - 1 : 0) * segs[s].stride >= n_mats) {
+            set_error("aceqd_tlmap_run: segment %lld outside the matrix pool", (long long)s);
+            return ACEQD_ERR_ARG;
+        }
+    ACEQD_CUDA(cudaSetDevice(c->device));
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+    const size_t vec = (size_t)NL * 16;
+    UP(c->tl_pool, mats, (size_t)n_mats * NL * vec);
+    UP(c->tl_v0, v0, (size_t)n_chains * vec);
+    UP(c->tl_segoff, seg_off, (size_t)(n_chains + 1) * sizeof(int64_t));
+    UP(c->tl_segs, segs, (size_t)n_segs * sizeof(aceqd_tlseg));
+    UP(c->tl_w, w, (size_t)n_w * vec);
+    int rc;
+    const size_t out_bytes = (size_t)n_chains * n_emit_max * n_w * 16;
+    if (out && (rc = c->tl_out.reserve(out_bytes ? out_bytes : 16))) return rc;
+    if (final_v && (rc = c->tl_final.reserve((size_t)n_chains * vec))) return rc;
+    if (out && out_bytes) ACEQD_CUDA(cudaMemsetAsync(c->tl_out.p, 0, out_bytes, c->stream));
+    ACEQD_CUDA(cudaEventRecord(c->ev[4], c->stream));
+    if ((rc = launch_tlmap(NL, n_chains, n_w, n_emit_max, (const double*)c->tl_pool.p,
+                           (const double*)c->tl_v0.p, (const long long*)c->tl_segoff.p,
+                           (const aceqd_tlseg*)c->tl_segs.p, (const double*)c->tl_w.p,
+                           out ? (double*)c->tl_out.p : nullptr,
+                           final_v ? (double*)c->tl_final.p : nullptr, c->stream, &c->launches)))
+        return rc;
+    ACEQD_CUDA(cudaEventRecord(c->ev[5], c->stream));
+    c->have_tl = true;
+    if (out && out_bytes)
+        ACEQD_CUDA(cudaMemcpyAsync(out, c->tl_out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (final_v)
+        ACEQD_CUDA(cudaMemcpyAsync(final_v, c->tl_final.p, (size_t)n_chains * vec,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+    return ACEQD_OK;
+}
+
+int aceqd_tlmap_last_ms(aceqd_ctx* c, float* ms) {
+    if (!c || !ms) return ACEQD_ERR_ARG;
+    *ms = 0.f;
+    ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->have_tl) ACEQD_CUDA(cudaEventElapsedTime(ms, c->ev[4], c->ev[5]));
     return ACEQD_OK;
 }
 

@@ -117,6 +117,9 @@ int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, cu
 int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, long long* launches);
 int launch_step_check(const StepParams& p, double* scratch, cudaStream_t s, long long* launches);
 size_t step_smem_bytes(int NL, int chi_pad, int T, int stages, int wov_doubles);
+int launch_tlmap(int NL, int n_chains, int n_w, int n_emit_max, const double* pool, const double* v0,
+                 const long long* seg_off, const aceqd_tlseg* segs, const double* w, double* out,
+                 double* final_v, cudaStream_t s, long long* launches);
 int launch_fp64_peak(int kind, int iters, double* sink_dev, int* blocks, int* threads,
                      cudaStream_t s, long long* launches);
 

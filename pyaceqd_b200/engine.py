@@ -35,6 +35,7 @@ T_EVAL = {"half_mid": (0.25, 0.75), "step_mid": (0.5, 0.5), "start": (0.0, 0.5)}
 SEQ_DT = np.dtype([("set", "<i4"), ("step0", "<i4"), ("len", "<i4"), ("first_has_prev", "<i4")], align=True)
 ENTRY_DT = np.dtype([("set", "<i4"), ("step", "<i4"), ("sb", "<i4"), ("sa", "<i4"), ("has_prev", "<i4")],
                     align=True)
+TLSEG_DT = np.dtype([("start", "<i4"), ("count", "<i4"), ("emit", "<i4"), ("stride", "<i4")], align=True)
 TRAJ_DT = np.dtype([("ent0", "<i8"), ("out_off", "<i8"), ("step0", "<i4"), ("n_steps", "<i4"),
                     ("init_kind", "<i4"), ("init_index", "<i4"), ("n_ovr", "<i4"),
                     ("ovr_step", "<i4", (MAX_OVR,)), ("ovr_ent", "<i4", (MAX_OVR,)),
@@ -99,6 +100,9 @@ def load_library():
     lib.aceqd_build_operators.argtypes = [c_void_p, c_void_p, POINTER(_Batch)]
     lib.aceqd_snapshot_read.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p]
     lib.aceqd_expm_batch.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
+    lib.aceqd_tlmap_run.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                                    c_int, c_void_p, c_int, c_void_p, c_void_p]
+    lib.aceqd_tlmap_last_ms.argtypes = [c_void_p, POINTER(c_float)]
     lib.aceqd_max_tile.argtypes = [c_int, c_int]
     lib.aceqd_fp64_peak.argtypes = [c_void_p, c_int, c_int, POINTER(c_double)]
     lib.aceqd_host_alloc.argtypes = [ctypes.c_size_t, POINTER(c_void_p)]
@@ -244,6 +248,33 @@ class Engine:
         _check(self.lib.aceqd_expm_batch(self.ctx, a.shape[1], a.shape[0], a.ctypes.data,
                                          out.ctypes.data), "aceqd_expm_batch")
         return out
+
+    def tlmap_run(self, mats: np.ndarray, v0: np.ndarray, seg_off: np.ndarray, segs: np.ndarray,
+                  w: Optional[np.ndarray] = None, n_emit_max: int = 0, want_final: bool = False):
+        """Batched time-local map chains (``aceqd_tlmap_run``): ``mats[n_mats, NL, NL]`` matrix pool,
+        ``v0[n_chains, NL]`` start vectors, chain ``i`` runs segments ``segs[seg_off[i]:seg_off[i+1]]``
+        (dtype ``TLSEG_DT``).  Returns ``(out[n_chains, n_emit_max, n_w] | None, final[n_chains, NL] | None)``."""
+        mats, v0 = _c128(mats), _c128(v0)
+        NL = mats.shape[-1]
+        n_chains = v0.shape[0]
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+        segs = np.ascontiguousarray(segs, dtype=TLSEG_DT)
+        w = _c128(w).reshape(-1, NL) if w is not None else np.zeros((0, NL), complex)
+        out = np.zeros((n_chains, n_emit_max, w.shape[0]), dtype=np.complex128) if n_emit_max and len(w) else None
+        fin = np.empty((n_chains, NL), dtype=np.complex128) if want_final else None
+        if out is None and fin is None:
+            raise ValueError("nothing to compute: ask for emitted outputs and/or final vectors")
+        _check(self.lib.aceqd_tlmap_run(self.ctx, NL, mats.shape[0], mats.ctypes.data, n_chains, v0.ctypes.data,
+                                        seg_off.ctypes.data, len(segs), segs.ctypes.data if len(segs) else None,
+                                        w.shape[0], w.ctypes.data if len(w) else None, int(n_emit_max),
+                                        out.ctypes.data if out is not None else None,
+                                        fin.ctypes.data if fin is not None else None), "aceqd_tlmap_run")
+        return out, fin
+
+    def tlmap_last_ms(self) -> float:
+        v = c_float()
+        _check(self.lib.aceqd_tlmap_last_ms(self.ctx, ctypes.byref(v)), "aceqd_tlmap_last_ms")
+        return v.value
 
     def fp64_peak(self, kind: str = "dmma", iters: int = 20000) -> float:
         v = c_double()
@@ -462,9 +493,18 @@ class Engine:
         seqs, entries, trajs = [], [], []
         trunk_seqs, trunk_trajs, snap_steps = [], [], []
         n_slots = 0
-        groups: Dict[Tuple[int, float], List[int]] = {}
+        groups: Dict[Tuple[int, float, int], List[int]] = {}
+        rho0s = [_c128(prob.rho0).reshape(NL)]      # slot 0: the problem's own initial state
+        rho0_slot = {}
         for i, jb in enumerate(jobs):
-            groups.setdefault((int(set_of_job[i]), round(jb.t_start / dt)), []).append(i)
+            slot = 0
+            if jb.rho0 is not None:
+                key = _c128(jb.rho0).reshape(NL).tobytes()
+                if key not in rho0_slot:
+                    rho0_slot[key] = len(rho0s)
+                    rho0s.append(_c128(jb.rho0).reshape(NL))
+                slot = rho0_slot[key]
+            groups.setdefault((int(set_of_job[i]), round(jb.t_start / dt), slot), []).append(i)
 
         out_off = np.zeros(len(jobs), dtype=np.int64)
         # only the last `tail_rows` output rows of a job are kept (consumers index from the end)
@@ -475,7 +515,7 @@ class Engine:
         out_elems = int(np.sum(n_rows * n_out))
         copy_from_trunk = []  # (job, rows, trunk_job_index)
 
-        for (sset, _), members in groups.items():
+        for (sset, _, r0), members in groups.items():
             # a separate time origin per group keeps `step` = steps since the group's t_start
             t_start = jobs[members[0]].t_start
             step_shift = int(round((t_start - t0_ref) / dt))  # table/time bookkeeping only
@@ -490,7 +530,7 @@ class Engine:
                 trunk_seqs.append((sset, step_shift, trunk_len + 1, 0))
                 slot_of_step = {f: n_slots + k for k, f in enumerate(fork_steps)}
                 trunk_trajs.append(dict(seq=q_trunk, off=0, step0=0, n_steps=trunk_len, init_kind=0,
-                                        init_index=0, ovr=[], snap=(len(snap_steps), len(fork_steps), n_slots),
+                                        init_index=r0, ovr=[], snap=(len(snap_steps), len(fork_steps), n_slots),
                                         shift=step_shift, members=members))
                 snap_steps.extend(fork_steps)
                 n_slots += len(fork_steps)
@@ -507,7 +547,7 @@ class Engine:
                         entries.append((sset, step_shift + k, sb, sa, 1 if k > 0 else 0))
                     if f is None or f == 0:
                         trajs.append(dict(job=i, seq=q_main, off=0, step0=0, n_steps=jb.n_steps, init_kind=0,
-                                          init_index=0, ovr=ovr, row0=0, out_from=int(g0[i])))
+                                          init_index=r0, ovr=ovr, row0=0, out_from=int(g0[i])))
                     elif g0[i] >= f:     # every kept row lies on the branch
                         trajs.append(dict(job=i, seq=q_main, off=f, step0=f, n_steps=jb.n_steps - f,
                                           init_kind=1, init_index=slot_of_step[f],
@@ -527,10 +567,10 @@ class Engine:
                         ovr.append((k, len(entries)))
                         entries.append((sset, step_shift + k, sb, sa, 1 if k > 0 else 0))
                     trajs.append(dict(job=i, seq=q, off=0, step0=0, n_steps=jb.n_steps, init_kind=0,
-                                      init_index=0, ovr=ovr, row0=0, out_from=int(g0[i])))
+                                      init_index=r0, ovr=ovr, row0=0, out_from=int(g0[i])))
 
         common = dict(prob=prob, pt=pt, dt=dt, t0=t0_ref, off=(off1, off2), packed=packed, grid=grid,
-                      mats=mats, chi_pad=chi_pad, kernel=kernel, tile_T=tile_T)
+                      mats=mats, chi_pad=chi_pad, kernel=kernel, tile_T=tile_T, rho0s=np.asarray(rho0s))
         main = dict(seqs=seqs, entries=entries, trajs=trajs, snap_steps=[], n_slots=0)
         trunk = None
         if trunk_trajs:
@@ -578,7 +618,7 @@ class Engine:
         tile_traj = np.full(n_tiles * T, -1, dtype=np.int32)
         tile_traj[:len(tr)] = order
         mats = _c128(np.asarray(common["mats"]).reshape(-1, NL, NL)) if common["mats"] else np.zeros((0, NL, NL), complex)
-        rho0 = _c128(prob.rho0).reshape(1, NL)
+        rho0 = _c128(common["rho0s"]).reshape(-1, NL)
         snap_steps = np.asarray(part["snap_steps"], dtype=np.int32)
         out = out_buf if out_buf is not None else np.zeros(out_elems, dtype=np.complex128)
         packed = common["packed"]
@@ -591,7 +631,7 @@ class Engine:
         b.n_seq, b.seqs = len(seqs), seqs.ctypes.data
         b.n_entries, b.entries = len(entries), (entries.ctypes.data if len(entries) else None)
         b.n_mto_mats, b.mto_mats = len(mats), (mats.ctypes.data if len(mats) else None)
-        b.n_rho0, b.rho0s = 1, rho0.ctypes.data
+        b.n_rho0, b.rho0s = rho0.shape[0], rho0.ctypes.data
         b.n_traj, b.trajs = len(trajs), trajs.ctypes.data
         b.tile_T, b.n_tiles, b.tile_traj = T, n_tiles, tile_traj.ctypes.data
         b.n_snap_steps = len(snap_steps)

@@ -330,25 +330,31 @@ def run_requests(reqs: List[Request]):
 
 
 def _run_dynmap(eng, req: Request):
-    """``DynamicalMap.E`` (reference ``:328-335``): propagate the NL unit vectors with identity
-    outputs in the same batch as the physical initial state."""
+    """``DynamicalMap.E`` (reference ``:328-335``): the physical run plus the NL unit vectors as
+    initial states with identity outputs, all in ONE batch.  Layout as the reference's consumers
+    expect (``tools.py:470-479``): ``E[i] = E_{t_{i+1}, t_0}``, i.e. ``E[0] rho0 = rho(t_1)`` -- the
+    identity at ``t_0`` is not part of the array unless ``constants.dynmap_includes_t0`` is set."""
     import copy
     prob = req.problem
     NL = prob.NL
     res = _finish(req, eng.run_jobs(prob, req.pt, [req.job])[0])
-    E = np.empty((req.job.n_steps + 1, NL, NL), dtype=complex)
     key = ("dynmap", id(prob))
     with _cache_lock:
         basis = _problem_cache.get(key)
         if basis is None:
-            basis = []
-            for j in range(NL):
-                p = copy.copy(prob)
-                p.rho0 = np.zeros(NL, dtype=complex)
-                p.rho0[j] = 1.0
-                p.out_w = np.eye(NL, dtype=complex)
-                basis.append(p)
+            basis = copy.copy(prob)
+            basis.out_w = np.eye(NL, dtype=complex)
+            basis.meta = dict(prob.meta)
             _problem_cache[key] = basis
-    for j, p in enumerate(basis):
-        E[:, :, j] = eng.run_jobs(p, req.pt, [req.job])[0].T
-    return res, E
+    jobs = []
+    for j in range(NL):
+        jb = copy.copy(req.job)
+        jb.rho0 = np.zeros(NL, dtype=complex)
+        jb.rho0[j] = 1.0
+        jb.tail_rows = 0
+        jobs.append(jb)
+    cols = eng.run_jobs(basis, req.pt, jobs)
+    E = np.empty((req.job.n_steps + 1, NL, NL), dtype=complex)
+    for j, c in enumerate(cols):
+        E[:, :, j] = c.T
+    return res, (E if getattr(constants, "dynmap_includes_t0", False) else E[1:])

@@ -8,7 +8,7 @@ multi-time operator list (``:281-286``).
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List
+from typing import Dict, List, Optional
 
 import numpy as np
 
@@ -34,6 +34,7 @@ class Job:
     tables: Dict[str, FieldTable] = field(default_factory=dict)  # "x", "y", "rf"
     mtos: List[MTO] = field(default_factory=list)
     tail_rows: int = 0   # > 0: only the last `tail_rows` output rows are needed (0 = all)
+    rho0: Optional[np.ndarray] = None   # initial vectorised state overriding the problem's (dynamical maps)
 
     @property
     def n_steps(self) -> int:

@@ -202,3 +202,98 @@ def nm_to_mev(lambda_light):
 
 def mev_to_nm(energy_light):
     return 1239.84198 / energy_light
+
+
+# ------------------------------------------------------------------------------------ dynamical-map algebra
+def calc_tl_dynmap_pseudo(dm, times, debug=False):
+    """Time-local maps from maps-since-t0: ``tl[0] = dm[0]`` and ``tl[i] = dm[i] pinv(dm[i-1])`` so that
+    ``tl[i] rho(t_i) = rho(t_{i+1})`` (reference ``tools.py:446-484``; ``dm[i] = E_{t_{i+1}, t_0}``,
+    pseudo-inverse with ``rcond=1e-12`` because decayed maps are singular).  The pseudo-inverses are
+    computed in one batched SVD instead of the reference's per-step loop."""
+    dm = np.asarray(dm, dtype=complex)
+    n_tl = len(times) - 1
+    tl = np.zeros((n_tl,) + dm.shape[1:], dtype=complex)
+    if n_tl <= 0:
+        return tl
+    tl[0] = dm[0]
+    if n_tl > 1:
+        tl[1:] = dm[1:n_tl] @ np.linalg.pinv(dm[:n_tl - 1], rcond=1e-12)
+    return tl
+
+
+def extract_dms(dm, times, tau_c, t_MTOs):
+    """Split time-local maps into the stationary map (first step beyond the memory time ``tau_c``) and
+    the explicit blocks of ``tau_c`` length at the start and after every ``t_MTO`` (reference
+    ``tools.py:486-545``)."""
+    beyond = np.where(times > times[0] + tau_c)[0]
+    n_c = int(beyond[0])
+    starts = []
+    for t_mto in t_MTOs:
+        hit = np.where(times == t_mto)[0]
+        if len(hit) == 0:
+            print(f"Available times: {times}")
+            print(f"Requested t_MTO: {t_mto}")
+            raise ValueError(f"t_MTO {t_mto} not found in times array. Make sure that t_MTO is included in the times array.")
+        starts.append(int(hit[0]))
+    return dm[n_c], [dm[:n_c]] + [dm[s:s + n_c] for s in starts]
+
+
+def check_tl_map_params(tl_map, rho0):
+    n = int(rho0.shape[0])
+    if rho0.shape[1] != n:
+        raise ValueError("rho0 must be a {n}x{n} matrix")
+    if tl_map.shape != (n ** 2, n ** 2):
+        raise ValueError("tl_map must be a {}x{} matrix, is {}".format(n ** 2, n ** 2, np.shape(tl_map)))
+    return n
+
+
+def _chain(maps, v0, n_out):
+    """``[v0, M_0 v0, M_1 M_0 v0, ...]`` for an iterable of maps (row-major vectorisation)."""
+    out = np.zeros((n_out, len(v0)), dtype=complex)
+    out[0] = v0
+    for k, m in zip(range(1, n_out), maps):
+        out[k] = m @ out[k - 1]
+    return out
+
+
+def use_tl_map(tl_map, times, rho0):
+    """Stationary propagation ``rho_{k+1} = tl_map rho_k`` on ``times`` (reference ``tools.py:567-588``)."""
+    n = check_tl_map_params(tl_map, rho0)
+    return _chain(itertools.repeat(tl_map), rho0.reshape(n * n), len(times)).reshape(len(times), n, n)
+
+
+def use_dm_block(dm, rho0):
+    """One explicit map per step (reference ``tools.py:590-609``); returns ``len(dm) + 1`` states."""
+    n = check_tl_map_params(dm[0], rho0)
+    return _chain(dm, rho0.reshape(n * n), len(dm) + 1).reshape(len(dm) + 1, n, n)
+
+
+def tl_pad_stationary_nsteps(tl_map, n_steps, rho):
+    """Extend a state sequence to ``n_steps`` entries with the stationary map (reference ``:622-631``)."""
+    n = rho.shape[-1]
+    have = len(rho)
+    out = np.zeros((n_steps, n * n), dtype=complex)
+    out[:have] = rho.reshape(have, n * n)
+    for i in range(have, n_steps):
+        out[i] = tl_map @ out[i - 1]
+    return out.reshape(n_steps, n, n)
+
+
+def tl_pad_stationary(tl_map, times, rho):
+    return tl_pad_stationary_nsteps(tl_map, len(times), rho)
+
+
+def use_tl_map_mto(tl_map, dm_1, dm_2, times, rho0, t_MTO, debug=False):
+    """Piecewise propagation with one multi-time operator (reference ``tools.py:633-675``): explicit
+    maps ``dm_1`` for the first memory time, the stationary map up to ``t_MTO``, explicit maps
+    ``dm_2`` (which contain the operator) for one memory time after it, stationary again."""
+    n = check_tl_map_params(tl_map, rho0)
+    times = np.round(times, 5)
+    i_mto = int(np.where(times >= t_MTO)[0][0])
+    n1 = min(i_mto, len(dm_1))
+    if i_mto < len(dm_1):
+        print("caution: t_MTO is smaller than tau_c")
+    if debug:
+        print("info on piecewise application: ", i_mto, times[i_mto], len(dm_1), len(dm_2))
+    schedule = itertools.chain(dm_1[:n1], itertools.repeat(tl_map, i_mto - n1), dm_2, itertools.repeat(tl_map))
+    return _chain(schedule, rho0.reshape(n * n), len(times)).reshape(len(times), n, n)

@@ -71,6 +71,27 @@ out["concurrence_bell"] = float(rt.concurrence(bell))
 m = rt.op_to_matrix("(|1><0|_3)")
 out["op_to_matrix"] = np.real(m).tolist()
 
+# --- dynamical-map algebra (tools.py:446-675): seeded maps-since-t0 -> time-local maps, pieces, chains
+n, nt = 2, 24
+times = np.round(0.1 * np.arange(nt), 6)
+rng = np.random.default_rng(11)
+steps = [np.eye(n * n) + 0.08 * (rng.standard_normal((n * n, n * n)) + 1j * rng.standard_normal((n * n, n * n)))
+         for _ in range(nt)]
+dm = [steps[0]]
+for k in range(1, nt):
+    dm.append(steps[k] @ dm[-1])
+dm = np.array(dm)
+tl = rt.calc_tl_dynmap_pseudo(dm, times)
+tl_map, pieces = rt.extract_dms(tl, times, 0.5, [1.0])
+rho0 = np.array([[0.6, 0.1 - 0.2j], [0.1 + 0.2j, 0.4]])
+cplx = lambda a: dict(re=np.real(a).tolist(), im=np.imag(a).tolist())
+out["dynmap"] = dict(times=times.tolist(), dm=cplx(dm), tl=cplx(tl), tl_map=cplx(tl_map),
+                     pieces=[cplx(x) for x in pieces], rho0=cplx(rho0),
+                     use_tl_map=cplx(rt.use_tl_map(tl_map, times, rho0)),
+                     use_dm_block=cplx(rt.use_dm_block(pieces[0], rho0)),
+                     use_tl_map_mto=cplx(rt.use_tl_map_mto(tl_map, pieces[0], pieces[1], times, rho0, 1.0)),
+                     tl_pad_stationary=cplx(rt.tl_pad_stationary(tl_map, times, rt.use_dm_block(pieces[0], rho0))))
+
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_host.json"), "w") as fh:
     json.dump(out, fh, default=lambda o: o.item() if hasattr(o, "item") else o.tolist())
 print("wrote reference_host.json")

@@ -44,3 +44,28 @@ def oracle_backend():
         yield eng
     finally:
         eng_mod.default_engine = saved
+
+
+def run_programs_numpy(mats, v0, seg_off, segs, w=None, n_emit_max=0, want_final=False):
+    """Plain interpreter of chain programs (same contract as ``Engine.tlmap_run``)."""
+    mats = np.asarray(mats, dtype=complex)
+    NL = mats.shape[-1]
+    n_chains = len(v0)
+    w = np.asarray(w, dtype=complex).reshape(-1, NL) if w is not None else np.zeros((0, NL), complex)
+    out = np.zeros((n_chains, n_emit_max, len(w)), dtype=complex) if n_emit_max and len(w) else None
+    fin = np.zeros((n_chains, NL), dtype=complex) if want_final else None
+    for c in range(n_chains):
+        v = np.array(v0[c], dtype=complex)
+        e = 0
+        for s in segs[seg_off[c]:seg_off[c + 1]]:
+            for k in range(int(s["count"])):
+                v = mats[int(s["start"]) + k * int(s["stride"])] @ v
+                if s["emit"] and out is not None and e < n_emit_max:
+                    out[c, e] = w @ v
+                    e += 1
+        if fin is not None:
+            fin[c] = v
+    return out, fin
+
+
+OracleEngine.tlmap_run = staticmethod(run_programs_numpy)

@@ -118,10 +118,15 @@ def test_calc_dynmap_and_get_M_t():
     from pyaceqd_b200.two_level_system.tls import tls
     p = ChirpedPulse(tau_0=1.5, e_start=0.2, alpha=0, t0=3, e0=1.5)
     res, E = tls(0, 6, p, dt=0.1, lindblad=True, calc_dynmap=True)
-    assert E.shape == (61, 4, 4) and res.shape == (5, 61)
-    assert np.allclose(E[0], np.eye(4))
+    assert E.shape == (60, 4, 4) and res.shape == (5, 61)     # E[i] = E_{t_{i+1}, t_0} (tools.py:470-479)
     rho_t = E @ np.array([1, 0, 0, 0], dtype=complex)        # map applied to |0><0|
-    assert np.abs(rho_t[:, 3] - res[2]).max() < 1e-12        # x population
+    assert np.abs(rho_t[:, 3] - res[2][1:]).max() < 1e-12    # x population
+    from pyaceqd_b200.tools import calc_tl_dynmap_pseudo
+    tl = calc_tl_dynmap_pseudo(E, res[0].real)
+    v = np.array([1, 0, 0, 0], dtype=complex)
+    for k in range(len(tl)):
+        v = tl[k] @ v
+        assert abs(v[3] - res[2][k + 1]) < 1e-9              # time-local maps reproduce the trajectory
     M = tls(0, 6, p, dt=0.1, lindblad=True, get_M_t=1.0)
     assert M.shape == (4, 4) and np.abs(np.ones(4) @ np.eye(2).reshape(-1)[:, None] * 0).max() == 0
     tr = np.eye(2).reshape(-1)
