@@ -210,7 +210,34 @@ def system_ace_stream(t_start, t_end, *pulses, dt=0.01, phonons=False, t_mem=20.
     if dressedstates or print_H:
         raise NotImplementedError("timedep_eigenstates / print_H are ACE diagnostics binaries; out of scope")
     if prepare_only:
-        # the reference writes the param file and returns dummies (:292-296); nothing to prepare here
+        # like the reference (:292-296): write the parameter file + pulse files and return dummies.
+        # The files are what `ACE <file>` (scripts/ACE -> pyaceqd_b200.ace_cli) consumes.
+        from pyaceqd_b200.ace_cli import write_param_file
+        from pyaceqd_b200.tools import export_csv
+        stem = temp_dir + "{}_{}".format(system_prefix, suffix)
+        t = np.arange(t_start, t_end, step=dt / 1)
+        px_file, py_file, rf_out = pulse_file_x, pulse_file_y, rf_file
+        if rf_op is not None and rf_file is None:
+            rf, px, py = sample_rf(t, pulses, firstonly=firstonly)
+            rf_out = stem + "_rf.dat"
+            export_csv(rf_out, t, rf.real, rf.imag, precision=8, delimit=' ')
+            px_file = None
+        elif pulse_file_x is None:
+            px, py = sample_pulses(t, [pulses[0]] if firstonly else pulses)
+        if px_file is None:
+            px_file, py_file = stem + "_pulse_x.dat", stem + "_pulse_y.dat"
+            export_csv(px_file, t, px.real, px.imag, precision=8, delimit=' ')
+            export_csv(py_file, t, py.real, py.imag, precision=8, delimit=' ')
+        if phonons and pt_file is None:
+            pt_file = "{}_{}nm_{}k_th{}_{}dt{}.pt{}".format(system_prefix, ae, temperature, threshold,
+                                                          "" if use_infinite else "tmem{}_".format(t_mem), dt,
+                                                          "" if use_infinite else "r")
+        write_param_file(stem + ".param", dt=dt, t_start=t_start, t_end=t_end, dict_zero=dict_zero,
+                         precision=precision, pt_file=pt_file if phonons else None, initial=initial,
+                         system_op=system_op, rf_op=rf_op, rf_file=rf_out, lindblad_ops=lindblad_ops,
+                         interaction_ops=interaction_ops, pulse_file_x=px_file, pulse_file_y=py_file,
+                         multitime_op=multitime_op, output_ops=output_ops, out_file=stem + ".out")
+        print("prepared file {}, exiting.".format(stem + ".param"))
         return [np.array([0, 0]) for _ in range(1 + len(output_ops))]
 
     problem = _problem_for(system_op=system_op, boson_op=boson_op if phonons else None, initial=initial,

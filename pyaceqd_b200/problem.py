@@ -177,7 +177,7 @@ def coupling_classes(diag: np.ndarray, tol: float = 1e-12) -> Tuple[np.ndarray, 
 def build_problem(*, system_op=None, boson_op=None, initial=None, lindblad_ops=None,
                   interaction_ops=None, output_ops=(), rf_op=None, rho0=None, dim=None,
                   dict_zero: float = 1e-12, polaron_shift: float = 0.0,
-                  hbar: float = constants.hbar) -> Problem:
+                  hbar: float = constants.hbar, raw_pulse_ops=None, coupling_diag=None) -> Problem:
     """Turn the keyword strings of ``system_ace_stream`` into a :class:`Problem`.
 
     Argument meaning follows ``general_system.py:128-131``:
@@ -186,12 +186,16 @@ def build_problem(*, system_op=None, boson_op=None, initial=None, lindblad_ops=N
     ``rf_op`` entering as ``-0.5*hbar*(rf_op)`` driven by the (real) rf table (``:255``).
     ``polaron_shift``: energy (meV) subtracted as ``-shift * boson_op^2`` -- the
     ``Boson_subtract_polaron_shift`` renormalisation of ``:175`` when a PT is attached.
+    ``raw_pulse_ops``: list of ``(op, table)`` taken literally as ``add_Pulse file F {op}`` lines
+    (prefactors already inside ``op``; ``table`` in "x", "y", "rf") -- the parameter-file reader.
+    ``coupling_diag``: diagonal of the bath coupling operator when it comes with the process tensor
+    instead of a ``boson_op`` string.
     """
     # discover the Hilbert dimension from the first operator we can parse
     probe = None
     for cand in ([initial] if initial else []) + list(output_ops or []) + \
-            [o[0] for o in (interaction_ops or [])] + list(system_op or []) + \
-            ([boson_op] if boson_op else []):
+            [o[0] for o in (interaction_ops or [])] + [o[0] for o in (raw_pulse_ops or [])] + \
+            list(system_op or []) + ([boson_op] if boson_op else []):
         probe = cand
         break
     if dim is None:
@@ -208,7 +212,7 @@ def build_problem(*, system_op=None, boson_op=None, initial=None, lindblad_ops=N
     for s in (system_op or []):
         H0 += parse_operator(s, N)
 
-    coupling_diag = np.zeros(N)
+    coupling_diag_arg, coupling_diag = coupling_diag, np.zeros(N)
     if boson_op is not None:
         bop = parse_operator(boson_op, N)
         off = bop - np.diag(np.diag(bop))
@@ -217,6 +221,8 @@ def build_problem(*, system_op=None, boson_op=None, initial=None, lindblad_ops=N
         coupling_diag = np.real(np.diag(bop))
         if polaron_shift != 0.0:
             H0 = H0 - polaron_shift * np.diag(coupling_diag ** 2)
+    elif coupling_diag_arg is not None:
+        coupling_diag = np.asarray(coupling_diag_arg, dtype=float).reshape(N)
     cls, keys = coupling_classes(coupling_diag, dict_zero)
 
     L0 = commutator_generator(H0, hbar)
@@ -234,6 +240,11 @@ def build_problem(*, system_op=None, boson_op=None, initial=None, lindblad_ops=N
         LA.append(commutator_generator(a, hbar))
         LB.append(commutator_generator(a.conj().T, hbar))
         pol.append("y" if p == "y" else "x")
+    for op, table in (raw_pulse_ops or []):
+        a = parse_operator(op, N)
+        LA.append(commutator_generator(a, hbar))
+        LB.append(commutator_generator(a.conj().T, hbar))
+        pol.append(table)
     LA = np.asarray(LA, dtype=complex).reshape(-1, NL, NL)
     LB = np.asarray(LB, dtype=complex).reshape(-1, NL, NL)
 

@@ -84,6 +84,8 @@ class ProcessTensor:
                 "n_slices": np.int64(self.n_slices)}
         if self.keys is not None:
             arrs["keys"] = np.asarray(self.keys, dtype=float)
+        if self.meta and self.meta.get("coupling_diag") is not None:
+            arrs["coupling_diag"] = np.asarray(self.meta["coupling_diag"], dtype=float)
         for i, (s, q) in enumerate(zip(self.slices, self.closures)):
             arrs[f"A{i}"] = s
             arrs[f"q{i}"] = q
@@ -97,7 +99,8 @@ class ProcessTensor:
             return ProcessTensor(slices=[z[f"A{i}"] for i in range(n)],
                                  closures=[z[f"q{i}"] for i in range(n)],
                                  n_initial=int(z["n_initial"]), dt=float(z["dt"]),
-                                 keys=z["keys"] if "keys" in z.files else None)
+                                 keys=z["keys"] if "keys" in z.files else None,
+                                 meta={"coupling_diag": z["coupling_diag"]} if "coupling_diag" in z.files else None)
 
 
 def trivial_pt(n_cls: int = 1, dt: float = 0.1) -> ProcessTensor:

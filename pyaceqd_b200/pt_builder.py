@@ -202,7 +202,9 @@ def build_gaussian_pt(coupling_diag: Sequence[float], J: np.ndarray, w: np.ndarr
     K = max(1, int(round(t_mem / dt)))
     eta = eta_coefficients(J, w, dt, K, temperature)
     shift = polaron_shift_rate(J, w) if subtract_polaron_shift else 0.0
-    return uniform_pt(keys, eta, dt, threshold=threshold, chi_max=chi_max, shift_rate=shift, verbose=verbose)
+    pt = uniform_pt(keys, eta, dt, threshold=threshold, chi_max=chi_max, shift_rate=shift, verbose=verbose)
+    pt.meta["coupling_diag"] = np.asarray(coupling_diag, dtype=float)     # travels with the file (ace_cli)
+    return pt
 
 
 def build_qd_phonon_pt(coupling_diag: Sequence[float], dt: float, t_mem: float, a_e: float = 5.0,
