@@ -57,18 +57,24 @@ def write_param_file(path, *, dt, t_start, t_end, dict_zero="16", precision="12"
         fh.write("\n".join(lines) + "\n")
 
 
-def parse_param_file(path) -> Dict[str, list]:
-    """``{key: [entry, ...]}`` in file order; every entry is ``(words outside braces, [brace contents])``."""
-    params: Dict[str, list] = {}
-    with open(path) as fh:
-        for raw in fh:
-            line = raw.split("#")[0].strip()
-            if not line:
-                continue
-            braces = [b.strip() for b in _BRACED.findall(line)]
-            words = _BRACED.sub(" ", line).split()
-            params.setdefault(words[0], []).append((words[1:], braces))
+def parse_param_lines(lines) -> Dict[str, list]:
+    """``{key: [entry, ...]}`` in file order; every entry is ``(words outside braces, [brace contents])``.
+    The raw lines are kept under ``"__lines__"`` (operator order matters for coinciding times)."""
+    params: Dict[str, list] = {"__lines__": []}
+    for raw in lines:
+        line = raw.split("#")[0].strip()
+        if not line:
+            continue
+        params["__lines__"].append(line)
+        braces = [b.strip() for b in _BRACED.findall(line)]
+        words = _BRACED.sub(" ", line).split()
+        params.setdefault(words[0], []).append((words[1:], braces))
     return params
+
+
+def parse_param_file(path) -> Dict[str, list]:
+    with open(path) as fh:
+        return parse_param_lines(fh.readlines())
 
 
 def _one(params, key, default=None):
@@ -105,7 +111,7 @@ def problem_from_params(params, coupling_diag=None):
         dict_zero=float(dz), coupling_diag=coupling_diag)
     mtos = []
     for key, entries in params.items():
-        if not key.startswith("apply_Operator"):
+        if key == "__lines__" or not key.startswith("apply_Operator"):
             continue
         for words, braces in entries:
             mtos.append({"operator": braces[0], "time": float(words[0]), "applyFrom": key[len("apply_Operator"):],
@@ -114,19 +120,43 @@ def problem_from_params(params, coupling_diag=None):
     return prob, tables, mtos
 
 
-def _mtos_in_file_order(path, prob: Problem) -> List[MTO]:
+def _mtos_in_file_order(params, prob: Problem) -> List[MTO]:
     out = []
-    with open(path) as fh:
-        for raw in fh:
-            line = raw.split("#")[0].strip()
-            if not line.startswith("apply_Operator"):
-                continue
-            braces = _BRACED.findall(line)
-            words = _BRACED.sub(" ", line).split()
-            out.append({"operator": braces[0].strip(), "time": float(words[1]),
-                        "applyFrom": words[0][len("apply_Operator"):],
-                        "applyBefore": words[2] if len(words) > 2 else "false"})
+    for line in params["__lines__"]:
+        if not line.startswith("apply_Operator"):
+            continue
+        braces = _BRACED.findall(line)
+        words = _BRACED.sub(" ", line).split()
+        out.append({"operator": braces[0].strip(), "time": float(words[1]),
+                    "applyFrom": words[0][len("apply_Operator"):],
+                    "applyBefore": words[2] if len(words) > 2 else "false"})
     return prob.parse_mtos(out)
+
+
+def setup_from_params(params):
+    """``(Problem, ProcessTensor | None, Job)`` of a parsed propagation file."""
+    pt = None
+    coupling = None
+    if "add_PT" in params:
+        pt = ProcessTensor.load(_one(params, "add_PT"))
+        coupling = (pt.meta or {}).get("coupling_diag")
+        if coupling is None:
+            raise ValueError("process tensor file carries no coupling operator; rebuild it with this engine")
+    prob, tables, _ = problem_from_params(params, coupling_diag=coupling)
+    job = Job(float(_one(params, "ta")), float(_one(params, "te")), float(_one(params, "dt")), tables=tables,
+              mtos=_mtos_in_file_order(params, prob))
+    return prob, pt, job
+
+
+def write_outfile(params, job, out):
+    """``t Re Im Re Im ...`` rows with ``set_precision`` significant digits (what ``:342`` parses)."""
+    rows = np.empty((out.shape[1], 1 + 2 * out.shape[0]))
+    rows[:, 0] = job.times()
+    rows[:, 1::2] = out.real.T
+    rows[:, 2::2] = out.imag.T
+    np.savetxt(_one(params, "outfile", "ACE.out"), rows, fmt="%.{}g".format(int(_one(params, "set_precision", 12))),
+               delimiter=" ")
+    return rows
 
 
 def _generate_pt(params, path):
@@ -159,27 +189,11 @@ def run_param_file(path, engine=None):
     params = parse_param_file(path)
     if "write_PT" in params:
         return _generate_pt(params, path)
-    pt = None
-    coupling = None
-    if "add_PT" in params:
-        pt = ProcessTensor.load(_one(params, "add_PT"))
-        coupling = (pt.meta or {}).get("coupling_diag")
-        if coupling is None:
-            raise ValueError("process tensor file carries no coupling operator; rebuild it with this engine")
-    prob, tables, _ = problem_from_params(params, coupling_diag=coupling)
-    job = Job(float(_one(params, "ta")), float(_one(params, "te")), float(_one(params, "dt")), tables=tables,
-              mtos=_mtos_in_file_order(path, prob))
+    prob, pt, job = setup_from_params(params)
     if engine is None:
         import pyaceqd_b200.engine as _engine
         engine = _engine.default_engine()
-    out = engine.run_jobs(prob, pt, [job])[0]
-    rows = np.empty((out.shape[1], 1 + 2 * out.shape[0]))
-    rows[:, 0] = job.times()
-    rows[:, 1::2] = out.real.T
-    rows[:, 2::2] = out.imag.T
-    digits = int(_one(params, "set_precision", 12))
-    np.savetxt(_one(params, "outfile", "ACE.out"), rows, fmt="%.{}g".format(digits), delimiter=" ")
-    return rows
+    return write_outfile(params, job, engine.run_jobs(prob, pt, [job])[0])
 
 
 def main(argv=None) -> int:

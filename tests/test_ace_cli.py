@@ -113,3 +113,31 @@ def test_cli_subprocess_round_trip_on_gpu(tmp_path):
     parsed = gs.read_result(np.genfromtxt(tmp + "b_linear_k7.out"), 3)
     assert (np.abs(parsed - direct) / np.maximum(np.abs(direct), 1e-30)).max() < 5e-11
     _round_trip(tmp, contextlib.nullcontext)
+
+
+def test_aceutils_surface_runs_the_reference_dynmap_branch(tmp_path):
+    """The object sequence of general_system.py:313-336 on the stand-in module."""
+    from pyaceqd_b200 import ACEutils as au
+    from pyaceqd_b200.two_level_system.tls import tls
+    tmp = str(tmp_path) + "/"
+    p = ChirpedPulse(tau_0=1.0, e_start=0.2, alpha=0, t0=3.0, e0=1.5)
+    tls(0, 6.0, p, dt=0.25, lindblad=True, temp_dir=tmp, suffix="dm", prepare_only=True)
+    with oracle_backend():
+        plist = open(tmp + "tls_dm.param").readlines()
+        param = au.Parameters(plist)
+        initial_state = au.InitialState(param)
+        fprop = au.FreePropagator(param)
+        fprop.update(1.0, 0.25)
+        PT, outp, tgrid, sim = au.ProcessTensors(param), au.OutputPrinter(param), au.TimeGrid(param), au.Simulation(param)
+        sim.run(fprop, PT, initial_state, tgrid, outp)
+        dm = np.array(au.DynamicalMap(fprop, PT, sim, tgrid).E)
+        direct, E = tls(0, 6.0, p, dt=0.25, lindblad=True, calc_dynmap=True)
+        M = tls(0, 6.0, p, dt=0.25, lindblad=True, get_M_t=1.0)
+    data = np.genfromtxt(tmp + "tls_dm.out", usecols=list(range(9)))
+    assert np.abs(gs.read_result(data, 4) - direct).max() < 1e-10
+    assert dm.shape == (24, 4, 4) and np.abs(dm - E).max() < 1e-12
+    assert np.abs(fprop.M - M).max() < 1e-12
+    rho_t = dm @ np.array([1, 0, 0, 0], dtype=complex)
+    assert np.abs(rho_t[:, 3] - direct[2][1:]).max() < 1e-10
+    other = au.InitialState(np.array([[0, 0], [0, 1.0]]))
+    assert np.allclose(other.rho, [0, 0, 0, 1])
