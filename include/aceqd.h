@@ -156,6 +156,10 @@ typedef struct {
     double* out;
     int32_t device_resident;
     int32_t kernel;            /* 0: DMMA persistent kernel (product), 1: plain-FMA check kernel */
+    int32_t cluster;           /* CTAs per tile (0/1, 2 or 4): a thread-block cluster shares one tile,   */
+                               /* splitting its GEMM passes and exchanging rows through distributed     */
+                               /* shared memory -- for batches too small to fill 148 SMs otherwise      */
+    int32_t pad_;
 } aceqd_batch;
 
 /*
@@ -218,6 +222,10 @@ void aceqd_struct_sizes(int32_t out[4]);
 /* Largest trajectories-per-tile T for which (NL, chi_pad) fits the step kernel's shared
  * memory budget (0 if even T=1 does not fit). */
 int aceqd_max_tile(int NL, int chi_pad);
+
+/* DMMA m-tiles (8 rows) the most loaded CTA computes per step when a tile of T trajectories is shared
+ * by a cluster of `cluster` CTAs (planner cost model; -1 on error). */
+int aceqd_pass_load(const aceqd_problem* prob, int T, int cluster);
 
 /* Register-resident FP64 micro-benchmarks (roofline denominators):
  * kind 0 = DMMA.8x8x4 tensor pipe, kind 1 = DFMA.  Returns TFLOP/s in *tflops. */

@@ -446,7 +446,7 @@ int aceqd_build_operators(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_b
     return ACEQD_OK;
 }
 
-static int build_passes(const aceqd_problem* prob, int T, std::vector<PassDesc>& passes) {
+static int build_passes(const aceqd_problem* prob, int T, int cluster, std::vector<PassDesc>& passes) {
     const int NL = prob->d.NL;
     std::vector<int> blk_of_pos(NL);
     for (int a = 0; a < NL; ++a) blk_of_pos[prob->pos_of_alpha[a]] = prob->block_of_alpha[a];
@@ -474,7 +474,34 @@ static int build_passes(const aceqd_problem* prob, int T, std::vector<PassDesc>&
         set_error("tile needs %zu GEMM passes (max %d)", passes.size(), MAX_PASSES);
         return ACEQD_ERR_CAPACITY;
     }
+    // owners: heaviest pass first onto the least loaded CTA of the cluster (load = m-tiles)
+    std::vector<int> order(passes.size()), load(std::max(1, cluster), 0);
+    auto weight = [&](int i) {
+        int w = 0;
+        for (int mc = 0; mc < MC; ++mc) w += passes[i].nvalid[mc] > 0;
+        return w;
+    };
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weight(a) > weight(b); });
+    for (int i : order) {
+        int best = 0;
+        for (int r = 1; r < (int)load.size(); ++r)
+            if (load[r] < load[best]) best = r;
+        passes[i].owner = best;
+        load[best] += weight(i);
+    }
     return ACEQD_OK;
+}
+
+/* m-tiles the most loaded CTA of a `cluster` computes per step for tile size T (planner cost model) */
+extern "C" int aceqd_pass_load(const aceqd_problem* prob, int T, int cluster) {
+    if (!prob || T < 1 || cluster < 1) return -1;
+    std::vector<PassDesc> passes;
+    if (build_passes(prob, T, cluster, passes)) return -1;
+    std::vector<int> load(cluster, 0);
+    for (auto& pd : passes)
+        for (int mc = 0; mc < MC; ++mc) load[pd.owner] += pd.nvalid[mc] > 0;
+    return *std::max_element(load.begin(), load.end());
 }
 
 int aceqd_max_tile(int NL, int chi_pad) {
@@ -575,8 +602,13 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
                 set_error("batch: tile list references trajectory %d", b->tile_traj[i]);
                 return ACEQD_ERR_ARG;
             }
+        const int cluster = b->cluster <= 1 ? 1 : b->cluster;
+        if (cluster != 1 && cluster != 2 && cluster != 4) {
+            set_error("batch: cluster must be 0/1, 2 or 4");
+            return ACEQD_ERR_ARG;
+        }
         std::vector<PassDesc> passes;
-        if ((rc = build_passes(prob, T, passes))) return rc;
+        if ((rc = build_passes(prob, T, cluster, passes))) return rc;
         UP(c->passes, passes.data(), passes.size() * sizeof(PassDesc));
         UP(c->tiles, b->tile_traj, (size_t)b->n_tiles * T * sizeof(int32_t));
         // prefer staging the per-row operators in shared memory (hides their DRAM latency) if at
@@ -603,6 +635,7 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
         sp.stages = stages;
         sp.wov_doubles = wov;
         sp.n_tiles = b->n_tiles;
+        sp.cluster = cluster;
         sp.passes = (const PassDesc*)c->passes.p;
         sp.tile_traj = (const int*)c->tiles.p;
         const size_t smem = step_smem_bytes(pd.NL, chi_pad, T, stages, wov);

@@ -70,7 +70,7 @@ struct PassDesc {
     int blk;
     int row0[MC];
     int nvalid[MC];  // 0 = absent
-    int pad_;
+    int owner;       // cluster rank that computes this pass (0 without clusters)
 };
 
 struct StepParams {
@@ -81,6 +81,7 @@ struct StepParams {
     int stages;      // chunk pipeline depth
     int wov_doubles; // per-trajectory smem staging of W|OV (0: read operators from global)
     int n_tiles;
+    int cluster;     // CTAs per tile (1, 2 or 4): the tile's GEMM passes are split over a thread-block cluster
     const PassDesc* passes;   // [n_pass]
     const aceqd_traj* trajs;
     const int* tile_traj;     // [n_tiles][T]

@@ -19,7 +19,7 @@ namespace aceqd {
 namespace {
 
 struct SmemLayout {
-    size_t bar, traj, pass, pos, r, q, snapn, meta, wov, state, chunks, total;
+    size_t bar, traj, pass, pos, r, rall, own, q, snapn, meta, wov, state, chunks, total;
     size_t plane;  // doubles per state plane
 };
 
@@ -40,6 +40,8 @@ __host__ __device__ inline SmemLayout make_layout(int NL, int chi_pad, int T, in
     L.pos = o;   o += align_up(sizeof(int) * MAX_NL, 16);
     L.snapn = o; o += align_up(sizeof(int) * MAX_TILE_T, 16);
     L.r = o;     o += align_up(16 * R * N_COMPUTE_WARPS, 16);   // per-warp partial closures
+    L.rall = o;  o += align_up(16 * R, 16);                     // closure rho[row] of the current output row
+    L.own = o;   o += align_up(sizeof(int) * MAX_NL, 16);       // alpha position computed by this CTA?
     L.meta = o;  o += align_up(sizeof(int) * 2 * META_SLICES, 16);
     L.q = o;     o += align_up(16 * (size_t)chi_pad, 16);
     o = align_up(o, 128);
@@ -84,6 +86,44 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
         : "memory");
+}
+// ---- thread-block cluster / distributed shared memory primitives
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {  // same offset in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_CWAIT:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_CDONE;\n"
+        "bra LAB_CWAIT;\n"
+        "LAB_CDONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void st_cluster_c128(uint32_t cluster_addr, double2 v) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(cluster_addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void compute_bar() {  // the 8 compute warps only
     asm volatile("bar.sync 1, %0;" ::"n"(N_COMPUTE_WARPS * 32) : "memory");
@@ -174,6 +214,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     int* pos = reinterpret_cast<int*>(smem_raw + L.pos);
     int* snapn = reinterpret_cast<int*>(smem_raw + L.snapn);
     double2* rpart = reinterpret_cast<double2*>(smem_raw + L.r);   // [warp][row]
+    double2* rall = reinterpret_cast<double2*>(smem_raw + L.rall); // [row]
+    int* own_pos = reinterpret_cast<int*>(smem_raw + L.own);       // [alpha position] rows computed here?
     double2* qbuf = reinterpret_cast<double2*>(smem_raw + L.q);
     int* smeta = reinterpret_cast<int*>(smem_raw + L.meta);
     double* Wst = reinterpret_cast<double*>(smem_raw + L.wov);
@@ -182,7 +224,13 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     double* chunks = reinterpret_cast<double*>(smem_raw + L.chunks);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x;
+    // a tile may be shared by a cluster of C CTAs: GEMM passes (row blocks of one PT block) are split
+    // between the CTAs, every CTA keeps a full copy of the bond state and receives the rows its peers
+    // computed through distributed shared memory (cp.async.bulk shared::cta -> shared::cluster)
+    const int C = p.cluster;
+    const uint32_t crank = C > 1 ? cluster_ctarank() : 0u;
+    const int tile = blockIdx.x / C;
+    const uint32_t bar_y = smem_u32(bars + 2 * MAX_STAGES + 4), bar_free = smem_u32(bars + 2 * MAX_STAGES + 5);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
     const uint32_t bar_wfull = smem_u32(bars + 2 * MAX_STAGES), bar_wempty = smem_u32(bars + 2 * MAX_STAGES + 2);
     // offset (doubles) of state row (pos, j) inside a plane; rows are alpha-major with a skew
@@ -203,7 +251,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         snapn[j] = 0;
     }
     for (int j = tid; j < p.n_pass; j += blockDim.x) passes[j] = p.passes[j];
-    for (int j = tid; j < NL; j += blockDim.x) pos[j] = p.prob.pos_of_alpha[j];
+    for (int j = tid; j < NL; j += blockDim.x) {
+        pos[j] = p.prob.pos_of_alpha[j];
+        own_pos[j] = 0;
+    }
     for (int j = tid; j < min(p.pt.n_slices, META_SLICES); j += blockDim.x) {
         smeta[2 * j] = p.pt.kin_pad[j];
         smeta[2 * j + 1] = p.pt.nout_pad[j];
@@ -218,10 +269,33 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             mbar_init(bar_wfull + 8 * s, 1);
             mbar_init(bar_wempty + 8 * s, N_COMPUTE_WARPS);
         }
+        mbar_init(bar_y, (uint32_t)C);                       // own expect_tx arrival + one arrival per peer
+        mbar_init(bar_free, (uint32_t)(C > 1 ? C - 1 : 1));  // "I have read your rows" from every peer
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
+    // which alpha positions (blocks of T rows) this CTA computes, and how many bytes its peers push per step
+    // (T divides the 8-row m-tile or is a multiple of it, so an alpha block never straddles two passes)
+    auto pass_push_bytes = [&](const PassDesc& pd) -> uint32_t {
+        uint32_t b = 0;
+#pragma unroll
+        for (int mc = 0; mc < MC; ++mc) b += (uint32_t)pd.nvalid[mc] * (uint32_t)strideA * 16u;  // re + im planes
+        return b;
+    };
+    uint32_t rx_bytes = 0;
+    for (int ps = 0; ps < p.n_pass; ++ps) {
+        const PassDesc& pd = passes[ps];
+        if (pd.owner == (int)crank) {
+            if (tid == 0)
+                for (int mc = 0; mc < MC; ++mc)
+                    for (int r = pd.row0[mc]; r < pd.row0[mc] + pd.nvalid[mc]; r += 1) own_pos[r / T] = 1;
+        } else {
+            rx_bytes += pass_push_bytes(pd);
+        }
+    }
+    if (C > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
+    else __syncthreads();
     int n_begin = 0x7fffffff, n_end = -1;
     for (int j = 0; j < T; ++j) {
         if (trj[j].n_steps < 0) continue;
@@ -294,6 +368,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 const int nch = (s < META_SLICES ? smeta[2 * s] : p.pt.kin_pad[s]) / KC;
                 const double* sl = p.pt.blob + p.pt.off[s];
                 for (int ps = 0; ps < p.n_pass; ++ps) {
+                    if (passes[ps].owner != (int)crank) continue;
                     const double* src = sl + (size_t)passes[ps].blk * nch * p.pt.chunk_doubles;
                     for (int j = 0; j < nch; ++j) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
@@ -305,11 +380,39 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 }
             }
         }
+        if (C > 1) cluster_sync_all();   // no CTA of a cluster exits while a peer may still address it
         return;
     }
 
     // ------------------------------------------------------------------ compute warps
     const int g = lane >> 2, tq = lane & 3;  // DMMA fragment coordinates
+    uint32_t yph = 0u, fph = 0u;             // phases of the row-exchange barriers
+    bool free_waited = false;
+    // push the freshly computed rows of one pass into every peer's copy of the state (tid 0 only)
+    auto push_pass = [&](const PassDesc& pd) {
+        if (!free_waited) {              // peers have finished reading the previous contents
+            mbar_wait_cluster(bar_free, fph);
+            free_waited = true;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+        for (int mc = 0; mc < MC; ++mc) {
+            int r = pd.row0[mc];
+            const int r_end = r + pd.nvalid[mc];
+            while (r < r_end) {          // rows of one alpha block are contiguous in a plane
+                const int m = min((r / T + 1) * T, r_end) - r;
+                const size_t off = (size_t)r * strideA + (size_t)(r / T) * SKEW;
+                const uint32_t bytes = (uint32_t)m * (uint32_t)strideA * 8u;
+                for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) {
+                    if (peer == crank) continue;
+                    const uint32_t rb = mapa(bar_y, peer);
+                    bulk_s2s(mapa(smem_u32(Xre + off), peer), smem_u32(Xre + off), bytes, rb);
+                    bulk_s2s(mapa(smem_u32(Xim + off), peer), smem_u32(Xim + off), bytes, rb);
+                }
+                r += m;
+            }
+        }
+    };
     const int NT = chi_pad / 8;
     const int n_out = p.prob.n_out;
     const int NLp4 = p.prob.NLp4, MTU = p.prob.NLp8 / 8, KSU = NLp4 / 4;
@@ -318,8 +421,15 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
 
     for (int n = n_begin; n <= n_end; ++n) {
         const int buf = n & 1;
-        // ---------------- phase A: outputs (closure partials come from the previous GEMM epilogue)
-        // rows of trajectories that START at this row have no partials yet: generic closure pass
+        if (C > 1) {
+            if (n > n_begin) {           // rows and closures computed by the peers in step n-1 have landed
+                mbar_wait_cluster(bar_y, yph);
+                yph ^= 1u;
+            }
+            if (n < n_end && tid == 0) mbar_expect_tx(bar_y, rx_bytes);   // arm this step's exchange
+        }
+        // ---------------- phase A: outputs (closures rall[] come from the previous GEMM epilogue)
+        // rows of trajectories that START at this row have no closure yet: generic closure pass
         bool any_start = false, any_snap = false;
         for (int j = 0; j < T; ++j) {
             const aceqd_traj& t = trj[j];
@@ -352,7 +462,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
                     acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
                 }
-                if (lane < N_COMPUTE_WARPS) rpart[lane * R + row] = lane == 0 ? acc : make_double2(0.0, 0.0);
+                if (lane == 0) rall[row] = acc;
             }
             compute_bar();
         }
@@ -360,6 +470,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         for (int it = tid; it < T * n_out; it += N_COMPUTE_WARPS * 32) {
             const int j = it / n_out, o = it - j * n_out;
             const aceqd_traj& t = trj[j];
+            if (C > 1 && (uint32_t)(j % C) != crank) continue;   // every CTA holds all closures: split the writes
             if (t.n_steps < 0 || n < t.step0 + t.out_from || n > t.step0 + t.n_steps) continue;
             const int i = n - t.step0;
             const double2* ov;
@@ -373,20 +484,13 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             double2 acc = make_double2(0.0, 0.0);
             for (int a = 0; a < NL; ++a) {
                 const double2 w = ov[a];
-                const int row = pos[a] * T + j;
-                double2 r = rpart[row];
-#pragma unroll
-                for (int w8 = 1; w8 < N_COMPUTE_WARPS; ++w8) {
-                    const double2 r2 = rpart[w8 * R + row];
-                    r.x += r2.x;
-                    r.y += r2.y;
-                }
+                const double2 r = rall[pos[a] * T + j];
                 acc.x += w.x * r.x - w.y * r.y;
                 acc.y += w.x * r.y + w.y * r.x;
             }
             reinterpret_cast<double2*>(p.out)[t.out_off + (long long)(i - t.out_from) * n_out + o] = acc;
         }
-        if (any_snap) {
+        if (any_snap && crank == 0) {
             for (int j = 0; j < T; ++j) {
                 const aceqd_traj& t = trj[j];
                 if (t.n_steps < 0 || snapn[j] >= t.snap_cnt) continue;
@@ -469,6 +573,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                     }
                 __syncwarp();
                 for (int mt = 0; mt < MTU; ++mt) {
+                    if (C > 1) {     // only the rows this CTA feeds into its own GEMM passes are needed
+                        bool need = false;
+                        for (int a8 = 8 * mt; a8 < min(8 * mt + 8, NL); ++a8) need |= own_pos[pos[a8]] != 0;
+                        if (!need) continue;
+                    }
                     double cr[JU][NBB][2], ci[JU][NBB][2];
 #pragma unroll
                     for (int jj = 0; jj < JU; ++jj)
@@ -506,7 +615,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                         }
                     }
                     const int a = 8 * mt + g;
-                    if (a < NL) {
+                    if (a < NL && (C == 1 || own_pos[pos[a]])) {
 #pragma unroll
                         for (int jj = 0; jj < JU; ++jj)
 #pragma unroll
@@ -527,6 +636,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             if (buf) wph1 ^= 1u; else wph0 ^= 1u;
         }
         compute_bar();
+        if (C > 1 && tid == 0) {   // every warp of this CTA has read the peers' rows: they may overwrite them
+            for (uint32_t peer = 0; peer < (uint32_t)C; ++peer)
+                if (peer != crank) mbar_arrive_remote(mapa(bar_free, peer));
+        }
 
         // ---------------- phase C: PT slice, Y = X A_n[beta]
         const int s = slice_of(p.pt, n);
@@ -539,8 +652,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         bool nbv[NB];
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) nbv[nb] = 8 * (warp + N_COMPUTE_WARPS * nb) < nout;
+        int pending_push = -1;     // own pass whose new rows still have to be sent to the peers
+        free_waited = false;
         for (int ps = 0; ps < p.n_pass; ++ps) {
             const PassDesc pd = passes[ps];
+            if (pd.owner != (int)crank) continue;
             double cre[MC][NB][2], cim[MC][NB][2];
 #pragma unroll
             for (int mc = 0; mc < MC; ++mc)
@@ -588,6 +704,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 gemm_pass<NB, 1, false>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
                                         warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
             compute_bar();  // every warp has finished reading this pass's X rows
+            if (C > 1) {    // ... and has finished writing the previous pass's rows: send them
+                if (tid == 0 && pending_push >= 0) push_pass(passes[pending_push]);
+                pending_push = ps;
+            }
 #pragma unroll
             for (int mc = 0; mc < MC; ++mc) {
                 if (!mcv[mc]) continue;   // warp-uniform
@@ -618,7 +738,30 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             }
         }
         compute_bar();
+        // closure of the rows computed here: sum the per-warp partials; peers get a copy
+        for (int row = tid; row < R; row += N_COMPUTE_WARPS * 32) {
+            if (C > 1 && !own_pos[row / T]) continue;
+            double2 r = rpart[row];
+#pragma unroll
+            for (int w8 = 1; w8 < N_COMPUTE_WARPS; ++w8) {
+                const double2 r2 = rpart[w8 * R + row];
+                r.x += r2.x;
+                r.y += r2.y;
+            }
+            rall[row] = r;
+            for (uint32_t peer = 0; C > 1 && peer < (uint32_t)C; ++peer)
+                if (peer != crank) st_cluster_c128(mapa(smem_u32(rall + row), peer), r);
+        }
+        compute_bar();
+        if (C > 1 && tid == 0) {
+            if (pending_push >= 0) push_pass(passes[pending_push]);
+            if (!free_waited) mbar_wait_cluster(bar_free, fph);   // keep the phase in step without own passes
+            for (uint32_t peer = 0; peer < (uint32_t)C; ++peer)   // release: closures above are visible first
+                if (peer != crank) mbar_arrive_remote(mapa(bar_y, peer));
+        }
+        fph ^= 1u;
     }
+    if (C > 1) cluster_sync_all();   // no CTA of a cluster exits while a peer may still address it
 }
 
 // -------------------------------------------------------------------------------------------
@@ -732,7 +875,19 @@ static int launch_nb(const StepParams& p, size_t smem_bytes, cudaStream_t s) {
         ACEQD_CUDA(cudaFuncSetAttribute(k_step_dmma<NB, KS>,                                    \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                                         (int)smem_bytes));                                      \
-        k_step_dmma<NB, KS><<<p.n_tiles, STEP_THREADS, smem_bytes, s>>>(p);                     \
+        cudaLaunchConfig_t cfg = {};                                                            \
+        cfg.gridDim = dim3((unsigned)(p.n_tiles * p.cluster), 1, 1);                            \
+        cfg.blockDim = dim3(STEP_THREADS, 1, 1);                                                \
+        cfg.dynamicSmemBytes = smem_bytes;                                                      \
+        cfg.stream = s;                                                                         \
+        cudaLaunchAttribute attr[1];                                                            \
+        attr[0].id = cudaLaunchAttributeClusterDimension;                                       \
+        attr[0].val.clusterDim.x = (unsigned)p.cluster;                                         \
+        attr[0].val.clusterDim.y = 1;                                                           \
+        attr[0].val.clusterDim.z = 1;                                                           \
+        cfg.attrs = attr;                                                                       \
+        cfg.numAttrs = p.cluster > 1 ? 1 : 0;                                                   \
+        ACEQD_CUDA(cudaLaunchKernelEx(&cfg, k_step_dmma<NB, KS>, p));                           \
     } while (0)
     if (ksu <= 1) ACEQD_LAUNCH(1);
     else if (ksu <= 4) ACEQD_LAUNCH(4);

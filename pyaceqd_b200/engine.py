@@ -56,7 +56,7 @@ class _Batch(ctypes.Structure):
         ("tile_T", c_int32), ("n_tiles", c_int32), ("tile_traj", c_void_p),
         ("n_snap_steps", c_int32), ("snap_steps", c_void_p), ("n_snap_slots", c_int32),
         ("out_elems", c_int64), ("out", c_void_p),
-        ("device_resident", c_int32), ("kernel", c_int32),
+        ("device_resident", c_int32), ("kernel", c_int32), ("cluster", c_int32), ("pad_", c_int32),
     ]
 
 
@@ -104,6 +104,7 @@ def load_library():
                                     c_int, c_void_p, c_int, c_void_p, c_void_p]
     lib.aceqd_tlmap_last_ms.argtypes = [c_void_p, POINTER(c_float)]
     lib.aceqd_max_tile.argtypes = [c_int, c_int]
+    lib.aceqd_pass_load.argtypes = [c_void_p, c_int, c_int]
     lib.aceqd_fp64_peak.argtypes = [c_void_p, c_int, c_int, POINTER(c_double)]
     lib.aceqd_host_alloc.argtypes = [ctypes.c_size_t, POINTER(c_void_p)]
     lib.aceqd_host_free.argtypes = [c_void_p]
@@ -150,6 +151,30 @@ def choose_tile(n_traj: int, rows_per_block: Sequence[int], t_max: int, n_sm: in
             best_t, best_cost = t, cost
         t *= 2
     return best_t
+
+
+CLUSTER_CAPACITY = {1: N_SM, 2: N_SM, 4: 132}   # co-resident CTAs per cluster size (GPC packing)
+
+
+def choose_tile_cluster(n_traj: int, pass_load, t_max: int, clusters: Sequence[int] = (1, 2, 4)) -> Tuple[int, int]:
+    """(trajectories per tile, CTAs per tile): minimise waves x (m-tiles of the most loaded CTA per
+    step).  ``pass_load(T, C)`` is ``aceqd_pass_load``.  A cluster splits a tile's GEMM passes over C
+    SMs, which only pays when the batch alone cannot fill the GPU; it costs a row exchange per step
+    (5 % per doubling assumed) so ties go to the smaller cluster and then to the larger tile."""
+    best, best_cost = (1, 1), None
+    t = 1
+    while t <= t_max:
+        tiles = -(-n_traj // t)
+        for c in clusters:
+            load = pass_load(t, c)
+            if load <= 0:
+                continue
+            waves = -(-(tiles * c) // CLUSTER_CAPACITY[c])
+            cost = waves * load * (1.0 + 0.05 * (c.bit_length() - 1))
+            if best_cost is None or cost < best_cost - 1e-9 or (abs(cost - best_cost) <= 1e-9 and c <= best[1]):
+                best, best_cost = (t, c), cost
+        t *= 2
+    return best
 
 
 @dataclass
@@ -318,7 +343,7 @@ class Engine:
     def plan_sweep(self, prob: Problem, pt: ProcessTensor, n_traj: int, n_steps: int, dt: float,
                    t_start: float, n_sets: int, n_samples: int, grid: Tuple[float, float], *,
                    sets: Optional[np.ndarray] = None, kernel: str = "dmma", t_eval: str = "half_mid",
-                   tile_T: Optional[int] = None) -> "_Plan":
+                   tile_T: Optional[int] = None, cluster: Optional[int] = None) -> "_Plan":
         """Descriptors of a pulse-parameter sweep: `n_traj` MTO-free trajectories of equal length
         starting at the PT origin (reference fan-out
         ``two_level_system/rabi_rotations.py:172-198``).  Table / output pointers are filled in
@@ -329,8 +354,7 @@ class Engine:
         t_max = self.max_tile(NL, chi_pad)
         if t_max < 1:
             raise EngineError(f"NL={NL}, chi={chi_pad} does not fit the step kernel's shared memory")
-        rows_per_block = [r for r in np.bincount(blk_of_alpha).tolist() if r]
-        T = min(tile_T or choose_tile(n_traj, rows_per_block, t_max), t_max)
+        T, C = self._tile_and_cluster(prob, pt, n_traj, t_max, tile_T, cluster)
         n_tiles = -(-n_traj // T)
         sets = np.arange(n_traj, dtype=np.int32) if sets is None else np.asarray(sets, dtype=np.int32)
         seqs = np.zeros(n_traj, dtype=SEQ_DT)
@@ -355,8 +379,19 @@ class Engine:
         b.n_snap_steps, b.snap_steps, b.n_snap_slots = 0, None, 0
         b.out_elems = int(n_traj) * (n_steps + 1) * n_out
         b.kernel = 0 if kernel == "dmma" else 1
+        b.cluster = C
         return _Plan(batch=b, keep=[seqs, trajs, tile_traj, rho0], out=None,
                      out_off=trajs["out_off"], n_rows=trajs["n_steps"] + 1)
+
+    def _tile_and_cluster(self, prob, pt, n_traj, t_max, tile_T=None, cluster=None) -> Tuple[int, int]:
+        hp, _ = self.problem_handle(prob, pt)
+        load = lambda t, c: int(self.lib.aceqd_pass_load(hp, t, c))
+        if tile_T and cluster:
+            return min(tile_T, t_max), cluster
+        if tile_T:
+            t = min(tile_T, t_max)
+            return t, choose_tile_cluster(n_traj, lambda tt, c: load(t, c) if tt == t else 0, t)[1]
+        return choose_tile_cluster(n_traj, load, t_max, clusters=(cluster,) if cluster else (1, 2, 4))
 
     def run_sweep(self, prob: Problem, pt: Optional[ProcessTensor], tables: np.ndarray,
                   grid: Tuple[float, float], t_start: float, n_steps: int, dt: float, *,
@@ -469,7 +504,8 @@ class Engine:
         return out
 
     def plan(self, prob: Problem, pt: ProcessTensor, jobs: Sequence[Job], *, kernel: str = "dmma",
-             t_eval: str = "half_mid", fork: bool = True, tile_T: Optional[int] = None):
+             t_eval: str = "half_mid", fork: bool = True, tile_T: Optional[int] = None,
+             cluster: Optional[int] = None):
         """Build the trunk batch (may be None) and the main batch for `jobs`."""
         if not jobs:
             raise ValueError("no jobs")
@@ -570,7 +606,8 @@ class Engine:
                                       init_index=r0, ovr=ovr, row0=0, out_from=int(g0[i])))
 
         common = dict(prob=prob, pt=pt, dt=dt, t0=t0_ref, off=(off1, off2), packed=packed, grid=grid,
-                      mats=mats, chi_pad=chi_pad, kernel=kernel, tile_T=tile_T, rho0s=np.asarray(rho0s))
+                      mats=mats, chi_pad=chi_pad, kernel=kernel, tile_T=tile_T, cluster=cluster,
+                      rho0s=np.asarray(rho0s))
         main = dict(seqs=seqs, entries=entries, trajs=trajs, snap_steps=[], n_slots=0)
         trunk = None
         if trunk_trajs:
@@ -612,8 +649,7 @@ class Engine:
         t_max = self.max_tile(NL, common["chi_pad"])
         if t_max < 1:
             raise EngineError(f"NL={NL}, chi={common['chi_pad']} does not fit the step kernel's shared memory")
-        T = common["tile_T"] or choose_tile(len(tr), [r for r in rows_per_block if r], t_max)
-        T = min(T, t_max)
+        T, C = self._tile_and_cluster(prob, pt, len(tr), t_max, common["tile_T"], common.get("cluster"))
         n_tiles = -(-len(tr) // T)
         tile_traj = np.full(n_tiles * T, -1, dtype=np.int32)
         tile_traj[:len(tr)] = order
@@ -640,20 +676,21 @@ class Engine:
         b.out_elems, b.out = out_elems, out.ctypes.data
         b.device_resident = 0
         b.kernel = 0 if common["kernel"] == "dmma" else 1
+        b.cluster = C
         return _Plan(batch=b, keep=[seqs, entries, trajs, tile_traj, mats, rho0, snap_steps, packed, out],
                      out=out, out_off=np.asarray(out_off_of_traj), n_rows=trajs["n_steps"] + 1)
 
     # -------------------------------------------------------------- running
     def run_jobs(self, prob: Problem, pt: Optional[ProcessTensor], jobs: Sequence[Job], *,
                  kernel: str = "dmma", t_eval: str = "half_mid", fork: bool = True,
-                 tile_T: Optional[int] = None) -> List[np.ndarray]:
+                 tile_T: Optional[int] = None, cluster: Optional[int] = None) -> List[np.ndarray]:
         """Propagate `jobs`; returns one ``[n_out, n_steps+1]`` complex array per job."""
         if pt is None:
             pt = self._trivial(prob)
         hp, _ = self.problem_handle(prob, pt)
         hpt = self.pt_handle(pt)
         common, trunk, main, (out_off, n_rows, out_elems, copy_list) = self.plan(
-            prob, pt, jobs, kernel=kernel, t_eval=t_eval, fork=fork, tile_T=tile_T)
+            prob, pt, jobs, kernel=kernel, t_eval=t_eval, fork=fork, tile_T=tile_T, cluster=cluster)
         n_out = prob.n_out
         trunk_out = None
         if trunk is not None:
@@ -687,6 +724,7 @@ class Engine:
         step_ms, op_ms = self.last_timings()
         self.timing_log.append(dict(kind=kind, step_ms=step_ms, opbuild_ms=op_ms, NL=prob.NL, chi_pad=chi_pad,
                                     n_traj=int(plan.batch.n_traj), tile_T=int(plan.batch.tile_T),
+                                    cluster=int(plan.batch.cluster),
                                     n_tiles=int(plan.batch.n_tiles),
                                     traj_steps=int(np.sum(np.asarray(plan.n_rows) - 1))))
 

@@ -116,3 +116,58 @@ def test_tile_sizes_agree(engine):
     for T in (1, 2, 4, 8, 16):
         got = engine.run_jobs(prob, pt, jobs, kernel="dmma", tile_T=T)
         assert max(np.abs(g - r).max() for g, r in zip(got, ref)) < 1e-12, T
+
+
+# ------------------------------------------------------------------ thread-block clusters (row exchange over DSMEM)
+def _g2_jobs(prob, n_t=6, dt=0.25, tau_max=3.0, opA="|3><1|_4", opC="|1><3|_4", tail=0):
+    p = ChirpedPulse(tau_0=1.0, e_start=-2.0, alpha=0, t0=2.0, e0=4.0, polar_x=0.8)
+    tabs = make_tables([p], 0.0, n_t * dt * 2 + tau_max + 1, dt)
+    jobs = []
+    for i in range(n_t):
+        t1 = 2 * i * dt
+        mt = prob.parse_mtos([{"operator": opA, "applyFrom": "_right", "time": t1},
+                              {"operator": opC, "applyFrom": "_left", "time": t1}])
+        jobs.append(Job(0.0, t1 + tau_max, dt, tables=tabs, mtos=mt, tail_rows=tail))
+    return jobs
+
+
+@pytest.mark.parametrize("cluster", [2, 4])
+@pytest.mark.parametrize("tile_T", [1, 2, 4])
+def test_cluster_biexciton_fork_and_tails(engine, cluster, tile_T):
+    """Tile shared by a cluster of CTAs: forked G2-style batch (trunk with snapshots + branches)."""
+    prob = biexciton_problem(outputs=["|1><1|_4", "(|3><1|_4*|1><1|_4*|1><3|_4)", "|0><3|_4"])
+    pt = synthetic_pt(40, len(prob.cls_keys), n_slices=2, kind="unitary", scale=0.999)
+    jobs = _g2_jobs(prob)
+    _compare(engine, prob, pt, jobs, "dmma", cluster=cluster, tile_T=tile_T)
+    tails = engine.run_jobs(prob, pt, _g2_jobs(prob, tail=5), cluster=cluster, tile_T=tile_T)
+    full = engine.run_jobs(prob, pt, jobs, cluster=1, tile_T=tile_T)
+    assert max(np.abs(f[:, -5:] - t).max() for f, t in zip(full, tails)) < 1e-12
+
+
+@pytest.mark.parametrize("cluster", [2, 4])
+def test_cluster_tls_sweep_and_sixlevel(engine, cluster):
+    prob = tls_problem()
+    pt = synthetic_pt(64, len(prob.cls_keys), n_slices=2, kind="unitary", scale=0.999)
+    _compare(engine, prob, pt, sweep_jobs(5, 5, t_end=3.0), "dmma", cluster=cluster, tile_T=8)
+    pt = synthetic_growing_pt(24, len(prob.cls_keys), n_initial=5, n_repeat=3)
+    p = ChirpedPulse(tau_0=1, e_start=0.5, alpha=0, t0=3, e0=2)
+    jobs = [Job(0.0, te, 0.1, tables=make_tables([p], 0.0, te, 0.1)) for te in (0.0, 0.1, 0.3, 1.0, 2.7, 5.0)]
+    _compare(engine, prob, pt, jobs, "dmma", cluster=cluster, tile_T=4)         # ragged lengths, growing bond
+    six = sixls_problem()
+    pt6 = synthetic_pt(24, len(six.cls_keys), kind="unitary", scale=0.999)
+    p6 = ChirpedPulse(tau_0=1.0, e_start=-1.0, alpha=0, t0=2.0, e0=3.0, polar_x=0.7)
+    jobs6 = [Job(0.0, 3.0, 0.1, tables=make_tables([p6], 0.0, 3.0, 0.1)) for _ in range(3)]
+    _compare(engine, six, pt6, jobs6, "dmma", cluster=cluster, tile_T=2)
+
+
+def test_planner_picks_clusters_for_small_batches(engine):
+    """256 biexciton branches at chi=128 cannot fill 148 SMs with one CTA per tile."""
+    prob = biexciton_problem()
+    pt = synthetic_pt(128, len(prob.cls_keys), kind="unitary", scale=0.999)
+    t_max = engine.max_tile(prob.NL, 128)
+    T, C = engine._tile_and_cluster(prob, pt, 256, t_max)
+    assert (T, C) == (4, 2)
+    assert engine._tile_and_cluster(prob, pt, 1, t_max) == (1, 4)
+    tls = tls_problem()
+    ptt = synthetic_pt(128, len(tls.cls_keys), kind="unitary", scale=0.999)
+    assert engine._tile_and_cluster(tls, ptt, 4096, engine.max_tile(4, 128)) == (16, 1)
