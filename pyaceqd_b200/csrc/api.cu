@@ -506,7 +506,7 @@ extern "C" int aceqd_pass_load(const aceqd_problem* prob, int T, int cluster) {
 
 int aceqd_max_tile(int NL, int chi_pad) {
     for (int T = MAX_TILE_T; T >= 1; T >>= 1)
-        if (step_smem_bytes(NL, chi_pad, T, 2, 0) <= (size_t)SMEM_BUDGET) return T;
+        if (step_smem_bytes(NL, chi_pad, T, 2, 0, 1) <= (size_t)SMEM_BUDGET) return T;
     return 0;
 }
 
@@ -613,14 +613,18 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
         UP(c->tiles, b->tile_traj, (size_t)b->n_tiles * T * sizeof(int32_t));
         // prefer staging the per-row operators in shared memory (hides their DRAM latency) if at
         // least 3 chunk stages still fit; otherwise read them from global memory
+        // prefer staging the per-row operators in shared memory (hides their DRAM latency): double
+        // buffered if >= 3 chunk stages still fit, else single buffered (refilled during phase C),
+        // else read them from global memory
         const int wov_full = pd.w_doubles + pd.ov_doubles;
-        int stages = 0, wov = 0;
-        for (int cand_wov : {wov_full, 0}) {
-            const int min_stages = cand_wov ? 3 : 2;
-            for (int st = MAX_STAGES; st >= min_stages; --st)
-                if (step_smem_bytes(pd.NL, chi_pad, T, st, cand_wov) <= (size_t)SMEM_BUDGET) {
+        int stages = 0, wov = 0, wbufs = 1;
+        struct Cand { int wov, bufs, min_stages; };
+        for (const Cand cd : {Cand{wov_full, 2, 3}, Cand{wov_full, 1, 3}, Cand{wov_full, 1, 2}, Cand{0, 1, 2}}) {
+            for (int st = MAX_STAGES; st >= cd.min_stages; --st)
+                if (step_smem_bytes(pd.NL, chi_pad, T, st, cd.wov, cd.bufs) <= (size_t)SMEM_BUDGET) {
                     stages = st;
-                    wov = cand_wov;
+                    wov = cd.wov;
+                    wbufs = cd.bufs;
                     break;
                 }
             if (stages) break;
@@ -634,11 +638,12 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
         sp.n_pass = (int)passes.size();
         sp.stages = stages;
         sp.wov_doubles = wov;
+        sp.wbufs = wbufs;
         sp.n_tiles = b->n_tiles;
         sp.cluster = cluster;
         sp.passes = (const PassDesc*)c->passes.p;
         sp.tile_traj = (const int*)c->tiles.p;
-        const size_t smem = step_smem_bytes(pd.NL, chi_pad, T, stages, wov);
+        const size_t smem = step_smem_bytes(pd.NL, chi_pad, T, stages, wov, wbufs);
         ACEQD_CUDA(cudaEventRecord(c->ev[0], c->stream));
         if ((rc = launch_step_dmma(sp, smem, c->stream, &c->launches))) return rc;
         ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));

@@ -80,6 +80,7 @@ struct StepParams {
     int n_pass;
     int stages;      // chunk pipeline depth
     int wov_doubles; // per-trajectory smem staging of W|OV (0: read operators from global)
+    int wbufs;       // staging buffers: 2 = double buffered, 1 = refilled during phase C
     int n_tiles;
     int cluster;     // CTAs per tile (1, 2 or 4): the tile's GEMM passes are split over a thread-block cluster
     const PassDesc* passes;   // [n_pass]
@@ -117,7 +118,7 @@ int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, cu
                       long long* launches);
 int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, long long* launches);
 int launch_step_check(const StepParams& p, double* scratch, cudaStream_t s, long long* launches);
-size_t step_smem_bytes(int NL, int chi_pad, int T, int stages, int wov_doubles);
+size_t step_smem_bytes(int NL, int chi_pad, int T, int stages, int wov_doubles, int wbufs);
 int launch_tlmap(int NL, int n_chains, int n_w, int n_emit_max, const double* pool, const double* v0,
                  const long long* seg_off, const aceqd_tlseg* segs, const double* w, double* out,
                  double* final_v, cudaStream_t s, long long* launches);

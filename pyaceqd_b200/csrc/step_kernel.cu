@@ -29,7 +29,7 @@ constexpr int SKEW = 4;  // extra doubles after every alpha block of T rows (ban
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 __host__ __device__ inline SmemLayout make_layout(int NL, int chi_pad, int T, int stages,
-                                                  int wov_doubles) {
+                                                  int wov_doubles, int wbufs) {
     SmemLayout L;
     const size_t R = (size_t)T * NL;
     const size_t strideA = chi_pad + 4;
@@ -45,7 +45,7 @@ __host__ __device__ inline SmemLayout make_layout(int NL, int chi_pad, int T, in
     L.meta = o;  o += align_up(sizeof(int) * 2 * META_SLICES, 16);
     L.q = o;     o += align_up(16 * (size_t)chi_pad, 16);
     o = align_up(o, 128);
-    L.wov = o;   o += (size_t)2 * T * wov_doubles * 8;   // double-buffered W|OV of the tile (0 = global mode)
+    L.wov = o;   o += (size_t)wbufs * T * wov_doubles * 8;   // staged W|OV of the tile (0 = global mode)
     o = align_up(o, 128);
     L.plane = R * strideA + (size_t)NL * SKEW;
     L.state = o; o += 2 * L.plane * 8;
@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     const int stages = p.stages;
     const int wov = p.wov_doubles;          // 0: operators are read from global memory
     const bool wsm = wov > 0;
-    const SmemLayout L = make_layout(NL, chi_pad, T, stages, wov);
+    const int wbufs = p.wbufs;              // 2: W(n+1) is prefetched during step n; 1: during phase C of step n
+    const SmemLayout L = make_layout(NL, chi_pad, T, stages, wov, wbufs);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
     aceqd_traj* trj = reinterpret_cast<aceqd_traj*>(smem_raw + L.traj);
     PassDesc* passes = reinterpret_cast<PassDesc*>(smem_raw + L.pass);
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             const uint32_t w_bytes = (uint32_t)p.prob.w_doubles * 8u, ov_bytes = (uint32_t)p.prob.ov_doubles * 8u;
             // stage the per-row operators W_n | OV_n of every active trajectory into buffer n & 1
             auto issue_wov = [&](int n) {
-                const int buf = n & 1;
+                const int buf = wbufs == 2 ? (n & 1) : 0;
                 mbar_wait(bar_wempty + 8 * buf, (buf ? wph1 : wph0) ^ 1u);
                 if (buf) wph1 ^= 1u; else wph0 ^= 1u;
                 uint32_t total = 0;
@@ -363,7 +364,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             };
             if (wsm) issue_wov(n_begin);
             for (int n = n_begin; n < n_end; ++n) {
-                if (wsm) issue_wov(n + 1);
+                bool w_next = wsm;
+                if (w_next && wbufs == 2) {
+                    issue_wov(n + 1);
+                    w_next = false;
+                }
                 const int s = slice_of(p.pt, n);
                 const int nch = (s < META_SLICES ? smeta[2 * s] : p.pt.kin_pad[s]) / KC;
                 const double* sl = p.pt.blob + p.pt.off[s];
@@ -377,7 +382,12 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                                  src + (size_t)j * p.pt.chunk_doubles, bytes, bar_full + 8 * stage);
                         if (++stage == stages) { stage = 0; phase ^= 1u; }
                     }
+                    if (w_next) {   // single buffer: the consumers are in phase C now, W(n) has been released
+                        issue_wov(n + 1);
+                        w_next = false;
+                    }
                 }
+                if (w_next) issue_wov(n + 1);   // this CTA owns no pass
             }
         }
         if (C > 1) cluster_sync_all();   // no CTA of a cluster exits while a peer may still address it
@@ -420,7 +430,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     uint32_t phase = 0, wph0 = 0u, wph1 = 0u;
 
     for (int n = n_begin; n <= n_end; ++n) {
-        const int buf = n & 1;
+        const int buf = wbufs == 2 ? (n & 1) : 0;
         if (C > 1) {
             if (n > n_begin) {           // rows and closures computed by the peers in step n-1 have landed
                 mbar_wait_cluster(bar_y, yph);
@@ -863,8 +873,8 @@ __global__ void __launch_bounds__(256) k_step_check(const StepParams p, double* 
 
 }  // namespace
 
-size_t step_smem_bytes(int NL, int chi_pad, int T, int stages, int wov_doubles) {
-    return make_layout(NL, chi_pad, T, stages, wov_doubles).total;
+size_t step_smem_bytes(int NL, int chi_pad, int T, int stages, int wov_doubles, int wbufs) {
+    return make_layout(NL, chi_pad, T, stages, wov_doubles, wbufs).total;
 }
 
 template <int NB>

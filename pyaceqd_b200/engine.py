@@ -159,8 +159,9 @@ CLUSTER_CAPACITY = {1: N_SM, 2: N_SM, 4: 132}   # co-resident CTAs per cluster s
 def choose_tile_cluster(n_traj: int, pass_load, t_max: int, clusters: Sequence[int] = (1, 2, 4)) -> Tuple[int, int]:
     """(trajectories per tile, CTAs per tile): minimise waves x (m-tiles of the most loaded CTA per
     step).  ``pass_load(T, C)`` is ``aceqd_pass_load``.  A cluster splits a tile's GEMM passes over C
-    SMs, which only pays when the batch alone cannot fill the GPU; it costs a row exchange per step
-    (5 % per doubling assumed) so ties go to the smaller cluster and then to the larger tile."""
+    SMs, which only pays when the batch alone cannot fill the GPU; it costs a row exchange per step and
+    repeats the small system product in every CTA (25 % per doubling assumed; measured:
+    profiles/r01k_*), and ties go to the smaller cluster and then to the larger tile."""
     best, best_cost = (1, 1), None
     t = 1
     while t <= t_max:
@@ -169,8 +170,10 @@ def choose_tile_cluster(n_traj: int, pass_load, t_max: int, clusters: Sequence[i
             load = pass_load(t, c)
             if load <= 0:
                 continue
+            if t > max(1, n_traj):
+                continue     # no point in tiles wider than the batch
             waves = -(-(tiles * c) // CLUSTER_CAPACITY[c])
-            cost = waves * load * (1.0 + 0.05 * (c.bit_length() - 1))
+            cost = waves * load * (1.0 + 0.25 * (c.bit_length() - 1))
             if best_cost is None or cost < best_cost - 1e-9 or (abs(cost - best_cost) <= 1e-9 and c <= best[1]):
                 best, best_cost = (t, c), cost
         t *= 2

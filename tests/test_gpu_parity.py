@@ -160,6 +160,15 @@ def test_cluster_tls_sweep_and_sixlevel(engine, cluster):
     _compare(engine, six, pt6, jobs6, "dmma", cluster=cluster, tile_T=2)
 
 
+@pytest.mark.parametrize("cluster", [1, 2])
+def test_large_tile_single_buffered_operators(engine, cluster):
+    """NL=16, chi=128, T=4 leaves room for only one staging buffer of the per-row operators (refilled
+    during the PT GEMM) -- the cfg3 configuration."""
+    prob = biexciton_problem(outputs=["|1><1|_4", "(|3><1|_4*|1><1|_4*|1><3|_4)"])
+    pt = synthetic_pt(128, len(prob.cls_keys), kind="unitary", scale=0.999)
+    _compare(engine, prob, pt, _g2_jobs(prob, n_t=8, tau_max=2.0), "dmma", cluster=cluster, tile_T=4)
+
+
 def test_planner_picks_clusters_for_small_batches(engine):
     """256 biexciton branches at chi=128 cannot fill 148 SMs with one CTA per tile."""
     prob = biexciton_problem()
