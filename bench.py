@@ -115,7 +115,11 @@ def cpu_rate(prob, pt, tables, n_steps, dt, seconds=10.0, threads=0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_c
     from pyaceqd_b200.jobs import FieldTable, Job
-    cores = oracle_c.max_threads() if threads <= 0 else threads
+    if threads <= 0:
+        # all host threads: torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently
+        # turn the CPU baseline into a single-thread run
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = threads
 
     def run(n):
         idx = np.linspace(0, tables.shape[0] - 1, n).astype(int)
@@ -228,11 +232,11 @@ def run_cfg3(args):
         tt = np.arange(0.0, t_axis[-1] + tau_max, dt)
         px, py = gs.sample_pulses(tt, [pulse])
         tabs = {"x": FieldTable(0.0, dt, px), "y": FieldTable(0.0, dt, py)}
-        cores = oracle_c.max_threads()
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else oracle_c.max_threads()
         idx = np.linspace(0, n_t - 1, max(cores, 16)).astype(int)
         jobs = [Job(0.0, float(t_axis[i] + tau_max), dt, tables=tabs) for i in idx]
         t = time.perf_counter()
-        oracle_c.propagate_sweep(prob, pt, jobs)
+        oracle_c.propagate_sweep(prob, pt, jobs, n_threads=cores)
         el = time.perf_counter() - t
         nst = sum(j.n_steps for j in jobs)
         rate = nst / el
