@@ -530,6 +530,55 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         // ---------------- phase B: X = W_n Y.  Warp w owns bond columns of its n-tiles for every
         // trajectory (column-local, in place, no block barrier); JU trajectories x NBB n-tiles are
         // kept in flight for instruction-level parallelism (bounded by the register budget).
+        if constexpr (KSU_T == 1) {
+            // NL <= 4 (two-level system): a DMMA m-tile would be half empty and its operand traffic heavy.
+            // The FP64 FMA pipe has the same peak on this part (profiles/r01_fp64_peaks.log): warp w takes
+            // trajectories w, w+8, ..., keeps W_n in registers, lane = bond column, 16 complex FMAs per column.
+            for (int j = warp; j < T; j += N_COMPUTE_WARPS) {
+                const aceqd_traj& t = trj[j];
+                if (!(t.n_steps >= 0 && n >= t.step0 && n < t.step0 + t.n_steps)) continue;
+                const double2* Wp;
+                if (wsm) {
+                    Wp = reinterpret_cast<const double2*>(Wst + (size_t)(buf * T + j) * wov);
+                } else {
+                    const long long e = entry_of(t, n - t.step0, p.ovr_base);
+                    Wp = reinterpret_cast<const double2*>(p.W + (size_t)e * p.prob.w_doubles);
+                }
+                double2 w[4][4];
+                size_t ro[4];
+                bool own[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    ro[a] = a < NL ? rowoff(pos[a], j) : 0;
+                    own[a] = a < NL && (C == 1 || own_pos[pos[a]]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        w[a][k] = (a < NL && k < NL) ? (wsm ? Wp[a * NLp4 + k] : __ldg(Wp + a * NLp4 + k))
+                                                     : make_double2(0.0, 0.0);
+                }
+                for (int c = lane; c < chi_pad; c += 32) {
+                    double2 y[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        y[k] = k < NL ? make_double2(Xre[ro[k] + c], Xim[ro[k] + c]) : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        double xr = 0.0, xi = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            xr = fma(w[a][k].x, y[k].x, xr);
+                            xr = fma(-w[a][k].y, y[k].y, xr);
+                            xi = fma(w[a][k].x, y[k].y, xi);
+                            xi = fma(w[a][k].y, y[k].x, xi);
+                        }
+                        if (own[a]) {
+                            Xre[ro[a] + c] = xr;
+                            Xim[ro[a] + c] = xi;
+                        }
+                    }
+                }
+            }
+        } else {
         constexpr int NBB = (KSU_T * NB <= 8) ? NB : 1;
         constexpr int JU_ = 8 / (KSU_T * NBB);
         constexpr int JU = JU_ < 1 ? 1 : (JU_ > 4 ? 4 : JU_);
@@ -639,6 +688,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 }
                 __syncwarp();
             }
+        }
         }
         if (wsm) {  // this row's operators are consumed: hand the buffer back to the producer
             __syncwarp();
