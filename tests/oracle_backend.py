@@ -4,6 +4,7 @@ Lets the ``-m "not gpu"`` suite exercise every batch issuer (two_time, pol_entan
 rabi / tpe sweeps) end to end through the deferred-execution path, and gives the GPU suite a
 workflow-level parity reference.  Test infrastructure only (it imports ``oracle/``)."""
 import contextlib
+import copy
 
 import numpy as np
 import scipy.linalg
@@ -22,7 +23,11 @@ class OracleEngine:
         self.calls.append((len(jobs), sum(j.n_steps for j in jobs)))
         out = []
         for j in jobs:
-            full = oracle.propagate(prob, pt, j, t_eval=kw.get("t_eval", "half_mid"))
+            pj = prob
+            if getattr(j, "rho0", None) is not None:      # per-job initial state (dynamical maps)
+                pj = copy.copy(prob)
+                pj.rho0 = np.asarray(j.rho0, dtype=complex).reshape(-1)
+            full = oracle.propagate(pj, pt, j, t_eval=kw.get("t_eval", "half_mid"))
             out.append(np.ascontiguousarray(full[:, -j.tail_rows:]) if j.tail_rows else full)
         return out
 

@@ -84,7 +84,38 @@ def scenario_rabi(tmp):
     return {"areas": areas, "final": final, "tpe": xyb}
 
 
-SCENARIOS = {"g1": scenario_g1, "polent": scenario_polent, "timebin": scenario_timebin,
+def _indist(tmp, dm):
+    from pyaceqd_b200.two_level_system.tls import tls
+    from pyaceqd_b200.two_time.purity import Indistinguishability
+    p = ChirpedPulse(tau_0=0.15, e_start=0, alpha=0, t0=0.8, e0=1.0)
+    opts = {"lindblad": True, "gamma_e": 1.5, "phonons": False, "temp_dir": tmp}
+    return Indistinguishability(tls, "|0><1|_2", "|1><0|_2", p, dt=0.1, tb=4.0, dt_small=0.1, gaussian_t=2.0,
+                                simple_exp=False, dt_big=0.5, options=opts, dm=dm)
+
+
+def scenario_purity(tmp):
+    direct = _indist(tmp, dm=False)
+    ind, pur = direct.calc_indistinguishability()
+    t2, g2 = direct.G2()
+    tl = _indist(tmp, dm=True)
+    ind_tl, pur_tl = tl.calc_indistinguishability()
+    return {"t1": direct.t1, "ind": ind, "pur": pur, "pur2": direct.calc_purity(), "g2": g2, "ind_tl": ind_tl,
+            "pur_tl": pur_tl}
+
+
+def scenario_dynmap(tmp):
+    """Dynamical map (general_system.py:328-335 consumers) applied to a state other than the problem's
+    initial one must equal the direct run from that state."""
+    from pyaceqd_b200.two_level_system.tls import tls
+    p = ChirpedPulse(tau_0=0.5, e_start=0.4, alpha=0, t0=1.5, e0=1.3)
+    kw = dict(dt=0.1, lindblad=True, gamma_e=0.3, temp_dir=tmp)
+    res, E = tls(0, 4.0, p, calc_dynmap=True, **kw)
+    rho0 = np.array([[0.3, 0.2 - 0.1j], [0.2 + 0.1j, 0.7]])
+    direct = tls(0, 4.0, p, rho0=rho0, **kw)
+    return {"E": E, "via_map": E @ rho0.reshape(-1), "direct": direct}
+
+
+SCENARIOS = {"dynmap": scenario_dynmap, "purity": scenario_purity, "g1": scenario_g1, "polent": scenario_polent, "timebin": scenario_timebin,
              "onephoton": scenario_onephoton, "rabi": scenario_rabi}
 
 
@@ -172,6 +203,25 @@ def test_onephoton_and_area_sweeps(tmp_path):
     assert np.abs(out["final"] - np.sin(np.pi * out["areas"] / 2) ** 2).max() < 2e-3    # Rabi rotations
     assert out["tpe"].shape == (3, 4) and np.all(out["tpe"] >= -1e-12)
     assert [c[0] for c in eng.calls] == [9, 4]
+
+
+def test_dynmap_acts_on_arbitrary_states(tmp_path):
+    out, _ = _run_oracle("dynmap", tmp_path)
+    assert out["E"].shape == (40, 4, 4)
+    # outputs of tls: g = rho_00, x = rho_11, <|0><1|> = rho_10, <|1><0|> = rho_01 (row-major vec: 00, 01, 10, 11)
+    assert np.abs(out["via_map"][:, 0] - out["direct"][1][1:]).max() < 1e-12
+    assert np.abs(out["via_map"][:, 3] - out["direct"][2][1:]).max() < 1e-12
+    assert np.abs(out["via_map"][:, 2] - out["direct"][3][1:]).max() < 1e-12
+    assert np.linalg.matrix_rank(out["E"][5]) == 4
+
+
+def test_purity_and_indistinguishability_routes(tmp_path):
+    out, eng = _run_oracle("purity", tmp_path)
+    assert abs(out["pur"] - out["pur2"]) < 1e-13
+    assert 0.5 < out["pur"] <= 1.0 + 1e-9 and 0.3 < out["ind"] <= 1.0 + 1e-9      # short pi-pulse: nearly pure photons
+    # the time-local route (per-period dynamical map + chain kernel) reproduces the direct route; both
+    # integrate the same (t, tau) grid, the map route cuts the pulse tail at gaussian_t
+    assert abs(out["pur_tl"] - out["pur"]) < 5e-3 and abs(out["ind_tl"] - out["ind"]) < 5e-3
 
 
 def test_planner_tail_rows_and_fork_bookkeeping():
