@@ -77,6 +77,16 @@ def all_gather_blocks(local: np.ndarray, counts: Sequence[int], device=None, gro
     return out.reshape((out.shape[0],) + tuple(row_shape))
 
 
+def is_multi_rank(group=None) -> bool:
+    """True inside an initialised torch.distributed job with more than one rank (never imports torch
+    itself: a process that has not imported torch cannot have a process group)."""
+    import sys
+    if "torch" not in sys.modules:
+        return False
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
 def run_jobs_sharded(engine, prob, pt, jobs, device=None, group=None, **kw) -> List[np.ndarray]:
     """Propagate this rank's share of `jobs` and all-gather the results (every rank returns the
     full list, like ``wait(futures)`` in the reference).  Requires an initialised process group;
@@ -86,12 +96,16 @@ def run_jobs_sharded(engine, prob, pt, jobs, device=None, group=None, **kw) -> L
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return engine.run_jobs(prob, pt, jobs, **kw)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if device is None and dist.get_backend(group) == "nccl":
+        import torch
+        device = torch.device("cuda", int(getattr(engine, "device", 0)))
     costs = [max(1, j.n_steps) for j in jobs]
     blocks = balanced_blocks(costs, world)
     a, b = blocks[rank]
     mine = engine.run_jobs(prob, pt, jobs[a:b], **kw) if b > a else []
     n_out = prob.n_out
-    rows = [j.n_steps + 1 for j in jobs]
+    # rows every rank can predict: all output rows, or only the requested tail
+    rows = [min(j.n_steps + 1, getattr(j, "tail_rows", 0) or j.n_steps + 1) for j in jobs]
     # pack ragged [n_out, rows_i] results into one [sum rows, n_out] block per rank
     local = (np.concatenate([m.T for m in mine], axis=0) if mine else np.zeros((0, n_out), complex))
     counts = [int(sum(rows[x:y])) for (x, y) in blocks]

@@ -345,7 +345,12 @@ def run_requests(reqs: List[Request]):
                     reqs[i].job.tables = tabs
         plain = [i for i in idx if not reqs[i].calc_dynmap]
         if plain:
-            outs = eng.run_jobs(prob, pt, [reqs[i].job for i in plain])
+            from pyaceqd_b200 import distributed as _dist
+            jobs = [reqs[i].job for i in plain]
+            # inside a torch.distributed job the sweep shards over the ranks (one GPU each) and is
+            # all-gathered once; every rank returns the full result like wait(futures) in the reference
+            outs = _dist.run_jobs_sharded(eng, prob, pt, jobs) if (_dist.is_multi_rank() and len(jobs) > 1) \
+                else eng.run_jobs(prob, pt, jobs)
             for i, o in zip(plain, outs):
                 results[i] = _finish(reqs[i], o)
         for i in idx:

@@ -61,7 +61,21 @@ def _worker(rank, world, port, q):
         jobs = [_Job(n) for n in (3, 9, 1, 4, 4, 7)]
         res = run_jobs_sharded(_Eng(), _Prob(), None, jobs)
         ok2 = all(r.shape == (2, j.n_steps + 1) and np.all(r == j.n_steps + 0.5j) for r, j in zip(res, jobs))
-        q.put((rank, bool(ok), bool(ok2)))
+        # a whole workflow inside the process group: the G2 sweep shards over the ranks (oracle backend)
+        import sys
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+        from oracle_backend import oracle_backend
+        from pyaceqd_b200.pulses import ChirpedPulse
+        from pyaceqd_b200.two_level_system.tls import tls
+        from pyaceqd_b200.two_time.correlations import three_op_two_time
+        p = ChirpedPulse(tau_0=0.5, e_start=0, alpha=0, t0=1.5, e0=2.0)
+        with oracle_backend() as eng:
+            eng.device = 0
+            t1, tau, G = three_op_two_time(tls, np.round(np.arange(0.0, 3.0, 0.5), 6), p, tau_max=2.0, dt=0.25,
+                                           options={"lindblad": True, "phonons": False, "gamma_e": 0.2})
+            shard_sizes = [c[0] for c in eng.calls]
+        q.put((rank, bool(ok), bool(ok2), G.shape, float(np.abs(G).sum()), shard_sizes))
     finally:
         dist.destroy_process_group()
 
@@ -77,4 +91,16 @@ def test_gather_world2_gloo():
     got = sorted(q.get(timeout=100) for _ in range(2))
     for p in procs:
         p.join(30)
-    assert got == [(0, True, True), (1, True, True)]
+    assert [g[:3] for g in got] == [(0, True, True), (1, True, True)]
+    # both ranks hold the full, identical G2 map; each computed only its share of the 6 trajectories
+    assert got[0][3] == got[1][3] == (6, 9) and abs(got[0][4] - got[1][4]) < 1e-15 and got[0][4] > 0
+    assert sum(got[0][5]) + sum(got[1][5]) == 6 and all(0 < sum(g[5]) < 6 for g in got)
+    from oracle_backend import oracle_backend
+    from pyaceqd_b200.pulses import ChirpedPulse
+    from pyaceqd_b200.two_level_system.tls import tls
+    from pyaceqd_b200.two_time.correlations import three_op_two_time
+    with oracle_backend():
+        _, _, G = three_op_two_time(tls, np.round(np.arange(0.0, 3.0, 0.5), 6),
+                                    ChirpedPulse(tau_0=0.5, e_start=0, alpha=0, t0=1.5, e0=2.0), tau_max=2.0, dt=0.25,
+                                    options={"lindblad": True, "phonons": False, "gamma_e": 0.2})
+    assert abs(float(np.abs(G).sum()) - got[0][4]) < 1e-12
