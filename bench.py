@@ -211,7 +211,7 @@ def run_cfg3(args):
         eng.close()
         return
     line = {
-        "metric": METRIC, "value": world * (steps_main + steps_trunk) / wall, "unit": UNIT, "n_gpus": world,
+        "metric": METRIC, "value": (n_t * n_t + world * steps_trunk) / wall, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg3: biexciton two-photon excitation + synthetic PT (seed 1234), lindblad, "
