@@ -123,3 +123,94 @@ def G2_spectral_integral(t1, tau, G):
     """Time-integrated second-order correlation ``int dt int dtau G(t, tau)`` on the given axes
     (what the consumers of ``three_op_two_time`` compute, e.g. ``pol_entanglement/G2.py:292-299``)."""
     return np.trapezoid(np.trapezoid(G, tau, axis=1), t1)
+
+
+# ------------------------------------------------------------------------------------ time-local maps
+def _tl_correlation(system, t_axis, pulses, left, right, out, tau0, t_mem, tau_max, dt, rho0, options, use_dm,
+                    fortran_args):
+    """Shared body of the ``tl_*_two_time`` functions (reference ``:450-616,696-864``).
+
+    ``G[i, 0] = Tr(tau0 rho(t_i))`` and ``G[i, k] = Tr(out E_k[left rho(t_i) right])`` where ``E_k`` is the
+    propagation over ``k`` steps after ``t_i``: with ``use_dm`` the time-local maps of the whole window
+    (one dynamical-map run, then matrix-vector chains on the GPU chain kernel), otherwise -- valid
+    for time-independent dynamics only -- powers of the stationary map extracted after ``t_mem``.
+    ``fortran_args`` switches to the reference's ``fortran_only`` call of ``calc_onetime_parallel``
+    with its column-major conventions (``:534,782``)."""
+    from pyaceqd_b200.tlmap import Programs
+    from pyaceqd_b200.tools import calc_tl_dynmap_pseudo, extract_dms
+    from pyaceqd_b200.two_time import propagate_tau_module
+    if not t_axis[0] == 0:
+        raise ValueError("t_axis must start at 0.")
+    dim = len(rho0[0])
+    NL = dim * dim
+    n_tau = int(tau_max / dt)
+    tau = np.linspace(0, tau_max, n_tau + 1)
+    v0 = np.asarray(rho0, dtype=complex).reshape(NL)
+    start = np.kron(left, right.T)                     # row-major: vec(L rho R) = (L (x) R^T) vec(rho)
+    w_out, w_tau0 = out.T.reshape(-1), tau0.T.reshape(-1)
+    if use_dm:
+        result, dm = system(0, t_axis[-1] + tau_max, *pulses, dt=dt, rho0=rho0, multitime_op=[], calc_dynmap=True,
+                            **options)
+        t_sim = np.round(result[0].real, 6)
+        tl = calc_tl_dynmap_pseudo(dm, t_sim)
+        if fortran_args is not None:
+            return t_axis, tau, propagate_tau_module.calc_onetime_parallel(
+                np.asfortranarray(tl.transpose(1, 2, 0)), v0, n_tau, dim, *fortran_args, t_sim, t_axis)
+        pr = Programs(NL)
+        off = pr.add(tl)
+        G = np.zeros((len(t_axis), n_tau + 1), dtype=complex)
+        v, j = v0.copy(), 0
+        for i, t in enumerate(t_axis):
+            while t_sim[j] < t:
+                v = tl[j] @ v
+                j += 1
+            G[i, 0] = w_tau0 @ v
+            pr.chain(start @ v, [(off + j, n_tau, 1, 1)])
+        out_vals, _ = pr.run(w=w_out[None])
+        G[:, 1:] = out_vals[:, :n_tau, 0]
+        return t_axis, tau, G
+    if options.get("phonons"):
+        print("phonons not implemented yet")
+        return t_axis, tau, np.zeros((len(t_axis), n_tau + 1), dtype=complex)
+    # stationary map from a short dynamical-map run (the operators at 2 t_mem are part of the reference's
+    # call but do not enter the stationary map, which is read off before them)
+    result, dm = system(0, 4 * t_mem, *pulses, dt=dt, rho0=rho0, multitime_op=[], calc_dynmap=True, **options)
+    t_sim = np.round(result[0].real, 6)
+    tl_map, _ = extract_dms(calc_tl_dynmap_pseudo(dm, t_sim), t_sim, t_mem, [2 * t_mem])
+    pr = Programs(NL)
+    off = pr.add(tl_map)
+    G = np.zeros((len(t_axis), n_tau + 1), dtype=complex)
+    v = v0.copy()
+    for i, t in enumerate(t_axis):
+        if i > 0:
+            v = np.linalg.matrix_power(tl_map, int((t - t_axis[i - 1]) / dt)) @ v
+        G[i, 0] = w_tau0 @ v
+        pr.chain(start @ v, [(off, n_tau, 1, 0)])     # column k = after k applications of the stationary map
+    out_vals, _ = pr.run(w=w_out[None])
+    # (the reference's stationary branch shifts the tau axis by one step and repeats the first `dim`
+    #  entries, an artefact of passing a matrix to tl_pad_stationary_nsteps, :612-614; the layout here
+    #  is the one of its use_dm branch, :583-587)
+    G[:, 1:] = out_vals[:, :n_tau, 0]
+    return t_axis, tau, G
+
+
+def tl_two_op_two_time(system, t_axis, *pulses, t_mem=10, opA="|1><0|_2", opB="|0><1|_2", tau_max=500, dt=0.1,
+                       rho0=np.array([[1, 0], [0, 0]], dtype=complex), options={"lindblad": True, "phonons": False},
+                       debug=False, workers=15, use_dm=False, fortran_only=False):
+    """``<A(t + tau) B(t)>`` from time-local dynamical maps (reference ``:450-616``)."""
+    from pyaceqd_b200.tools import op_to_matrix
+    A, B = op_to_matrix(opA), op_to_matrix(opB)
+    I = np.identity(len(rho0[0]))
+    return _tl_correlation(system, t_axis, pulses, B, I, A, A @ B, t_mem, tau_max, dt, rho0, options, use_dm,
+                           (I, A, B) if fortran_only else None)
+
+
+def tl_three_op_two_time(system, t_axis, *pulses, t_mem=10, opA="|1><0|_2", opB="|1><1|_2", opC="|0><1|_2",
+                         tau_max=500, dt=0.1, rho0=np.array([[1, 0], [0, 0]], dtype=complex),
+                         options={"lindblad": True, "phonons": False}, debug=False, workers=15, use_dm=False,
+                         fortran_only=False):
+    """``<A(t) B(t + tau) C(t)>`` from time-local dynamical maps (reference ``:696-864``)."""
+    from pyaceqd_b200.tools import op_to_matrix
+    A, B, C = op_to_matrix(opA), op_to_matrix(opB), op_to_matrix(opC)
+    return _tl_correlation(system, t_axis, pulses, C, A, B, A @ B @ C, t_mem, tau_max, dt, rho0, options, use_dm,
+                           (A, B, C) if fortran_only else None)

@@ -115,7 +115,29 @@ def scenario_dynmap(tmp):
     return {"E": E, "via_map": E @ rho0.reshape(-1), "direct": direct}
 
 
-SCENARIOS = {"dynmap": scenario_dynmap, "purity": scenario_purity, "g1": scenario_g1, "polent": scenario_polent, "timebin": scenario_timebin,
+def scenario_tl_correlations(tmp):
+    """Time-local-map G1 / G2 (reference correlations.py:450-864) next to the direct MTO sweeps."""
+    from pyaceqd_b200.two_level_system.tls import tls
+    from pyaceqd_b200.two_time.correlations import (three_op_two_time, tl_three_op_two_time, tl_two_op_two_time,
+                                                    two_op_two_time)
+    p = ChirpedPulse(tau_0=0.4, e_start=0.3, alpha=0, t0=1.2, e0=1.7)
+    t_axis = np.round(np.arange(0.0, 3.0, 0.5), 6)
+    opts = {"lindblad": True, "phonons": False, "gamma_e": 0.4, "temp_dir": tmp}
+    rho0 = np.array([[1, 0], [0, 0]], dtype=complex)
+    _, tau, g1_tl = tl_two_op_two_time(tls, t_axis, p, tau_max=2.0, dt=0.1, rho0=rho0, options=dict(opts), use_dm=True)
+    _, _, g2_tl = tl_three_op_two_time(tls, t_axis, p, tau_max=2.0, dt=0.1, rho0=rho0, options=dict(opts), use_dm=True)
+    _, _, g2_f = tl_three_op_two_time(tls, t_axis, p, tau_max=2.0, dt=0.1, rho0=rho0, options=dict(opts), use_dm=True,
+                                      fortran_only=True)
+    _, _, g1 = two_op_two_time(tls, t_axis, p, tau_max=2.0, dt=0.1, options=dict(opts))
+    _, _, g2 = three_op_two_time(tls, t_axis, p, tau_max=2.0, dt=0.1, options=dict(opts))
+    # undriven emitter: the stationary map alone is exact
+    free = dict(opts)
+    _, _, g2_stat = tl_three_op_two_time(tls, t_axis, t_mem=0.5, tau_max=2.0, dt=0.1,
+                                         rho0=np.array([[0.2, 0.1], [0.1, 0.8]], dtype=complex), options=free)
+    return {"tau": tau, "g1_tl": g1_tl, "g2_tl": g2_tl, "g2_f": g2_f, "g1": g1, "g2": g2, "g2_stat": g2_stat}
+
+
+SCENARIOS = {"tl_corr": scenario_tl_correlations, "dynmap": scenario_dynmap, "purity": scenario_purity, "g1": scenario_g1, "polent": scenario_polent, "timebin": scenario_timebin,
              "onephoton": scenario_onephoton, "rabi": scenario_rabi}
 
 
@@ -213,6 +235,17 @@ def test_dynmap_acts_on_arbitrary_states(tmp_path):
     assert np.abs(out["via_map"][:, 3] - out["direct"][2][1:]).max() < 1e-12
     assert np.abs(out["via_map"][:, 2] - out["direct"][3][1:]).max() < 1e-12
     assert np.linalg.matrix_rank(out["E"][5]) == 4
+
+
+def test_tl_correlations_equal_direct_sweeps(tmp_path):
+    """Without phonons the quantum regression theorem is exact: chains of time-local maps reproduce the
+    multi-time-operator trajectories (up to the pseudo-inverse's conditioning)."""
+    out, _ = _run_oracle("tl_corr", tmp_path)
+    assert np.abs(out["g1_tl"] - out["g1"]).max() < 1e-8
+    assert np.abs(out["g2_tl"] - out["g2"]).max() < 1e-8
+    assert np.abs(out["g2_f"] - out["g2"]).max() < 1e-8      # real operators: the column-major reading agrees
+    g = out["g2_stat"]
+    assert np.allclose(g[:, 0], 0) and np.all(np.abs(g[:, 1:]) < 1e-12)    # G2 of a single emitter stays 0 undriven
 
 
 def test_purity_and_indistinguishability_routes(tmp_path):
