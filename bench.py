@@ -434,6 +434,9 @@ def main():
         k_avg = float(np.mean(k_ms))
         fl = flops_per_step(NL, args.chi) * n_traj * args.n_steps
         achieved = fl / (k_avg * 1e-3) / 1e12
+        algo_bytes = n_traj * (args.n_steps + 1) * (768.0 + 16.0 * n_out)
+        default_cfg = (args.chi, args.n_area, args.n_det, args.n_steps) == (128, 64, 64, 400)
+        traffic = 1.270547e9 + 104.552448e6 if default_cfg else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -443,7 +446,10 @@ def main():
                     "d2h_bytes_per_step": int(res.nbytes), "ms_per_step": 1e3 * float(te.item()) / args.steps,
                     "api": "Engine.run_sweep -> aceqd_propagate_batch (host pinned buffers)"},
             "roofline": {"bound": "tensor", "kernel": "k_step_dmma", "achieved": achieved, "peak": peak_dmma,
-                         "unit": "TFLOP/s", "frac": achieved / peak_dmma, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak_dmma, "traffic": traffic,
+                         "traffic_note": "DRAM bytes (read+write) of one step-kernel launch of this exact config from "
+                                         "the ncu --set full capture profiles/r01w_cfg2_full_step_kernel_ncu.txt; "
+                                         "algorithmic bytes (per-row operators + outputs) = %.4g" % algo_bytes,
                          "peak_source": "FP64 DMMA.8x8x4 register-resident micro-benchmark (aceqd_fp64_peak) measured in this run; "
                                         "MEASURED_PEAKS.json holds no FP64 figure; nominal B200 FP64 ~40 TFLOP/s",
                          "dfma_peak": peak_dfma, "kernel_ms": k_avg, "opbuild_ms": float(np.mean(op_ms)),
