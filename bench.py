@@ -226,7 +226,10 @@ def run_cfg3(args):
                 "api": "two_time.correlations.three_op_two_time(biexciton, ...) -> BatchExecutor -> aceqd_propagate_batch",
                 "reference_equivalent_steps": ref_steps,
                 "reference_equivalent_steps_per_s": ref_steps / wall},
-        "roofline": {"bound": "tensor", "kernel": "k_step_dmma (branch launch)", "achieved": achieved,
+        "roofline": {"bound": "tensor",
+                     "kernel": ("k_step_stream" if main[0].get("kernel") == 2 else "k_step_dmma") + " (branch launch)",
+                     "achieved": achieved,
+                     "achieved_trunk_and_branches": fl * (steps_main + steps_trunk) / ((k_main + k_trunk) * 1e-3) / 1e12,
                      "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma, "traffic": None,
                      "kernel_ms": k_main, "trunk_kernel_ms": k_trunk,
                      "opbuild_ms": float(np.mean([l["opbuild_ms"] for l in main])),

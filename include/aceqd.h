@@ -155,8 +155,10 @@ typedef struct {
     int64_t out_elems;         /* total complex elements of `out`                              */
     double* out;
     int32_t device_resident;
-    int32_t kernel;            /* 0: DMMA persistent kernel (product), 1: plain-FMA check kernel */
-    int32_t cluster;           /* CTAs per tile (0/1, 2 or 4): a thread-block cluster shares one tile,   */
+    int32_t kernel;            /* 0: persistent DMMA kernel (state in shared memory), 1: plain-FMA check  */
+                               /* kernel, 2: step-synchronous DMMA kernel (state in HBM/L2, PT GEMM      */
+                               /* batched over trajectories per coupling class; for large NL)           */
+    int32_t cluster;           /* CTAs per tile (0/1, 2, 4 or 8): a thread-block cluster shares one tile, */
                                /* splitting its GEMM passes and exchanging rows through distributed     */
                                /* shared memory -- for batches too small to fill 148 SMs otherwise      */
     int32_t pad_;

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libaceqd.so")
-SOURCES = ["api.cu", "expm.cu", "step_kernel.cu", "tlmap.cu", "peak.cu"]
+SOURCES = ["api.cu", "expm.cu", "step_kernel.cu", "stream_kernel.cu", "tlmap.cu", "peak.cu"]
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
               "-lineinfo", "-O3", "-std=c++17", "-diag-suppress", "177"]
 
@@ -17,7 +17,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + ["common.cuh"]]
+    deps = [os.path.join(CSRC, f) for f in SOURCES + ["common.cuh", "kernel_common.cuh"]]
     deps.append(os.path.join(HERE, "..", "include", "aceqd.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 

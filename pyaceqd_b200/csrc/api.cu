@@ -58,7 +58,7 @@ struct aceqd_ctx {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // step, opbuild, tlmap start/stop
     bool have_step = false, have_op = false, have_tl = false;
     DevBuf W, OV, tables, seqs, seq_base, entries, mto, rho0s, trajs, tiles, snap_steps, snaps,
-        out, passes, scratch, misc, tl_pool, tl_v0, tl_segoff, tl_segs, tl_w, tl_out, tl_final;
+        out, passes, scratch, misc, st_x, st_order, st_bar, st_apos, tl_pool, tl_v0, tl_segoff, tl_segs, tl_w, tl_out, tl_final;
     // layout of the operators currently in the workspace
     long long n_seq_entries = 0;
 };
@@ -126,7 +126,7 @@ void aceqd_ctx_destroy(aceqd_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->W, &c->OV, &c->tables, &c->seqs, &c->seq_base, &c->entries, &c->mto,
                       &c->rho0s, &c->trajs, &c->tiles, &c->snap_steps, &c->snaps, &c->out,
-                      &c->passes, &c->scratch, &c->misc, &c->tl_pool, &c->tl_v0, &c->tl_segoff,
+                      &c->passes, &c->scratch, &c->misc, &c->st_x, &c->st_order, &c->st_bar, &c->st_apos, &c->tl_pool, &c->tl_v0, &c->tl_segoff,
                       &c->tl_segs, &c->tl_w, &c->tl_out, &c->tl_final})
         b->release();
     for (auto& ev : c->ev)
@@ -589,7 +589,93 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
     sp.snaps = (double*)c->snaps.p;
     sp.out = out_dev;
 
-    if (b->kernel == 1) {
+    if (b->kernel == 2) {
+        // ---- step-synchronous streaming kernel: state in HBM/L2, class-batched PT GEMM
+        const int NL = pd.NL;
+        StreamParams st{};
+        st.pt = pt->d;
+        st.prob = pd;
+        st.n_traj = b->n_traj;
+        std::vector<int> order(b->n_traj), apos(NL);
+        for (int i = 0; i < b->n_traj; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(),
+                         [&](int x, int y) { return b->trajs[x].step0 < b->trajs[y].step0; });
+        int n_begin = 0x7fffffff, n_end = -1;
+        for (int i = 0; i < b->n_traj; ++i) {
+            n_begin = std::min(n_begin, b->trajs[i].step0);
+            n_end = std::max(n_end, b->trajs[i].step0 + b->trajs[i].n_steps);
+        }
+        st.n_begin = n_begin;
+        st.n_end = n_end;
+        for (int a = 0; a < NL; ++a) apos[prob->pos_of_alpha[a]] = a;
+        int ncls = 0;
+        long long tasks = b->n_traj;
+        for (int p0 = 0; p0 < NL;) {
+            int p1 = p0;
+            const int blk = prob->block_of_alpha[apos[p0]];
+            while (p1 < NL && prob->block_of_alpha[apos[p1]] == blk) ++p1;
+            if (ncls >= STREAM_MAX_CLS) {
+                set_error("more than %d coupling classes", STREAM_MAX_CLS);
+                return ACEQD_ERR_CAPACITY;
+            }
+            st.cls_p0[ncls] = p0;
+            st.cls_rc[ncls] = p1 - p0;
+            st.cls_blk[ncls] = blk;
+            ++ncls;
+            p0 = p1;
+        }
+        st.n_classes = ncls;
+        long long gemm_tasks = 0;
+        for (int cidx = 0; cidx < ncls; ++cidx)
+            gemm_tasks += ((long long)b->n_traj * st.cls_rc[cidx] + 15) / 16;
+        tasks = std::max(tasks, gemm_tasks);
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
+        st.grid = (int)std::max<long long>(1, std::min<long long>(n_sm, tasks));
+        int stages = 0;
+        const int wov_full = pd.w_doubles + pd.ov_doubles;
+        for (int stg = MAX_STAGES; stg >= 2; --stg)
+            if (stream_smem_bytes(NL, chi_pad, stg, wov_full) <= (size_t)SMEM_BUDGET) {
+                stages = stg;
+                break;
+            }
+        if (!stages) {
+            set_error("NL=%d chi_pad=%d does not fit the streaming kernel's shared memory", NL, chi_pad);
+            return ACEQD_ERR_CAPACITY;
+        }
+        st.stages = stages;
+        const size_t plane = (size_t)b->n_traj * NL * chi_pad * 8;
+        if ((rc = c->st_x.reserve(4 * plane + 64))) return rc;
+        UP(c->st_order, order.data(), order.size() * sizeof(int));
+        std::vector<int> pa(2 * NL);
+        for (int a = 0; a < NL; ++a) {
+            pa[a] = prob->pos_of_alpha[a];
+            pa[NL + a] = apos[a];
+        }
+        UP(c->st_apos, pa.data(), pa.size() * sizeof(int));
+        if ((rc = c->st_bar.reserve(64))) return rc;
+        ACEQD_CUDA(cudaMemsetAsync(c->st_bar.p, 0, 64, c->stream));
+        st.trajs = sp.trajs;
+        st.order = (const int*)c->st_order.p;
+        st.pos_of_alpha = (const int*)c->st_apos.p;
+        st.alpha_of_pos = (const int*)c->st_apos.p + NL;
+        st.W = sp.W;
+        st.OV = sp.OV;
+        st.ovr_base = sp.ovr_base;
+        st.rho0s = sp.rho0s;
+        st.snap_steps = sp.snap_steps;
+        st.snaps = sp.snaps;
+        st.out = out_dev;
+        st.Xre = (double*)c->st_x.p;
+        st.Xim = (double*)((char*)c->st_x.p + plane);
+        st.Yre = (double*)((char*)c->st_x.p + 2 * plane);
+        st.Yim = (double*)((char*)c->st_x.p + 3 * plane);
+        st.barrier = (unsigned*)c->st_bar.p;
+        const size_t smem = stream_smem_bytes(NL, chi_pad, stages, wov_full);
+        ACEQD_CUDA(cudaEventRecord(c->ev[0], c->stream));
+        if ((rc = launch_step_stream(st, smem, c->stream, &c->launches))) return rc;
+        ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    } else if (b->kernel == 1) {
         sp.T = 1;
         sp.n_tiles = b->n_traj;
         if ((rc = c->scratch.reserve((size_t)b->n_traj * 2 * pd.NL * chi_pad * 16))) return rc;
@@ -603,8 +689,8 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
                 return ACEQD_ERR_ARG;
             }
         const int cluster = b->cluster <= 1 ? 1 : b->cluster;
-        if (cluster != 1 && cluster != 2 && cluster != 4) {
-            set_error("batch: cluster must be 0/1, 2 or 4");
+        if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) {
+            set_error("batch: cluster must be 0/1, 2, 4 or 8");
             return ACEQD_ERR_ARG;
         }
         std::vector<PassDesc> passes;

@@ -95,6 +95,30 @@ struct StepParams {
     double* out;
 };
 
+// Step-synchronous streaming kernel (stream_kernel.cu): state in HBM/L2, class-batched PT GEMM.
+constexpr int STREAM_MAX_CLS = 64;
+struct StreamParams {
+    PtDev pt;
+    ProbDev prob;
+    int n_traj, n_begin, n_end, stages, grid, n_classes;
+    int cls_p0[STREAM_MAX_CLS];   // first alpha position of the class
+    int cls_rc[STREAM_MAX_CLS];   // alpha positions (rows per trajectory) in the class
+    int cls_blk[STREAM_MAX_CLS];  // PT block of the class
+    const aceqd_traj* trajs;
+    const int* order;             // trajectory indices sorted by start step
+    const int* pos_of_alpha;
+    const int* alpha_of_pos;
+    const double* W;
+    const double* OV;
+    long long ovr_base;
+    const double* rho0s;
+    const int* snap_steps;
+    double* snaps;
+    double* out;
+    double *Xre, *Xim, *Yre, *Yim;   // [rank in `order`][alpha position][chi_pad]
+    unsigned* barrier;            // grid barrier counter (zeroed before the launch)
+};
+
 // ---------------------------------------------------------------- operator builder
 struct OpBuildParams {
     ProbDev prob;
@@ -119,6 +143,8 @@ int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, cu
 int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, long long* launches);
 int launch_step_check(const StepParams& p, double* scratch, cudaStream_t s, long long* launches);
 size_t step_smem_bytes(int NL, int chi_pad, int T, int stages, int wov_doubles, int wbufs);
+int launch_step_stream(const StreamParams& p, size_t smem, cudaStream_t s, long long* launches);
+size_t stream_smem_bytes(int NL, int chi_pad, int stages, int wov_doubles);
 int launch_tlmap(int NL, int n_chains, int n_w, int n_emit_max, const double* pool, const double* v0,
                  const long long* seg_off, const aceqd_tlseg* segs, const double* w, double* out,
                  double* final_v, cudaStream_t s, long long* launches);

@@ -12,7 +12,7 @@
 //
 // Replaces the inner loop of ACE's Simulation.run (pyaceqd/general_system/general_system.py:331
 // / the `ACE <param>` subprocess of :339-341) for a whole batch of trajectories.
-#include "common.cuh"
+#include "kernel_common.cuh"
 
 namespace aceqd {
 
@@ -53,146 +53,6 @@ __host__ __device__ inline SmemLayout make_layout(int NL, int chi_pad, int T, in
     L.chunks = o; o += (size_t)stages * 2 * KC * strideA * 8;  // strideB == strideA
     L.total = o;
     return L;
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LAB_DONE;\n"
-        "bra LAB_WAIT;\n"
-        "LAB_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
-                                         uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-        : "memory");
-}
-// ---- thread-block cluster / distributed shared memory primitives
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {  // same offset in CTA `rank`
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_CWAIT:\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LAB_CDONE;\n"
-        "bra LAB_CWAIT;\n"
-        "LAB_CDONE:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void st_cluster_c128(uint32_t cluster_addr, double2 v) {
-    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(cluster_addr), "d"(v.x), "d"(v.y) : "memory");
-}
-__device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster)
-        : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void compute_bar() {  // the 8 compute warps only
-    asm volatile("bar.sync 1, %0;" ::"n"(N_COMPUTE_WARPS * 32) : "memory");
-}
-__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-        : "+d"(c0), "+d"(c1)
-        : "d"(a), "d"(b));
-}
-__device__ __forceinline__ int slice_of(const PtDev& pt, int n) {
-    return n < pt.n_initial ? n : pt.n_initial + (n - pt.n_initial) % pt.n_repeat;
-}
-__device__ __forceinline__ long long entry_of(const aceqd_traj& t, int i, long long ovr_base) {
-    long long e = t.ent0 + i;
-    for (int q = 0; q < t.n_ovr; ++q)
-        if (t.ovr_step[q] == i) e = ovr_base + t.ovr_ent[q];
-    return e;
-}
-
-// Main loop of one GEMM pass: MCV (<= MC) m-tiles x NB n-tiles of this warp over all k-chunks of
-// one PT block.  ALLNB: every n-tile of the warp is inside the slice (no predicates at all).
-template <int NB, int MCV, bool ALLNB>
-__device__ __forceinline__ void gemm_pass(double (&cre)[MC][NB][2], double (&cim)[MC][NB][2],
-                                          const double* const (&are)[MC], const double* const (&aim)[MC],
-                                          const bool (&aval)[MC], const bool (&nbv)[NB],
-                                          const double* chunks, int chunk_doubles, int strideB, int nch,
-                                          int warp, int g, int tq, uint32_t bar_full, uint32_t bar_empty,
-                                          int& stage, uint32_t& phase, int stages, int lane) {
-    for (int jc = 0; jc < nch; ++jc) {
-        mbar_wait(bar_full + 8 * stage, phase);
-        const double* bre = chunks + (size_t)stage * chunk_doubles;
-        const double* bim = bre + KC * strideB;
-#pragma unroll
-        for (int ks = 0; ks < KC / 4; ++ks) {
-            const int k = jc * KC + 4 * ks;
-            double a_re[MCV], a_im[MCV], b_re[NB], b_im[NB];
-#pragma unroll
-            for (int mc = 0; mc < MCV; ++mc) {
-                a_re[mc] = aval[mc] ? are[mc][k] : 0.0;
-                a_im[mc] = aval[mc] ? aim[mc][k] : 0.0;
-            }
-#pragma unroll
-            for (int nb = 0; nb < NB; ++nb) {
-                const int bo = (4 * ks + tq) * strideB + 8 * (warp + N_COMPUTE_WARPS * nb) + g;
-                b_re[nb] = (ALLNB || nbv[nb]) ? bre[bo] : 0.0;
-                b_im[nb] = (ALLNB || nbv[nb]) ? bim[bo] : 0.0;
-            }
-            // two sweeps so that consecutive DMMAs never share an accumulator
-#pragma unroll
-            for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-                for (int mc = 0; mc < MCV; ++mc)
-                    if (ALLNB || nbv[nb]) {
-                        dmma(cre[mc][nb][0], cre[mc][nb][1], a_re[mc], b_re[nb]);
-                        dmma(cim[mc][nb][0], cim[mc][nb][1], a_re[mc], b_im[nb]);
-                    }
-#pragma unroll
-            for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-                for (int mc = 0; mc < MCV; ++mc)
-                    if (ALLNB || nbv[nb]) {
-                        dmma(cre[mc][nb][0], cre[mc][nb][1], -a_im[mc], b_im[nb]);
-                        dmma(cim[mc][nb][0], cim[mc][nb][1], a_im[mc], b_re[nb]);
-                    }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
-        if (++stage == stages) { stage = 0; phase ^= 1u; }
-    }
 }
 
 // NB   = n-tiles (8 bond columns) per compute warp; KSU_T = compile-time bound on the number of

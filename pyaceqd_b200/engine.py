@@ -30,6 +30,24 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libaceqd.so")
 MAX_OVR = 6
 N_SM = 148
 
+# step kernels: persistent DMMA (state in shared memory), plain-FMA check kernel, step-synchronous DMMA
+# (state in HBM/L2, PT GEMM batched over trajectories per coupling class)
+KERNELS = {"dmma": 0, "check": 1, "stream": 2}
+
+
+def resolve_kernel(kernel: str, NL: int) -> str:
+    """``"auto"`` (or the ``ACEQD_KERNEL`` environment override) -> persistent kernel for small Liouville
+    spaces, step-synchronous streaming kernel for large ones (csrc/stream_kernel.cu header)."""
+    if kernel == "auto":
+        kernel = os.environ.get("ACEQD_KERNEL", "auto")
+    if kernel == "auto":
+        # measured (scripts/bench_kernels_nl16.py, DESIGN.md): the persistent kernel wins at every batch size
+        # tried, also for NL = 16; the streaming kernel stays selectable
+        return "dmma"
+    if kernel not in KERNELS:
+        raise ValueError(f"unknown kernel {kernel!r}; choose from {sorted(KERNELS)} or 'auto'")
+    return kernel
+
 T_EVAL = {"half_mid": (0.25, 0.75), "step_mid": (0.5, 0.5), "start": (0.0, 0.5)}
 
 SEQ_DT = np.dtype([("set", "<i4"), ("step0", "<i4"), ("len", "<i4"), ("first_has_prev", "<i4")], align=True)
@@ -153,10 +171,10 @@ def choose_tile(n_traj: int, rows_per_block: Sequence[int], t_max: int, n_sm: in
     return best_t
 
 
-CLUSTER_CAPACITY = {1: N_SM, 2: N_SM, 4: 132}   # co-resident CTAs per cluster size (GPC packing)
+CLUSTER_CAPACITY = {1: N_SM, 2: N_SM, 4: 132, 8: 128}   # co-resident CTAs per cluster size (GPC packing)
 
 
-def choose_tile_cluster(n_traj: int, pass_load, t_max: int, clusters: Sequence[int] = (1, 2, 4)) -> Tuple[int, int]:
+def choose_tile_cluster(n_traj: int, pass_load, t_max: int, clusters: Sequence[int] = (1, 2, 4, 8)) -> Tuple[int, int]:
     """(trajectories per tile, CTAs per tile): minimise waves x (m-tiles of the most loaded CTA per
     step).  ``pass_load(T, C)`` is ``aceqd_pass_load``.  A cluster splits a tile's GEMM passes over C
     SMs, which only pays when the batch alone cannot fill the GPU; it costs a row exchange per step and
@@ -345,13 +363,14 @@ class Engine:
     # -------------------------------------------------------------- uniform sweeps (vectorised)
     def plan_sweep(self, prob: Problem, pt: ProcessTensor, n_traj: int, n_steps: int, dt: float,
                    t_start: float, n_sets: int, n_samples: int, grid: Tuple[float, float], *,
-                   sets: Optional[np.ndarray] = None, kernel: str = "dmma", t_eval: str = "half_mid",
+                   sets: Optional[np.ndarray] = None, kernel: str = "auto", t_eval: str = "half_mid",
                    tile_T: Optional[int] = None, cluster: Optional[int] = None) -> "_Plan":
         """Descriptors of a pulse-parameter sweep: `n_traj` MTO-free trajectories of equal length
         starting at the PT origin (reference fan-out
         ``two_level_system/rabi_rotations.py:172-198``).  Table / output pointers are filled in
         by :meth:`run_sweep`."""
         NL, n_out = prob.NL, prob.n_out
+        kernel = resolve_kernel(kernel, NL)
         _, blk_of_alpha = self.problem_handle(prob, pt)
         chi_pad = -(-pt.chi_max // 8) * 8
         t_max = self.max_tile(NL, chi_pad)
@@ -381,7 +400,7 @@ class Engine:
         b.tile_T, b.n_tiles, b.tile_traj = T, n_tiles, tile_traj.ctypes.data
         b.n_snap_steps, b.snap_steps, b.n_snap_slots = 0, None, 0
         b.out_elems = int(n_traj) * (n_steps + 1) * n_out
-        b.kernel = 0 if kernel == "dmma" else 1
+        b.kernel = KERNELS[kernel]
         b.cluster = C
         return _Plan(batch=b, keep=[seqs, trajs, tile_traj, rho0], out=None,
                      out_off=trajs["out_off"], n_rows=trajs["n_steps"] + 1)
@@ -394,11 +413,11 @@ class Engine:
         if tile_T:
             t = min(tile_T, t_max)
             return t, choose_tile_cluster(n_traj, lambda tt, c: load(t, c) if tt == t else 0, t)[1]
-        return choose_tile_cluster(n_traj, load, t_max, clusters=(cluster,) if cluster else (1, 2, 4))
+        return choose_tile_cluster(n_traj, load, t_max, clusters=(cluster,) if cluster else (1, 2, 4, 8))
 
     def run_sweep(self, prob: Problem, pt: Optional[ProcessTensor], tables: np.ndarray,
                   grid: Tuple[float, float], t_start: float, n_steps: int, dt: float, *,
-                  plan: Optional["_Plan"] = None, copy: bool = True, kernel: str = "dmma",
+                  plan: Optional["_Plan"] = None, copy: bool = True, kernel: str = "auto",
                   t_eval: str = "half_mid", tile_T: Optional[int] = None) -> np.ndarray:
         """End-to-end sweep through the C ABI with HOST buffers: `tables[n_traj, 3, n_samples]`
         (x, y, rf drive samples of every trajectory; ideally :meth:`pinned_empty` memory) is
@@ -506,7 +525,7 @@ class Engine:
             out[k] = (ids[0], ids[1])
         return out
 
-    def plan(self, prob: Problem, pt: ProcessTensor, jobs: Sequence[Job], *, kernel: str = "dmma",
+    def plan(self, prob: Problem, pt: ProcessTensor, jobs: Sequence[Job], *, kernel: str = "auto",
              t_eval: str = "half_mid", fork: bool = True, tile_T: Optional[int] = None,
              cluster: Optional[int] = None):
         """Build the trunk batch (may be None) and the main batch for `jobs`."""
@@ -521,6 +540,7 @@ class Engine:
         packed, set_of_job, grid = self._tables_of(jobs)
         chi_pad = -(-pt.chi_max // 8) * 8
         NL, n_out = prob.NL, prob.n_out
+        kernel = resolve_kernel(kernel, NL)
         off1, off2 = T_EVAL[t_eval]
 
         # ---- absolute time origin: every job starts its own PT at its t_start (ACE: ta)
@@ -678,14 +698,14 @@ class Engine:
         b.n_snap_slots = part["n_slots"]
         b.out_elems, b.out = out_elems, out.ctypes.data
         b.device_resident = 0
-        b.kernel = 0 if common["kernel"] == "dmma" else 1
+        b.kernel = KERNELS[common["kernel"]]
         b.cluster = C
         return _Plan(batch=b, keep=[seqs, entries, trajs, tile_traj, mats, rho0, snap_steps, packed, out],
                      out=out, out_off=np.asarray(out_off_of_traj), n_rows=trajs["n_steps"] + 1)
 
     # -------------------------------------------------------------- running
     def run_jobs(self, prob: Problem, pt: Optional[ProcessTensor], jobs: Sequence[Job], *,
-                 kernel: str = "dmma", t_eval: str = "half_mid", fork: bool = True,
+                 kernel: str = "auto", t_eval: str = "half_mid", fork: bool = True,
                  tile_T: Optional[int] = None, cluster: Optional[int] = None) -> List[np.ndarray]:
         """Propagate `jobs`; returns one ``[n_out, n_steps+1]`` complex array per job."""
         if pt is None:
@@ -726,6 +746,7 @@ class Engine:
             return
         step_ms, op_ms = self.last_timings()
         self.timing_log.append(dict(kind=kind, step_ms=step_ms, opbuild_ms=op_ms, NL=prob.NL, chi_pad=chi_pad,
+                                    kernel=int(plan.batch.kernel),
                                     n_traj=int(plan.batch.n_traj), tile_T=int(plan.batch.tile_T),
                                     cluster=int(plan.batch.cluster),
                                     n_tiles=int(plan.batch.n_tiles),

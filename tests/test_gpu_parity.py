@@ -131,8 +131,7 @@ def _g2_jobs(prob, n_t=6, dt=0.25, tau_max=3.0, opA="|3><1|_4", opC="|1><3|_4", 
     return jobs
 
 
-@pytest.mark.parametrize("cluster", [2, 4])
-@pytest.mark.parametrize("tile_T", [1, 2, 4])
+@pytest.mark.parametrize("cluster,tile_T", [(2, 1), (2, 2), (2, 4), (4, 1), (4, 2), (4, 4), (8, 1), (8, 2)])
 def test_cluster_biexciton_fork_and_tails(engine, cluster, tile_T):
     """Tile shared by a cluster of CTAs: forked G2-style batch (trunk with snapshots + branches)."""
     prob = biexciton_problem(outputs=["|1><1|_4", "(|3><1|_4*|1><1|_4*|1><3|_4)", "|0><3|_4"])
@@ -176,7 +175,37 @@ def test_planner_picks_clusters_for_small_batches(engine):
     t_max = engine.max_tile(prob.NL, 128)
     T, C = engine._tile_and_cluster(prob, pt, 256, t_max)
     assert (T, C) == (4, 2)
-    assert engine._tile_and_cluster(prob, pt, 1, t_max) == (1, 4)
+    assert engine._tile_and_cluster(prob, pt, 1, t_max) == (1, 8)
     tls = tls_problem()
     ptt = synthetic_pt(128, len(tls.cls_keys), kind="unitary", scale=0.999)
     assert engine._tile_and_cluster(tls, ptt, 4096, engine.max_tile(4, 128)) == (16, 1)
+
+
+# ------------------------------------------------------------------ step-synchronous streaming kernel
+def test_stream_kernel_biexciton_fork_tails_and_sixlevel(engine):
+    prob = biexciton_problem(outputs=["|1><1|_4", "(|3><1|_4*|1><1|_4*|1><3|_4)", "|0><3|_4"])
+    pt = synthetic_pt(40, len(prob.cls_keys), n_slices=2, kind="unitary", scale=0.999)
+    jobs = _g2_jobs(prob)
+    _compare(engine, prob, pt, jobs, "stream")
+    tails = engine.run_jobs(prob, pt, _g2_jobs(prob, tail=5), kernel="stream")
+    full = engine.run_jobs(prob, pt, jobs, kernel="dmma")
+    assert max(np.abs(f[:, -5:] - t).max() for f, t in zip(full, tails)) < 1e-12
+    _compare(engine, prob, pt, jobs, "stream", fork=False)
+    six = sixls_problem()
+    pt6 = synthetic_pt(24, len(six.cls_keys), kind="unitary", scale=0.999)
+    p6 = ChirpedPulse(tau_0=1.0, e_start=-1.0, alpha=0, t0=2.0, e0=3.0, polar_x=0.7)
+    jobs6 = [Job(0.0, 3.0, 0.1, tables=make_tables([p6], 0.0, 3.0, 0.1)) for _ in range(3)]
+    _compare(engine, six, pt6, jobs6, "stream")
+    pt128 = synthetic_pt(128, len(prob.cls_keys), kind="unitary", scale=0.999)
+    _compare(engine, prob, pt128, _g2_jobs(prob, n_t=8, tau_max=2.0), "stream")
+
+
+def test_stream_kernel_tls_growing_pt_ragged_and_sweep(engine):
+    prob = tls_problem()
+    pt = synthetic_growing_pt(24, len(prob.cls_keys), n_initial=5, n_repeat=3)
+    p = ChirpedPulse(tau_0=1, e_start=0.5, alpha=0, t0=3, e0=2)
+    jobs = [Job(0.0, te, 0.1, tables=make_tables([p], 0.0, te, 0.1)) for te in (0.0, 0.1, 0.3, 1.0, 2.7, 5.0)]
+    _compare(engine, prob, pt, jobs, "stream")
+    pt2 = synthetic_pt(64, len(prob.cls_keys), n_slices=2, kind="unitary", scale=0.999)
+    _compare(engine, prob, pt2, sweep_jobs(9, 9, t_end=3.0), "stream")
+    _compare(engine, tls_problem(phonons=False), trivial_pt(4), jobs[:3], "stream")
