@@ -9,8 +9,8 @@ component out as its own thread-pool loop; here they are instances of two sweep 
 sweep -- for the triangular ones all ``n(n+1)/2`` trajectories -- is issued as GPU batches in
 which trajectories sharing a prefix are forked from one trunk.
 
-The time-local dynamical-map fast path (``calc_densitymatrix_tl`` ``:100-181``) lives in
-:mod:`pyaceqd_b200.timebin.timebin_tl`.
+The time-local dynamical-map fast path (``calc_densitymatrix_tl`` ``:100-181``) is the mixin
+:class:`pyaceqd_b200.timebin.twophoton_tl.TimeLocalTimebin` on top of the chain kernel.
 """
 from __future__ import annotations
 
@@ -19,6 +19,7 @@ import numpy as np
 import pyaceqd_b200.constants as constants
 from pyaceqd_b200.sweeps import at_time, run_sweep, tail_series
 from pyaceqd_b200.timebin.timebin import TimeBin
+from pyaceqd_b200.timebin.twophoton_tl import TimeLocalTimebin
 from pyaceqd_b200.tools import concurrence, construct_t, simple_t_gaussian
 
 temp_dir = constants.temp_dir
@@ -37,7 +38,7 @@ def _R(op):
     return {"operator": op, "applyFrom": "_right", "applyBefore": "false"}
 
 
-class TwoPhotonTimebinNew(TimeBin):
+class TwoPhotonTimebinNew(TimeLocalTimebin, TimeBin):
     def __init__(self, system, sigma_x, sigma_xdag, sigma_b, sigma_bdag, *pulses, dt=0.02, dim=5, tb=800,
                  dt_small=0.1, n_tbig=10, dt_exp=None, simple_exp=True, gaussian_t=None, verbose=False, workers=15,
                  simple_t=False, options={}) -> None:

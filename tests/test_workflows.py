@@ -137,7 +137,26 @@ def scenario_tl_correlations(tmp):
     return {"tau": tau, "g1_tl": g1_tl, "g2_tl": g2_tl, "g2_f": g2_f, "g1": g1, "g2": g2, "g2_stat": g2_stat}
 
 
-SCENARIOS = {"tl_corr": scenario_tl_correlations, "dynmap": scenario_dynmap, "purity": scenario_purity, "g1": scenario_g1, "polent": scenario_polent, "timebin": scenario_timebin,
+def scenario_timebin_tl(tmp):
+    """Time-local route of the time-bin density matrix next to the direct (multi-time-operator) route."""
+    from pyaceqd_b200.four_level_system.linear import biexciton
+    from pyaceqd_b200.timebin.twophoton_new import TwoPhotonTimebinNew
+    tb = 4.0
+    p1 = ChirpedPulse(tau_0=0.25, e_start=-2.0, alpha=0, t0=1.5, e0=4.0)
+    p2 = ChirpedPulse(tau_0=0.25, e_start=-2.0, alpha=0, t0=1.5 + tb, e0=4.0)
+    opts = {"lindblad": True, "gamma_e": 0.5, "delta_b": 4.0, "phonons": False, "temp_dir": tmp, "initial": "|0><0|_4"}
+    tbn = TwoPhotonTimebinNew(biexciton, "|0><1|_4", "|1><0|_4", "|1><3|_4", "|3><1|_4", p1, p2, dt=0.25, dim=4, tb=tb,
+                              dt_small=0.5, n_tbig=2, simple_exp=False, gaussian_t=3.0, simple_t=True, options=opts)
+    conc_tl, rho_tl, _ = tbn.calc_densitymatrix_tl(reduced=True)
+    _, _, eell_4, grid_4 = tbn.eell_tl_f()
+    _, _, eell_8, grid_8 = tbn.eell_tl_8ops()
+    _, _, _, d00, g1, g2, _ = tbn.rho_ee_ee(use_second_zero=True)
+    _, _, d03, _, _, _ = tbn.rho_ee_ll(use_second_zero=True)
+    return {"rho_tl": rho_tl, "conc_tl": conc_tl, "eell_4": eell_4, "eell_8": eell_8, "grid_4": grid_4, "grid_8": grid_8,
+            "direct_00": d00, "direct_03": d03}
+
+
+SCENARIOS = {"timebin_tl": scenario_timebin_tl, "tl_corr": scenario_tl_correlations, "dynmap": scenario_dynmap, "purity": scenario_purity, "g1": scenario_g1, "polent": scenario_polent, "timebin": scenario_timebin,
              "onephoton": scenario_onephoton, "rabi": scenario_rabi}
 
 
@@ -235,6 +254,19 @@ def test_dynmap_acts_on_arbitrary_states(tmp_path):
     assert np.abs(out["via_map"][:, 3] - out["direct"][2][1:]).max() < 1e-12
     assert np.abs(out["via_map"][:, 2] - out["direct"][3][1:]).max() < 1e-12
     assert np.linalg.matrix_rank(out["E"][5]) == 4
+
+
+def test_timebin_time_local_route(tmp_path):
+    out, _ = _run_oracle("timebin_tl", tmp_path)
+    rho = out["rho_tl"]
+    assert np.abs(rho - rho.conj().T).max() < 1e-14 and np.all(np.diag(rho).real > 0)
+    assert 0.0 <= out["conc_tl"] <= 1.0 + 1e-12
+    # four-operator and eight-operator chain programs describe the same element
+    assert np.abs(out["grid_4"] - out["grid_8"]).max() < 1e-12 and abs(out["eell_4"] - out["eell_8"]) < 1e-13
+    # and agree with the direct multi-time-operator route (first time ordering) up to the quadrature:
+    # the direct route integrates t2 on the simulation grid, the map route on the coarse t1 grid
+    assert abs(rho[0, 0] - out["direct_00"]) < 5e-2 * abs(out["direct_00"])
+    assert abs(rho[0, 3] - out["direct_03"]) < 5e-2 * abs(out["direct_03"]) + 1e-6
 
 
 def test_tl_correlations_equal_direct_sweeps(tmp_path):
