@@ -156,7 +156,25 @@ def scenario_timebin_tl(tmp):
             "direct_00": d00, "direct_03": d03}
 
 
-SCENARIOS = {"timebin_tl": scenario_timebin_tl, "tl_corr": scenario_tl_correlations, "dynmap": scenario_dynmap, "purity": scenario_purity, "g1": scenario_g1, "polent": scenario_polent, "timebin": scenario_timebin,
+def scenario_adapters(tmp):
+    """Remaining system adapters: sensors / cavities around the two-level emitter, 3- and 4-level dark models."""
+    from pyaceqd_b200.four_level_system.dark_model import darkmodel
+    from pyaceqd_b200.two_level_system.reduced_dark import darkmodel as darkmodel3
+    from pyaceqd_b200.two_level_system.tls import tls, tls_one_sensor, tls_photon, tls_photons, tls_two_sensor
+    p = ChirpedPulse(tau_0=0.5, e_start=0, alpha=0, t0=2.0, e0=1.0, polar_x=0.8)
+    kw = dict(dt=0.1, lindblad=True, gamma_e=0.2, temp_dir=tmp)
+    return {"tls": tls(0, 5, p, **kw)[2],
+            "one": tls_one_sensor(0, 5, p, epsilon=1e-6, **kw)[2],
+            "two": tls_two_sensor(0, 5, p, epsilon=0.05, linewidth1=0.5, delta_s2=0.3,
+                                  output_ops=["|1><1|_2 otimes Id_2 otimes Id_2", "Id_2 otimes |1><1|_2 otimes Id_2",
+                                              "Id_2 otimes Id_2 otimes |1><1|_2"], **kw),
+            "cav": tls_photon(0, 5, p, n_phot1=2, cav_coupl1=0.4, delta_cx1=0.0, cav_loss1=0.3,
+                              output_ops=["|1><1|_2 otimes Id_3", "Id_2 otimes n_3"], **kw),
+            "cav2": tls_photons(0, 5, p, n_phot1=1, n_phot2=1, cav_coupl1=0.3, delta_cx1=0, delta_cx2=0.5, **kw),
+            "dark4": darkmodel(0, 5, p, delta_xd=0.5, **kw), "dark3": darkmodel3(0, 5, p, delta_xd=0.5, **kw)}
+
+
+SCENARIOS = {"adapters": scenario_adapters, "timebin_tl": scenario_timebin_tl, "tl_corr": scenario_tl_correlations, "dynmap": scenario_dynmap, "purity": scenario_purity, "g1": scenario_g1, "polent": scenario_polent, "timebin": scenario_timebin,
              "onephoton": scenario_onephoton, "rabi": scenario_rabi}
 
 
@@ -254,6 +272,23 @@ def test_dynmap_acts_on_arbitrary_states(tmp_path):
     assert np.abs(out["via_map"][:, 3] - out["direct"][2][1:]).max() < 1e-12
     assert np.abs(out["via_map"][:, 2] - out["direct"][3][1:]).max() < 1e-12
     assert np.linalg.matrix_rank(out["E"][5]) == 4
+
+
+def test_composite_and_dark_adapters(tmp_path):
+    out, _ = _run_oracle("adapters", tmp_path)
+    assert np.abs(out["one"] - out["tls"]).max() < 1e-9            # a sensor coupled with epsilon -> 0 does not act back
+    x, s1, s2 = out["two"][1].real, out["two"][2].real, out["two"][3].real
+    assert s1.max() > 1e-4 and s2.max() > 1e-5 and s1.max() < 0.05 * x.max()       # sensors pick up a little signal
+    assert out["cav"][2].real.max() > 0.05 and np.abs(out["cav"][1].real).max() <= 1 + 1e-9   # photons appear
+    assert out["cav2"].shape[0] == 3
+    for key, n in (("dark4", 4), ("dark3", 3)):
+        pops = out[key][1:1 + n].real
+        assert np.abs(pops.sum(axis=0) - 1).max() < 1e-10 and pops.min() > -1e-12          # trace, positivity
+    from pyaceqd_b200.two_level_system.tls import tls_photon_sensor, tls_photon_two_sensor
+    with pytest.raises(ValueError):
+        tls_photon_sensor(0, 1, ChirpedPulse(tau_0=0.5, e_start=0, alpha=0, t0=2.0, e0=1.0), n_phot1=2)
+    with pytest.raises(ValueError):
+        tls_photon_two_sensor(0, 1)
 
 
 def test_timebin_time_local_route(tmp_path):
