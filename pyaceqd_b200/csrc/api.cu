@@ -58,7 +58,7 @@ struct aceqd_ctx {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // step, opbuild, tlmap start/stop
     bool have_step = false, have_op = false, have_tl = false;
     DevBuf W, OV, tables, seqs, seq_base, entries, mto, rho0s, trajs, tiles, snap_steps, snaps,
-        out, passes, scratch, misc, st_x, st_order, st_bar, st_apos, tl_pool, tl_v0, tl_segoff, tl_segs, tl_w, tl_out, tl_final;
+        out, passes, scratch, misc, opscratch, st_x, st_order, st_bar, st_apos, tl_pool, tl_v0, tl_segoff, tl_segs, tl_w, tl_out, tl_final;
     // layout of the operators currently in the workspace
     long long n_seq_entries = 0;
 };
@@ -126,7 +126,7 @@ void aceqd_ctx_destroy(aceqd_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->W, &c->OV, &c->tables, &c->seqs, &c->seq_base, &c->entries, &c->mto,
                       &c->rho0s, &c->trajs, &c->tiles, &c->snap_steps, &c->snaps, &c->out,
-                      &c->passes, &c->scratch, &c->misc, &c->st_x, &c->st_order, &c->st_bar, &c->st_apos, &c->tl_pool, &c->tl_v0, &c->tl_segoff,
+                      &c->passes, &c->scratch, &c->misc, &c->opscratch, &c->st_x, &c->st_order, &c->st_bar, &c->st_apos, &c->tl_pool, &c->tl_v0, &c->tl_segoff,
                       &c->tl_segs, &c->tl_w, &c->tl_out, &c->tl_final})
         b->release();
     for (auto& ev : c->ev)
@@ -439,6 +439,15 @@ int aceqd_build_operators(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_b
     op.mto_mats = (const double*)c->mto.p;
     op.W = (double*)c->W.p;
     op.OV = (double*)c->OV.p;
+    {
+        int ctas = 0;
+        const size_t need = opbuild_scratch_bytes(pd.NL, &ctas);
+        if (need) {
+            if ((rc = c->opscratch.reserve(need))) return rc;
+            op.scratch = (double*)c->opscratch.p;
+            op.scratch_ctas = ctas;
+        }
+    }
     ACEQD_CUDA(cudaEventRecord(c->ev[2], c->stream));
     if ((rc = launch_opbuild(op, c->stream, &c->launches))) return rc;
     ACEQD_CUDA(cudaEventRecord(c->ev[3], c->stream));
@@ -773,7 +782,16 @@ int aceqd_expm_batch(aceqd_ctx* c, int n, int count, const double* a_host, doubl
     double* a_dev = (double*)c->misc.p;
     double* o_dev = (double*)((char*)c->misc.p + (bytes + 15) / 16 * 16);
     ACEQD_CUDA(cudaMemcpyAsync(a_dev, a_host, bytes, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = launch_expm_batch(n, count, a_dev, o_dev, c->stream, &c->launches))) return rc;
+    double* scratch = nullptr;
+    {
+        int ctas = 0;
+        const size_t need = opbuild_scratch_bytes(n, &ctas);   // sized for the larger operator-builder footprint
+        if (need) {
+            if ((rc = c->opscratch.reserve(need))) return rc;
+            scratch = (double*)c->opscratch.p;
+        }
+    }
+    if ((rc = launch_expm_batch(n, count, a_dev, o_dev, scratch, c->stream, &c->launches))) return rc;
     ACEQD_CUDA(cudaMemcpyAsync(out_host, o_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
     ACEQD_CUDA(cudaStreamSynchronize(c->stream));
     return ACEQD_OK;

@@ -135,11 +135,15 @@ struct OpBuildParams {
     const double* mto_mats;
     double* W;
     double* OV;
+    double* scratch;             // global workspace for NL too large for shared memory (else null)
+    int scratch_ctas;            // CTAs the workspace was sized for
 };
 
+// bytes of global workspace the operator builder / expm kernel need for this NL (0: shared memory suffices)
+size_t opbuild_scratch_bytes(int NL, int* ctas);
 int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches);
-int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, cudaStream_t s,
-                      long long* launches);
+int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, double* scratch,
+                      cudaStream_t s, long long* launches);
 int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, long long* launches);
 int launch_step_check(const StepParams& p, double* scratch, cudaStream_t s, long long* launches);
 size_t step_smem_bytes(int NL, int chi_pad, int T, int stages, int wov_doubles, int wbufs);

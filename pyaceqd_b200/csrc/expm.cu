@@ -12,6 +12,8 @@
 // X = W_n * Y, where Y is the bond state right after the previous PT slice.
 //
 // One thread group (32..256 threads) owns one entry; matrices live in shared memory.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace aceqd {
@@ -180,7 +182,9 @@ __global__ void __launch_bounds__(256) k_opbuild(OpBuildParams p) {
     const int groups = blockDim.x / G;
     const int gid = threadIdx.x / G, tid = threadIdx.x - gid * G;
     const size_t per_group = (size_t)(EXPM_BUFS + 2) * n2 + MAX_NL;  // expm buffers, V, X + scratch
-    double2* A = sm + gid * per_group;
+    // large Liouville spaces (NL > ~40): the work matrices live in a per-CTA slab of global memory
+    double2* base = p.scratch ? reinterpret_cast<double2*>(p.scratch) + (size_t)blockIdx.x * groups * per_group : sm;
+    double2* A = base + gid * per_group;
     double2* V = A + (size_t)EXPM_BUFS * n2;
     double2* X = V + n2;
     double* red = reinterpret_cast<double*>(X + n2);
@@ -263,13 +267,14 @@ __global__ void __launch_bounds__(256) k_opbuild(OpBuildParams p) {
 
 template <int G>
 __global__ void __launch_bounds__(256) k_expm_batch(int n, int count, const double* a,
-                                                    double* out) {
+                                                    double* out, double* scratch) {
     extern __shared__ double2 sm[];
     const int n2 = n * n;
     const int groups = blockDim.x / G;
     const int gid = threadIdx.x / G, tid = threadIdx.x - gid * G;
     const size_t per_group = (size_t)EXPM_BUFS * n2 + MAX_NL;
-    double2* A = sm + gid * per_group;
+    double2* base = scratch ? reinterpret_cast<double2*>(scratch) + (size_t)blockIdx.x * groups * per_group : sm;
+    double2* A = base + gid * per_group;
     double* red = reinterpret_cast<double*>(A + (size_t)EXPM_BUFS * n2);
     for (int e = blockIdx.x * groups + gid; e < count; e += gridDim.x * groups) {
         const double2* src = reinterpret_cast<const double2*>(a) + (size_t)e * n2;
@@ -300,6 +305,15 @@ int set_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
+constexpr int SCRATCH_CTAS = 296;   // two CTAs per SM when the work matrices live in global memory
+
+size_t opbuild_scratch_bytes(int NL, int* ctas) {
+    const int groups = 256 / pick_group(NL);
+    const size_t per_cta = groups * ((size_t)(EXPM_BUFS + 2) * NL * NL + MAX_NL) * sizeof(double2);
+    if (ctas) *ctas = SCRATCH_CTAS;
+    return per_cta > (size_t)SMEM_BUDGET ? per_cta * SCRATCH_CTAS : 0;
+}
+
 int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches) {
     const long long total = p.n_seq_entries + p.n_entries;
     if (total <= 0) return ACEQD_OK;
@@ -310,13 +324,17 @@ int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches) 
     }
     const int G = pick_group(n);
     const int groups = 256 / G;
-    const size_t smem = groups * ((size_t)(EXPM_BUFS + 2) * n * n + MAX_NL) * sizeof(double2);
-    if (smem > (size_t)SMEM_BUDGET) {
-        set_error("operator builder: NL=%d needs %zu B shared memory", n, smem);
-        return ACEQD_ERR_CAPACITY;
-    }
+    size_t smem = groups * ((size_t)(EXPM_BUFS + 2) * n * n + MAX_NL) * sizeof(double2);
     long long blocks = (total + groups - 1) / groups;
     if (blocks > 148LL * 64) blocks = 148LL * 64;
+    if (smem > (size_t)SMEM_BUDGET) {
+        if (!p.scratch || p.scratch_ctas <= 0) {
+            set_error("operator builder: NL=%d needs %zu B of work matrices and no global workspace was given", n, smem);
+            return ACEQD_ERR_CAPACITY;
+        }
+        smem = 0;
+        blocks = std::min<long long>(blocks, p.scratch_ctas);
+    }
     int rc = ACEQD_OK;
     switch (G) {
         case 16:
@@ -345,8 +363,8 @@ int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches) 
     return ACEQD_OK;
 }
 
-int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, cudaStream_t s,
-                      long long* launches) {
+int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, double* scratch,
+                      cudaStream_t s, long long* launches) {
     if (count <= 0) return ACEQD_OK;
     if (n > MAX_NL) {
         set_error("n=%d exceeds MAX_NL=%d", n, MAX_NL);
@@ -354,30 +372,40 @@ int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, cu
     }
     const int G = pick_group(n);
     const int groups = 256 / G;
-    const size_t smem = groups * ((size_t)EXPM_BUFS * n * n + MAX_NL) * sizeof(double2);
+    size_t smem = groups * ((size_t)EXPM_BUFS * n * n + MAX_NL) * sizeof(double2);
     int blocks = (count + groups - 1) / groups;
     if (blocks > 148 * 64) blocks = 148 * 64;
+    if (smem > (size_t)SMEM_BUDGET) {
+        if (!scratch) {
+            set_error("expm: n=%d needs a global workspace", n);
+            return ACEQD_ERR_CAPACITY;
+        }
+        smem = 0;
+        blocks = std::min(blocks, SCRATCH_CTAS);
+    } else {
+        scratch = nullptr;
+    }
     int rc = ACEQD_OK;
     switch (G) {
         case 16:
             if ((rc = set_smem(k_expm_batch<16>, smem))) return rc;
-            k_expm_batch<16><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev);
+            k_expm_batch<16><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev, scratch);
             break;
         case 32:
             if ((rc = set_smem(k_expm_batch<32>, smem))) return rc;
-            k_expm_batch<32><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev);
+            k_expm_batch<32><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev, scratch);
             break;
         case 64:
             if ((rc = set_smem(k_expm_batch<64>, smem))) return rc;
-            k_expm_batch<64><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev);
+            k_expm_batch<64><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev, scratch);
             break;
         case 128:
             if ((rc = set_smem(k_expm_batch<128>, smem))) return rc;
-            k_expm_batch<128><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev);
+            k_expm_batch<128><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev, scratch);
             break;
         default:
             if ((rc = set_smem(k_expm_batch<256>, smem))) return rc;
-            k_expm_batch<256><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev);
+            k_expm_batch<256><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev, scratch);
             break;
     }
     ++*launches;

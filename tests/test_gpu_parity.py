@@ -29,7 +29,7 @@ def test_dmma_fragment_layout_via_expm(engine):
     """Device expm (Taylor scaling-and-squaring) vs scipy Pade."""
     from scipy.linalg import expm
     rng = np.random.default_rng(0)
-    for n in (4, 9, 16, 25, 36):
+    for n in (4, 9, 16, 25, 36, 49, 64):
         a = (rng.standard_normal((7, n, n)) + 1j * rng.standard_normal((7, n, n))) * rng.uniform(0.01, 3.0, (7, 1, 1))
         got = engine.expm(a)
         for i in range(7):
