@@ -54,6 +54,8 @@ struct aceqd_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;   // device->host copy of finished waves while later waves run
+    cudaEvent_t ev_wave = nullptr;
     long long launches = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // step, opbuild, tlmap start/stop
     bool have_step = false, have_op = false, have_tl = false;
@@ -131,6 +133,8 @@ void aceqd_ctx_destroy(aceqd_ctx* c) {
         b->release();
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
+    if (c->ev_wave) cudaEventDestroy(c->ev_wave);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -739,7 +743,51 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
         sp.passes = (const PassDesc*)c->passes.p;
         sp.tile_traj = (const int*)c->tiles.p;
         const size_t smem = step_smem_bytes(pd.NL, chi_pad, T, stages, wov, wbufs);
+        // End-to-end path with more tiles than SMs: the persistent CTAs run in waves.  Launch the full
+        // waves and the last wave separately and copy the finished waves' outputs to the host while the
+        // last wave computes (needs their output ranges to be disjoint and ordered, as in a sweep).
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
+        long long split_elems = 0;
+        int n_a = 0;
+        if (!b->device_resident && cluster == 1 && b->n_tiles > n_sm) {
+            n_a = (b->n_tiles - 1) / n_sm * n_sm;
+            long long max_a = 0, min_b = b->out_elems;
+            for (long long i = 0; i < (long long)b->n_tiles * T; ++i) {
+                const int idx = b->tile_traj[i];
+                if (idx < 0) continue;
+                const aceqd_traj& t = b->trajs[idx];
+                const long long lo = t.out_off, hi = lo + (long long)(t.n_steps + 1 - t.out_from) * pd.n_out;
+                if (i < (long long)n_a * T) max_a = std::max(max_a, hi);
+                else min_b = std::min(min_b, lo);
+            }
+            if (max_a > 0 && max_a <= min_b) split_elems = max_a;
+        }
         ACEQD_CUDA(cudaEventRecord(c->ev[0], c->stream));
+        if (split_elems > 0) {
+            if (!c->copy_stream) {
+                ACEQD_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+                ACEQD_CUDA(cudaEventCreateWithFlags(&c->ev_wave, cudaEventDisableTiming));
+            }
+            StepParams sa = sp, sb2 = sp;
+            sa.n_tiles = n_a;
+            sb2.n_tiles = b->n_tiles - n_a;
+            sb2.tile_traj = sp.tile_traj + (size_t)n_a * T;
+            if ((rc = launch_step_dmma(sa, smem, c->stream, &c->launches))) return rc;
+            ACEQD_CUDA(cudaEventRecord(c->ev_wave, c->stream));
+            if ((rc = launch_step_dmma(sb2, smem, c->stream, &c->launches))) return rc;
+            ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
+            ACEQD_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_wave, 0));
+            ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)split_elems * 16, cudaMemcpyDeviceToHost,
+                                       c->copy_stream));
+            ACEQD_CUDA(cudaMemcpyAsync(b->out + 2 * split_elems, out_dev + 2 * split_elems,
+                                       (size_t)(b->out_elems - split_elems) * 16, cudaMemcpyDeviceToHost,
+                                       c->stream));
+            c->have_step = true;
+            ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+            ACEQD_CUDA(cudaStreamSynchronize(c->copy_stream));
+            return ACEQD_OK;
+        }
         if ((rc = launch_step_dmma(sp, smem, c->stream, &c->launches))) return rc;
         ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
     }

@@ -209,3 +209,16 @@ def test_stream_kernel_tls_growing_pt_ragged_and_sweep(engine):
     pt2 = synthetic_pt(64, len(prob.cls_keys), n_slices=2, kind="unitary", scale=0.999)
     _compare(engine, prob, pt2, sweep_jobs(9, 9, t_end=3.0), "stream")
     _compare(engine, tls_problem(phonons=False), trivial_pt(4), jobs[:3], "stream")
+
+
+def test_wave_split_copy_overlap_path(engine):
+    """More tiles than SMs through host buffers: full waves and the last wave are separate launches and the
+    finished waves' outputs are copied while the last wave runs -- results must not depend on it."""
+    prob = tls_problem()
+    pt = synthetic_pt(8, len(prob.cls_keys), kind="unitary", scale=0.999)
+    jobs = sweep_jobs(20, 30, t_end=2.0)                          # 600 trajectories
+    split = engine.run_jobs(prob, pt, jobs, kernel="dmma", tile_T=2)      # 300 tiles > 148 SMs
+    whole = engine.run_jobs(prob, pt, jobs, kernel="dmma", tile_T=16)     # 38 tiles: single launch
+    assert max(np.abs(a - b).max() for a, b in zip(split, whole)) < 1e-12
+    for k in (0, 147 * 2, 148 * 2, 599):                          # around the wave boundary
+        assert np.abs(split[k] - oracle.propagate(prob, pt, jobs[k])).max() < TOL
