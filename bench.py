@@ -335,7 +335,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # a real (non-default) stream: handle 0 would make the library create its own stream and the
     # torch events below would not see the kernels
-    stream = torch.cuda.Stream()
+    # high priority: the library builds the later waves' operators on a low-priority side stream that
+    # should only fill the SMs the first (partial) wave of persistent CTAs leaves idle
+    stream = torch.cuda.Stream(priority=-1)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     eng = Engine(local, stream=stream.cuda_stream)

@@ -56,6 +56,12 @@ struct aceqd_ctx {
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;   // device->host copy of finished waves while later waves run
     cudaEvent_t ev_wave = nullptr;
+    cudaStream_t build_stream = nullptr;  // low priority: operators of the later waves, built on the SMs the
+    cudaEvent_t ev_built = nullptr;       // first (partial) wave leaves idle
+    // wave split decided by aceqd_propagate_batch for the current batch (0 = none)
+    int split_tiles = 0;
+    long long split_entries = 0, split_out = 0;
+    bool split_ops_pending = false;
     long long launches = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // step, opbuild, tlmap start/stop
     bool have_step = false, have_op = false, have_tl = false;
@@ -114,7 +120,10 @@ int aceqd_ctx_create(int device, void* stream, aceqd_ctx** out) {
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {
-        ACEQD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        // high priority: the side stream that builds later waves' operators must only fill idle SMs
+        int least = 0, greatest = 0;
+        ACEQD_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        ACEQD_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, greatest));
         c->own_stream = true;
     }
     for (auto& ev : c->ev) ACEQD_CUDA(cudaEventCreate(&ev));
@@ -135,6 +144,8 @@ void aceqd_ctx_destroy(aceqd_ctx* c) {
         if (ev) cudaEventDestroy(ev);
     if (c->ev_wave) cudaEventDestroy(c->ev_wave);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_built) cudaEventDestroy(c->ev_built);
+    if (c->build_stream) cudaStreamDestroy(c->build_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -453,6 +464,32 @@ int aceqd_build_operators(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_b
         }
     }
     ACEQD_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    c->split_ops_pending = false;
+    if (c->split_entries > 0 && c->split_entries < n_ent && b->n_entries == 0) {
+        // operators of the first (partial) wave now; those of the later waves on a low-priority stream
+        // that fills the SMs the first wave leaves idle (aceqd_run_steps waits for them before wave 2)
+        if (!c->build_stream) {
+            int lo_prio = 0, hi_prio = 0;
+            ACEQD_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+            ACEQD_CUDA(cudaStreamCreateWithPriority(&c->build_stream, cudaStreamNonBlocking, lo_prio));
+            ACEQD_CUDA(cudaEventCreateWithFlags(&c->ev_built, cudaEventDisableTiming));
+        }
+        OpBuildParams first = op, rest = op;
+        first.e_begin = 0;
+        first.e_end = c->split_entries;
+        rest.e_begin = c->split_entries;
+        rest.e_end = n_ent;
+        if ((rc = launch_opbuild(first, c->stream, &c->launches))) return rc;
+        ACEQD_CUDA(cudaEventRecord(c->ev[3], c->stream));
+        // the uploads above were enqueued on the main stream: order the side stream after them
+        ACEQD_CUDA(cudaEventRecord(c->ev_built, c->stream));
+        ACEQD_CUDA(cudaStreamWaitEvent(c->build_stream, c->ev_built, 0));
+        if ((rc = launch_opbuild(rest, c->build_stream, &c->launches))) return rc;
+        ACEQD_CUDA(cudaEventRecord(c->ev_built, c->build_stream));
+        c->split_ops_pending = true;
+        c->have_op = true;
+        return ACEQD_OK;
+    }
     if ((rc = launch_opbuild(op, c->stream, &c->launches))) return rc;
     ACEQD_CUDA(cudaEventRecord(c->ev[3], c->stream));
     c->have_op = true;
@@ -743,50 +780,55 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
         sp.passes = (const PassDesc*)c->passes.p;
         sp.tile_traj = (const int*)c->tiles.p;
         const size_t smem = step_smem_bytes(pd.NL, chi_pad, T, stages, wov, wbufs);
-        // End-to-end path with more tiles than SMs: the persistent CTAs run in waves.  Launch the full
-        // waves and the last wave separately and copy the finished waves' outputs to the host while the
-        // last wave computes (needs their output ranges to be disjoint and ordered, as in a sweep).
-        int n_sm = 148;
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
-        long long split_elems = 0;
-        int n_a = 0;
-        if (!b->device_resident && cluster == 1 && b->n_tiles > n_sm) {
-            n_a = (b->n_tiles - 1) / n_sm * n_sm;
-            long long max_a = 0, min_b = b->out_elems;
-            for (long long i = 0; i < (long long)b->n_tiles * T; ++i) {
-                const int idx = b->tile_traj[i];
-                if (idx < 0) continue;
-                const aceqd_traj& t = b->trajs[idx];
-                const long long lo = t.out_off, hi = lo + (long long)(t.n_steps + 1 - t.out_from) * pd.n_out;
-                if (i < (long long)n_a * T) max_a = std::max(max_a, hi);
-                else min_b = std::min(min_b, lo);
-            }
-            if (max_a > 0 && max_a <= min_b) split_elems = max_a;
-        }
+        // More tiles than SMs: the persistent CTAs run in waves.  aceqd_propagate_batch may have planned a
+        // split (first the partial wave, then the full waves): the later waves' operators are built on a
+        // side stream meanwhile, and on the end-to-end path the first wave's outputs are copied to the
+        // host while the later waves compute.
         ACEQD_CUDA(cudaEventRecord(c->ev[0], c->stream));
-        if (split_elems > 0) {
-            if (!c->copy_stream) {
-                ACEQD_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-                ACEQD_CUDA(cudaEventCreateWithFlags(&c->ev_wave, cudaEventDisableTiming));
-            }
+        if (c->split_tiles > 0 && c->split_tiles < b->n_tiles && cluster == 1) {
+            const int n_a = c->split_tiles;
             StepParams sa = sp, sb2 = sp;
             sa.n_tiles = n_a;
             sb2.n_tiles = b->n_tiles - n_a;
             sb2.tile_traj = sp.tile_traj + (size_t)n_a * T;
             if ((rc = launch_step_dmma(sa, smem, c->stream, &c->launches))) return rc;
-            ACEQD_CUDA(cudaEventRecord(c->ev_wave, c->stream));
+            if (c->split_ops_pending) {
+                ACEQD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_built, 0));
+                c->split_ops_pending = false;
+            }
+            const bool copy_early = !b->device_resident && c->split_out > 0;
+            if (copy_early) {
+                if (!c->copy_stream) {
+                    ACEQD_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+                    ACEQD_CUDA(cudaEventCreateWithFlags(&c->ev_wave, cudaEventDisableTiming));
+                }
+                ACEQD_CUDA(cudaEventRecord(c->ev_wave, c->stream));
+            }
             if ((rc = launch_step_dmma(sb2, smem, c->stream, &c->launches))) return rc;
             ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
-            ACEQD_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_wave, 0));
-            ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)split_elems * 16, cudaMemcpyDeviceToHost,
-                                       c->copy_stream));
-            ACEQD_CUDA(cudaMemcpyAsync(b->out + 2 * split_elems, out_dev + 2 * split_elems,
-                                       (size_t)(b->out_elems - split_elems) * 16, cudaMemcpyDeviceToHost,
-                                       c->stream));
             c->have_step = true;
-            ACEQD_CUDA(cudaStreamSynchronize(c->stream));
-            ACEQD_CUDA(cudaStreamSynchronize(c->copy_stream));
+            c->split_tiles = 0;
+            if (copy_early) {
+                ACEQD_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_wave, 0));
+                ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)c->split_out * 16, cudaMemcpyDeviceToHost,
+                                           c->copy_stream));
+                ACEQD_CUDA(cudaMemcpyAsync(b->out + 2 * c->split_out, out_dev + 2 * c->split_out,
+                                           (size_t)(b->out_elems - c->split_out) * 16, cudaMemcpyDeviceToHost,
+                                           c->stream));
+                ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+                ACEQD_CUDA(cudaStreamSynchronize(c->copy_stream));
+                return ACEQD_OK;
+            }
+            if (!b->device_resident) {
+                ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)b->out_elems * 16, cudaMemcpyDeviceToHost,
+                                           c->stream));
+                ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+            }
             return ACEQD_OK;
+        }
+        if (c->split_ops_pending) {      // a planned split that this launch does not use: just order the streams
+            ACEQD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_built, 0));
+            c->split_ops_pending = false;
         }
         if ((rc = launch_step_dmma(sp, smem, c->stream, &c->launches))) return rc;
         ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
@@ -800,11 +842,57 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
     return ACEQD_OK;
 }
 
+// Decide whether the batch runs as "partial wave first, full waves after": needs more tiles than SMs, no
+// explicit (MTO) entries, and the first group's operator entries and output rows to lie entirely before the
+// second group's (true for sweeps, whose trajectories are tiled in order).
+static void plan_wave_split(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_batch* b) {
+    c->split_tiles = 0;
+    c->split_entries = c->split_out = 0;
+    if (!c || !prob || !b || b->kernel != 0 || b->cluster > 1 || b->n_entries != 0 || !b->tile_traj ||
+        b->tile_T < 1 || !b->trajs)
+        return;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
+    if (b->n_tiles <= n_sm) return;
+    const int T = b->tile_T;
+    const int n_a = b->n_tiles - (b->n_tiles - 1) / n_sm * n_sm;      // the partial wave goes first
+    if (n_a <= 0 || n_a >= b->n_tiles) return;
+    long long ent_a = 0, ent_b = -1, out_a = 0, out_b = -1;
+    for (long long i = 0; i < (long long)b->n_tiles * T; ++i) {
+        const int idx = b->tile_traj[i];
+        if (idx < 0 || idx >= b->n_traj) continue;
+        const aceqd_traj& t = b->trajs[idx];
+        if (t.n_ovr != 0 || t.n_steps < 0) return;
+        const long long e0 = t.ent0, e1 = t.ent0 + t.n_steps + 1;
+        const long long o0 = t.out_off, o1 = o0 + (long long)(t.n_steps + 1 - t.out_from) * prob->d.n_out;
+        if (i < (long long)n_a * T) {
+            ent_a = std::max(ent_a, e1);
+            out_a = std::max(out_a, o1);
+        } else {
+            ent_b = ent_b < 0 ? e0 : std::min(ent_b, e0);
+            out_b = out_b < 0 ? o0 : std::min(out_b, o0);
+        }
+    }
+    if (ent_b < 0 || ent_a > ent_b) return;
+    c->split_tiles = n_a;
+    c->split_entries = ent_a;
+    c->split_out = (out_b >= 0 && out_a <= out_b) ? out_a : 0;
+}
+
 int aceqd_propagate_batch(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
                           const aceqd_batch* b) {
+    if (c && check_batch(prob, b) == ACEQD_OK) plan_wave_split(c, prob, b);
     int rc = aceqd_build_operators(c, prob, b);
-    if (rc) return rc;
-    return aceqd_run_steps(c, prob, pt, b);
+    if (rc) {
+        if (c) c->split_tiles = 0;
+        return rc;
+    }
+    rc = aceqd_run_steps(c, prob, pt, b);
+    if (c) {
+        c->split_tiles = 0;
+        c->split_entries = 0;
+    }
+    return rc;
 }
 
 int aceqd_snapshot_read(aceqd_ctx* c, int slot, int NL, int chi_pad, double* host_out) {

@@ -137,6 +137,7 @@ struct OpBuildParams {
     double* OV;
     double* scratch;             // global workspace for NL too large for shared memory (else null)
     int scratch_ctas;            // CTAs the workspace was sized for
+    long long e_begin, e_end;    // entries built by this launch (0, 0 = all)
 };
 
 // bytes of global workspace the operator builder / expm kernel need for this NL (0: shared memory suffices)

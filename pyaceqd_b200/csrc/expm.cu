@@ -189,9 +189,9 @@ __global__ void __launch_bounds__(256) k_opbuild(OpBuildParams p) {
     double2* X = V + n2;
     double* red = reinterpret_cast<double*>(X + n2);
 
-    const long long total = p.n_seq_entries + p.n_entries;
+    const long long total = p.e_end > p.e_begin ? p.e_end : p.n_seq_entries + p.n_entries;
     const double half = 0.5 * p.dt;
-    for (long long e = (long long)blockIdx.x * groups + gid; e < total;
+    for (long long e = p.e_begin + (long long)blockIdx.x * groups + gid; e < total;
          e += (long long)gridDim.x * groups) {
         int set, step, sb = -1, sa = -1, has_prev;
         if (e < p.n_seq_entries) {
@@ -315,7 +315,7 @@ size_t opbuild_scratch_bytes(int NL, int* ctas) {
 }
 
 int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches) {
-    const long long total = p.n_seq_entries + p.n_entries;
+    const long long total = p.e_end > p.e_begin ? p.e_end - p.e_begin : p.n_seq_entries + p.n_entries;
     if (total <= 0) return ACEQD_OK;
     const int n = p.prob.NL;
     if (n > MAX_NL) {
