@@ -219,13 +219,14 @@ def system_ace_stream(t_start, t_end, *pulses, dt=0.01, phonons=False, t_mem=20.
         px_file, py_file, rf_out = pulse_file_x, pulse_file_y, rf_file
         if rf_op is not None and rf_file is None:
             rf, px, py = sample_rf(t, pulses, firstonly=firstonly)
-            rf_out = stem + "_rf.dat"
+            rf_out = temp_dir + "{}_rf_{}.dat".format(system_prefix, suffix)       # reference :77
             export_csv(rf_out, t, rf.real, rf.imag, precision=8, delimit=' ')
             px_file = None
         elif pulse_file_x is None:
             px, py = sample_pulses(t, [pulses[0]] if firstonly else pulses)
         if px_file is None:
-            px_file, py_file = stem + "_pulse_x.dat", stem + "_pulse_y.dat"
+            px_file = temp_dir + "{}_pulse_x_{}.dat".format(system_prefix, suffix)     # reference :56-57
+            py_file = temp_dir + "{}_pulse_y_{}.dat".format(system_prefix, suffix)
             export_csv(px_file, t, px.real, px.imag, precision=8, delimit=' ')
             export_csv(py_file, t, py.real, py.imag, precision=8, delimit=' ')
         if phonons and pt_file is None:

@@ -14,6 +14,9 @@ import numpy as np
 sys.path.insert(0, "/root/reference")
 for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.collections", "ACEutils"):
     sys.modules.setdefault(name, types.ModuleType(name))
+for name in ("Parameters", "FreePropagator", "ProcessTensors", "InitialState", "OutputPrinter", "TimeGrid", "Simulation",
+             "read_outfile", "DynamicalMap"):          # names general_system.py:14 imports from the absent pybind module
+    setattr(sys.modules["ACEutils"], name, None)
 
 import pyaceqd.pulses as rp  # noqa: E402
 import pyaceqd.tools as rt  # noqa: E402
@@ -91,6 +94,26 @@ out["dynmap"] = dict(times=times.tolist(), dm=cplx(dm), tl=cplx(tl), tl_map=cplx
                      use_dm_block=cplx(rt.use_dm_block(pieces[0], rho0)),
                      use_tl_map_mto=cplx(rt.use_tl_map_mto(tl_map, pieces[0], pieces[1], times, rho0, 1.0)),
                      tl_pad_stationary=cplx(rt.tl_pad_stationary(tl_map, times, rt.use_dm_block(pieces[0], rho0))))
+
+# --- the reference's own parameter / pulse / rotating-frame files (general_system.py:55-102,227-296), written
+#     by its prepare_only mode; the temp dir is replaced by the placeholder <TMP>
+import tempfile  # noqa: E402
+from pyaceqd.four_level_system.linear import biexciton as ref_biexciton  # noqa: E402
+from pyaceqd.two_level_system.tls import tls as ref_tls  # noqa: E402
+
+tmp = tempfile.mkdtemp() + "/"
+pb = rp.ChirpedPulse(tau_0=1.0, e_start=-2.0, alpha=0, t0=3.0, e0=4.0, polar_x=0.8)
+mtos = [{"operator": "|1><3|_4", "applyFrom": "_left", "applyBefore": "false", "time": 2.5},
+        {"operator": "|3><1|_4", "applyFrom": "_right", "applyBefore": "false", "time": 2.5},
+        {"operator": "|0><1|_4", "applyFrom": "", "applyBefore": "true", "time": 4.0}]
+ref_biexciton(0, 8.0, pb, dt=0.25, lindblad=True, delta_b=4.0, delta_xy=0.1, temp_dir=tmp, suffix="k7", multitime_op=mtos,
+              output_ops=["|1><1|_4", "|0><3|_4", "(|3><1|_4*|1><1|_4*|1><3|_4)"], prepare_only=True)
+pc = rp.ChirpedPulse(tau_0=1.5, e_start=1.0, alpha=3.0, t0=4.0, e0=2.0)
+ref_tls(0, 8.0, pc, dt=0.25, lindblad=True, rf=True, temp_dir=tmp, suffix="rf", prepare_only=True)
+files = {}
+for name in sorted(os.listdir(tmp)):
+    files[name] = open(tmp + name).read().replace(tmp, "<TMP>")
+out["prepare_only_files"] = files
 
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_host.json"), "w") as fh:
     json.dump(out, fh, default=lambda o: o.item() if hasattr(o, "item") else o.tolist())

@@ -37,7 +37,7 @@ def test_param_file_keys_and_parse_round_trip(tmp_path):
                         "use_symmetric_Trotter true"]
     assert text[6] == "initial    { |0><0|_4 }" and text[-1] == "outfile " + tmp + "b_linear_k7.out"
     assert "apply_Operator_left 2.5 { |1><3|_4 } false" in text and "apply_Operator 4.0 { |0><1|_4 } true" in text
-    assert any(l.startswith("add_Pulse file " + tmp + "b_linear_k7_pulse_y.dat  { -0.5*pi*hbar*(|2><0|_4+|3><2|_4) }")
+    assert any(l.startswith("add_Pulse file " + tmp + "b_linear_pulse_y_k7.dat  { -0.5*pi*hbar*(|2><0|_4+|3><2|_4) }")
                for l in text)
     params = ace_cli.parse_param_file(param)
     prob, tables, mtos = ace_cli.problem_from_params(params)
