@@ -225,6 +225,14 @@ void aceqd_struct_sizes(int32_t out[4]);
  * memory budget (0 if even T=1 does not fit). */
 int aceqd_max_tile(int NL, int chi_pad);
 
+/* With more tiles than SMs the step kernel does not run in waves: the tiles are laid end to end and cut into
+ * one equal piece of steps per SM; a tile that straddles a cut is started by one CTA and finished by the next
+ * (bond state handed over through HBM).  This returns that schedule for `n_sm` CTAs (host only, no GPU):
+ * segs_out = 5 ints per segment (tile, n_lo, n_hi, save_slot, load_slot; +-0x7fffffff = unbounded, -1 = none)
+ * in execution order, seg_off_out = n_ctas+1 offsets into it. */
+int aceqd_segment_plan(const aceqd_batch* batch, int n_sm, int max_segs, int32_t* segs_out,
+                       int32_t* seg_off_out, int32_t* n_ctas, int32_t* n_slots);
+
 /* DMMA m-tiles (8 rows) the most loaded CTA computes per step when a tile of T trajectories is shared
  * by a cluster of `cluster` CTAs (planner cost model; -1 on error). */
 int aceqd_pass_load(const aceqd_problem* prob, int T, int cluster);

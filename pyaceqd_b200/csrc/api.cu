@@ -66,7 +66,7 @@ struct aceqd_ctx {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // step, opbuild, tlmap start/stop
     bool have_step = false, have_op = false, have_tl = false;
     DevBuf W, OV, tables, seqs, seq_base, entries, mto, rho0s, trajs, tiles, snap_steps, snaps,
-        out, passes, scratch, misc, opscratch, st_x, st_order, st_bar, st_apos, tl_pool, tl_v0, tl_segoff, tl_segs, tl_w, tl_out, tl_final;
+        out, passes, scratch, misc, segs, seg_off, seg_state, seg_flags, opscratch, st_x, st_order, st_bar, st_apos, tl_pool, tl_v0, tl_segoff, tl_segs, tl_w, tl_out, tl_final;
     // layout of the operators currently in the workspace
     long long n_seq_entries = 0;
 };
@@ -137,7 +137,7 @@ void aceqd_ctx_destroy(aceqd_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->W, &c->OV, &c->tables, &c->seqs, &c->seq_base, &c->entries, &c->mto,
                       &c->rho0s, &c->trajs, &c->tiles, &c->snap_steps, &c->snaps, &c->out,
-                      &c->passes, &c->scratch, &c->misc, &c->opscratch, &c->st_x, &c->st_order, &c->st_bar, &c->st_apos, &c->tl_pool, &c->tl_v0, &c->tl_segoff,
+                      &c->passes, &c->scratch, &c->misc, &c->segs, &c->seg_off, &c->seg_state, &c->seg_flags, &c->opscratch, &c->st_x, &c->st_order, &c->st_bar, &c->st_apos, &c->tl_pool, &c->tl_v0, &c->tl_segoff,
                       &c->tl_segs, &c->tl_w, &c->tl_out, &c->tl_final})
         b->release();
     for (auto& ev : c->ev)
@@ -543,6 +543,107 @@ static int build_passes(const aceqd_problem* prob, int T, int cluster, std::vect
     return ACEQD_OK;
 }
 
+// More tiles than SMs: instead of running the persistent CTAs in waves (the last one partial), lay the
+// tiles end to end on a line of step counts and cut it into n_sm equal pieces (McNaughton's wrap-around
+// rule for preemptive scheduling: makespan = max(longest tile, total / n_sm)).  A tile that straddles a
+// cut is STARTED by the left CTA and FINISHED by the right one; every CTA runs its piece right to left,
+// so the head of a cut tile is the first thing its CTA does and the tail the last thing the next CTA
+// does (never a circular wait; the producer of a slot has the lower block index).
+static int segment_ctas(const aceqd_ctx* c) {   // CTAs of a segmented launch: one per SM (ACEQD_SEG_SMS overrides: tests)
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
+    const char* env = getenv("ACEQD_SEG_SMS");
+    if (env && atoi(env) > 0) n_sm = std::min(n_sm, atoi(env));
+    return n_sm;
+}
+
+static bool use_segments(const aceqd_ctx* c, const aceqd_batch* b) {
+    if (!c || !b || b->kernel != 0 || b->cluster > 1 || !b->tile_traj || b->tile_T < 1) return false;
+    const char* env = getenv("ACEQD_SEGMENTS");
+    if (env && env[0] == '0') return false;
+    return b->n_tiles > segment_ctas(c);
+}
+
+static bool plan_segments(const aceqd_batch* b, int n_sm, std::vector<SegDesc>& segs, std::vector<int>& seg_off,
+                          int& n_slots) {
+    const int T = b->tile_T, MINSEG = 8;
+    const int INF = 0x7fffffff;
+    std::vector<int> t_begin(b->n_tiles, INF), t_len(b->n_tiles, 0);
+    long long total = 0;
+    int longest = 1;
+    for (int i = 0; i < b->n_tiles; ++i) {
+        int e_max = -1;
+        for (int j = 0; j < T; ++j) {
+            const int idx = b->tile_traj[(size_t)i * T + j];
+            if (idx < 0) continue;
+            const aceqd_traj& t = b->trajs[idx];
+            t_begin[i] = std::min(t_begin[i], t.step0);
+            e_max = std::max(e_max, t.step0 + t.n_steps);
+        }
+        if (e_max < 0) continue;                       // empty tile: no work
+        t_len[i] = std::max(1, e_max - t_begin[i]);    // a zero-step tile still writes its row 0
+        total += t_len[i];
+        longest = std::max(longest, t_len[i]);
+    }
+    if (total == 0) return false;
+    struct Piece { int cta, tile, lo, hi, save, load; };
+    std::vector<Piece> pieces;
+    long long piece = std::max<long long>(longest, (total + n_sm - 1) / n_sm);
+    for (int attempt = 0; attempt < 64; ++attempt, piece += MINSEG) {
+        pieces.clear();
+        n_slots = 0;
+        int cta = 0;
+        long long room = piece;
+        for (int i = 0; i < b->n_tiles; ++i) {
+            if (t_len[i] == 0) continue;
+            int done = 0, pending_slot = -1;
+            while (done < t_len[i]) {
+                if (room <= 0) {
+                    ++cta;
+                    room = piece;
+                }
+                const int r = t_len[i] - done;
+                long long take = std::min<long long>(r, room);
+                if (take < r) {                        // a cut inside the tile
+                    if (take < MINSEG || done > 0) {   // too short a head (or a third piece): start in the next CTA
+                        room = 0;
+                        if (done > 0) take = r;        // (cannot happen: r <= piece) keep the tail whole
+                        else continue;
+                    } else if (r - take < MINSEG) {
+                        take = r;                      // too short a tail: overfill this CTA slightly
+                    }
+                }
+                Piece pc{cta, i, -INF, INF, -1, -1};
+                if (done > 0) {
+                    pc.lo = t_begin[i] + done;
+                    pc.load = pending_slot;
+                }
+                if (take < r) {
+                    pc.hi = t_begin[i] + done + (int)take;
+                    pc.save = pending_slot = n_slots++;
+                }
+                pieces.push_back(pc);
+                done += (int)take;
+                room -= take;
+            }
+        }
+        if (cta < n_sm) break;
+        if (attempt == 63) return false;
+    }
+    const int n_ctas = pieces.back().cta + 1;
+    seg_off.assign(n_ctas + 1, 0);
+    for (const Piece& pc : pieces) ++seg_off[pc.cta + 1];
+    for (int k = 0; k < n_ctas; ++k) seg_off[k + 1] += seg_off[k];
+    segs.assign(pieces.size(), SegDesc{});
+    std::vector<int> fill(n_ctas, 0);
+    for (const Piece& pc : pieces) {                   // right to left within a CTA
+        const int cnt = seg_off[pc.cta + 1] - seg_off[pc.cta];
+        const int at = seg_off[pc.cta] + (cnt - 1 - fill[pc.cta]++);
+        segs[at] = SegDesc{pc.tile, pc.lo, pc.hi, pc.save, pc.load};
+    }
+    return true;
+}
+
 /* m-tiles the most loaded CTA of a `cluster` computes per step for tile size T (planner cost model) */
 extern "C" int aceqd_pass_load(const aceqd_problem* prob, int T, int cluster) {
     if (!prob || T < 1 || cluster < 1) return -1;
@@ -552,6 +653,36 @@ extern "C" int aceqd_pass_load(const aceqd_problem* prob, int T, int cluster) {
     for (auto& pd : passes)
         for (int mc = 0; mc < MC; ++mc) load[pd.owner] += pd.nvalid[mc] > 0;
     return *std::max_element(load.begin(), load.end());
+}
+
+/* The segment schedule of a batch on n_sm CTAs (host only; tests).  segs_out: 5 ints per segment
+ * (tile, n_lo, n_hi, save_slot, load_slot) in execution order per CTA; seg_off_out: n_ctas+1 offsets. */
+int aceqd_segment_plan(const aceqd_batch* b, int n_sm, int max_segs, int32_t* segs_out, int32_t* seg_off_out,
+                       int32_t* n_ctas, int32_t* n_slots) {
+    if (!b || !b->tile_traj || !b->trajs || b->tile_T < 1 || n_sm < 1 || !segs_out || !seg_off_out || !n_ctas ||
+        !n_slots) {
+        set_error("aceqd_segment_plan: invalid argument");
+        return ACEQD_ERR_ARG;
+    }
+    std::vector<SegDesc> segs;
+    std::vector<int> off;
+    int slots = 0;
+    if (!plan_segments(b, n_sm, segs, off, slots)) {
+        set_error("aceqd_segment_plan: no schedule");
+        return ACEQD_ERR_CAPACITY;
+    }
+    if ((int)segs.size() > max_segs) {
+        set_error("aceqd_segment_plan: %zu segments exceed the caller's buffer", segs.size());
+        return ACEQD_ERR_CAPACITY;
+    }
+    for (size_t i = 0; i < segs.size(); ++i) {
+        const int32_t v[5] = {segs[i].tile, segs[i].n_lo, segs[i].n_hi, segs[i].save_slot, segs[i].load_slot};
+        memcpy(segs_out + 5 * i, v, sizeof(v));
+    }
+    for (size_t i = 0; i < off.size(); ++i) seg_off_out[i] = off[i];
+    *n_ctas = (int)off.size() - 1;
+    *n_slots = slots;
+    return ACEQD_OK;
 }
 
 int aceqd_max_tile(int NL, int chi_pad) {
@@ -780,6 +911,27 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
         sp.passes = (const PassDesc*)c->passes.p;
         sp.tile_traj = (const int*)c->tiles.p;
         const size_t smem = step_smem_bytes(pd.NL, chi_pad, T, stages, wov, wbufs);
+        if (use_segments(c, b)) {
+            int n_slots = 0;
+            const int n_sm = segment_ctas(c);
+            std::vector<SegDesc> segs;
+            std::vector<int> seg_off;
+            if (plan_segments(b, n_sm, segs, seg_off, n_slots)) {
+                UP(c->segs, segs.data(), segs.size() * sizeof(SegDesc));
+                UP(c->seg_off, seg_off.data(), seg_off.size() * sizeof(int));
+                const size_t slot = step_seg_slot_doubles(pd.NL, chi_pad, T);
+                if ((rc = c->seg_state.reserve(std::max<size_t>(1, n_slots) * slot * 8))) return rc;
+                if ((rc = c->seg_flags.reserve(std::max<size_t>(1, n_slots) * sizeof(unsigned)))) return rc;
+                ACEQD_CUDA(cudaMemsetAsync(c->seg_flags.p, 0, std::max<size_t>(1, n_slots) * sizeof(unsigned), c->stream));
+                sp.segs = (const SegDesc*)c->segs.p;
+                sp.seg_off = (const int*)c->seg_off.p;
+                sp.seg_state = (double*)c->seg_state.p;
+                sp.seg_slot_doubles = slot;
+                sp.seg_flags = (unsigned*)c->seg_flags.p;
+                sp.seg_epoch = 1u;
+                sp.n_ctas = (int)seg_off.size() - 1;
+            }
+        }
         // More tiles than SMs: the persistent CTAs run in waves.  aceqd_propagate_batch may have planned a
         // split (first the partial wave, then the full waves): the later waves' operators are built on a
         // side stream meanwhile, and on the end-to-end path the first wave's outputs are copied to the
@@ -851,6 +1003,7 @@ static void plan_wave_split(aceqd_ctx* c, const aceqd_problem* prob, const aceqd
     if (!c || !prob || !b || b->kernel != 0 || b->cluster > 1 || b->n_entries != 0 || !b->tile_traj ||
         b->tile_T < 1 || !b->trajs)
         return;
+    if (use_segments(c, b)) return;   // one balanced launch instead of waves
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
     if (b->n_tiles <= n_sm) return;

@@ -73,6 +73,14 @@ struct PassDesc {
     int owner;       // cluster rank that computes this pass (0 without clusters)
 };
 
+// One piece of work of a persistent CTA: steps [n_lo, n_hi) of a tile (clipped to the tile's own range).
+// A tile cut in two is started by one CTA, which saves the bond state to slot `save_slot` of the segment
+// workspace and raises the slot's flag, and finished by another one, which waits on `load_slot`.
+struct SegDesc {
+    int tile, n_lo, n_hi;
+    int save_slot, load_slot;   // -1: none
+};
+
 struct StepParams {
     PtDev pt;
     ProbDev prob;
@@ -93,6 +101,14 @@ struct StepParams {
     const int* snap_steps;
     double* snaps;            // [slots][NL][chi_pad] complex
     double* out;
+    // segment schedule (null: CTA i runs tile i / cluster as a whole)
+    const SegDesc* segs;      // segments of CTA i: segs[seg_off[i] .. seg_off[i+1])
+    const int* seg_off;
+    double* seg_state;        // [slot][seg_slot_doubles]: state planes, closures, snapshot cursors
+    size_t seg_slot_doubles;
+    unsigned* seg_flags;      // [slot] == seg_epoch once the slot has been written in this launch
+    unsigned seg_epoch;
+    int n_ctas;               // grid size with a segment schedule
 };
 
 // Step-synchronous streaming kernel (stream_kernel.cu): state in HBM/L2, class-batched PT GEMM.
@@ -148,6 +164,7 @@ int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, do
 int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, long long* launches);
 int launch_step_check(const StepParams& p, double* scratch, cudaStream_t s, long long* launches);
 size_t step_smem_bytes(int NL, int chi_pad, int T, int stages, int wov_doubles, int wbufs);
+size_t step_seg_slot_doubles(int NL, int chi_pad, int T);
 int launch_step_stream(const StreamParams& p, size_t smem, cudaStream_t s, long long* launches);
 size_t stream_smem_bytes(int NL, int chi_pad, int stages, int wov_doubles);
 int launch_tlmap(int NL, int n_chains, int n_w, int n_emit_max, const double* pool, const double* v0,

@@ -90,7 +90,6 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     // computed through distributed shared memory (cp.async.bulk shared::cta -> shared::cluster)
     const int C = p.cluster;
     const uint32_t crank = C > 1 ? cluster_ctarank() : 0u;
-    const int tile = blockIdx.x / C;
     const uint32_t bar_y = smem_u32(bars + 2 * MAX_STAGES + 4), bar_free = smem_u32(bars + 2 * MAX_STAGES + 5);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
     const uint32_t bar_wfull = smem_u32(bars + 2 * MAX_STAGES), bar_wempty = smem_u32(bars + 2 * MAX_STAGES + 2);
@@ -98,19 +97,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     auto rowoff = [&](int ps, int j) -> size_t { return (size_t)(ps * T + j) * strideA + (size_t)ps * SKEW; };
     auto rowoff_r = [&](int row) -> size_t { return (size_t)row * strideA + (size_t)(row / T) * SKEW; };
 
-    // ------------------------------------------------------------------ setup
-    for (int j = tid; j < T; j += blockDim.x) {
-        const int idx = p.tile_traj[(size_t)tile * T + j];
-        if (idx >= 0) {
-            trj[j] = p.trajs[idx];
-        } else {
-            aceqd_traj z;
-            memset(&z, 0, sizeof(z));
-            z.n_steps = -1;
-            trj[j] = z;
-        }
-        snapn[j] = 0;
-    }
+    // ------------------------------------------------------------------ setup (once per CTA)
     for (int j = tid; j < p.n_pass; j += blockDim.x) passes[j] = p.passes[j];
     for (int j = tid; j < NL; j += blockDim.x) {
         pos[j] = p.prob.pos_of_alpha[j];
@@ -120,7 +107,6 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         smeta[2 * j] = p.pt.kin_pad[j];
         smeta[2 * j + 1] = p.pt.nout_pad[j];
     }
-    for (size_t e = tid; e < 2 * L.plane; e += blockDim.x) Xre[e] = 0.0;
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
@@ -157,13 +143,69 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     }
     if (C > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
     else __syncthreads();
+
+    // A CTA works through a list of SEGMENTS (tile, step range): with more tiles than SMs the host lays
+    // the tiles end to end and cuts the line into equal pieces, one per CTA (wrap-around rule), so a tile
+    // may be started by one CTA (which saves the bond state of the tile to HBM) and finished by the next.
+    // Without a segment list a CTA (cluster) runs exactly one whole tile.
+    const int seg_first = p.segs ? p.seg_off[blockIdx.x] : 0;
+    const int n_seg = p.segs ? p.seg_off[blockIdx.x + 1] - seg_first : 1;
+    // pipeline positions persist across segments (producer and consumers advance identically)
+    int stage = 0;
+    uint32_t phase = 0, wph0 = 0u, wph1 = 0u;
+    for (int si = 0; si < n_seg; ++si) {
+    SegDesc sg;
+    if (p.segs) {
+        sg = p.segs[seg_first + si];
+    } else {
+        sg.tile = blockIdx.x / C;
+        sg.n_lo = -0x7fffffff;
+        sg.n_hi = 0x7fffffff;
+        sg.save_slot = sg.load_slot = -1;
+    }
+    const int tile = sg.tile;
+    if (si > 0) __syncthreads();   // every warp (producer included) has left the previous segment
+    for (int j = tid; j < T; j += blockDim.x) {
+        const int idx = p.tile_traj[(size_t)tile * T + j];
+        if (idx >= 0) {
+            trj[j] = p.trajs[idx];
+        } else {
+            aceqd_traj z;
+            memset(&z, 0, sizeof(z));
+            z.n_steps = -1;
+            trj[j] = z;
+        }
+        snapn[j] = 0;
+    }
+    if (sg.load_slot < 0)
+        for (size_t e = tid; e < 2 * L.plane; e += blockDim.x) Xre[e] = 0.0;
+    __syncthreads();
     int n_begin = 0x7fffffff, n_end = -1;
     for (int j = 0; j < T; ++j) {
         if (trj[j].n_steps < 0) continue;
         n_begin = min(n_begin, trj[j].step0);
         n_end = max(n_end, trj[j].step0 + trj[j].n_steps);
     }
-    if (n_end < 0) return;  // empty tile
+    if (n_end < 0) continue;  // empty tile
+    const int n_lo = max(n_begin, sg.n_lo), n_hi = min(n_end, sg.n_hi);
+    const bool final_seg = n_hi == n_end;   // else: stop BEFORE output row n_hi and save the state
+    if (sg.load_slot >= 0) {
+        // resume a tile another CTA started: wait for its state, then restore planes, closures, cursors
+        if (tid == 0) {
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.seg_flags + sg.load_slot) : "memory");
+                if (v != p.seg_epoch) __nanosleep(200);
+            } while (v != p.seg_epoch);
+        }
+        __syncthreads();
+        const double2* src = reinterpret_cast<const double2*>(p.seg_state + (size_t)sg.load_slot * p.seg_slot_doubles);
+        double2* dst = reinterpret_cast<double2*>(Xre);
+        for (size_t e = tid; e < L.plane; e += blockDim.x) dst[e] = src[e];
+        for (int e = tid; e < R; e += blockDim.x) rall[e] = src[L.plane + e];
+        const int* sn = reinterpret_cast<const int*>(src + L.plane + R);
+        for (int e = tid; e < T; e += blockDim.x) snapn[e] = sn[e];
+    } else {
     // initial states (Y form)
     for (int j = 0; j < T; ++j) {
         if (trj[j].n_steps < 0) continue;
@@ -186,10 +228,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             }
         }
     }
+    }
     // closure of the slice before the first row (used by snapshot-started trajectories)
-    if (n_begin > 0) {
+    if (n_lo > 0) {
         const double2* cl = reinterpret_cast<const double2*>(p.pt.closure) +
-                            (size_t)slice_of(p.pt, n_begin - 1) * chi_pad;
+                            (size_t)slice_of(p.pt, n_lo - 1) * chi_pad;
         for (int d = tid; d < chi_pad; d += blockDim.x) qbuf[d] = cl[d];
     }
     __syncthreads();
@@ -197,8 +240,6 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     // ------------------------------------------------------------------ producer warp
     if (warp == N_COMPUTE_WARPS) {
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0, wph0 = 0u, wph1 = 0u;
             const uint32_t bytes = (uint32_t)p.pt.chunk_doubles * 8u;
             const uint32_t w_bytes = (uint32_t)p.prob.w_doubles * 8u, ov_bytes = (uint32_t)p.prob.ov_doubles * 8u;
             // stage the per-row operators W_n | OV_n of every active trajectory into buffer n & 1
@@ -222,9 +263,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                              bar_wfull + 8 * buf);
                 }
             };
-            if (wsm) issue_wov(n_begin);
-            for (int n = n_begin; n < n_end; ++n) {
-                bool w_next = wsm;
+            if (wsm) issue_wov(n_lo);
+            for (int n = n_lo; n < n_hi; ++n) {
+                bool w_next = wsm && (n + 1 < n_hi || final_seg);   // row n_hi of an unfinished tile belongs to the next segment
                 if (w_next && wbufs == 2) {
                     issue_wov(n + 1);
                     w_next = false;
@@ -250,8 +291,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 if (w_next) issue_wov(n + 1);   // this CTA owns no pass
             }
         }
-        if (C > 1) cluster_sync_all();   // no CTA of a cluster exits while a peer may still address it
-        return;
+        continue;   // next segment (all lanes meet the compute warps at its first barrier)
     }
 
     // ------------------------------------------------------------------ compute warps
@@ -286,13 +326,12 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     const int NT = chi_pad / 8;
     const int n_out = p.prob.n_out;
     const int NLp4 = p.prob.NLp4, MTU = p.prob.NLp8 / 8, KSU = NLp4 / 4;
-    int stage = 0;
-    uint32_t phase = 0, wph0 = 0u, wph1 = 0u;
 
-    for (int n = n_begin; n <= n_end; ++n) {
+    for (int n = n_lo; n <= n_hi; ++n) {
+        if (n == n_hi && !final_seg) break;   // the next segment of this tile starts with output row n_hi
         const int buf = wbufs == 2 ? (n & 1) : 0;
         if (C > 1) {
-            if (n > n_begin) {           // rows and closures computed by the peers in step n-1 have landed
+            if (n > n_lo) {           // rows and closures computed by the peers in step n-1 have landed
                 mbar_wait_cluster(bar_y, yph);
                 yph ^= 1u;
             }
@@ -375,7 +414,14 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 }
             }
         }
-        if (n == n_end) break;
+        if (n == n_end) {
+            if (wsm) {  // last row: hand the buffer back (the CTA may go on with another segment)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_wempty + 8 * buf);
+                if (buf) wph1 ^= 1u; else wph0 ^= 1u;
+            }
+            break;
+        }
         if (any_snap) {
             compute_bar();   // snapshot reads of the state precede phase B's in-place update
             if (tid < T) {   // advance snapshot cursors (read again only after later barriers)
@@ -681,6 +727,20 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         }
         fph ^= 1u;
     }
+    if (!final_seg && sg.save_slot >= 0) {
+        // unfinished tile: bond state, closures of row n_hi and snapshot cursors go to HBM for the CTA that resumes it
+        double2* dst = reinterpret_cast<double2*>(p.seg_state + (size_t)sg.save_slot * p.seg_slot_doubles);
+        const double2* src = reinterpret_cast<const double2*>(Xre);
+        for (size_t e = tid; e < L.plane; e += N_COMPUTE_WARPS * 32) dst[e] = src[e];
+        for (int e = tid; e < R; e += N_COMPUTE_WARPS * 32) dst[L.plane + e] = rall[e];
+        int* sn = reinterpret_cast<int*>(dst + L.plane + R);
+        for (int e = tid; e < T; e += N_COMPUTE_WARPS * 32) sn[e] = snapn[e];
+        __threadfence();
+        compute_bar();
+        if (tid == 0)
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.seg_flags + sg.save_slot), "r"(p.seg_epoch) : "memory");
+    }
+    }   // segments
     if (C > 1) cluster_sync_all();   // no CTA of a cluster exits while a peer may still address it
 }
 
@@ -787,6 +847,11 @@ size_t step_smem_bytes(int NL, int chi_pad, int T, int stages, int wov_doubles, 
     return make_layout(NL, chi_pad, T, stages, wov_doubles, wbufs).total;
 }
 
+size_t step_seg_slot_doubles(int NL, int chi_pad, int T) {
+    const SmemLayout L = make_layout(NL, chi_pad, T, 2, 0, 1);
+    return 2 * L.plane + 2 * (size_t)T * NL + 8;   // planes, closures, <= 16 snapshot cursors
+}
+
 template <int NB>
 static int launch_nb(const StepParams& p, size_t smem_bytes, cudaStream_t s) {
     const int ksu = p.prob.NLp4 / 4;
@@ -796,7 +861,7 @@ static int launch_nb(const StepParams& p, size_t smem_bytes, cudaStream_t s) {
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                                         (int)smem_bytes));                                      \
         cudaLaunchConfig_t cfg = {};                                                            \
-        cfg.gridDim = dim3((unsigned)(p.n_tiles * p.cluster), 1, 1);                            \
+        cfg.gridDim = dim3((unsigned)(p.segs ? p.n_ctas : p.n_tiles * p.cluster), 1, 1);       \
         cfg.blockDim = dim3(STEP_THREADS, 1, 1);                                                \
         cfg.dynamicSmemBytes = smem_bytes;                                                      \
         cfg.stream = s;                                                                         \
