@@ -233,6 +233,10 @@ int aceqd_max_tile(int NL, int chi_pad);
 int aceqd_segment_plan(const aceqd_batch* batch, int n_sm, int max_segs, int32_t* segs_out,
                        int32_t* seg_off_out, int32_t* n_ctas, int32_t* n_slots);
 
+/* Debug aid: per-phase cycle counters of the step kernel's CTA 0 (enable != 0 switches the clock on and zeroes it;
+ * out8, if not NULL, receives the counters accumulated so far). */
+int aceqd_debug_phase_ticks(aceqd_ctx* ctx, int enable, long long* out8);
+
 /* DMMA m-tiles (8 rows) the most loaded CTA computes per step when a tile of T trajectories is shared
  * by a cluster of `cluster` CTAs (planner cost model; -1 on error). */
 int aceqd_pass_load(const aceqd_problem* prob, int T, int cluster);

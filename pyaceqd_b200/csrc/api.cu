@@ -67,6 +67,7 @@ struct aceqd_ctx {
     bool have_step = false, have_op = false, have_tl = false;
     DevBuf W, OV, tables, seqs, seq_base, entries, mto, rho0s, trajs, tiles, snap_steps, snaps,
         out, passes, scratch, misc, segs, seg_off, seg_state, seg_flags, opscratch, st_x, st_order, st_bar, st_apos, tl_pool, tl_v0, tl_segoff, tl_segs, tl_w, tl_out, tl_final;
+    long long* ticks = nullptr;           // debug phase clock of the step kernel (aceqd_debug_phase_ticks)
     // layout of the operators currently in the workspace
     long long n_seq_entries = 0;
 };
@@ -146,6 +147,7 @@ void aceqd_ctx_destroy(aceqd_ctx* c) {
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_built) cudaEventDestroy(c->ev_built);
     if (c->build_stream) cudaStreamDestroy(c->build_stream);
+    if (c->ticks) cudaFree(c->ticks);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -685,6 +687,25 @@ int aceqd_segment_plan(const aceqd_batch* b, int n_sm, int max_segs, int32_t* se
     return ACEQD_OK;
 }
 
+/* Debug: phase clock of the step kernel.  enable != 0 switches it on (and zeroes it); out8 (may be NULL) gets the
+ * cycles CTA 0 spent after each of its 7 marks: [0] outputs wait, [1] outputs, [2] system product + barrier,
+ * [3] PT GEMM passes, [4] barrier after the passes, [5] closure sums + barrier, [6] step tail. */
+int aceqd_debug_phase_ticks(aceqd_ctx* c, int enable, long long* out8) {
+    if (!c) return ACEQD_ERR_ARG;
+    ACEQD_CUDA(cudaSetDevice(c->device));
+    ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+    if (out8 && c->ticks) ACEQD_CUDA(cudaMemcpy(out8, c->ticks, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    else if (out8) memset(out8, 0, 8 * sizeof(long long));
+    if (enable) {
+        if (!c->ticks) ACEQD_CUDA(cudaMalloc(&c->ticks, 8 * sizeof(long long)));
+        ACEQD_CUDA(cudaMemset(c->ticks, 0, 8 * sizeof(long long)));
+    } else if (c->ticks) {
+        cudaFree(c->ticks);
+        c->ticks = nullptr;
+    }
+    return ACEQD_OK;
+}
+
 int aceqd_max_tile(int NL, int chi_pad) {
     for (int T = MAX_TILE_T; T >= 1; T >>= 1)
         if (step_smem_bytes(NL, chi_pad, T, 2, 0, 1) <= (size_t)SMEM_BUDGET) return T;
@@ -769,6 +790,7 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
     sp.snap_steps = (const int*)c->snap_steps.p;
     sp.snaps = (double*)c->snaps.p;
     sp.out = out_dev;
+    sp.ticks = c->ticks;
 
     if (b->kernel == 2) {
         // ---- step-synchronous streaming kernel: state in HBM/L2, class-batched PT GEMM

@@ -109,6 +109,7 @@ struct StepParams {
     unsigned* seg_flags;      // [slot] == seg_epoch once the slot has been written in this launch
     unsigned seg_epoch;
     int n_ctas;               // grid size with a segment schedule
+    long long* ticks;         // debug: [8] phase cycle counters of CTA 0 (null = off)
 };
 
 // Step-synchronous streaming kernel (stream_kernel.cu): state in HBM/L2, class-batched PT GEMM.

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     const uint32_t bar_y = smem_u32(bars + 2 * MAX_STAGES + 4), bar_free = smem_u32(bars + 2 * MAX_STAGES + 5);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
     const uint32_t bar_wfull = smem_u32(bars + 2 * MAX_STAGES), bar_wempty = smem_u32(bars + 2 * MAX_STAGES + 2);
+    const uint32_t bar_rd = smem_u32(bars + 2 * MAX_STAGES + 6);   // [2] "every warp has read the X rows of pass p"
     // offset (doubles) of state row (pos, j) inside a plane; rows are alpha-major with a skew
     auto rowoff = [&](int ps, int j) -> size_t { return (size_t)(ps * T + j) * strideA + (size_t)ps * SKEW; };
     auto rowoff_r = [&](int row) -> size_t { return (size_t)row * strideA + (size_t)(row / T) * SKEW; };
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             mbar_init(bar_wfull + 8 * s, 1);
             mbar_init(bar_wempty + 8 * s, N_COMPUTE_WARPS);
         }
+        for (int s = 0; s < 2; ++s) mbar_init(bar_rd + 8 * s, N_COMPUTE_WARPS);
         mbar_init(bar_y, (uint32_t)C);                       // own expect_tx arrival + one arrival per peer
         mbar_init(bar_free, (uint32_t)(C > 1 ? C - 1 : 1));  // "I have read your rows" from every peer
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     const int n_seg = p.segs ? p.seg_off[blockIdx.x + 1] - seg_first : 1;
     // pipeline positions persist across segments (producer and consumers advance identically)
     int stage = 0;
-    uint32_t phase = 0, wph0 = 0u, wph1 = 0u;
+    uint32_t phase = 0, wph0 = 0u, wph1 = 0u, rdph0 = 0u, rdph1 = 0u;
     for (int si = 0; si < n_seg; ++si) {
     SegDesc sg;
     if (p.segs) {
@@ -327,6 +329,18 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     const int n_out = p.prob.n_out;
     const int NLp4 = p.prob.NLp4, MTU = p.prob.NLp8 / 8, KSU = NLp4 / 4;
 
+    // optional phase clock (debug): CTA 0 / thread 0 accumulates the cycles between consecutive marks
+    long long tick_prev = 0;
+    int tick_last = -1;
+#define TICK(k)                                                                           \
+    do {                                                                                  \
+        if (p.ticks && blockIdx.x == 0 && tid == 0) {                                     \
+            const long long now_ = clock64();                                             \
+            if (tick_last >= 0) p.ticks[tick_last] += now_ - tick_prev;                   \
+            tick_prev = now_;                                                             \
+            tick_last = (k);                                                              \
+        }                                                                                 \
+    } while (0)
     for (int n = n_lo; n <= n_hi; ++n) {
         if (n == n_hi && !final_seg) break;   // the next segment of this tile starts with output row n_hi
         const int buf = wbufs == 2 ? (n & 1) : 0;
@@ -337,6 +351,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             }
             if (n < n_end && tid == 0) mbar_expect_tx(bar_y, rx_bytes);   // arm this step's exchange
         }
+        TICK(0);
         // ---------------- phase A: outputs (closures rall[] come from the previous GEMM epilogue)
         // rows of trajectories that START at this row have no closure yet: generic closure pass
         bool any_start = false, any_snap = false;
@@ -376,6 +391,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             compute_bar();
         }
         if (wsm) mbar_wait(bar_wfull + 8 * buf, buf ? wph1 : wph0);
+        TICK(1);
         for (int it = tid; it < T * n_out; it += N_COMPUTE_WARPS * 32) {
             const int j = it / n_out, o = it - j * n_out;
             const aceqd_traj& t = trj[j];
@@ -433,6 +449,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             }
         }
 
+        TICK(2);
         // ---------------- phase B: X = W_n Y.  Warp w owns bond columns of its n-tiles for every
         // trajectory (column-local, in place, no block barrier); JU trajectories x NBB n-tiles are
         // kept in flight for instruction-level parallelism (bounded by the register budget).
@@ -451,11 +468,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                     Wp = reinterpret_cast<const double2*>(p.W + (size_t)e * p.prob.w_doubles);
                 }
                 double2 w[4][4];
-                size_t ro[4];
+                int ro[4];
                 bool own[4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    ro[a] = a < NL ? rowoff(pos[a], j) : 0;
+                    ro[a] = a < NL ? (int)rowoff(pos[a], j) : 0;
                     own[a] = a < NL && (C == 1 || own_pos[pos[a]]);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
@@ -602,6 +619,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             if (buf) wph1 ^= 1u; else wph0 ^= 1u;
         }
         compute_bar();
+        TICK(3);
         if (C > 1 && tid == 0) {   // every warp of this CTA has read the peers' rows: they may overwrite them
             for (uint32_t peer = 0; peer < (uint32_t)C; ++peer)
                 if (peer != crank) mbar_arrive_remote(mapa(bar_free, peer));
@@ -620,6 +638,53 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         for (int nb = 0; nb < NB; ++nb) nbv[nb] = 8 * (warp + N_COMPUTE_WARPS * nb) < nout;
         int pending_push = -1;     // own pass whose new rows still have to be sent to the peers
         free_waited = false;
+        // epilogue of one pass: new rows into the state (in place) + this warp's closure partials
+        auto epilogue = [&](const PassDesc& pd, const double (&cre)[MC][NB][2], const double (&cim)[MC][NB][2]) {
+#pragma unroll
+            for (int mc = 0; mc < MC; ++mc) {
+                if (pd.nvalid[mc] <= 0) continue;   // warp-uniform
+                const bool av = g < pd.nvalid[mc];
+                const int row = pd.row0[mc] + (av ? g : 0);
+                const aceqd_traj& t = trj[row % T];
+                const bool wr = av && t.n_steps >= 0 && n >= t.step0 && n < t.step0 + t.n_steps;
+                // closure partial of this warp's columns: r[row] += sum_col Y[row, col] q[col]
+                double pr = 0.0, pi = 0.0;
+                const size_t ro = rowoff_r(row);
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    if (nbv[nb]) {
+                        const int c0 = 8 * (warp + N_COMPUTE_WARPS * nb) + 2 * tq;
+                        const double2 q0 = qbuf[c0], q1 = qbuf[c0 + 1];
+                        pr += cre[mc][nb][0] * q0.x - cim[mc][nb][0] * q0.y + cre[mc][nb][1] * q1.x - cim[mc][nb][1] * q1.y;
+                        pi += cre[mc][nb][0] * q0.y + cim[mc][nb][0] * q0.x + cre[mc][nb][1] * q1.y + cim[mc][nb][1] * q1.x;
+                        if (wr) {
+                            const size_t o = ro + c0;
+                            *reinterpret_cast<double2*>(Xre + o) = make_double2(cre[mc][nb][0], cre[mc][nb][1]);
+                            *reinterpret_cast<double2*>(Xim + o) = make_double2(cim[mc][nb][0], cim[mc][nb][1]);
+                        }
+                    }
+                }
+                pr += __shfl_xor_sync(0xffffffffu, pr, 1);
+                pi += __shfl_xor_sync(0xffffffffu, pi, 1);
+                pr += __shfl_xor_sync(0xffffffffu, pr, 2);
+                pi += __shfl_xor_sync(0xffffffffu, pi, 2);
+                if (wr && tq == 0) rpart[warp * R + row] = make_double2(pr, pi);
+            }
+        };
+        // Without a cluster the in-place row update of pass p is DEFERRED until this warp has issued the GEMM of
+        // pass p+1: "every warp has read the rows of pass p" is a split barrier (mbarrier arrive after the main
+        // loop, wait before the write), so the warps never meet between passes and one warp's epilogue overlaps
+        // the other warps' DMMAs.
+        // (two accumulator sets: only while they fit the 168 registers a 9-warp CTA leaves per thread)
+        constexpr bool DEFER = NB <= 2;
+        constexpr int NBP = DEFER ? NB : 1;
+        double pre[MC][NBP][2], pim[MC][NBP][2];
+        PassDesc ppd{};
+        int pend = -1;
+        auto rd_wait = [&](int b) {
+            mbar_wait(bar_rd + 8 * b, b ? rdph1 : rdph0);
+            if (b) rdph1 ^= 1u; else rdph0 ^= 1u;
+        };
         for (int ps = 0; ps < p.n_pass; ++ps) {
             const PassDesc pd = passes[ps];
             if (pd.owner != (int)crank) continue;
@@ -651,6 +716,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 allnb &= nbv[nb];
                 anynb |= nbv[nb];
             }
+            TICK(3);
             if (!anynb) {  // this warp owns no bond column of the slice: keep the pipeline moving only
                 for (int jc = 0; jc < nch; ++jc) {
                     mbar_wait(bar_full + 8 * stage, phase);
@@ -669,41 +735,40 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             else
                 gemm_pass<NB, 1, false>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
                                         warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
-            compute_bar();  // every warp has finished reading this pass's X rows
-            if (C > 1) {    // ... and has finished writing the previous pass's rows: send them
-                if (tid == 0 && pending_push >= 0) push_pass(passes[pending_push]);
-                pending_push = ps;
-            }
-#pragma unroll
-            for (int mc = 0; mc < MC; ++mc) {
-                if (!mcv[mc]) continue;   // warp-uniform
-                const int row = pd.row0[mc] + (aval[mc] ? g : 0);
-                const aceqd_traj& t = trj[row % T];
-                const bool wr = aval[mc] && t.n_steps >= 0 && n >= t.step0 && n < t.step0 + t.n_steps;
-                // closure partial of this warp's columns: r[row] += sum_col Y[row, col] q[col]
-                double pr = 0.0, pi = 0.0;
-#pragma unroll
-                for (int nb = 0; nb < NB; ++nb) {
-                    if (nbv[nb]) {
-                        const int c0 = 8 * (warp + N_COMPUTE_WARPS * nb) + 2 * tq;
-                        const double2 q0 = qbuf[c0], q1 = qbuf[c0 + 1];
-                        pr += cre[mc][nb][0] * q0.x - cim[mc][nb][0] * q0.y + cre[mc][nb][1] * q1.x - cim[mc][nb][1] * q1.y;
-                        pi += cre[mc][nb][0] * q0.y + cim[mc][nb][0] * q0.x + cre[mc][nb][1] * q1.y + cim[mc][nb][1] * q1.x;
-                        if (wr) {
-                            const size_t o = rowoff_r(row) + c0;
-                            *reinterpret_cast<double2*>(Xre + o) = make_double2(cre[mc][nb][0], cre[mc][nb][1]);
-                            *reinterpret_cast<double2*>(Xim + o) = make_double2(cim[mc][nb][0], cim[mc][nb][1]);
-                        }
-                    }
+            TICK(7);
+            if (DEFER && C == 1) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_rd + 8 * (ps & 1));
+                if (pend >= 0) {
+                    rd_wait(pend & 1);
+                    if constexpr (DEFER) epilogue(ppd, pre, pim);
                 }
-                pr += __shfl_xor_sync(0xffffffffu, pr, 1);
-                pi += __shfl_xor_sync(0xffffffffu, pi, 1);
-                pr += __shfl_xor_sync(0xffffffffu, pr, 2);
-                pi += __shfl_xor_sync(0xffffffffu, pi, 2);
-                if (wr && tq == 0) rpart[warp * R + row] = make_double2(pr, pi);
+#pragma unroll
+                for (int mc = 0; mc < MC; ++mc)
+#pragma unroll
+                    for (int nb = 0; nb < NBP; ++nb) {
+                        pre[mc][nb][0] = cre[mc][nb][0];
+                        pre[mc][nb][1] = cre[mc][nb][1];
+                        pim[mc][nb][0] = cim[mc][nb][0];
+                        pim[mc][nb][1] = cim[mc][nb][1];
+                    }
+                ppd = pd;
+                pend = ps;
+                continue;
             }
+            compute_bar();  // every warp has finished reading this pass's X rows
+            // ... and has finished writing the previous pass's rows: send them
+            if (tid == 0 && pending_push >= 0) push_pass(passes[pending_push]);
+            pending_push = ps;
+            epilogue(pd, cre, cim);
         }
+        if (pend >= 0) {
+            rd_wait(pend & 1);
+            if constexpr (DEFER) epilogue(ppd, pre, pim);
+        }
+        TICK(4);
         compute_bar();
+        TICK(5);
         // closure of the rows computed here: sum the per-warp partials; peers get a copy
         for (int row = tid; row < R; row += N_COMPUTE_WARPS * 32) {
             if (C > 1 && !own_pos[row / T]) continue;
@@ -719,6 +784,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 if (peer != crank) st_cluster_c128(mapa(smem_u32(rall + row), peer), r);
         }
         compute_bar();
+        TICK(6);
         if (C > 1 && tid == 0) {
             if (pending_push >= 0) push_pass(passes[pending_push]);
             if (!free_waited) mbar_wait_cluster(bar_free, fph);   // keep the phase in step without own passes
@@ -740,6 +806,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         if (tid == 0)
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.seg_flags + sg.save_slot), "r"(p.seg_epoch) : "memory");
     }
+#undef TICK
     }   // segments
     if (C > 1) cluster_sync_all();   // no CTA of a cluster exits while a peer may still address it
 }
