@@ -1218,7 +1218,7 @@ int aceqd_fp64_peak(aceqd_ctx* c, int kind, int iters, double* tflops) {
     cudaEventDestroy(e1);
     const double warps = (double)blocks * threads / 32.0;
     double flops;
-    if (kind == 0)
+    if (kind == 0 || kind >= 10)
         flops = warps * (double)iters * 8.0 * 512.0;  // 8 DMMA.8x8x4 per iteration per warp
     else
         flops = (double)blocks * threads * (double)iters * 16.0 * 2.0;

@@ -97,53 +97,75 @@ __device__ __forceinline__ long long entry_of(const aceqd_traj& t, int i, long l
 
 // Main loop of one GEMM pass: MCV (<= MC) m-tiles x NB n-tiles of this warp over all k-chunks of
 // one PT block.  ALLNB: every n-tile of the warp is inside the slice (no predicates at all).
-template <int NB, int MCV, bool ALLNB>
+struct NoHook {
+    __device__ __forceinline__ void operator()(int) const {}
+};
+
+// `hook(jc)` runs after the DMMAs of chunk jc have been issued (scalar work that overlaps the tensor pipe).
+template <int NB, int MCV, bool ALLNB, class Hook = NoHook>
 __device__ __forceinline__ void gemm_pass(double (&cre)[MC][NB][2], double (&cim)[MC][NB][2],
                                           const double* const (&are)[MC], const double* const (&aim)[MC],
                                           const bool (&aval)[MC], const bool (&nbv)[NB],
                                           const double* chunks, int chunk_doubles, int strideB, int nch,
                                           int warp, int g, int tq, uint32_t bar_full, uint32_t bar_empty,
-                                          int& stage, uint32_t& phase, int stages, int lane) {
-    for (int jc = 0; jc < nch; ++jc) {
-        mbar_wait(bar_full + 8 * stage, phase);
-        const double* bre = chunks + (size_t)stage * chunk_doubles;
+                                          int& stage, uint32_t& phase, int stages, int lane, Hook hook = Hook()) {
+    static_assert(KC == 8, "the main loop is written for two DMMA k-steps per chunk");
+    // Software-pipelined over k-steps: the fragments of the NEXT k-step are loaded before the DMMAs of the current
+    // one are issued -- across the chunk boundary too (wait for the next stage, load its first fragments, release
+    // the current stage, THEN issue the last DMMA batch of the current chunk), so a warp's DMMA stream has no gap
+    // at a chunk boundary (the two warps of a sub-partition alternate on the tensor pipe in lockstep and would
+    // otherwise idle it together there).
+    double a_re[2][MCV], a_im[2][MCV], b_re[2][NB], b_im[2][NB];
+    auto load = [&](int buf, const double* bre, int ks, int k) {
         const double* bim = bre + KC * strideB;
 #pragma unroll
-        for (int ks = 0; ks < KC / 4; ++ks) {
-            const int k = jc * KC + 4 * ks;
-            double a_re[MCV], a_im[MCV], b_re[NB], b_im[NB];
+        for (int mc = 0; mc < MCV; ++mc) {
+            a_re[buf][mc] = aval[mc] ? are[mc][k] : 0.0;
+            a_im[buf][mc] = aval[mc] ? aim[mc][k] : 0.0;
+        }
 #pragma unroll
-            for (int mc = 0; mc < MCV; ++mc) {
-                a_re[mc] = aval[mc] ? are[mc][k] : 0.0;
-                a_im[mc] = aval[mc] ? aim[mc][k] : 0.0;
-            }
+        for (int nb = 0; nb < NB; ++nb) {
+            const int bo = (4 * ks + tq) * strideB + 8 * (warp + N_COMPUTE_WARPS * nb) + g;
+            b_re[buf][nb] = (ALLNB || nbv[nb]) ? bre[bo] : 0.0;
+            b_im[buf][nb] = (ALLNB || nbv[nb]) ? bim[bo] : 0.0;
+        }
+    };
+    auto batch = [&](int buf) {
+        // two sweeps so that consecutive DMMAs never share an accumulator
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) {
-                const int bo = (4 * ks + tq) * strideB + 8 * (warp + N_COMPUTE_WARPS * nb) + g;
-                b_re[nb] = (ALLNB || nbv[nb]) ? bre[bo] : 0.0;
-                b_im[nb] = (ALLNB || nbv[nb]) ? bim[bo] : 0.0;
-            }
-            // two sweeps so that consecutive DMMAs never share an accumulator
+        for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb)
+            for (int mc = 0; mc < MCV; ++mc)
+                if (ALLNB || nbv[nb]) {
+                    dmma(cre[mc][nb][0], cre[mc][nb][1], a_re[buf][mc], b_re[buf][nb]);
+                    dmma(cim[mc][nb][0], cim[mc][nb][1], a_re[buf][mc], b_im[buf][nb]);
+                }
 #pragma unroll
-                for (int mc = 0; mc < MCV; ++mc)
-                    if (ALLNB || nbv[nb]) {
-                        dmma(cre[mc][nb][0], cre[mc][nb][1], a_re[mc], b_re[nb]);
-                        dmma(cim[mc][nb][0], cim[mc][nb][1], a_re[mc], b_im[nb]);
-                    }
+        for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-                for (int mc = 0; mc < MCV; ++mc)
-                    if (ALLNB || nbv[nb]) {
-                        dmma(cre[mc][nb][0], cre[mc][nb][1], -a_im[mc], b_im[nb]);
-                        dmma(cim[mc][nb][0], cim[mc][nb][1], a_im[mc], b_re[nb]);
-                    }
+            for (int mc = 0; mc < MCV; ++mc)
+                if (ALLNB || nbv[nb]) {
+                    dmma(cre[mc][nb][0], cre[mc][nb][1], -a_im[buf][mc], b_im[buf][nb]);
+                    dmma(cim[mc][nb][0], cim[mc][nb][1], a_im[buf][mc], b_re[buf][nb]);
+                }
+    };
+    if (nch <= 0) return;
+    mbar_wait(bar_full + 8 * stage, phase);
+    load(0, chunks + (size_t)stage * chunk_doubles, 0, 0);
+    for (int jc = 0; jc < nch; ++jc) {
+        const double* bre = chunks + (size_t)stage * chunk_doubles;
+        load(1, bre, 1, jc * KC + 4);
+        batch(0);
+        const int cur = stage;
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+        if (jc + 1 < nch) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            load(0, chunks + (size_t)stage * chunk_doubles, 0, (jc + 1) * KC);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
-        if (++stage == stages) { stage = 0; phase ^= 1u; }
+        if (lane == 0) mbar_arrive(bar_empty + 8 * cur);     // every fragment of this chunk has been read
+        batch(1);
+        hook(jc);
     }
 }
 

@@ -11,7 +11,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // 8 independent accumulator chains per warp; 512 flop per DMMA.
-__global__ void __launch_bounds__(256) k_dmma_peak(double* sink, int iters) {
+__global__ void __launch_bounds__(1024) k_dmma_peak(double* sink, int iters) {
     double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
     double c[16];
 #pragma unroll
@@ -49,7 +49,15 @@ int launch_fp64_peak(int kind, int iters, double* sink_dev, int* blocks, int* th
     ACEQD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     *blocks = sms * 4;
     *threads = 256;
-    if (kind == 0)
+    if (kind >= 10) {   // occupancy probes: ONE block per SM with (kind - 10) warps per SM sub-partition
+        *blocks = sms;
+        *threads = 128 * (kind - 10);
+        if (*threads < 128 || *threads > 1024) {
+            set_error("aceqd_fp64_peak: kind %d out of range", kind);
+            return ACEQD_ERR_ARG;
+        }
+        k_dmma_peak<<<*blocks, *threads, 0, s>>>(sink_dev, iters);
+    } else if (kind == 0)
         k_dmma_peak<<<*blocks, *threads, 0, s>>>(sink_dev, iters);
     else
         k_dfma_peak<<<*blocks, *threads, 0, s>>>(sink_dev, iters);

@@ -93,10 +93,12 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     const uint32_t bar_y = smem_u32(bars + 2 * MAX_STAGES + 4), bar_free = smem_u32(bars + 2 * MAX_STAGES + 5);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
     const uint32_t bar_wfull = smem_u32(bars + 2 * MAX_STAGES), bar_wempty = smem_u32(bars + 2 * MAX_STAGES + 2);
-    const uint32_t bar_rd = smem_u32(bars + 2 * MAX_STAGES + 6);   // [2] "every warp has read the X rows of pass p"
     // offset (doubles) of state row (pos, j) inside a plane; rows are alpha-major with a skew
     auto rowoff = [&](int ps, int j) -> size_t { return (size_t)(ps * T + j) * strideA + (size_t)ps * SKEW; };
-    auto rowoff_r = [&](int row) -> size_t { return (size_t)row * strideA + (size_t)(row / T) * SKEW; };
+    // row / T for row < 1024, T <= 16 by a reciprocal multiplication (exact in that range)
+    const unsigned invT = ((1u << 20) + (unsigned)T - 1u) / (unsigned)T;
+    auto divT = [&](int row) -> int { return (int)(((unsigned)row * invT) >> 20); };
+    auto rowoff_r = [&](int row) -> size_t { return (size_t)row * strideA + (size_t)divT(row) * SKEW; };
 
     // ------------------------------------------------------------------ setup (once per CTA)
     for (int j = tid; j < p.n_pass; j += blockDim.x) passes[j] = p.passes[j];
@@ -117,7 +119,6 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             mbar_init(bar_wfull + 8 * s, 1);
             mbar_init(bar_wempty + 8 * s, N_COMPUTE_WARPS);
         }
-        for (int s = 0; s < 2; ++s) mbar_init(bar_rd + 8 * s, N_COMPUTE_WARPS);
         mbar_init(bar_y, (uint32_t)C);                       // own expect_tx arrival + one arrival per peer
         mbar_init(bar_free, (uint32_t)(C > 1 ? C - 1 : 1));  // "I have read your rows" from every peer
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     const int n_seg = p.segs ? p.seg_off[blockIdx.x + 1] - seg_first : 1;
     // pipeline positions persist across segments (producer and consumers advance identically)
     int stage = 0;
-    uint32_t phase = 0, wph0 = 0u, wph1 = 0u, rdph0 = 0u, rdph1 = 0u;
+    uint32_t phase = 0, wph0 = 0u, wph1 = 0u;
     for (int si = 0; si < n_seg; ++si) {
     SegDesc sg;
     if (p.segs) {
@@ -189,6 +190,18 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         n_end = max(n_end, trj[j].step0 + trj[j].n_steps);
     }
     if (n_end < 0) continue;  // empty tile
+    // tile-level facts that let the step loop skip per-trajectory checks
+    int s0_max = -1, e_min = 0x7fffffff;
+    bool all_valid = true, has_snap = false;
+    for (int j = 0; j < T; ++j) {
+        if (trj[j].n_steps < 0) {
+            all_valid = false;
+            continue;
+        }
+        s0_max = max(s0_max, trj[j].step0);
+        e_min = min(e_min, trj[j].step0 + trj[j].n_steps);
+        has_snap |= trj[j].snap_cnt > 0;
+    }
     const int n_lo = max(n_begin, sg.n_lo), n_hi = min(n_end, sg.n_hi);
     const bool final_seg = n_hi == n_end;   // else: stop BEFORE output row n_hi and save the state
     if (sg.load_slot >= 0) {
@@ -354,7 +367,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         TICK(0);
         // ---------------- phase A: outputs (closures rall[] come from the previous GEMM epilogue)
         // rows of trajectories that START at this row have no closure yet: generic closure pass
+        const bool full_act = all_valid && n >= s0_max && n < e_min;   // every trajectory of the tile steps n -> n+1
         bool any_start = false, any_snap = false;
+        if (n <= s0_max || has_snap)
         for (int j = 0; j < T; ++j) {
             const aceqd_traj& t = trj[j];
             if (t.n_steps < 0) continue;
@@ -365,7 +380,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         }
         if (any_start) {
             for (int row = warp; row < R; row += N_COMPUTE_WARPS) {
-                const int j = row % T;
+                const int j = row - divT(row) * T;
                 const aceqd_traj& t = trj[j];
                 if (t.n_steps < 0 || n != t.step0) continue;
                 double2 acc = make_double2(0.0, 0.0);
@@ -640,50 +655,49 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         free_waited = false;
         // epilogue of one pass: new rows into the state (in place) + this warp's closure partials
         auto epilogue = [&](const PassDesc& pd, const double (&cre)[MC][NB][2], const double (&cim)[MC][NB][2]) {
+            // both m-tiles side by side (independent dependency chains: the FP64 latency is exposed here)
+            double pr[MC], pi[MC];
+            int row[MC];
+            bool wr[MC];
 #pragma unroll
             for (int mc = 0; mc < MC; ++mc) {
-                if (pd.nvalid[mc] <= 0) continue;   // warp-uniform
                 const bool av = g < pd.nvalid[mc];
-                const int row = pd.row0[mc] + (av ? g : 0);
-                const aceqd_traj& t = trj[row % T];
-                const bool wr = av && t.n_steps >= 0 && n >= t.step0 && n < t.step0 + t.n_steps;
-                // closure partial of this warp's columns: r[row] += sum_col Y[row, col] q[col]
-                double pr = 0.0, pi = 0.0;
-                const size_t ro = rowoff_r(row);
+                row[mc] = pd.row0[mc] + (av ? g : 0);
+                const aceqd_traj& t = trj[row[mc] - divT(row[mc]) * T];
+                wr[mc] = av && (full_act || (t.n_steps >= 0 && n >= t.step0 && n < t.step0 + t.n_steps));
+                pr[mc] = pi[mc] = 0.0;
+            }
 #pragma unroll
-                for (int nb = 0; nb < NB; ++nb) {
-                    if (nbv[nb]) {
-                        const int c0 = 8 * (warp + N_COMPUTE_WARPS * nb) + 2 * tq;
-                        const double2 q0 = qbuf[c0], q1 = qbuf[c0 + 1];
-                        pr += cre[mc][nb][0] * q0.x - cim[mc][nb][0] * q0.y + cre[mc][nb][1] * q1.x - cim[mc][nb][1] * q1.y;
-                        pi += cre[mc][nb][0] * q0.y + cim[mc][nb][0] * q0.x + cre[mc][nb][1] * q1.y + cim[mc][nb][1] * q1.x;
-                        if (wr) {
-                            const size_t o = ro + c0;
-                            *reinterpret_cast<double2*>(Xre + o) = make_double2(cre[mc][nb][0], cre[mc][nb][1]);
-                            *reinterpret_cast<double2*>(Xim + o) = make_double2(cim[mc][nb][0], cim[mc][nb][1]);
-                        }
+            for (int nb = 0; nb < NB; ++nb) {
+                if (!nbv[nb]) continue;
+                const int c0 = 8 * (warp + N_COMPUTE_WARPS * nb) + 2 * tq;
+                const double2 q0 = qbuf[c0], q1 = qbuf[c0 + 1];
+#pragma unroll
+                for (int mc = 0; mc < MC; ++mc) {
+                    if (pd.nvalid[mc] <= 0) continue;   // warp-uniform
+                    // closure partial of this warp's columns: r[row] += sum_col Y[row, col] q[col]
+                    const double r0 = cre[mc][nb][0], r1 = cre[mc][nb][1], i0 = cim[mc][nb][0], i1 = cim[mc][nb][1];
+                    pr[mc] += (r0 * q0.x - i0 * q0.y) + (r1 * q1.x - i1 * q1.y);
+                    pi[mc] += (r0 * q0.y + i0 * q0.x) + (r1 * q1.y + i1 * q1.x);
+                    if (wr[mc]) {
+                        const size_t o = rowoff_r(row[mc]) + c0;
+                        *reinterpret_cast<double2*>(Xre + o) = make_double2(r0, r1);
+                        *reinterpret_cast<double2*>(Xim + o) = make_double2(i0, i1);
                     }
                 }
-                pr += __shfl_xor_sync(0xffffffffu, pr, 1);
-                pi += __shfl_xor_sync(0xffffffffu, pi, 1);
-                pr += __shfl_xor_sync(0xffffffffu, pr, 2);
-                pi += __shfl_xor_sync(0xffffffffu, pi, 2);
-                if (wr && tq == 0) rpart[warp * R + row] = make_double2(pr, pi);
             }
-        };
-        // Without a cluster the in-place row update of pass p is DEFERRED until this warp has issued the GEMM of
-        // pass p+1: "every warp has read the rows of pass p" is a split barrier (mbarrier arrive after the main
-        // loop, wait before the write), so the warps never meet between passes and one warp's epilogue overlaps
-        // the other warps' DMMAs.
-        // (two accumulator sets: only while they fit the 168 registers a 9-warp CTA leaves per thread)
-        constexpr bool DEFER = NB <= 2;
-        constexpr int NBP = DEFER ? NB : 1;
-        double pre[MC][NBP][2], pim[MC][NBP][2];
-        PassDesc ppd{};
-        int pend = -1;
-        auto rd_wait = [&](int b) {
-            mbar_wait(bar_rd + 8 * b, b ? rdph1 : rdph0);
-            if (b) rdph1 ^= 1u; else rdph0 ^= 1u;
+#pragma unroll
+            for (int mc = 0; mc < MC; ++mc) {
+                pr[mc] += __shfl_xor_sync(0xffffffffu, pr[mc], 1);
+                pi[mc] += __shfl_xor_sync(0xffffffffu, pi[mc], 1);
+            }
+#pragma unroll
+            for (int mc = 0; mc < MC; ++mc) {
+                if (pd.nvalid[mc] <= 0) continue;
+                pr[mc] += __shfl_xor_sync(0xffffffffu, pr[mc], 2);
+                pi[mc] += __shfl_xor_sync(0xffffffffu, pi[mc], 2);
+                if (wr[mc] && tq == 0) rpart[warp * R + row[mc]] = make_double2(pr[mc], pi[mc]);
+            }
         };
         for (int ps = 0; ps < p.n_pass; ++ps) {
             const PassDesc pd = passes[ps];
@@ -736,42 +750,19 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 gemm_pass<NB, 1, false>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
                                         warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
             TICK(7);
-            if (DEFER && C == 1) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_rd + 8 * (ps & 1));
-                if (pend >= 0) {
-                    rd_wait(pend & 1);
-                    if constexpr (DEFER) epilogue(ppd, pre, pim);
-                }
-#pragma unroll
-                for (int mc = 0; mc < MC; ++mc)
-#pragma unroll
-                    for (int nb = 0; nb < NBP; ++nb) {
-                        pre[mc][nb][0] = cre[mc][nb][0];
-                        pre[mc][nb][1] = cre[mc][nb][1];
-                        pim[mc][nb][0] = cim[mc][nb][0];
-                        pim[mc][nb][1] = cim[mc][nb][1];
-                    }
-                ppd = pd;
-                pend = ps;
-                continue;
-            }
             compute_bar();  // every warp has finished reading this pass's X rows
-            // ... and has finished writing the previous pass's rows: send them
-            if (tid == 0 && pending_push >= 0) push_pass(passes[pending_push]);
-            pending_push = ps;
+            if (C > 1) {    // ... and has finished writing the previous pass's rows: send them
+                if (tid == 0 && pending_push >= 0) push_pass(passes[pending_push]);
+                pending_push = ps;
+            }
             epilogue(pd, cre, cim);
-        }
-        if (pend >= 0) {
-            rd_wait(pend & 1);
-            if constexpr (DEFER) epilogue(ppd, pre, pim);
         }
         TICK(4);
         compute_bar();
         TICK(5);
         // closure of the rows computed here: sum the per-warp partials; peers get a copy
         for (int row = tid; row < R; row += N_COMPUTE_WARPS * 32) {
-            if (C > 1 && !own_pos[row / T]) continue;
+            if (C > 1 && !own_pos[divT(row)]) continue;
             double2 r = rpart[row];
 #pragma unroll
             for (int w8 = 1; w8 < N_COMPUTE_WARPS; ++w8) {

@@ -324,7 +324,9 @@ class Engine:
 
     def fp64_peak(self, kind: str = "dmma", iters: int = 20000) -> float:
         v = c_double()
-        _check(self.lib.aceqd_fp64_peak(self.ctx, 0 if kind == "dmma" else 1, iters, ctypes.byref(v)),
+        # "dmma", "dfma", or an int: 10 + w = DMMA with ONE block per SM and w warps per SM sub-partition
+        code = kind if isinstance(kind, int) else (0 if kind == "dmma" else 1)
+        _check(self.lib.aceqd_fp64_peak(self.ctx, code, iters, ctypes.byref(v)),
                "aceqd_fp64_peak")
         return v.value
 
