@@ -265,6 +265,225 @@ __global__ void __launch_bounds__(256) k_opbuild(OpBuildParams p) {
     }
 }
 
+// -------------------------------------------------------------------------------------------
+// Register-resident operator builder for small Liouville spaces (NL = N <= 4: two-level emitters, i.e. the
+// pulse-parameter sweeps of two_level_system/rabi_rotations.py:172-198).  The group kernel above is bound by
+// shared-memory traffic there (one LDS.128 per complex FMA); here ONE THREAD owns one entry, the matrices live in
+// registers and the exponential is the same degree-12 Taylor polynomial, evaluated by Horner's rule with RIGHT
+// multiplications   P <- I + (P A)/k ,  k = 12 .. 1   so that row i of the new P needs only row i of the old one
+// (in place, one row of temporaries).
+template <int N>
+__device__ __forceinline__ void expm_reg(double2 (&A)[N][N], double2 (&P)[N][N]) {
+    double nrm = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double cs = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) cs += sqrt(A[i][j].x * A[i][j].x + A[i][j].y * A[i][j].y);
+        nrm = fmax(nrm, cs);
+    }
+    int s = 0;
+    if (nrm > THETA) {
+        int ex;
+        frexp(nrm / THETA, &ex);
+        s = ex > 60 ? 60 : ex;
+    }
+    const double sc = ldexp(1.0, -s);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            A[i][j].x *= sc;
+            A[i][j].y *= sc;
+            P[i][j] = make_double2(A[i][j].x * (1.0 / 12.0) + (i == j ? 1.0 : 0.0), A[i][j].y * (1.0 / 12.0));
+        }
+#pragma unroll 1
+    for (int k = 11; k >= 1; --k) {
+        const double inv = 1.0 / (double)k;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double2 row[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int m = 0; m < N; ++m) cfma(acc, P[i][m], A[m][j]);
+                row[j] = acc;
+            }
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+                P[i][j] = make_double2(row[j].x * inv + (i == j ? 1.0 : 0.0), row[j].y * inv);
+        }
+    }
+#pragma unroll 1
+    for (int q = 0; q < s; ++q) {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) A[i][j] = P[i][j];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int m = 0; m < N; ++m) cfma(acc, A[i][m], A[m][j]);
+                P[i][j] = acc;
+            }
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void assemble_reg(double2 (&A)[N][N], const OpBuildParams& p, int set, double t,
+                                             double delta) {
+    const double2* L0 = reinterpret_cast<const double2*>(p.prob.L0);
+    const double2* LA = reinterpret_cast<const double2*>(p.prob.LA);
+    const double2* LB = reinterpret_cast<const double2*>(p.prob.LB);
+    const double2* tabs = reinterpret_cast<const double2*>(p.tables);
+    const double x = (t - p.tab_t0) / p.tab_dt;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) A[i][j] = __ldg(L0 + i * N + j);
+    for (int k = 0; k < p.prob.n_fields; ++k) {
+        const int tb = p.prob.field_table[k];
+        if (tb < 0 || tb >= p.n_tables) continue;
+        const double2 f = sample_table(tabs + ((size_t)set * p.n_tables + tb) * p.n_samples, p.n_samples, x);
+        const double2 fc = make_double2(f.x, -f.y);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                cfma(A[i][j], f, __ldg(LA + (size_t)k * N * N + i * N + j));
+                cfma(A[i][j], fc, __ldg(LB + (size_t)k * N * N + i * N + j));
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            A[i][j].x *= delta;
+            A[i][j].y *= delta;
+        }
+}
+
+constexpr int OPREG_THREADS = 128;
+
+template <int N>
+__global__ void __launch_bounds__(OPREG_THREADS) k_opbuild_reg(OpBuildParams p) {
+    __shared__ double2 park[N * N * OPREG_THREADS];   // X = Sa V of every thread, element-major (conflict-free)
+    const long long total = p.e_end > p.e_begin ? p.e_end : p.n_seq_entries + p.n_entries;
+    const double half = 0.5 * p.dt;
+    const double2* mto = reinterpret_cast<const double2*>(p.mto_mats);
+    double2* mine = park + threadIdx.x;
+    const int ld = p.prob.NLp4, n_out = p.prob.n_out;
+    for (long long e = p.e_begin + (long long)blockIdx.x * OPREG_THREADS + threadIdx.x; e < total;
+         e += (long long)gridDim.x * OPREG_THREADS) {
+        int set, step, sb = -1, sa = -1, has_prev;
+        if (e < p.n_seq_entries) {
+            int lo = 0, hi = p.n_seq;  // seq_base[lo] <= e < seq_base[hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (p.seq_base[mid] <= e) lo = mid; else hi = mid;
+            }
+            const aceqd_seq sq = p.seqs[lo];
+            const int i = (int)(e - p.seq_base[lo]);
+            set = sq.set;
+            step = sq.step0 + i;
+            has_prev = (i > 0) || sq.first_has_prev;
+        } else {
+            const aceqd_entry en = p.entries[e - p.n_seq_entries];
+            set = en.set; step = en.step; sb = en.sb; sa = en.sa; has_prev = en.has_prev;
+        }
+        const double t_n = p.t0 + (double)step * p.dt;
+        double2 A[N][N], P[N][N];
+        // ---- V = Sb * M2_{n-1}
+        if (has_prev) {
+            assemble_reg<N>(A, p, set, t_n - p.dt + p.eval_off2 * p.dt, half);
+            expm_reg<N>(A, P);
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+#pragma unroll
+                for (int j = 0; j < N; ++j) P[i][j] = make_double2(i == j ? 1.0 : 0.0, 0.0);
+        }
+        if (sb >= 0) {   // rare (multi-time operator rows)
+            const double2* S = mto + (size_t)sb * N * N;
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int m = 0; m < N; ++m) cfma(acc, S[i * N + m], P[m][j]);
+                    A[i][j] = acc;
+                }
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+#pragma unroll
+                for (int j = 0; j < N; ++j) P[i][j] = A[i][j];
+        }
+        // ---- OV = out_w * V
+        {
+            const double2* ow = reinterpret_cast<const double2*>(p.prob.out_w);
+            double2* ov = reinterpret_cast<double2*>(p.OV + (size_t)e * p.prob.ov_doubles);
+            for (int j = 0; j < n_out; ++j) {
+                double2 o4[N];
+#pragma unroll
+                for (int a = 0; a < N; ++a) o4[a] = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    const double2 w = __ldg(ow + j * N + k);
+#pragma unroll
+                    for (int a = 0; a < N; ++a) cfma(o4[a], w, P[k][a]);
+                }
+#pragma unroll
+                for (int a = 0; a < N; ++a) ov[j * N + a] = o4[a];
+            }
+        }
+        // ---- X = Sa * V  -> parked in shared memory while M1 is built
+        if (sa >= 0) {
+            const double2* S = mto + (size_t)sa * N * N;
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int m = 0; m < N; ++m) cfma(acc, S[i * N + m], P[m][j]);
+                    mine[(i * N + j) * OPREG_THREADS] = acc;
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+#pragma unroll
+                for (int j = 0; j < N; ++j) mine[(i * N + j) * OPREG_THREADS] = P[i][j];
+        }
+        // ---- W = M1_n * X   (zero padded to [NLp8][NLp4])
+        assemble_reg<N>(A, p, set, t_n + p.eval_off1 * p.dt, half);
+        expm_reg<N>(A, P);
+        double2* w = reinterpret_cast<double2*>(p.W + (size_t)e * p.prob.w_doubles);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double2 xc[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) xc[k] = mine[(k * N + j) * OPREG_THREADS];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int k = 0; k < N; ++k) cfma(acc, P[i][k], xc[k]);
+                A[i][j] = acc;
+            }
+        }
+        // NLp8 x NLp4 = 8 x 4 for N = 4 (checked by the launcher)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) w[i * ld + j] = i < N ? A[i < N ? i : 0][j] : make_double2(0.0, 0.0);
+    }
+}
+
 template <int G>
 __global__ void __launch_bounds__(256) k_expm_batch(int n, int count, const double* a,
                                                     double* out, double* scratch) {
@@ -321,6 +540,14 @@ int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches) 
     if (n > MAX_NL) {
         set_error("NL=%d exceeds MAX_NL=%d", n, MAX_NL);
         return ACEQD_ERR_CAPACITY;
+    }
+    if (n == 4 && p.prob.NLp8 == 8 && p.prob.NLp4 == 4 && !getenv("ACEQD_OPBUILD_GROUP")) {   // register-resident builder, one thread per entry
+        long long blocks = (total + OPREG_THREADS - 1) / OPREG_THREADS;
+        if (blocks > 148LL * 32) blocks = 148LL * 32;
+        k_opbuild_reg<4><<<(int)blocks, OPREG_THREADS, 0, s>>>(p);
+        ++*launches;
+        ACEQD_CUDA(cudaGetLastError());
+        return ACEQD_OK;
     }
     const int G = pick_group(n);
     const int groups = 256 / G;
