@@ -772,11 +772,21 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
         if ((rc = c->snaps.reserve((size_t)b->n_snap_slots * pd.NL * chi_pad * 16))) return rc;
     }
     double* out_dev = nullptr;
+    bool zero_copy = false;   // page-locked host output: the kernel writes its rows straight through PCIe
     if (b->device_resident) {
         out_dev = b->out;
     } else {
-        if ((rc = c->out.reserve((size_t)b->out_elems * 16))) return rc;
-        out_dev = (double*)c->out.p;
+        cudaPointerAttributes at{};
+        const char* env = getenv("ACEQD_NO_ZEROCOPY");
+        if (!(env && env[0] == '1') && cudaPointerGetAttributes(&at, b->out) == cudaSuccess &&
+            at.type == cudaMemoryTypeHost && at.devicePointer) {
+            out_dev = (double*)at.devicePointer;
+            zero_copy = true;
+        } else {
+            cudaGetLastError();
+            if ((rc = c->out.reserve((size_t)b->out_elems * 16))) return rc;
+            out_dev = (double*)c->out.p;
+        }
     }
 
     StepParams sp{};
@@ -970,7 +980,7 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
                 ACEQD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_built, 0));
                 c->split_ops_pending = false;
             }
-            const bool copy_early = !b->device_resident && c->split_out > 0;
+            const bool copy_early = !b->device_resident && !zero_copy && c->split_out > 0;
             if (copy_early) {
                 if (!c->copy_stream) {
                     ACEQD_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -994,8 +1004,9 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
                 return ACEQD_OK;
             }
             if (!b->device_resident) {
-                ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)b->out_elems * 16, cudaMemcpyDeviceToHost,
-                                           c->stream));
+                if (!zero_copy)
+                    ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)b->out_elems * 16, cudaMemcpyDeviceToHost,
+                                               c->stream));
                 ACEQD_CUDA(cudaStreamSynchronize(c->stream));
             }
             return ACEQD_OK;
@@ -1009,8 +1020,9 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
     }
     c->have_step = true;
     if (!b->device_resident) {
-        ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)b->out_elems * 16,
-                                   cudaMemcpyDeviceToHost, c->stream));
+        if (!zero_copy)
+            ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)b->out_elems * 16,
+                                       cudaMemcpyDeviceToHost, c->stream));
         ACEQD_CUDA(cudaStreamSynchronize(c->stream));
     }
     return ACEQD_OK;

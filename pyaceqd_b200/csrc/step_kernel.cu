@@ -472,9 +472,20 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             // NL <= 4 (two-level system): a DMMA m-tile would be half empty and its operand traffic heavy.
             // The FP64 FMA pipe has the same peak on this part (profiles/r01_fp64_peaks.log): warp w takes
             // trajectories w, w+8, ..., keeps W_n in registers, lane = bond column, 16 complex FMAs per column.
-            for (int j = warp; j < T; j += N_COMPUTE_WARPS) {
+            // With more than one trajectory per warp the two half-warps take one trajectory each (16 bond columns per
+            // sweep) so that the operator loads and the loop overhead of both are paid once, side by side.
+            const int LPT = T > N_COMPUTE_WARPS ? 16 : 32;        // lanes per trajectory
+            const int per_warp = 32 / LPT;
+            const int sub = lane / LPT, cl = lane - sub * LPT;
+            for (int jb = warp * per_warp; jb < T; jb += N_COMPUTE_WARPS * per_warp) {
+                const int j = jb + sub;
+                bool actj = false;
+                if (j < T) {
+                    const aceqd_traj& t = trj[j];
+                    actj = full_act || (t.n_steps >= 0 && n >= t.step0 && n < t.step0 + t.n_steps);
+                }
+                if (!actj) continue;     // no warp-level synchronisation inside this loop
                 const aceqd_traj& t = trj[j];
-                if (!(t.n_steps >= 0 && n >= t.step0 && n < t.step0 + t.n_steps)) continue;
                 const double2* Wp;
                 if (wsm) {
                     Wp = reinterpret_cast<const double2*>(Wst + (size_t)(buf * T + j) * wov);
@@ -494,7 +505,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                         w[a][k] = (a < NL && k < NL) ? (wsm ? Wp[a * NLp4 + k] : __ldg(Wp + a * NLp4 + k))
                                                      : make_double2(0.0, 0.0);
                 }
-                for (int c = lane; c < chi_pad; c += 32) {
+                for (int c = cl; c < chi_pad; c += LPT) {
                     double2 y[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
