@@ -801,6 +801,8 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
     sp.snaps = (double*)c->snaps.p;
     sp.out = out_dev;
     sp.ticks = c->ticks;
+    if (const char* tc = getenv("ACEQD_TICK_CLUSTER"))   // debug clock only for launches of this cluster size
+        if (atoi(tc) != (b->cluster <= 1 ? 1 : b->cluster)) sp.ticks = nullptr;
 
     if (b->kernel == 2) {
         // ---- step-synchronous streaming kernel: state in HBM/L2, class-batched PT GEMM
