@@ -441,7 +441,7 @@ def main():
         achieved = fl / (k_avg * 1e-3) / 1e12
         algo_bytes = n_traj * (args.n_steps + 1) * (768.0 + 16.0 * n_out)
         default_cfg = (args.chi, args.n_area, args.n_det, args.n_steps) == (128, 64, 64, 400)
-        traffic = 1.270547e9 + 104.552448e6 if default_cfg else None
+        traffic = 1.293501e9 + 123.809024e6 if default_cfg else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -453,8 +453,9 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "k_step_dmma", "achieved": achieved, "peak": peak_dmma,
                          "unit": "TFLOP/s", "frac": achieved / peak_dmma, "traffic": traffic,
                          "traffic_note": "DRAM bytes (read+write) of one step-kernel launch of this exact config from "
-                                         "the ncu --set full capture profiles/r01w_cfg2_full_step_kernel_ncu.txt; "
-                                         "algorithmic bytes (per-row operators + outputs) = %.4g" % algo_bytes,
+                                         "the ncu --set full capture profiles/r03n_cfg2_full_step_kernel_ncu.txt "
+                                         "(includes 0.04 GB of bond states handed between CTAs by the segment "
+                                         "schedule); algorithmic bytes (per-row operators + outputs) = %.4g" % algo_bytes,
                          "peak_source": "FP64 DMMA.8x8x4 register-resident micro-benchmark (aceqd_fp64_peak) measured in this run; "
                                         "MEASURED_PEAKS.json holds no FP64 figure; nominal B200 FP64 ~40 TFLOP/s",
                          "dfma_peak": peak_dfma, "kernel_ms": k_avg, "opbuild_ms": float(np.mean(op_ms)),
