@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libaceqd.so")
-SOURCES = ["api.cu", "expm.cu", "step_kernel.cu", "stream_kernel.cu", "tlmap.cu", "peak.cu"]
+SOURCES = ["api.cu", "expm.cu", "step_kernel.cu", "small_kernel.cu", "stream_kernel.cu", "tlmap.cu", "peak.cu"]
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
               "-lineinfo", "-O3", "-std=c++17", "-diag-suppress", "177"]
 

@@ -66,7 +66,7 @@ struct aceqd_ctx {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // step, opbuild, tlmap start/stop
     bool have_step = false, have_op = false, have_tl = false;
     DevBuf W, OV, tables, seqs, seq_base, entries, mto, rho0s, trajs, tiles, snap_steps, snaps,
-        out, passes, scratch, misc, segs, seg_off, seg_state, seg_flags, opscratch, st_x, st_order, st_bar, st_apos, tl_pool, tl_v0, tl_segoff, tl_segs, tl_w, tl_out, tl_final;
+        out, passes, scratch, misc, octets, segs, seg_off, seg_state, seg_flags, opscratch, st_x, st_order, st_bar, st_apos, tl_pool, tl_v0, tl_segoff, tl_segs, tl_w, tl_out, tl_final;
     long long* ticks = nullptr;           // debug phase clock of the step kernel (aceqd_debug_phase_ticks)
     // layout of the operators currently in the workspace
     long long n_seq_entries = 0;
@@ -76,6 +76,7 @@ struct aceqd_pt {
     aceqd_ctx* ctx = nullptr;
     PtDev d{};
     void *blob = nullptr, *closure = nullptr, *kin = nullptr, *nout = nullptr, *off = nullptr;
+    long long blob_doubles = 0;
 };
 
 struct aceqd_problem {
@@ -138,7 +139,7 @@ void aceqd_ctx_destroy(aceqd_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->W, &c->OV, &c->tables, &c->seqs, &c->seq_base, &c->entries, &c->mto,
                       &c->rho0s, &c->trajs, &c->tiles, &c->snap_steps, &c->snaps, &c->out,
-                      &c->passes, &c->scratch, &c->misc, &c->segs, &c->seg_off, &c->seg_state, &c->seg_flags, &c->opscratch, &c->st_x, &c->st_order, &c->st_bar, &c->st_apos, &c->tl_pool, &c->tl_v0, &c->tl_segoff,
+                      &c->passes, &c->scratch, &c->misc, &c->octets, &c->segs, &c->seg_off, &c->seg_state, &c->seg_flags, &c->opscratch, &c->st_x, &c->st_order, &c->st_bar, &c->st_apos, &c->tl_pool, &c->tl_v0, &c->tl_segoff,
                       &c->tl_segs, &c->tl_w, &c->tl_out, &c->tl_final})
         b->release();
     for (auto& ev : c->ev)
@@ -258,6 +259,7 @@ int aceqd_pt_create(aceqd_ctx* c, int n_cls, int n_slices, int n_initial, const 
         set_error("aceqd_pt_create: sync failed");
         return fail(ACEQD_ERR_CUDA);
     }
+    pt->blob_doubles = total;
     PtDev& d = pt->d;
     d.n_cls = n_cls;
     d.n_slices = n_slices;
@@ -907,6 +909,56 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
         if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) {
             set_error("batch: cluster must be 0/1, 2, 4 or 8");
             return ACEQD_ERR_ARG;
+        }
+        // ---- small-bond regime of two-level sweeps: one warp per 8 trajectories, PT resident in shared memory
+        {
+            const char* env = getenv("ACEQD_SMALL");
+            const bool allow = !(env && env[0] == '0');
+            int n_sm = 148;
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
+            if (allow && pd.NL == 4 && chi_pad <= 32 && cluster == 1 && b->n_snap_steps == 0 && pd.n_out <= 16 &&
+                pd.NLp4 == 4 && small_smem_bytes(pt->blob_doubles, pt->d.n_slices, chi_pad, pd.n_out, 1) <= (size_t)SMEM_BUDGET) {
+                std::vector<int32_t> oct;
+                oct.reserve((size_t)b->n_tiles * T + 8);
+                for (long long i = 0; i < (long long)b->n_tiles * T; ++i)
+                    if (b->tile_traj[i] >= 0) oct.push_back(b->tile_traj[i]);
+                const int n_oct = (int)((oct.size() + 7) / 8);
+                oct.resize((size_t)n_oct * 8, -1);
+                // fewest warps per CTA for which every CTA is resident at once (the PT copy is per CTA); else 4
+                int wpc = 4;
+                for (int w : {1, 2, 4, 8}) {
+                    const size_t sm = small_smem_bytes(pt->blob_doubles, pt->d.n_slices, chi_pad, pd.n_out, w);
+                    if (sm > (size_t)SMEM_BUDGET) break;
+                    const long long per_sm = std::min<long long>((long long)((size_t)SMEM_BUDGET / sm), 2048 / (32 * w));
+                    if ((long long)(n_oct + w - 1) / w <= per_sm * n_sm) {
+                        wpc = w;
+                        break;
+                    }
+                    wpc = w;
+                }
+                UP(c->octets, oct.data(), oct.size() * sizeof(int32_t));
+                sp.T = 8;
+                sp.n_tiles = n_oct;
+                sp.tile_traj = (const int*)c->octets.p;
+                sp.cluster = 1;
+                const size_t smem = small_smem_bytes(pt->blob_doubles, pt->d.n_slices, chi_pad, pd.n_out, wpc);
+                if (c->split_ops_pending) {      // operators of a planned wave split: all of them are needed here
+                    ACEQD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_built, 0));
+                    c->split_ops_pending = false;
+                }
+                c->split_tiles = 0;
+                ACEQD_CUDA(cudaEventRecord(c->ev[0], c->stream));
+                if ((rc = launch_step_small(sp, pt->blob_doubles, wpc, smem, c->stream, &c->launches))) return rc;
+                ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
+                c->have_step = true;
+                if (!b->device_resident) {
+                    if (!zero_copy)
+                        ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)b->out_elems * 16, cudaMemcpyDeviceToHost,
+                                                   c->stream));
+                    ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+                }
+                return ACEQD_OK;
+            }
         }
         std::vector<PassDesc> passes;
         if ((rc = build_passes(prob, T, cluster, passes))) return rc;

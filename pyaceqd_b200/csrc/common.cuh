@@ -166,6 +166,10 @@ int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, lon
 int launch_step_check(const StepParams& p, double* scratch, cudaStream_t s, long long* launches);
 size_t step_smem_bytes(int NL, int chi_pad, int T, int stages, int wov_doubles, int wbufs);
 size_t step_seg_slot_doubles(int NL, int chi_pad, int T);
+// small-bond kernel (small_kernel.cu): one warp per 8 trajectories, process tensor resident in shared memory
+size_t small_smem_bytes(long long pt_doubles, int n_slices, int chi_pad, int n_out, int warps);
+int launch_step_small(const StepParams& p, long long pt_doubles, int warps_per_cta, size_t smem_bytes, cudaStream_t s,
+                      long long* launches);
 int launch_step_stream(const StreamParams& p, size_t smem, cudaStream_t s, long long* launches);
 size_t stream_smem_bytes(int NL, int chi_pad, int stages, int wov_doubles);
 int launch_tlmap(int NL, int n_chains, int n_w, int n_emit_max, const double* pool, const double* v0,

@@ -222,3 +222,46 @@ def test_wave_split_copy_overlap_path(engine):
     assert max(np.abs(a - b).max() for a, b in zip(split, whole)) < 1e-12
     for k in (0, 147 * 2, 148 * 2, 599):                          # around the wave boundary
         assert np.abs(split[k] - oracle.propagate(prob, pt, jobs[k])).max() < TOL
+
+
+# ------------------------------------------------------------------ small-bond kernel (one warp per 8 trajectories)
+@pytest.mark.parametrize("chi", [5, 8, 16, 20, 32])
+def test_small_bond_kernel_matches_oracle_and_tile_kernel(engine, chi, monkeypatch):
+    """NL = 4, chi_pad <= 32 runs on k_step_small (PT resident in shared memory, warp-private state).  Ragged
+    lengths, multi-slice PTs, MTO rows (override entries), tails and a forked batch (branches start from snapshots
+    written by the tile kernel's trunk)."""
+    from pyaceqd_b200.opparser import parse_operator
+    prob = tls_problem()
+    pt = synthetic_pt(chi, len(prob.cls_keys), n_slices=2, kind="unitary", scale=0.999)
+    jobs = sweep_jobs(7, 9, t_end=6.0)                      # 63 trajectories: octets with a ragged tail
+    monkeypatch.setenv("ACEQD_SMALL", "1")
+    n0 = engine.launch_count()
+    got = engine.run_jobs(prob, pt, jobs, kernel="dmma")
+    for k in range(0, len(jobs), 5):
+        assert np.abs(got[k] - oracle.propagate(prob, pt, jobs[k])).max() < TOL
+    monkeypatch.setenv("ACEQD_SMALL", "0")
+    ref = engine.run_jobs(prob, pt, jobs, kernel="dmma")
+    assert max(np.abs(a - b).max() for a, b in zip(got, ref)) < 1e-12
+    monkeypatch.setenv("ACEQD_SMALL", "1")
+    # ragged lengths + MTOs at several times + tails
+    p = ChirpedPulse(tau_0=1.0, e_start=0.3, alpha=0, t0=2.0, e0=1.5)
+    s = parse_operator("|0><1|_2", 2)
+    rag = []
+    for te in (0.0, 0.1, 0.4, 1.0, 2.7, 3.3, 4.1, 5.0, 5.0, 2.2, 0.9):
+        tabs = make_tables([p], 0.0, max(te, 0.1), 0.1)
+        mt = [MTO(prob.mto_superop(s, ""), 0.0, False)]
+        if te >= 1.0:
+            mt += [MTO(prob.mto_superop(s.conj().T, "_left"), 0.5, True), MTO(prob.mto_superop(s, "_right"), 0.5, False)]
+        rag.append(Job(0.0, te, 0.1, tables=tabs, mtos=mt))
+    _compare(engine, prob, pt, rag, "dmma", fork=False)
+    # forked G1-style batch: trunk (tile kernel, snapshots) + branches (small kernel, init from snapshots)
+    tabs = make_tables([p], 0.0, 12.0, 0.1)
+    fj = []
+    for t1 in np.arange(0.5, 5.0, 0.5):
+        mt = prob.parse_mtos([{"operator": "|0><1|_2", "applyFrom": "_left", "time": float(t1)}])
+        fj.append(Job(0.0, float(t1 + 3.0), 0.1, tables=tabs, mtos=mt))
+    _compare(engine, prob, pt, fj, "dmma", fork=True)
+    tails = engine.run_jobs(prob, pt, [Job(j.t_start, j.t_end, j.dt, tables=j.tables, mtos=j.mtos, tail_rows=11)
+                                       for j in fj], kernel="dmma")
+    full = engine.run_jobs(prob, pt, fj, kernel="dmma")
+    assert max(np.abs(f[:, -11:] - t).max() for f, t in zip(full, tails)) < 1e-12
