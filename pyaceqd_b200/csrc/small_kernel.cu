@@ -60,7 +60,9 @@ template <int NT>
 __global__ void __launch_bounds__(256) k_step_small(const __grid_constant__ StepParams p, long long pt_doubles,
                                                    int warps_per_cta) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int chi_pad = p.pt.chi_pad, strideA = chi_pad + 4, strideB = p.pt.strideB;
+    // the bond dimension is a template parameter: every state / PT offset below folds into an immediate (a single
+    // warp per sub-partition cannot hide address arithmetic behind other warps)
+    constexpr int chi_pad = 8 * NT, strideA = chi_pad + 4, strideB = chi_pad + 4, CHUNK = 2 * KC * strideB;
     const int n_out = p.prob.n_out, n_slices = p.pt.n_slices;
     const SmallLayout L = small_layout(pt_doubles, n_slices, chi_pad, n_out, warps_per_cta);
     double* pt_s = reinterpret_cast<double*>(smem_raw + L.pt);
@@ -194,14 +196,16 @@ __global__ void __launch_bounds__(256) k_step_small(const __grid_constant__ Step
         }
         {   // snapshot-started rows hold quad-partial closures: complete them (uniform shuffles, selected per lane)
             const bool part = valid && i == 0 && t.init_kind != 0;
+            if (__any_sync(0xffffffffu, part)) {
 #pragma unroll
-            for (int a = 0; a < SMALL_NL; ++a) {
-                double sx = r[a].x, sy = r[a].y;
-                sx += __shfl_xor_sync(0xffffffffu, sx, 1);
-                sy += __shfl_xor_sync(0xffffffffu, sy, 1);
-                sx += __shfl_xor_sync(0xffffffffu, sx, 2);
-                sy += __shfl_xor_sync(0xffffffffu, sy, 2);
-                if (part) r[a] = make_double2(sx, sy);
+                for (int a = 0; a < SMALL_NL; ++a) {
+                    double sx = r[a].x, sy = r[a].y;
+                    sx += __shfl_xor_sync(0xffffffffu, sx, 1);
+                    sy += __shfl_xor_sync(0xffffffffu, sy, 1);
+                    sx += __shfl_xor_sync(0xffffffffu, sx, 2);
+                    sy += __shfl_xor_sync(0xffffffffu, sy, 2);
+                    if (part) r[a] = make_double2(sx, sy);
+                }
             }
         }
         if (row_on && i >= t.out_from) {
@@ -225,7 +229,9 @@ __global__ void __launch_bounds__(256) k_step_small(const __grid_constant__ Step
             for (int a = 0; a < SMALL_NL; ++a)
 #pragma unroll
                 for (int k = 0; k < SMALL_NL; ++k) w[a][k] = sw[a * 4 + k];
-            for (int c = tq; c < chi_pad; c += 4) {
+#pragma unroll
+            for (int cc = 0; cc < 2 * NT; ++cc) {          // chi_pad = 8 NT columns, every fourth one is this lane's
+                const int c = tq + 4 * cc;
                 double2 y[SMALL_NL];
 #pragma unroll
                 for (int k = 0; k < SMALL_NL; ++k) y[k] = make_double2(Xre[soff(k, g, c)], Xim[soff(k, g, c)]);
@@ -250,57 +256,83 @@ __global__ void __launch_bounds__(256) k_step_small(const __grid_constant__ Step
         const double* sl = pt_s + p.pt.off[s];
         const double2* q = clo_s + (size_t)s * chi_pad;
 #pragma unroll
-        for (int a = 0; a < SMALL_NL; ++a) {
-            double cre[NT][2], cim[NT][2];
+        for (int a0 = 0; a0 < SMALL_NL; a0 += 2) {      // two Liouville rows side by side: independent DMMA chains
+            double cre[2][NT][2], cim[2][NT][2];
+            const double* xre[2];
+            const double* xim[2];
+            const double* blk[2];
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) cre[nt][0] = cre[nt][1] = cim[nt][0] = cim[nt][1] = 0.0;
-            const double* xre = Xre + soff(a, g, tq);
-            const double* xim = Xim + soff(a, g, tq);
-            const double* blk = sl + (size_t)blk_of[a] * nch * p.pt.chunk_doubles;
-            for (int ks = 0; ks < nks; ++ks) {
-                const double a_re = xre[4 * ks], a_im = xim[4 * ks];
-                const double* bre = blk + (size_t)(ks >> 1) * p.pt.chunk_doubles + ((ks & 1) * 4 + tq) * strideB + g;
-                const double* bim = bre + KC * strideB;
-                double b_re[NT], b_im[NT];
+            for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    b_re[nt] = 8 * nt < nout ? bre[8 * nt] : 0.0;
-                    b_im[nt] = 8 * nt < nout ? bim[8 * nt] : 0.0;
-                }
-                // two sweeps so that consecutive DMMAs never share an accumulator (8 * nt < nout is warp-uniform)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
-                    if (8 * nt < nout) {
-                        dmma(cre[nt][0], cre[nt][1], a_re, b_re[nt]);
-                        dmma(cim[nt][0], cim[nt][1], a_re, b_im[nt]);
-                    }
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
-                    if (8 * nt < nout) {
-                        dmma(cre[nt][0], cre[nt][1], -a_im, b_im[nt]);
-                        dmma(cim[nt][0], cim[nt][1], a_im, b_re[nt]);
-                    }
+                for (int nt = 0; nt < NT; ++nt) cre[h][nt][0] = cre[h][nt][1] = cim[h][nt][0] = cim[h][nt][1] = 0.0;
+                xre[h] = Xre + soff(a0 + h, g, tq);
+                xim[h] = Xim + soff(a0 + h, g, tq);
+                blk[h] = sl + (size_t)blk_of[a0 + h] * nch * CHUNK;
             }
-            // new row a of trajectory g (columns 8nt + 2tq, +1) and its closure
-            double pr = 0.0, pi = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 2 * NT; ++ks) {       // kin_pad <= chi_pad = 8 NT
+                if (ks < nks) {                         // warp-uniform
+                    double a_re[2], a_im[2], b_re[2][NT], b_im[2][NT];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        a_re[h] = xre[h][4 * ks];
+                        a_im[h] = xim[h][4 * ks];
+                        const double* bre = blk[h] + (size_t)(ks >> 1) * CHUNK + ((ks & 1) * 4 + tq) * strideB + g;
+                        const double* bim = bre + KC * strideB;
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            b_re[h][nt] = 8 * nt < nout ? bre[8 * nt] : 0.0;
+                            b_im[h][nt] = 8 * nt < nout ? bim[8 * nt] : 0.0;
+                        }
+                    }
+                    // two sweeps so that consecutive DMMAs never share an accumulator (8 * nt < nout is warp-uniform)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+                            if (8 * nt < nout) {
+                                dmma(cre[h][nt][0], cre[h][nt][1], a_re[h], b_re[h][nt]);
+                                dmma(cim[h][nt][0], cim[h][nt][1], a_re[h], b_im[h][nt]);
+                            }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+                            if (8 * nt < nout) {
+                                dmma(cre[h][nt][0], cre[h][nt][1], -a_im[h], b_im[h][nt]);
+                                dmma(cim[h][nt][0], cim[h][nt][1], a_im[h], b_re[h][nt]);
+                            }
+                }
+            }
+            // new rows a0, a0+1 of trajectory g (columns 8nt + 2tq, +1) and their closures
+            double pr[2] = {0.0, 0.0}, pi[2] = {0.0, 0.0};
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 if (8 * nt < nout) {
                     const int c0 = 8 * nt + 2 * tq;
                     const double2 q0 = q[c0], q1 = q[c0 + 1];
-                    pr += (cre[nt][0] * q0.x - cim[nt][0] * q0.y) + (cre[nt][1] * q1.x - cim[nt][1] * q1.y);
-                    pi += (cre[nt][0] * q0.y + cim[nt][0] * q0.x) + (cre[nt][1] * q1.y + cim[nt][1] * q1.x);
-                    if (step_on) {
-                        *reinterpret_cast<double2*>(Xre + soff(a, g, c0)) = make_double2(cre[nt][0], cre[nt][1]);
-                        *reinterpret_cast<double2*>(Xim + soff(a, g, c0)) = make_double2(cim[nt][0], cim[nt][1]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        pr[h] += (cre[h][nt][0] * q0.x - cim[h][nt][0] * q0.y) + (cre[h][nt][1] * q1.x - cim[h][nt][1] * q1.y);
+                        pi[h] += (cre[h][nt][0] * q0.y + cim[h][nt][0] * q0.x) + (cre[h][nt][1] * q1.y + cim[h][nt][1] * q1.x);
+                        if (step_on) {
+                            *reinterpret_cast<double2*>(Xre + soff(a0 + h, g, c0)) = make_double2(cre[h][nt][0], cre[h][nt][1]);
+                            *reinterpret_cast<double2*>(Xim + soff(a0 + h, g, c0)) = make_double2(cim[h][nt][0], cim[h][nt][1]);
+                        }
                     }
                 }
             }
-            pr += __shfl_xor_sync(0xffffffffu, pr, 1);
-            pi += __shfl_xor_sync(0xffffffffu, pi, 1);
-            pr += __shfl_xor_sync(0xffffffffu, pr, 2);
-            pi += __shfl_xor_sync(0xffffffffu, pi, 2);
-            if (step_on) r[a] = make_double2(pr, pi);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                pr[h] += __shfl_xor_sync(0xffffffffu, pr[h], 1);
+                pi[h] += __shfl_xor_sync(0xffffffffu, pi[h], 1);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                pr[h] += __shfl_xor_sync(0xffffffffu, pr[h], 2);
+                pi[h] += __shfl_xor_sync(0xffffffffu, pi[h], 2);
+                if (step_on) r[a0 + h] = make_double2(pr[h], pi[h]);
+            }
         }
         __syncwarp();   // the C-fragment columns of a lane are read by the other lanes of its quad in the next phase B
     }
