@@ -46,44 +46,111 @@ __device__ __forceinline__ void group_sync(int gid) {
         asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(G) : "memory");
 }
 
+// Matrix products of a thread group: every thread owns 2 x 2 blocks of C, so that one k step costs 2 + 2 operand
+// loads for 4 complex FMAs -- the products of these small matrices are bound by shared-memory traffic (one
+// element per thread costs 2 loads per complex FMA: measured 14.5 ms of operator building next to a 23 ms step
+// kernel for a biexciton area sweep, profiles/r03x_shapes.jsonl).
 // C = scale * A*B (+ I)
-template <int G>
+template <int G, bool BLK>
 __device__ void gmm(double2* C, const double2* A, const double2* B, int n, int tid, int gid,
                     double scale, bool add_identity) {
-    const int n2 = n * n;
-    for (int e = tid; e < n2; e += G) {
-        const int i = e / n, j = e - i * n;
-        double2 acc = make_double2(0.0, 0.0);
-        for (int k = 0; k < n; ++k) cfma(acc, A[i * n + k], B[k * n + j]);
-        acc.x *= scale;
-        acc.y *= scale;
-        if (add_identity && i == j) acc.x += 1.0;
-        C[e] = acc;
+    if constexpr (!BLK) {   // small matrices: more threads per entry beat operand reuse (measured, r03z)
+        for (int e = tid; e < n * n; e += G) {
+            const int i = e / n, j = e - i * n;
+            double2 acc = make_double2(0.0, 0.0);
+            for (int k = 0; k < n; ++k) cfma(acc, A[i * n + k], B[k * n + j]);
+            acc.x *= scale;
+            acc.y *= scale;
+            if (add_identity && i == j) acc.x += 1.0;
+            C[e] = acc;
+        }
+        group_sync<G>(gid);
+        return;
+    }
+    else {
+    const int nb = (n + 1) >> 1;
+    for (int blk = tid; blk < nb * nb; blk += G) {
+        const int i0 = 2 * (blk / nb), j0 = 2 * (blk - (blk / nb) * nb);
+        const bool i1 = i0 + 1 < n, j1 = j0 + 1 < n;
+        const int ia = i0 * n, ib = (i1 ? i0 + 1 : i0) * n, ja = j0, jb = j1 ? j0 + 1 : j0;
+        double2 c00 = make_double2(0.0, 0.0), c01 = c00, c10 = c00, c11 = c00;
+#pragma unroll 4
+        for (int k = 0; k < n; ++k) {
+            const double2 a0 = A[ia + k], a1 = A[ib + k], b0 = B[k * n + ja], b1 = B[k * n + jb];
+            cfma(c00, a0, b0);
+            cfma(c01, a0, b1);
+            cfma(c10, a1, b0);
+            cfma(c11, a1, b1);
+        }
+        auto put = [&](int i, int j, double2 v) {
+            v.x *= scale;
+            v.y *= scale;
+            if (add_identity && i == j) v.x += 1.0;
+            C[i * n + j] = v;
+        };
+        put(i0, j0, c00);
+        if (j1) put(i0, j0 + 1, c01);
+        if (i1) put(i0 + 1, j0, c10);
+        if (i1 && j1) put(i0 + 1, j0 + 1, c11);
     }
     group_sync<G>(gid);
+    }
 }
 
 // C = A*B + (c0 I + c1 X1 + c2 X2 + c3 X3)   (any Xi may be null)
-template <int G>
+template <int G, bool BLK>
 __device__ void gmm_poly(double2* C, const double2* A, const double2* B, int n, int tid, int gid,
                          double c0, double c1, const double2* X1, double c2, const double2* X2,
                          double c3, const double2* X3) {
-    const int n2 = n * n;
-    for (int e = tid; e < n2; e += G) {
-        const int i = e / n, j = e - i * n;
-        double2 acc = make_double2(i == j ? c0 : 0.0, 0.0);
-        if (X1) { acc.x = fma(c1, X1[e].x, acc.x); acc.y = fma(c1, X1[e].y, acc.y); }
-        if (X2) { acc.x = fma(c2, X2[e].x, acc.x); acc.y = fma(c2, X2[e].y, acc.y); }
-        if (X3) { acc.x = fma(c3, X3[e].x, acc.x); acc.y = fma(c3, X3[e].y, acc.y); }
-        for (int k = 0; k < n; ++k) cfma(acc, A[i * n + k], B[k * n + j]);
-        C[e] = acc;
+    if constexpr (!BLK) {
+        for (int e = tid; e < n * n; e += G) {
+            const int i = e / n, j = e - i * n;
+            double2 acc = make_double2(i == j ? c0 : 0.0, 0.0);
+            if (X1) { acc.x = fma(c1, X1[e].x, acc.x); acc.y = fma(c1, X1[e].y, acc.y); }
+            if (X2) { acc.x = fma(c2, X2[e].x, acc.x); acc.y = fma(c2, X2[e].y, acc.y); }
+            if (X3) { acc.x = fma(c3, X3[e].x, acc.x); acc.y = fma(c3, X3[e].y, acc.y); }
+            for (int k = 0; k < n; ++k) cfma(acc, A[i * n + k], B[k * n + j]);
+            C[e] = acc;
+        }
+        group_sync<G>(gid);
+        return;
+    }
+    else {
+    const int nb = (n + 1) >> 1;
+    for (int blk = tid; blk < nb * nb; blk += G) {
+        const int i0 = 2 * (blk / nb), j0 = 2 * (blk - (blk / nb) * nb);
+        const bool i1 = i0 + 1 < n, j1 = j0 + 1 < n;
+        const int ia = i0 * n, ib = (i1 ? i0 + 1 : i0) * n, ja = j0, jb = j1 ? j0 + 1 : j0;
+        auto init = [&](int i, int j) {
+            const int e = i * n + j;
+            double2 acc = make_double2(i == j ? c0 : 0.0, 0.0);
+            if (X1) { acc.x = fma(c1, X1[e].x, acc.x); acc.y = fma(c1, X1[e].y, acc.y); }
+            if (X2) { acc.x = fma(c2, X2[e].x, acc.x); acc.y = fma(c2, X2[e].y, acc.y); }
+            if (X3) { acc.x = fma(c3, X3[e].x, acc.x); acc.y = fma(c3, X3[e].y, acc.y); }
+            return acc;
+        };
+        double2 c00 = init(i0, j0), c01 = init(i0, jb), c10 = init(i1 ? i0 + 1 : i0, j0),
+                c11 = init(i1 ? i0 + 1 : i0, jb);
+#pragma unroll 4
+        for (int k = 0; k < n; ++k) {
+            const double2 a0 = A[ia + k], a1 = A[ib + k], b0 = B[k * n + ja], b1 = B[k * n + jb];
+            cfma(c00, a0, b0);
+            cfma(c01, a0, b1);
+            cfma(c10, a1, b0);
+            cfma(c11, a1, b1);
+        }
+        C[i0 * n + j0] = c00;
+        if (j1) C[i0 * n + j0 + 1] = c01;
+        if (i1) C[(i0 + 1) * n + j0] = c10;
+        if (i1 && j1) C[(i0 + 1) * n + j0 + 1] = c11;
     }
     group_sync<G>(gid);
+    }
 }
 
 // exp(A) for the n x n matrix in buf[0..n2) (destroyed).  `buf` holds EXPM_BUFS matrices; the
 // result pointer is one of them.  `red` is a scratch of >= n doubles.
-template <int G>
+template <int G, bool BLK>
 __device__ double2* expm_group(double2* buf, double* red, int n, int tid, int gid) {
     const int n2 = n * n;
     double2 *A = buf, *A2 = A + n2, *A3 = A2 + n2, *A4 = A3 + n2, *P0 = A4 + n2, *P1 = P0 + n2;
@@ -114,10 +181,10 @@ __device__ double2* expm_group(double2* buf, double* red, int n, int tid, int gi
     constexpr double c2 = 1.0 / 2, c3 = 1.0 / 6, c4 = 1.0 / 24, c5 = 1.0 / 120, c6 = 1.0 / 720,
                      c7 = 1.0 / 5040, c8 = 1.0 / 40320, c9 = 1.0 / 362880, c10 = 1.0 / 3628800,
                      c11 = 1.0 / 39916800, c12 = 1.0 / 479001600;
-    gmm_poly<G>(A2, A, A, n, tid, gid, 0.0, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
-    gmm_poly<G>(A3, A2, A, n, tid, gid, 0.0, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
+    gmm_poly<G, BLK>(A2, A, A, n, tid, gid, 0.0, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
+    gmm_poly<G, BLK>(A3, A2, A, n, tid, gid, 0.0, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
     // P0 = c8 I + c9 A + c10 A2 + c11 A3 + c12 A4 ,  A4 = A2*A2  (one product gives both)
-    gmm_poly<G>(A4, A2, A2, n, tid, gid, 0.0, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
+    gmm_poly<G, BLK>(A4, A2, A2, n, tid, gid, 0.0, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
     for (int e = tid; e < n2; e += G) {
         const int i = e / n, j = e - i * n;
         double2 v = make_double2(i == j ? c8 : 0.0, 0.0);
@@ -127,12 +194,12 @@ __device__ double2* expm_group(double2* buf, double* red, int n, int tid, int gi
     }
     group_sync<G>(gid);
     // P1 = (c4 I + c5 A + c6 A2 + c7 A3) + A4 P0 ;  P0 = (I + A + c2 A2 + c3 A3) + A4 P1
-    gmm_poly<G>(P1, A4, P0, n, tid, gid, c4, c5, A, c6, A2, c7, A3);
-    gmm_poly<G>(P0, A4, P1, n, tid, gid, 1.0, 1.0, A, c2, A2, c3, A3);
+    gmm_poly<G, BLK>(P1, A4, P0, n, tid, gid, c4, c5, A, c6, A2, c7, A3);
+    gmm_poly<G, BLK>(P0, A4, P1, n, tid, gid, 1.0, 1.0, A, c2, A2, c3, A3);
     double2* cur = P0;
     double2* nxt = P1;
     for (int q = 0; q < s; ++q) {
-        gmm_poly<G>(nxt, cur, cur, n, tid, gid, 0.0, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
+        gmm_poly<G, BLK>(nxt, cur, cur, n, tid, gid, 0.0, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
         double2* t = cur;
         cur = nxt;
         nxt = t;
@@ -175,7 +242,7 @@ __device__ void assemble(double2* A, const OpBuildParams& p, int set, double t, 
     group_sync<G>(gid);
 }
 
-template <int G>
+template <int G, bool BLK>
 __global__ void __launch_bounds__(256) k_opbuild(OpBuildParams p) {
     extern __shared__ double2 sm[];
     const int n = p.prob.NL, n2 = n * n;
@@ -215,9 +282,9 @@ __global__ void __launch_bounds__(256) k_opbuild(OpBuildParams p) {
         // ---- V = Sb * M2_{n-1}
         if (has_prev) {
             assemble<G>(A, p, set, t_n - p.dt + p.eval_off2 * p.dt, half, tid, gid);
-            double2* M2 = expm_group<G>(A, red, n, tid, gid);
+            double2* M2 = expm_group<G, BLK>(A, red, n, tid, gid);
             if (sb >= 0) {
-                gmm<G>(V, mto + (size_t)sb * n2, M2, n, tid, gid, 1.0, false);
+                gmm<G, BLK>(V, mto + (size_t)sb * n2, M2, n, tid, gid, 1.0, false);
             } else {
                 for (int q = tid; q < n2; q += G) V[q] = M2[q];
                 group_sync<G>(gid);
@@ -244,12 +311,12 @@ __global__ void __launch_bounds__(256) k_opbuild(OpBuildParams p) {
         // ---- X = Sa * V
         const double2* Xp = V;
         if (sa >= 0) {
-            gmm<G>(X, mto + (size_t)sa * n2, V, n, tid, gid, 1.0, false);
+            gmm<G, BLK>(X, mto + (size_t)sa * n2, V, n, tid, gid, 1.0, false);
             Xp = X;
         }
         // ---- W = M1_n * X   (zero padded to [NLp8][NLp4])
         assemble<G>(A, p, set, t_n + p.eval_off1 * p.dt, half, tid, gid);
-        double2* M1 = expm_group<G>(A, red, n, tid, gid);
+        double2* M1 = expm_group<G, BLK>(A, red, n, tid, gid);
         {
             double2* w = reinterpret_cast<double2*>(p.W + (size_t)e * p.prob.w_doubles);
             const int ld = p.prob.NLp4, cnt = p.prob.NLp8 * ld;
@@ -484,7 +551,7 @@ __global__ void __launch_bounds__(OPREG_THREADS) k_opbuild_reg(OpBuildParams p) 
     }
 }
 
-template <int G>
+template <int G, bool BLK>
 __global__ void __launch_bounds__(256) k_expm_batch(int n, int count, const double* a,
                                                     double* out, double* scratch) {
     extern __shared__ double2 sm[];
@@ -499,19 +566,24 @@ __global__ void __launch_bounds__(256) k_expm_batch(int n, int count, const doub
         const double2* src = reinterpret_cast<const double2*>(a) + (size_t)e * n2;
         for (int q = tid; q < n2; q += G) A[q] = src[q];
         group_sync<G>(gid);
-        double2* R = expm_group<G>(A, red, n, tid, gid);
+        double2* R = expm_group<G, BLK>(A, red, n, tid, gid);
         double2* dst = reinterpret_cast<double2*>(out) + (size_t)e * n2;
         for (int q = tid; q < n2; q += G) dst[q] = R[q];
         group_sync<G>(gid);
     }
 }
 
-int pick_group(int n) {
+int pick_group(int n) {   // threads per entry (measured optima: gpurun_out/r03z_call.log)
+    if (const char* env = getenv("ACEQD_EXPM_GROUP")) {
+        const int g = atoi(env);
+        if (g == 16 || g == 32 || g == 64 || g == 128 || g == 256) return g;
+    }
     if (n <= 4) return 16;
     if (n <= 8) return 32;
     if (n <= 12) return 64;
     if (n <= 20) return 128;
-    return 256;
+    if (n <= 28) return 256;
+    return 128;   // NL = 36: two groups per CTA on the global workspace (2 CTAs per SM) beat one group in shared memory
 }
 
 template <typename K>
@@ -563,28 +635,25 @@ int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches) 
         blocks = std::min<long long>(blocks, p.scratch_ctas);
     }
     int rc = ACEQD_OK;
+    const bool blk = n > 16;   // 2 x 2 register blocks per thread for the larger matrices only (measured)
+#define ACEQD_OPB(GV)                                                                  \
+    do {                                                                               \
+        if (blk) {                                                                     \
+            if ((rc = set_smem(k_opbuild<GV, true>, smem))) return rc;                 \
+            k_opbuild<GV, true><<<(int)blocks, 256, smem, s>>>(p);                     \
+        } else {                                                                       \
+            if ((rc = set_smem(k_opbuild<GV, false>, smem))) return rc;                \
+            k_opbuild<GV, false><<<(int)blocks, 256, smem, s>>>(p);                    \
+        }                                                                              \
+    } while (0)
     switch (G) {
-        case 16:
-            if ((rc = set_smem(k_opbuild<16>, smem))) return rc;
-            k_opbuild<16><<<(int)blocks, 256, smem, s>>>(p);
-            break;
-        case 32:
-            if ((rc = set_smem(k_opbuild<32>, smem))) return rc;
-            k_opbuild<32><<<(int)blocks, 256, smem, s>>>(p);
-            break;
-        case 64:
-            if ((rc = set_smem(k_opbuild<64>, smem))) return rc;
-            k_opbuild<64><<<(int)blocks, 256, smem, s>>>(p);
-            break;
-        case 128:
-            if ((rc = set_smem(k_opbuild<128>, smem))) return rc;
-            k_opbuild<128><<<(int)blocks, 256, smem, s>>>(p);
-            break;
-        default:
-            if ((rc = set_smem(k_opbuild<256>, smem))) return rc;
-            k_opbuild<256><<<(int)blocks, 256, smem, s>>>(p);
-            break;
+        case 16: ACEQD_OPB(16); break;
+        case 32: ACEQD_OPB(32); break;
+        case 64: ACEQD_OPB(64); break;
+        case 128: ACEQD_OPB(128); break;
+        default: ACEQD_OPB(256); break;
     }
+#undef ACEQD_OPB
     ++*launches;
     ACEQD_CUDA(cudaGetLastError());
     return ACEQD_OK;
@@ -613,28 +682,25 @@ int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, do
         scratch = nullptr;
     }
     int rc = ACEQD_OK;
+    const bool blk = n > 16;
+#define ACEQD_EXB(GV)                                                                              \
+    do {                                                                                           \
+        if (blk) {                                                                                 \
+            if ((rc = set_smem(k_expm_batch<GV, true>, smem))) return rc;                          \
+            k_expm_batch<GV, true><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev, scratch);   \
+        } else {                                                                                   \
+            if ((rc = set_smem(k_expm_batch<GV, false>, smem))) return rc;                         \
+            k_expm_batch<GV, false><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev, scratch);  \
+        }                                                                                          \
+    } while (0)
     switch (G) {
-        case 16:
-            if ((rc = set_smem(k_expm_batch<16>, smem))) return rc;
-            k_expm_batch<16><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev, scratch);
-            break;
-        case 32:
-            if ((rc = set_smem(k_expm_batch<32>, smem))) return rc;
-            k_expm_batch<32><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev, scratch);
-            break;
-        case 64:
-            if ((rc = set_smem(k_expm_batch<64>, smem))) return rc;
-            k_expm_batch<64><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev, scratch);
-            break;
-        case 128:
-            if ((rc = set_smem(k_expm_batch<128>, smem))) return rc;
-            k_expm_batch<128><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev, scratch);
-            break;
-        default:
-            if ((rc = set_smem(k_expm_batch<256>, smem))) return rc;
-            k_expm_batch<256><<<blocks, 256, smem, s>>>(n, count, a_dev, out_dev, scratch);
-            break;
+        case 16: ACEQD_EXB(16); break;
+        case 32: ACEQD_EXB(32); break;
+        case 64: ACEQD_EXB(64); break;
+        case 128: ACEQD_EXB(128); break;
+        default: ACEQD_EXB(256); break;
     }
+#undef ACEQD_EXB
     ++*launches;
     ACEQD_CUDA(cudaGetLastError());
     return ACEQD_OK;
