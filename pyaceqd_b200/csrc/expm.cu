@@ -551,6 +551,319 @@ __global__ void __launch_bounds__(OPREG_THREADS) k_opbuild_reg(OpBuildParams p) 
     }
 }
 
+// -------------------------------------------------------------------------------------------
+// Tensor-core operator builder for mid-size Liouville spaces (4 < NL <= 16: three-level models, the biexciton of
+// four_level_system/tpe_rotations.py:182-207).  ONE WARP owns an entry; matrices live in shared memory as split
+// re/im planes [NPAD][NPAD + 4] (zero padded to a multiple of 8), and every product of the scaling-and-squaring
+// chain is a complex DMMA.8x8x4 GEMM of the warp: C fragments go back to shared memory and return as A / B
+// fragments of the next product after a __syncwarp().  Same polynomial and scaling rule as expm_group.
+constexpr int WM_BUFS = 8;    // A, A2, A3, A4, P0, P1, V, X
+
+__device__ __forceinline__ void dmma8(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+template <int NP>   // NP = NPAD / 8 tiles per dimension
+struct WMat {
+    static constexpr int NPAD = 8 * NP, LD = NPAD + 4, PLANE = NPAD * LD;
+    double* re;
+    __device__ __forceinline__ double* im() const { return re + PLANE; }
+};
+
+// C = A * B + Init, all NPAD x NPAD complex.  init(i, j, &re, &im) supplies the additive term of element (i, j).
+template <int NP, class Init>
+__device__ __forceinline__ void wmm(WMat<NP> C, WMat<NP> A, WMat<NP> B, int lane, Init init) {
+    constexpr int LD = WMat<NP>::LD, NPAD = WMat<NP>::NPAD;
+    const int g = lane >> 2, tq = lane & 3;
+    double cr[NP][NP][2], ci[NP][NP][2];
+#pragma unroll
+    for (int mi = 0; mi < NP; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NP; ++ni)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) init(8 * mi + g, 8 * ni + 2 * tq + h, cr[mi][ni][h], ci[mi][ni][h]);
+#pragma unroll
+    for (int ks = 0; ks < NPAD / 4; ++ks) {
+        double ar[NP], ai[NP], br[NP], bi[NP];
+#pragma unroll
+        for (int mi = 0; mi < NP; ++mi) {
+            ar[mi] = A.re[(8 * mi + g) * LD + 4 * ks + tq];
+            ai[mi] = A.im()[(8 * mi + g) * LD + 4 * ks + tq];
+        }
+#pragma unroll
+        for (int ni = 0; ni < NP; ++ni) {
+            br[ni] = B.re[(4 * ks + tq) * LD + 8 * ni + g];
+            bi[ni] = B.im()[(4 * ks + tq) * LD + 8 * ni + g];
+        }
+#pragma unroll
+        for (int mi = 0; mi < NP; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NP; ++ni) {
+                dmma8(cr[mi][ni][0], cr[mi][ni][1], ar[mi], br[ni]);
+                dmma8(ci[mi][ni][0], ci[mi][ni][1], ar[mi], bi[ni]);
+            }
+#pragma unroll
+        for (int mi = 0; mi < NP; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NP; ++ni) {
+                dmma8(cr[mi][ni][0], cr[mi][ni][1], -ai[mi], bi[ni]);
+                dmma8(ci[mi][ni][0], ci[mi][ni][1], ai[mi], br[ni]);
+            }
+    }
+#pragma unroll
+    for (int mi = 0; mi < NP; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NP; ++ni) {
+            const int o = (8 * mi + g) * LD + 8 * ni + 2 * tq;
+            *reinterpret_cast<double2*>(C.re + o) = make_double2(cr[mi][ni][0], cr[mi][ni][1]);
+            *reinterpret_cast<double2*>(C.im() + o) = make_double2(ci[mi][ni][0], ci[mi][ni][1]);
+        }
+    __syncwarp();
+}
+
+// plane offsets of the (at most 8) elements e = lane + 32 k < n*n a lane touches in element-wise passes (no divisions there)
+struct LaneOffs {
+    int o[8];
+    bool diag[8];
+    int cnt;
+};
+
+// exp(A) (A destroyed); buffers M[0..5] = A, A2, A3, A4, P0, P1; returns the index of the result buffer (4 or 5)
+template <int NP>
+__device__ int expm_warp(WMat<NP>* M, int n, int lane, const LaneOffs& lo) {
+    constexpr int LD = WMat<NP>::LD;
+    WMat<NP> A = M[0], A2 = M[1], A3 = M[2], A4 = M[3], P0 = M[4], P1 = M[5];
+    double cs = 0.0;
+    if (lane < n)
+        for (int i = 0; i < n; ++i) {
+            const double x = A.re[i * LD + lane], y = A.im()[i * LD + lane];
+            cs += sqrt(x * x + y * y);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cs = fmax(cs, __shfl_xor_sync(0xffffffffu, cs, o));
+    int s = 0;
+    if (cs > THETA) {
+        int ex;
+        frexp(cs / THETA, &ex);
+        s = ex > 60 ? 60 : ex;
+    }
+    const double sc = ldexp(1.0, -s);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < lo.cnt) {
+            A.re[lo.o[k]] *= sc;
+            A.im()[lo.o[k]] *= sc;
+        }
+    __syncwarp();
+    constexpr double c2 = 1.0 / 2, c3 = 1.0 / 6, c4 = 1.0 / 24, c5 = 1.0 / 120, c6 = 1.0 / 720,
+                     c7 = 1.0 / 5040, c8 = 1.0 / 40320, c9 = 1.0 / 362880, c10 = 1.0 / 3628800,
+                     c11 = 1.0 / 39916800, c12 = 1.0 / 479001600;
+    auto zero = [](int, int, double& r, double& i) { r = 0.0; i = 0.0; };
+    wmm<NP>(A2, A, A, lane, zero);
+    wmm<NP>(A3, A2, A, lane, zero);
+    wmm<NP>(A4, A2, A2, lane, zero);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < lo.cnt) {
+            const int o = lo.o[k];
+            P0.re[o] = (lo.diag[k] ? c8 : 0.0) + c9 * A.re[o] + c10 * A2.re[o] + c11 * A3.re[o] + c12 * A4.re[o];
+            P0.im()[o] = c9 * A.im()[o] + c10 * A2.im()[o] + c11 * A3.im()[o] + c12 * A4.im()[o];
+        }
+    __syncwarp();
+    // P1 = (c4 I + c5 A + c6 A2 + c7 A3) + A4 P0 ;  P0 = (I + A + c2 A2 + c3 A3) + A4 P1
+    wmm<NP>(P1, A4, P0, lane, [&](int i, int j, double& r, double& im_) {
+        const int o = i * LD + j;
+        r = ((i == j && i < n) ? c4 : 0.0) + c5 * A.re[o] + c6 * A2.re[o] + c7 * A3.re[o];
+        im_ = c5 * A.im()[o] + c6 * A2.im()[o] + c7 * A3.im()[o];
+    });
+    wmm<NP>(P0, A4, P1, lane, [&](int i, int j, double& r, double& im_) {
+        const int o = i * LD + j;
+        r = ((i == j && i < n) ? 1.0 : 0.0) + A.re[o] + c2 * A2.re[o] + c3 * A3.re[o];
+        im_ = A.im()[o] + c2 * A2.im()[o] + c3 * A3.im()[o];
+    });
+    int cur = 4, nxt = 5;
+    for (int q = 0; q < s; ++q) {
+        wmm<NP>(M[nxt], M[cur], M[cur], lane, zero);
+        const int t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    return cur;
+}
+
+// Lsm: L0 | LA[0..n_fields) | LB[0..n_fields) as row-major complex n x n (shared memory copy, or the global arrays)
+template <int NP>
+__device__ void assemble_warp(WMat<NP> A, const OpBuildParams& p, const double2* L0, const double2* LA,
+                              const double2* LB, int set, double t, double delta, int lane) {
+    constexpr int LD = WMat<NP>::LD;
+    const int n = p.prob.NL, n2 = n * n, nf = p.prob.n_fields;
+    const double2* tabs = reinterpret_cast<const double2*>(p.tables);
+    const double x = (t - p.tab_t0) / p.tab_dt;
+    // lane k samples drive field k once for the whole matrix
+    double2 fl = make_double2(0.0, 0.0);
+    if (lane < nf) {
+        const int tb = p.prob.field_table[lane];
+        if (tb >= 0 && tb < p.n_tables)
+            fl = sample_table(tabs + ((size_t)set * p.n_tables + tb) * p.n_samples, p.n_samples, x);
+    }
+    for (int e0 = 0; e0 < n2; e0 += 32) {          // warp-uniform trip count: the shuffles below need every lane
+        const int e = e0 + lane;
+        const bool on = e < n2;
+        double2 acc = on ? L0[e] : make_double2(0.0, 0.0);
+        for (int k = 0; k < nf; ++k) {
+            const double2 f = make_double2(__shfl_sync(0xffffffffu, fl.x, k), __shfl_sync(0xffffffffu, fl.y, k));
+            if (on) {
+                cfma(acc, f, LA[(size_t)k * n2 + e]);
+                cfma(acc, make_double2(f.x, -f.y), LB[(size_t)k * n2 + e]);
+            }
+        }
+        if (on) {
+            const int i = e / n;
+            const int o = i * LD + (e - i * n);
+            A.re[o] = acc.x * delta;
+            A.im()[o] = acc.y * delta;
+        }
+    }
+    __syncwarp();
+}
+
+template <int NP>
+__global__ void __launch_bounds__(128) k_opbuild_dmma(OpBuildParams p, int warps_per_cta, int lsm) {
+    extern __shared__ __align__(16) double wm_smem[];
+    constexpr int LD = WMat<NP>::LD, PLANE = WMat<NP>::PLANE;
+    const int n = p.prob.NL, n2 = n * n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* base = wm_smem + (size_t)warp * WM_BUFS * 2 * PLANE;
+    WMat<NP> M[WM_BUFS];
+#pragma unroll
+    for (int b = 0; b < WM_BUFS; ++b) M[b].re = base + (size_t)b * 2 * PLANE;
+    for (int e = lane; e < WM_BUFS * 2 * PLANE; e += 32) base[e] = 0.0;    // the zero padding stays zero throughout
+    // Liouvillian pieces: one copy per CTA in shared memory when it fits (they are read twice per entry)
+    const double2* L0 = reinterpret_cast<const double2*>(p.prob.L0);
+    const double2* LA = reinterpret_cast<const double2*>(p.prob.LA);
+    const double2* LB = reinterpret_cast<const double2*>(p.prob.LB);
+    if (lsm) {
+        double2* ls = reinterpret_cast<double2*>(wm_smem + (size_t)warps_per_cta * WM_BUFS * 2 * PLANE);
+        const int nf = p.prob.n_fields;
+        for (int e = threadIdx.x; e < n2; e += blockDim.x) ls[e] = L0[e];
+        for (int e = threadIdx.x; e < nf * n2; e += blockDim.x) {
+            ls[n2 + e] = LA[e];
+            ls[(1 + nf) * n2 + e] = LB[e];
+        }
+        L0 = ls;
+        LA = ls + n2;
+        LB = ls + (size_t)(1 + nf) * n2;
+        __syncthreads();
+    }
+    __syncwarp();
+    WMat<NP> V = M[6], X = M[7];
+    LaneOffs lo;
+    lo.cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int e = lane + 32 * k;
+        const int i = e / n, j = e - i * n;
+        lo.o[k] = e < n2 ? i * LD + j : 0;
+        lo.diag[k] = e < n2 && i == j;
+        if (e < n2) lo.cnt = k + 1;
+    }
+    auto load_global = [&](WMat<NP> D, const double2* src) {    // row-major complex n x n -> planes
+        for (int e = lane; e < n2; e += 32) {
+            const int o = (e / n) * LD + e % n;
+            D.re[o] = src[e].x;
+            D.im()[o] = src[e].y;
+        }
+        __syncwarp();
+    };
+    auto copy = [&](WMat<NP> D, WMat<NP> S) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < lo.cnt) {
+                D.re[lo.o[k]] = S.re[lo.o[k]];
+                D.im()[lo.o[k]] = S.im()[lo.o[k]];
+            }
+        __syncwarp();
+    };
+    auto zero = [](int, int, double& r, double& i) { r = 0.0; i = 0.0; };
+    const long long total = p.e_end > p.e_begin ? p.e_end : p.n_seq_entries + p.n_entries;
+    const double half = 0.5 * p.dt;
+    const double2* mto = reinterpret_cast<const double2*>(p.mto_mats);
+    for (long long e = p.e_begin + (long long)blockIdx.x * warps_per_cta + warp; e < total;
+         e += (long long)gridDim.x * warps_per_cta) {
+        int set, step, sb = -1, sa = -1, has_prev;
+        if (e < p.n_seq_entries) {
+            int lo = 0, hi = p.n_seq;  // seq_base[lo] <= e < seq_base[hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (p.seq_base[mid] <= e) lo = mid; else hi = mid;
+            }
+            const aceqd_seq sq = p.seqs[lo];
+            const int i = (int)(e - p.seq_base[lo]);
+            set = sq.set;
+            step = sq.step0 + i;
+            has_prev = (i > 0) || sq.first_has_prev;
+        } else {
+            const aceqd_entry en = p.entries[e - p.n_seq_entries];
+            set = en.set; step = en.step; sb = en.sb; sa = en.sa; has_prev = en.has_prev;
+        }
+        const double t_n = p.t0 + (double)step * p.dt;
+        // ---- V = Sb * M2_{n-1}
+        if (has_prev) {
+            assemble_warp<NP>(M[0], p, L0, LA, LB, set, t_n - p.dt + p.eval_off2 * p.dt, half, lane);
+            const int r = expm_warp<NP>(M, n, lane, lo);
+            if (sb >= 0) {
+                load_global(M[0], mto + (size_t)sb * n2);
+                wmm<NP>(V, M[0], M[r], lane, zero);
+            } else {
+                copy(V, M[r]);
+            }
+        } else {
+            for (int q = lane; q < n2; q += 32) {
+                const int i = q / n, j = q - i * n, o = i * LD + j;
+                const double2 v = (sb >= 0) ? mto[(size_t)sb * n2 + q] : make_double2(i == j ? 1.0 : 0.0, 0.0);
+                V.re[o] = v.x;
+                V.im()[o] = v.y;
+            }
+            __syncwarp();
+        }
+        // ---- OV = out_w * V
+        {
+            const double2* ow = reinterpret_cast<const double2*>(p.prob.out_w);
+            double2* ov = reinterpret_cast<double2*>(p.OV + (size_t)e * p.prob.ov_doubles);
+            const int cnt = p.prob.n_out * n;
+            for (int q = lane; q < cnt; q += 32) {
+                const int j = q / n, a = q - j * n;
+                double2 acc = make_double2(0.0, 0.0);
+                for (int k = 0; k < n; ++k) cfma(acc, ow[j * n + k], make_double2(V.re[k * LD + a], V.im()[k * LD + a]));
+                ov[q] = acc;
+            }
+        }
+        // ---- X = Sa * V
+        WMat<NP> Xp = V;
+        if (sa >= 0) {
+            load_global(M[0], mto + (size_t)sa * n2);
+            wmm<NP>(X, M[0], V, lane, zero);
+            Xp = X;
+        }
+        // ---- W = M1_n * X   (zero padded to [NLp8][NLp4])
+        assemble_warp<NP>(M[0], p, L0, LA, LB, set, t_n + p.eval_off1 * p.dt, half, lane);
+        const int r1 = expm_warp<NP>(M, n, lane, lo);
+        WMat<NP> Wm = M[r1 == 4 ? 5 : 4];
+        wmm<NP>(Wm, M[r1], Xp, lane, zero);
+        {
+            double2* w = reinterpret_cast<double2*>(p.W + (size_t)e * p.prob.w_doubles);
+            const int ld = p.prob.NLp4, cnt = p.prob.NLp8 * ld;
+            for (int q = lane; q < cnt; q += 32) {
+                const int i = q / ld, j = q - i * ld;
+                w[q] = (i < n && j < n) ? make_double2(Wm.re[i * LD + j], Wm.im()[i * LD + j]) : make_double2(0.0, 0.0);
+            }
+        }
+        __syncwarp();  // buffers are reused by the next entry
+    }
+}
+
 template <int G, bool BLK>
 __global__ void __launch_bounds__(256) k_expm_batch(int n, int count, const double* a,
                                                     double* out, double* scratch) {
@@ -617,6 +930,30 @@ int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches) 
         long long blocks = (total + OPREG_THREADS - 1) / OPREG_THREADS;
         if (blocks > 148LL * 32) blocks = 148LL * 32;
         k_opbuild_reg<4><<<(int)blocks, OPREG_THREADS, 0, s>>>(p);
+        ++*launches;
+        ACEQD_CUDA(cudaGetLastError());
+        return ACEQD_OK;
+    }
+    if (n > 4 && n <= 16 && !getenv("ACEQD_OPBUILD_GROUP")) {   // tensor-core builder, one warp per entry
+        const int np = (n + 7) / 8;
+        const size_t per_warp = (size_t)WM_BUFS * 2 * (8 * np) * (8 * np + 4) * sizeof(double);
+        // four warps per CTA = one per SM sub-partition (a single warp with 16 independent accumulators already
+        // saturates its tensor pipe); as many CTAs per SM as the shared-memory footprint allows
+        const int wpc = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)SMEM_BUDGET / per_warp));
+        const size_t l_bytes = (size_t)(1 + 2 * p.prob.n_fields) * n * n * sizeof(double2);
+        const int lsm = (size_t)wpc * per_warp + l_bytes <= (size_t)SMEM_BUDGET ? 1 : 0;
+        const size_t smem = (size_t)wpc * per_warp + (lsm ? l_bytes : 0);
+        const long long per_sm = std::max<long long>(1, (long long)((size_t)SMEM_BUDGET / smem));
+        long long blocks = (total + wpc - 1) / wpc;
+        if (blocks > 148LL * per_sm) blocks = 148LL * per_sm;
+        int rc;
+        if (np == 1) {
+            if ((rc = set_smem(k_opbuild_dmma<1>, smem))) return rc;
+            k_opbuild_dmma<1><<<(int)blocks, 32 * wpc, smem, s>>>(p, wpc, lsm);
+        } else {
+            if ((rc = set_smem(k_opbuild_dmma<2>, smem))) return rc;
+            k_opbuild_dmma<2><<<(int)blocks, 32 * wpc, smem, s>>>(p, wpc, lsm);
+        }
         ++*launches;
         ACEQD_CUDA(cudaGetLastError());
         return ACEQD_OK;
