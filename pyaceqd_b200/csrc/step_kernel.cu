@@ -23,6 +23,7 @@ struct SmemLayout {
     size_t plane;  // doubles per state plane
 };
 
+constexpr int PB_BUDGET = 16;    // (trajectories x n-tiles x k-steps) of Y fragments a warp keeps in flight in the system product
 constexpr int META_SLICES = 256;  // kin/nout of this many slices are cached in shared memory
 constexpr int SKEW = 4;  // extra doubles after every alpha block of T rows (bank skew for phase B)
 
@@ -528,8 +529,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 }
             }
         } else {
-        constexpr int NBB = (KSU_T * NB <= 8) ? NB : 1;
-        constexpr int JU_ = 8 / (KSU_T * NBB);
+        constexpr int NBB = (KSU_T * NB <= PB_BUDGET) ? NB : 1;
+        constexpr int JU_ = PB_BUDGET / (KSU_T * NBB);
         constexpr int JU = JU_ < 1 ? 1 : (JU_ > 4 ? 4 : JU_);
         for (int j0 = 0; j0 < T; j0 += JU) {
             bool act[JU];

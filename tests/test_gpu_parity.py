@@ -261,6 +261,9 @@ def test_small_bond_kernel_matches_oracle_and_tile_kernel(engine, chi, monkeypat
         mt = prob.parse_mtos([{"operator": "|0><1|_2", "applyFrom": "_left", "time": float(t1)}])
         fj.append(Job(0.0, float(t1 + 3.0), 0.1, tables=tabs, mtos=mt))
     _compare(engine, prob, pt, fj, "dmma", fork=True)
+    # more output functionals than lanes of a quad (full density matrix + two products)
+    prob6 = tls_problem(outputs=["|0><0|_2", "|1><1|_2", "|0><1|_2", "|1><0|_2", "(|1><0|_2*|0><1|_2)", "|0><0|_2+|1><1|_2"])
+    _compare(engine, prob6, pt, sweep_jobs(3, 5, t_end=3.0), "dmma")
     tails = engine.run_jobs(prob, pt, [Job(j.t_start, j.t_end, j.dt, tables=j.tables, mtos=j.mtos, tail_rows=11)
                                        for j in fj], kernel="dmma")
     full = engine.run_jobs(prob, pt, fj, kernel="dmma")
