@@ -97,18 +97,13 @@ __device__ __forceinline__ long long entry_of(const aceqd_traj& t, int i, long l
 
 // Main loop of one GEMM pass: MCV (<= MC) m-tiles x NB n-tiles of this warp over all k-chunks of
 // one PT block.  ALLNB: every n-tile of the warp is inside the slice (no predicates at all).
-struct NoHook {
-    __device__ __forceinline__ void operator()(int) const {}
-};
-
-// `hook(jc)` runs after the DMMAs of chunk jc have been issued (scalar work that overlaps the tensor pipe).
-template <int NB, int MCV, bool ALLNB, class Hook = NoHook>
+template <int NB, int MCV, bool ALLNB>
 __device__ __forceinline__ void gemm_pass(double (&cre)[MC][NB][2], double (&cim)[MC][NB][2],
                                           const double* const (&are)[MC], const double* const (&aim)[MC],
                                           const bool (&aval)[MC], const bool (&nbv)[NB],
                                           const double* chunks, int chunk_doubles, int strideB, int nch,
                                           int warp, int g, int tq, uint32_t bar_full, uint32_t bar_empty,
-                                          int& stage, uint32_t& phase, int stages, int lane, Hook hook = Hook()) {
+                                          int& stage, uint32_t& phase, int stages, int lane) {
     static_assert(KC == 8, "the main loop is written for two DMMA k-steps per chunk");
     // Software-pipelined over k-steps: the fragments of the NEXT k-step are loaded before the DMMAs of the current
     // one are issued -- across the chunk boundary too (wait for the next stage, load its first fragments, release
@@ -165,7 +160,6 @@ __device__ __forceinline__ void gemm_pass(double (&cre)[MC][NB][2], double (&cim
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * cur);     // every fragment of this chunk has been read
         batch(1);
-        hook(jc);
     }
 }
 
