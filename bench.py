@@ -48,7 +48,7 @@ def make_workload(chi, n_area, n_det, n_steps, dt, rank=0):
     prob = build_problem(boson_op="1.000*|1><1|_2", initial="|0><0|_2", lindblad_ops=[["|0><1|_2", 0.01]],
                          interaction_ops=[["|1><0|_2", "x"]],
                          output_ops=["|0><0|_2", "|1><1|_2", "|0><1|_2", "|1><0|_2"])
-    pt = synthetic_pt(chi, len(prob.cls_keys), dt=dt, seed=1234)
+    pt = synthetic_pt(chi, len(prob.cls_keys), dt=dt, seed=1234, kind="unitary", scale=0.999)   # keeps the signal O(1) over all steps
     t = dt * np.arange(n_steps)                       # pulse-file grid np.arange(t_start, t_end, dt)
     areas = np.linspace(0.0, 30.0, n_area)
     dets = np.linspace(-5.0, 5.0, n_det) + 10.0 * rank
@@ -163,7 +163,7 @@ def run_cfg3(args):
     eng = default_engine(local)
     eng.record_timings = True
     peak_dmma = eng.fp64_peak("dmma", 20000)
-    pt = synthetic_pt(args.chi, 9, dt=dt, seed=1234)
+    pt = synthetic_pt(args.chi, 9, dt=dt, seed=1234, kind="unitary", scale=0.999)
     tmp = tempfile.mkdtemp(prefix="aceqd_bench_")
     pt_file = os.path.join(tmp, "synthetic_chi%d.pt" % args.chi)
     pt.save(pt_file)

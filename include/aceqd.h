@@ -44,6 +44,12 @@ void aceqd_ctx_destroy(aceqd_ctx* ctx);
 int aceqd_ctx_sync(aceqd_ctx* ctx);
 /* Number of kernels of THIS library launched on the context so far (bench: gpu_launches). */
 long long aceqd_launch_count(const aceqd_ctx* ctx);
+/* Name of the kernel instantiation the last aceqd_run_steps / aceqd_build_operators / service call (expm, tl-map
+ * chains) launched on this context, e.g. "k_step_small<2> warps=4", "k_step_dmma<2,4> T=4 cluster=2 segments=0",
+ * "k_opbuild_dmma<2>".  Tests and the smoke run assert that the kernel they name is the one that ran. */
+const char* aceqd_last_step_kernel(const aceqd_ctx* ctx);
+const char* aceqd_last_opbuild_kernel(const aceqd_ctx* ctx);
+const char* aceqd_last_other_kernel(const aceqd_ctx* ctx);
 /* Device time (ms, CUDA events on the context's stream) of the last step-kernel launch and of
  * the last operator-builder launch; valid after aceqd_ctx_sync(). */
 int aceqd_last_timings(aceqd_ctx* ctx, float* step_kernel_ms, float* opbuild_kernel_ms);
@@ -97,6 +103,7 @@ typedef struct {
 } aceqd_entry;
 
 #define ACEQD_MAX_OVR 6
+#define ACEQD_SMALL_MIN_TRAJ 2048   /* kernel 0: smallest NL = 4 / chi_pad <= 32 batch that takes k_step_small */
 
 /* One trajectory = one `system(t_start, t_end, ...)` call of the reference. */
 typedef struct {
@@ -155,12 +162,17 @@ typedef struct {
     int64_t out_elems;         /* total complex elements of `out`                              */
     double* out;
     int32_t device_resident;
-    int32_t kernel;            /* 0: persistent DMMA kernel (state in shared memory), 1: plain-FMA check  */
-                               /* kernel, 2: step-synchronous DMMA kernel (state in HBM/L2, PT GEMM      */
-                               /* batched over trajectories per coupling class; for large NL)           */
-    int32_t cluster;           /* CTAs per tile (0/1, 2, 4 or 8): a thread-block cluster shares one tile, */
-                               /* splitting its GEMM passes and exchanging rows through distributed     */
-                               /* shared memory -- for batches too small to fill 148 SMs otherwise      */
+    int32_t kernel;            /* 0: persistent DMMA kernels, library's choice between the tile kernel    */
+                               /*    (k_step_dmma) and, for NL = 4 / chi_pad <= 32 batches of at least    */
+                               /*    ACEQD_SMALL_MIN_TRAJ trajectories, the small-bond kernel k_step_small */
+                               /* 1: plain-FMA check kernel (tests)                                        */
+                               /* 3: bond-column-split cluster kernel k_step_colsplit: `cluster` CTAs hold */
+                               /*    chi_pad/cluster bond columns each of tile_T trajectories (large NL)   */
+                               /* 4: k_step_small or ACEQD_ERR_CAPACITY;  5: k_step_dmma always            */
+    int32_t cluster;           /* CTAs per tile (0/1, 2, 4 or 8): a thread-block cluster shares one tile.  */
+                               /* kernel 0/5: its GEMM passes are split, rows exchanged through            */
+                               /* distributed shared memory, every CTA keeps the full bond state;          */
+                               /* kernel 3: the bond columns are split (see above)                         */
     int32_t pad_;
 } aceqd_batch;
 

@@ -39,11 +39,15 @@ class BatchFuture:
 class BatchExecutor:
     """Drop-in for ``concurrent.futures.ThreadPoolExecutor`` around ``system(...)`` calls."""
 
-    def __init__(self, max_workers=None, tail_rows=0, **_ignored):
+    def __init__(self, max_workers=None, tail_rows=0, distributed=None, **_ignored):
         """``tail_rows`` > 0: every deferred job returns only its last ``tail_rows`` output rows
         (the workflows index results from the end, e.g. ``res[1][-n_tau:]``
         ``two_time/correlations.py:182-183``), which bounds the device->host volume of a sweep."""
         self.max_workers = max_workers
+        # True: inside a torch.distributed job the sweep shards over the ranks (every rank must submit the same
+        # jobs in the same order); None: only if ACEQD_DISTRIBUTED=1.  Never implicit: a script that already
+        # splits its sweep per rank, or runs it on rank 0 only, must not meet a collective here.
+        self.distributed = distributed
         self.tail_rows = int(tail_rows or 0)
         self._requests = []     # (Request | immediate result, post-processing)
         self._results: list = []
@@ -69,35 +73,42 @@ class BatchExecutor:
         return fut
 
     def submit(self, fn, *args, **kwargs) -> BatchFuture:
+        """Record ``fn(*args, **kwargs)``.  A plain pass-through adapter (``tls``, ``biexciton``, ...) returns the
+        deferred :class:`Request` of ``system_ace_stream`` and joins the batch.  An adapter that post-processes the
+        result (unpacks it, indexes it, ...) cannot work on a placeholder: whatever it does to it -- raise or return
+        something else -- the captured requests are dropped and ``fn`` runs again eagerly, so any callable the
+        reference's ``ThreadPoolExecutor`` accepts is accepted here."""
         sink: list = []
         prev = getattr(_gs._capture, "sink", None)
         _gs._capture.sink = sink
+        ret, failed = None, None
         try:
             ret = fn(*args, **kwargs)
+        except Exception as exc:      # noqa: BLE001 - re-raised below unless a placeholder caused it
+            failed = exc
         finally:
             _gs._capture.sink = prev
         fut = BatchFuture(self, len(self._results))
         self._futures.append(fut)
         self._results.append(None)
-        # the adapter returned the Request itself (system_ace_stream's deferred value), possibly
-        # wrapped by post-processing that cannot run on a placeholder -> only plain pass-through
-        # adapters are deferred; anything else has already been computed eagerly.
-        if isinstance(ret, _gs.Request):
+        if failed is None and isinstance(ret, _gs.Request):
             ret.job.tail_rows = self.tail_rows
             self._requests.append((len(self._results) - 1, ret))
-        else:
-            if sink:  # adapter post-processed a placeholder: run it again eagerly
-                ret = fn(*args, **kwargs)
-            self._results[-1] = ret
-            for cb in fut._callbacks:
-                cb(fut)
+            return fut
+        if sink:      # the adapter handled (or choked on) a placeholder: run it for real
+            ret = fn(*args, **kwargs)
+        elif failed is not None:
+            raise failed
+        self._results[-1] = ret
+        for cb in fut._callbacks:
+            cb(fut)
         return fut
 
     def flush(self):
         pending = [(i, r) for (i, r) in self._requests if self._results[i] is None]
         if not pending:
             return
-        res = _gs.run_requests([r for _, r in pending])
+        res = _gs.run_requests([r for _, r in pending], distributed=self.distributed)
         for (i, _), out in zip(pending, res):
             self._results[i] = out
             for cb in self._futures[i]._callbacks:

@@ -20,6 +20,13 @@ void set_error(const char* fmt, ...) {
     g_err = buf;
 }
 
+void log_name(char (&dst)[128], const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, sizeof(dst), fmt, ap);
+    va_end(ap);
+}
+
 // grow-only device buffer
 struct DevBuf {
     void* p = nullptr;
@@ -62,11 +69,11 @@ struct aceqd_ctx {
     int split_tiles = 0;
     long long split_entries = 0, split_out = 0;
     bool split_ops_pending = false;
-    long long launches = 0;
+    LaunchLog log;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // step, opbuild, tlmap start/stop
     bool have_step = false, have_op = false, have_tl = false;
     DevBuf W, OV, tables, seqs, seq_base, entries, mto, rho0s, trajs, tiles, snap_steps, snaps,
-        out, passes, scratch, misc, octets, segs, seg_off, seg_state, seg_flags, opscratch, st_x, st_order, st_bar, st_apos, tl_pool, tl_v0, tl_segoff, tl_segs, tl_w, tl_out, tl_final;
+        out, passes, scratch, misc, octets, segs, seg_off, seg_state, seg_flags, opscratch, tl_pool, tl_v0, tl_segoff, tl_segs, tl_w, tl_out, tl_final;
     long long* ticks = nullptr;           // debug phase clock of the step kernel (aceqd_debug_phase_ticks)
     // layout of the operators currently in the workspace
     long long n_seq_entries = 0;
@@ -139,7 +146,7 @@ void aceqd_ctx_destroy(aceqd_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->W, &c->OV, &c->tables, &c->seqs, &c->seq_base, &c->entries, &c->mto,
                       &c->rho0s, &c->trajs, &c->tiles, &c->snap_steps, &c->snaps, &c->out,
-                      &c->passes, &c->scratch, &c->misc, &c->octets, &c->segs, &c->seg_off, &c->seg_state, &c->seg_flags, &c->opscratch, &c->st_x, &c->st_order, &c->st_bar, &c->st_apos, &c->tl_pool, &c->tl_v0, &c->tl_segoff,
+                      &c->passes, &c->scratch, &c->misc, &c->octets, &c->segs, &c->seg_off, &c->seg_state, &c->seg_flags, &c->opscratch, &c->tl_pool, &c->tl_v0, &c->tl_segoff,
                       &c->tl_segs, &c->tl_w, &c->tl_out, &c->tl_final})
         b->release();
     for (auto& ev : c->ev)
@@ -159,7 +166,10 @@ int aceqd_ctx_sync(aceqd_ctx* c) {
     return ACEQD_OK;
 }
 
-long long aceqd_launch_count(const aceqd_ctx* c) { return c ? c->launches : 0; }
+long long aceqd_launch_count(const aceqd_ctx* c) { return c ? c->log.count : 0; }
+const char* aceqd_last_step_kernel(const aceqd_ctx* c) { return c ? c->log.step : ""; }
+const char* aceqd_last_opbuild_kernel(const aceqd_ctx* c) { return c ? c->log.opbuild : ""; }
+const char* aceqd_last_other_kernel(const aceqd_ctx* c) { return c ? c->log.other : ""; }
 
 int aceqd_last_timings(aceqd_ctx* c, float* step_ms, float* op_ms) {
     if (!c) return ACEQD_ERR_ARG;
@@ -483,18 +493,18 @@ int aceqd_build_operators(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_b
         first.e_end = c->split_entries;
         rest.e_begin = c->split_entries;
         rest.e_end = n_ent;
-        if ((rc = launch_opbuild(first, c->stream, &c->launches))) return rc;
+        if ((rc = launch_opbuild(first, c->stream, &c->log))) return rc;
         ACEQD_CUDA(cudaEventRecord(c->ev[3], c->stream));
         // the uploads above were enqueued on the main stream: order the side stream after them
         ACEQD_CUDA(cudaEventRecord(c->ev_built, c->stream));
         ACEQD_CUDA(cudaStreamWaitEvent(c->build_stream, c->ev_built, 0));
-        if ((rc = launch_opbuild(rest, c->build_stream, &c->launches))) return rc;
+        if ((rc = launch_opbuild(rest, c->build_stream, &c->log))) return rc;
         ACEQD_CUDA(cudaEventRecord(c->ev_built, c->build_stream));
         c->split_ops_pending = true;
         c->have_op = true;
         return ACEQD_OK;
     }
-    if ((rc = launch_opbuild(op, c->stream, &c->launches))) return rc;
+    if ((rc = launch_opbuild(op, c->stream, &c->log))) return rc;
     ACEQD_CUDA(cudaEventRecord(c->ev[3], c->stream));
     c->have_op = true;
     return ACEQD_OK;
@@ -562,7 +572,7 @@ static int segment_ctas(const aceqd_ctx* c) {   // CTAs of a segmented launch: o
 }
 
 static bool use_segments(const aceqd_ctx* c, const aceqd_batch* b) {
-    if (!c || !b || b->kernel != 0 || b->cluster > 1 || !b->tile_traj || b->tile_T < 1) return false;
+    if (!c || !b || (b->kernel != 0 && b->kernel != 5) || b->cluster > 1 || !b->tile_traj || b->tile_T < 1) return false;
     const char* env = getenv("ACEQD_SEGMENTS");
     if (env && env[0] == '0') return false;
     return b->n_tiles > segment_ctas(c);
@@ -729,7 +739,7 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
             return ACEQD_ERR_ARG;
         }
     const int T = b->tile_T;
-    if (b->kernel == 0) {
+    if (b->kernel != 1) {
         if (T < 1 || T > MAX_TILE_T || b->n_tiles <= 0 || !b->tile_traj) {
             set_error("batch: tile_T must be 1..%d with a tile list", MAX_TILE_T);
             return ACEQD_ERR_ARG;
@@ -806,98 +816,12 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
     if (const char* tc = getenv("ACEQD_TICK_CLUSTER"))   // debug clock only for launches of this cluster size
         if (atoi(tc) != (b->cluster <= 1 ? 1 : b->cluster)) sp.ticks = nullptr;
 
-    if (b->kernel == 2) {
-        // ---- step-synchronous streaming kernel: state in HBM/L2, class-batched PT GEMM
-        const int NL = pd.NL;
-        StreamParams st{};
-        st.pt = pt->d;
-        st.prob = pd;
-        st.n_traj = b->n_traj;
-        std::vector<int> order(b->n_traj), apos(NL);
-        for (int i = 0; i < b->n_traj; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(),
-                         [&](int x, int y) { return b->trajs[x].step0 < b->trajs[y].step0; });
-        int n_begin = 0x7fffffff, n_end = -1;
-        for (int i = 0; i < b->n_traj; ++i) {
-            n_begin = std::min(n_begin, b->trajs[i].step0);
-            n_end = std::max(n_end, b->trajs[i].step0 + b->trajs[i].n_steps);
-        }
-        st.n_begin = n_begin;
-        st.n_end = n_end;
-        for (int a = 0; a < NL; ++a) apos[prob->pos_of_alpha[a]] = a;
-        int ncls = 0;
-        long long tasks = b->n_traj;
-        for (int p0 = 0; p0 < NL;) {
-            int p1 = p0;
-            const int blk = prob->block_of_alpha[apos[p0]];
-            while (p1 < NL && prob->block_of_alpha[apos[p1]] == blk) ++p1;
-            if (ncls >= STREAM_MAX_CLS) {
-                set_error("more than %d coupling classes", STREAM_MAX_CLS);
-                return ACEQD_ERR_CAPACITY;
-            }
-            st.cls_p0[ncls] = p0;
-            st.cls_rc[ncls] = p1 - p0;
-            st.cls_blk[ncls] = blk;
-            ++ncls;
-            p0 = p1;
-        }
-        st.n_classes = ncls;
-        long long gemm_tasks = 0;
-        for (int cidx = 0; cidx < ncls; ++cidx)
-            gemm_tasks += ((long long)b->n_traj * st.cls_rc[cidx] + 15) / 16;
-        tasks = std::max(tasks, gemm_tasks);
-        int n_sm = 148;
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
-        st.grid = (int)std::max<long long>(1, std::min<long long>(n_sm, tasks));
-        int stages = 0;
-        const int wov_full = pd.w_doubles + pd.ov_doubles;
-        for (int stg = MAX_STAGES; stg >= 2; --stg)
-            if (stream_smem_bytes(NL, chi_pad, stg, wov_full) <= (size_t)SMEM_BUDGET) {
-                stages = stg;
-                break;
-            }
-        if (!stages) {
-            set_error("NL=%d chi_pad=%d does not fit the streaming kernel's shared memory", NL, chi_pad);
-            return ACEQD_ERR_CAPACITY;
-        }
-        st.stages = stages;
-        const size_t plane = (size_t)b->n_traj * NL * chi_pad * 8;
-        if ((rc = c->st_x.reserve(4 * plane + 64))) return rc;
-        UP(c->st_order, order.data(), order.size() * sizeof(int));
-        std::vector<int> pa(2 * NL);
-        for (int a = 0; a < NL; ++a) {
-            pa[a] = prob->pos_of_alpha[a];
-            pa[NL + a] = apos[a];
-        }
-        UP(c->st_apos, pa.data(), pa.size() * sizeof(int));
-        if ((rc = c->st_bar.reserve(64))) return rc;
-        ACEQD_CUDA(cudaMemsetAsync(c->st_bar.p, 0, 64, c->stream));
-        st.trajs = sp.trajs;
-        st.order = (const int*)c->st_order.p;
-        st.pos_of_alpha = (const int*)c->st_apos.p;
-        st.alpha_of_pos = (const int*)c->st_apos.p + NL;
-        st.W = sp.W;
-        st.OV = sp.OV;
-        st.ovr_base = sp.ovr_base;
-        st.rho0s = sp.rho0s;
-        st.snap_steps = sp.snap_steps;
-        st.snaps = sp.snaps;
-        st.out = out_dev;
-        st.Xre = (double*)c->st_x.p;
-        st.Xim = (double*)((char*)c->st_x.p + plane);
-        st.Yre = (double*)((char*)c->st_x.p + 2 * plane);
-        st.Yim = (double*)((char*)c->st_x.p + 3 * plane);
-        st.barrier = (unsigned*)c->st_bar.p;
-        const size_t smem = stream_smem_bytes(NL, chi_pad, stages, wov_full);
-        ACEQD_CUDA(cudaEventRecord(c->ev[0], c->stream));
-        if ((rc = launch_step_stream(st, smem, c->stream, &c->launches))) return rc;
-        ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
-    } else if (b->kernel == 1) {
+    if (b->kernel == 1) {
         sp.T = 1;
         sp.n_tiles = b->n_traj;
         if ((rc = c->scratch.reserve((size_t)b->n_traj * 2 * pd.NL * chi_pad * 16))) return rc;
         ACEQD_CUDA(cudaEventRecord(c->ev[0], c->stream));
-        if ((rc = launch_step_check(sp, (double*)c->scratch.p, c->stream, &c->launches))) return rc;
+        if ((rc = launch_step_check(sp, (double*)c->scratch.p, c->stream, &c->log))) return rc;
         ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
     } else {
         for (long long i = 0; i < (long long)b->n_tiles * T; ++i)
@@ -910,14 +834,29 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
             set_error("batch: cluster must be 0/1, 2, 4 or 8");
             return ACEQD_ERR_ARG;
         }
-        // ---- small-bond regime of two-level sweeps: one warp per 8 trajectories, PT resident in shared memory
+        // ---- small-bond regime of two-level sweeps: one warp per 8 trajectories, PT resident in shared memory.
+        // kernel 4 forces it (error if the batch is not eligible), kernel 5 forces the tile kernel; kernel 0 takes it
+        // for batches large enough to fill the sub-partitions (one warp per octet: a small batch is latency-bound
+        // there and runs faster on tiles shared by clusters).
         {
             const char* env = getenv("ACEQD_SMALL");
-            const bool allow = !(env && env[0] == '0');
             int n_sm = 148;
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
-            if (allow && pd.NL == 4 && chi_pad <= 32 && cluster == 1 && b->n_snap_steps == 0 && pd.n_out <= 16 &&
-                pd.NLp4 == 4 && small_smem_bytes(pt->blob_doubles, pt->d.n_slices, chi_pad, pd.n_out, 1) <= (size_t)SMEM_BUDGET) {
+            const bool eligible = pd.NL == 4 && chi_pad <= 32 && b->n_snap_steps == 0 && pd.n_out <= 16 && pd.NLp4 == 4 &&
+                small_smem_bytes(pt->blob_doubles, pt->d.n_slices, chi_pad, pd.n_out, 1) <= (size_t)SMEM_BUDGET;
+            bool take = eligible && cluster == 1 && b->n_traj >= ACEQD_SMALL_MIN_TRAJ;
+            if (env && env[0] == '0') take = false;
+            if (env && env[0] == '1') take = eligible && cluster == 1;
+            if (b->kernel == 5) take = false;
+            if (b->kernel == 4) {
+                if (!eligible) {
+                    set_error("batch: the small-bond kernel needs NL == 4, chi_pad <= 32, n_out <= 16 and no snapshot "
+                              "requests (NL=%d chi_pad=%d n_out=%d snapshots=%d)", pd.NL, chi_pad, pd.n_out, b->n_snap_steps);
+                    return ACEQD_ERR_CAPACITY;
+                }
+                take = true;
+            }
+            if (take) {
                 std::vector<int32_t> oct;
                 oct.reserve((size_t)b->n_tiles * T + 8);
                 for (long long i = 0; i < (long long)b->n_tiles * T; ++i)
@@ -948,7 +887,7 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
                 }
                 c->split_tiles = 0;
                 ACEQD_CUDA(cudaEventRecord(c->ev[0], c->stream));
-                if ((rc = launch_step_small(sp, pt->blob_doubles, wpc, smem, c->stream, &c->launches))) return rc;
+                if ((rc = launch_step_small(sp, pt->blob_doubles, wpc, smem, c->stream, &c->log))) return rc;
                 ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
                 c->have_step = true;
                 if (!b->device_resident) {
@@ -1029,7 +968,7 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
             sa.n_tiles = n_a;
             sb2.n_tiles = b->n_tiles - n_a;
             sb2.tile_traj = sp.tile_traj + (size_t)n_a * T;
-            if ((rc = launch_step_dmma(sa, smem, c->stream, &c->launches))) return rc;
+            if ((rc = launch_step_dmma(sa, smem, c->stream, &c->log))) return rc;
             if (c->split_ops_pending) {
                 ACEQD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_built, 0));
                 c->split_ops_pending = false;
@@ -1042,7 +981,7 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
                 }
                 ACEQD_CUDA(cudaEventRecord(c->ev_wave, c->stream));
             }
-            if ((rc = launch_step_dmma(sb2, smem, c->stream, &c->launches))) return rc;
+            if ((rc = launch_step_dmma(sb2, smem, c->stream, &c->log))) return rc;
             ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
             c->have_step = true;
             c->split_tiles = 0;
@@ -1069,7 +1008,7 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
             ACEQD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_built, 0));
             c->split_ops_pending = false;
         }
-        if ((rc = launch_step_dmma(sp, smem, c->stream, &c->launches))) return rc;
+        if ((rc = launch_step_dmma(sp, smem, c->stream, &c->log))) return rc;
         ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
     }
     c->have_step = true;
@@ -1088,7 +1027,7 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
 static void plan_wave_split(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_batch* b) {
     c->split_tiles = 0;
     c->split_entries = c->split_out = 0;
-    if (!c || !prob || !b || b->kernel != 0 || b->cluster > 1 || b->n_entries != 0 || !b->tile_traj ||
+    if (!c || !prob || !b || (b->kernel != 0 && b->kernel != 5) || b->cluster > 1 || b->n_entries != 0 || !b->tile_traj ||
         b->tile_T < 1 || !b->trajs)
         return;
     if (use_segments(c, b)) return;   // one balanced launch instead of waves
@@ -1168,7 +1107,7 @@ int aceqd_expm_batch(aceqd_ctx* c, int n, int count, const double* a_host, doubl
             scratch = (double*)c->opscratch.p;
         }
     }
-    if ((rc = launch_expm_batch(n, count, a_dev, o_dev, scratch, c->stream, &c->launches))) return rc;
+    if ((rc = launch_expm_batch(n, count, a_dev, o_dev, scratch, c->stream, &c->log))) return rc;
     ACEQD_CUDA(cudaMemcpyAsync(out_host, o_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
     ACEQD_CUDA(cudaStreamSynchronize(c->stream));
     return ACEQD_OK;
@@ -1216,7 +1155,7 @@ int aceqd_tlmap_run(aceqd_ctx* c, int NL, int n_mats, const double* mats, int n_
                            (const double*)c->tl_v0.p, (const long long*)c->tl_segoff.p,
                            (const aceqd_tlseg*)c->tl_segs.p, (const double*)c->tl_w.p,
                            out ? (double*)c->tl_out.p : nullptr,
-                           final_v ? (double*)c->tl_final.p : nullptr, c->stream, &c->launches)))
+                           final_v ? (double*)c->tl_final.p : nullptr, c->stream, &c->log)))
         return rc;
     ACEQD_CUDA(cudaEventRecord(c->ev[5], c->stream));
     c->have_tl = true;
@@ -1270,11 +1209,11 @@ int aceqd_fp64_peak(aceqd_ctx* c, int kind, int iters, double* tflops) {
     ACEQD_CUDA(cudaEventCreate(&e1));
     // warm-up
     if ((rc = launch_fp64_peak(kind, iters / 8 + 1, (double*)c->misc.p, &blocks, &threads,
-                               c->stream, &c->launches)))
+                               c->stream, &c->log)))
         return rc;
     ACEQD_CUDA(cudaEventRecord(e0, c->stream));
     if ((rc = launch_fp64_peak(kind, iters, (double*)c->misc.p, &blocks, &threads, c->stream,
-                               &c->launches)))
+                               &c->log)))
         return rc;
     ACEQD_CUDA(cudaEventRecord(e1, c->stream));
     ACEQD_CUDA(cudaStreamSynchronize(c->stream));

@@ -24,6 +24,16 @@ constexpr int SMEM_BUDGET = 227 * 1024;
 
 void set_error(const char* fmt, ...);
 
+// What the context has launched: a counter (bench: gpu_launches) and the names of the last step kernel /
+// operator builder instantiation (tests and smoke assert that the kernel they name is the one that ran).
+struct LaunchLog {
+    long long count = 0;
+    char step[128] = "";
+    char opbuild[128] = "";
+    char other[128] = "";
+};
+void log_name(char (&dst)[128], const char* fmt, ...);
+
 #define ACEQD_CUDA(call)                                                              \
     do {                                                                              \
         cudaError_t e_ = (call);                                                      \
@@ -112,30 +122,6 @@ struct StepParams {
     long long* ticks;         // debug: [8] phase cycle counters of CTA 0 (null = off)
 };
 
-// Step-synchronous streaming kernel (stream_kernel.cu): state in HBM/L2, class-batched PT GEMM.
-constexpr int STREAM_MAX_CLS = 64;
-struct StreamParams {
-    PtDev pt;
-    ProbDev prob;
-    int n_traj, n_begin, n_end, stages, grid, n_classes;
-    int cls_p0[STREAM_MAX_CLS];   // first alpha position of the class
-    int cls_rc[STREAM_MAX_CLS];   // alpha positions (rows per trajectory) in the class
-    int cls_blk[STREAM_MAX_CLS];  // PT block of the class
-    const aceqd_traj* trajs;
-    const int* order;             // trajectory indices sorted by start step
-    const int* pos_of_alpha;
-    const int* alpha_of_pos;
-    const double* W;
-    const double* OV;
-    long long ovr_base;
-    const double* rho0s;
-    const int* snap_steps;
-    double* snaps;
-    double* out;
-    double *Xre, *Xim, *Yre, *Yim;   // [rank in `order`][alpha position][chi_pad]
-    unsigned* barrier;            // grid barrier counter (zeroed before the launch)
-};
-
 // ---------------------------------------------------------------- operator builder
 struct OpBuildParams {
     ProbDev prob;
@@ -159,23 +145,21 @@ struct OpBuildParams {
 
 // bytes of global workspace the operator builder / expm kernel need for this NL (0: shared memory suffices)
 size_t opbuild_scratch_bytes(int NL, int* ctas);
-int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches);
+int launch_opbuild(const OpBuildParams& p, cudaStream_t s, LaunchLog* log);
 int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, double* scratch,
-                      cudaStream_t s, long long* launches);
-int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, long long* launches);
-int launch_step_check(const StepParams& p, double* scratch, cudaStream_t s, long long* launches);
+                      cudaStream_t s, LaunchLog* log);
+int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, LaunchLog* log);
+int launch_step_check(const StepParams& p, double* scratch, cudaStream_t s, LaunchLog* log);
 size_t step_smem_bytes(int NL, int chi_pad, int T, int stages, int wov_doubles, int wbufs);
 size_t step_seg_slot_doubles(int NL, int chi_pad, int T);
 // small-bond kernel (small_kernel.cu): one warp per 8 trajectories, process tensor resident in shared memory
 size_t small_smem_bytes(long long pt_doubles, int n_slices, int chi_pad, int n_out, int warps);
 int launch_step_small(const StepParams& p, long long pt_doubles, int warps_per_cta, size_t smem_bytes, cudaStream_t s,
-                      long long* launches);
-int launch_step_stream(const StreamParams& p, size_t smem, cudaStream_t s, long long* launches);
-size_t stream_smem_bytes(int NL, int chi_pad, int stages, int wov_doubles);
+                      LaunchLog* log);
 int launch_tlmap(int NL, int n_chains, int n_w, int n_emit_max, const double* pool, const double* v0,
                  const long long* seg_off, const aceqd_tlseg* segs, const double* w, double* out,
-                 double* final_v, cudaStream_t s, long long* launches);
+                 double* final_v, cudaStream_t s, LaunchLog* log);
 int launch_fp64_peak(int kind, int iters, double* sink_dev, int* blocks, int* threads,
-                     cudaStream_t s, long long* launches);
+                     cudaStream_t s, LaunchLog* log);
 
 }  // namespace aceqd

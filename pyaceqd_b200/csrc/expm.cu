@@ -918,7 +918,7 @@ size_t opbuild_scratch_bytes(int NL, int* ctas) {
     return per_cta > (size_t)SMEM_BUDGET ? per_cta * SCRATCH_CTAS : 0;
 }
 
-int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches) {
+int launch_opbuild(const OpBuildParams& p, cudaStream_t s, LaunchLog* log) {
     const long long total = p.e_end > p.e_begin ? p.e_end - p.e_begin : p.n_seq_entries + p.n_entries;
     if (total <= 0) return ACEQD_OK;
     const int n = p.prob.NL;
@@ -930,7 +930,8 @@ int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches) 
         long long blocks = (total + OPREG_THREADS - 1) / OPREG_THREADS;
         if (blocks > 148LL * 32) blocks = 148LL * 32;
         k_opbuild_reg<4><<<(int)blocks, OPREG_THREADS, 0, s>>>(p);
-        ++*launches;
+        ++log->count;
+        log_name(log->opbuild, "k_opbuild_reg<4>");
         ACEQD_CUDA(cudaGetLastError());
         return ACEQD_OK;
     }
@@ -954,7 +955,8 @@ int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches) 
             if ((rc = set_smem(k_opbuild_dmma<2>, smem))) return rc;
             k_opbuild_dmma<2><<<(int)blocks, 32 * wpc, smem, s>>>(p, wpc, lsm);
         }
-        ++*launches;
+        ++log->count;
+        log_name(log->opbuild, "k_opbuild_dmma<%d>", np);
         ACEQD_CUDA(cudaGetLastError());
         return ACEQD_OK;
     }
@@ -991,13 +993,14 @@ int launch_opbuild(const OpBuildParams& p, cudaStream_t s, long long* launches) 
         default: ACEQD_OPB(256); break;
     }
 #undef ACEQD_OPB
-    ++*launches;
+    ++log->count;
+    log_name(log->opbuild, "k_opbuild<%d,%s>", G, blk ? "true" : "false");
     ACEQD_CUDA(cudaGetLastError());
     return ACEQD_OK;
 }
 
 int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, double* scratch,
-                      cudaStream_t s, long long* launches) {
+                      cudaStream_t s, LaunchLog* log) {
     if (count <= 0) return ACEQD_OK;
     if (n > MAX_NL) {
         set_error("n=%d exceeds MAX_NL=%d", n, MAX_NL);
@@ -1038,7 +1041,8 @@ int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, do
         default: ACEQD_EXB(256); break;
     }
 #undef ACEQD_EXB
-    ++*launches;
+    ++log->count;
+    log_name(log->other, "k_expm_batch<%d,%s>", G, blk ? "true" : "false");
     ACEQD_CUDA(cudaGetLastError());
     return ACEQD_OK;
 }

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* sink, int iters) {
 }
 
 int launch_fp64_peak(int kind, int iters, double* sink_dev, int* blocks, int* threads,
-                     cudaStream_t s, long long* launches) {
+                     cudaStream_t s, LaunchLog* log) {
     int dev = 0, sms = 0;
     ACEQD_CUDA(cudaGetDevice(&dev));
     ACEQD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -61,7 +61,7 @@ int launch_fp64_peak(int kind, int iters, double* sink_dev, int* blocks, int* th
         k_dmma_peak<<<*blocks, *threads, 0, s>>>(sink_dev, iters);
     else
         k_dfma_peak<<<*blocks, *threads, 0, s>>>(sink_dev, iters);
-    ++*launches;
+    ++log->count;
     ACEQD_CUDA(cudaGetLastError());
     return ACEQD_OK;
 }

@@ -346,7 +346,7 @@ size_t small_smem_bytes(long long pt_doubles, int n_slices, int chi_pad, int n_o
 
 // p.tile_traj must hold OCTETS (8 trajectory indices per entry, -1 = none), p.n_tiles their number.
 int launch_step_small(const StepParams& p, long long pt_doubles, int warps_per_cta, size_t smem_bytes, cudaStream_t s,
-                      long long* launches) {
+                      LaunchLog* log) {
     if (p.n_tiles <= 0) return ACEQD_OK;
     const int nt = p.pt.chi_pad / 8;
     const int grid = (p.n_tiles + warps_per_cta - 1) / warps_per_cta;
@@ -366,7 +366,8 @@ int launch_step_small(const StepParams& p, long long pt_doubles, int warps_per_c
             return ACEQD_ERR_CAPACITY;
     }
 #undef ACEQD_SMALL
-    ++*launches;
+    ++log->count;
+    log_name(log->step, "k_step_small<%d> warps=%d", nt, warps_per_cta);
     ACEQD_CUDA(cudaGetLastError());
     return ACEQD_OK;
 }

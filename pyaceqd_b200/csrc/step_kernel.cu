@@ -936,12 +936,21 @@ static int launch_nb(const StepParams& p, size_t smem_bytes, cudaStream_t s) {
         cfg.dynamicSmemBytes = smem_bytes;                                                      \
         cfg.stream = s;                                                                         \
         cudaLaunchAttribute attr[1];                                                            \
-        attr[0].id = cudaLaunchAttributeClusterDimension;                                       \
-        attr[0].val.clusterDim.x = (unsigned)p.cluster;                                         \
-        attr[0].val.clusterDim.y = 1;                                                           \
-        attr[0].val.clusterDim.z = 1;                                                           \
         cfg.attrs = attr;                                                                       \
-        cfg.numAttrs = p.cluster > 1 ? 1 : 0;                                                   \
+        cfg.numAttrs = 0;                                                                       \
+        if (p.cluster > 1) {                                                                    \
+            attr[0].id = cudaLaunchAttributeClusterDimension;                                   \
+            attr[0].val.clusterDim.x = (unsigned)p.cluster;                                     \
+            attr[0].val.clusterDim.y = 1;                                                       \
+            attr[0].val.clusterDim.z = 1;                                                       \
+            cfg.numAttrs = 1;                                                                   \
+        } else if (p.segs) {                                                                    \
+            /* CTAs of a segment schedule wait for each other (bond-state hand-over): a         \
+             * cooperative launch guarantees that all of them are resident at once */           \
+            attr[0].id = cudaLaunchAttributeCooperative;                                        \
+            attr[0].val.cooperative = 1;                                                        \
+            cfg.numAttrs = 1;                                                                   \
+        }                                                                                       \
         ACEQD_CUDA(cudaLaunchKernelEx(&cfg, k_step_dmma<NB, KS>, p));                           \
     } while (0)
     if (ksu <= 1) ACEQD_LAUNCH(1);
@@ -952,7 +961,7 @@ static int launch_nb(const StepParams& p, size_t smem_bytes, cudaStream_t s) {
     return ACEQD_OK;
 }
 
-int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, long long* launches) {
+int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, LaunchLog* log) {
     const int chi = p.pt.chi_pad;
     if (chi > 256) {
         set_error("chi_pad=%d exceeds the step kernel's 256 limit", chi);
@@ -964,16 +973,22 @@ int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, lon
     else if (chi <= 128) rc = launch_nb<2>(p, smem_bytes, s);
     else rc = launch_nb<4>(p, smem_bytes, s);
     if (rc) return rc;
-    ++*launches;
+    ++log->count;
+    {
+        const int ksu = p.prob.NLp4 / 4;
+        log_name(log->step, "k_step_dmma<%d,%d> T=%d cluster=%d segments=%d", chi <= 64 ? 1 : (chi <= 128 ? 2 : 4),
+                 ksu <= 1 ? 1 : (ksu <= 4 ? 4 : (ksu <= 9 ? 9 : 16)), p.T, p.cluster, p.segs ? 1 : 0);
+    }
     ACEQD_CUDA(cudaGetLastError());
     return ACEQD_OK;
 }
 
-int launch_step_check(const StepParams& p, double* scratch, cudaStream_t s, long long* launches) {
+int launch_step_check(const StepParams& p, double* scratch, cudaStream_t s, LaunchLog* log) {
     // n_tiles carries the trajectory count for this kernel
     if (p.n_tiles <= 0) return ACEQD_OK;
     k_step_check<<<p.n_tiles, 256, 0, s>>>(p, scratch);
-    ++*launches;
+    ++log->count;
+    log_name(log->step, "k_step_check");
     ACEQD_CUDA(cudaGetLastError());
     return ACEQD_OK;
 }

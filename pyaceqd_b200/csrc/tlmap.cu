@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32) k_tlmap_chains(const TlParams p
 
 int launch_tlmap(int NL, int n_chains, int n_w, int n_emit_max, const double* pool, const double* v0,
                  const long long* seg_off, const aceqd_tlseg* segs, const double* w, double* out,
-                 double* final_v, cudaStream_t s, long long* launches) {
+                 double* final_v, cudaStream_t s, LaunchLog* log) {
     if (NL > TL_MAX_NL) {
         set_error("tlmap: NL=%d exceeds %d", NL, TL_MAX_NL);
         return ACEQD_ERR_CAPACITY;
@@ -131,7 +131,8 @@ int launch_tlmap(int NL, int n_chains, int n_w, int n_emit_max, const double* po
     p.out = (double2*)out;
     p.final_v = (double2*)final_v;
     k_tlmap_chains<<<(n_chains + TL_WARPS - 1) / TL_WARPS, TL_WARPS * 32, 0, s>>>(p);
-    ++*launches;
+    ++log->count;
+    log_name(log->other, "k_tlmap_chains");
     ACEQD_CUDA(cudaGetLastError());
     return ACEQD_OK;
 }

@@ -87,6 +87,29 @@ def is_multi_rank(group=None) -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 
 
+def _check_same_jobs(jobs, device=None, group=None) -> None:
+    """Every rank must have submitted the same job list in the same order (the gather below assembles blocks by
+    position): compare a digest of (count, step counts, tail lengths, start times) across the ranks."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    h = hashlib.sha256()
+    h.update(np.asarray([len(jobs)], dtype=np.int64).tobytes())
+    h.update(np.asarray([[j.n_steps, getattr(j, "tail_rows", 0) or 0, len(getattr(j, "mtos", ()))] for j in jobs],
+                        dtype=np.int64).tobytes())
+    h.update(np.asarray([[getattr(j, "t_start", 0.0), getattr(j, "dt", 0.0)] for j in jobs], dtype=np.float64).tobytes())
+    mine = torch.from_numpy(np.frombuffer(h.digest()[:16], dtype=np.int64).copy())
+    if device is not None:
+        mine = mine.to(device)
+    world = dist.get_world_size(group)
+    allv = torch.empty(world * 2, dtype=torch.int64, device=mine.device)
+    dist.all_gather_into_tensor(allv, mine, group=group)
+    allv = allv.cpu().numpy().reshape(world, 2)
+    if not (allv == allv[0]).all():
+        raise RuntimeError("run_jobs_sharded: the ranks submitted different job lists (count / lengths / order); "
+                           "distributed sharding needs the same sweep on every rank")
+
+
 def run_jobs_sharded(engine, prob, pt, jobs, device=None, group=None, **kw) -> List[np.ndarray]:
     """Propagate this rank's share of `jobs` and all-gather the results (every rank returns the
     full list, like ``wait(futures)`` in the reference).  Requires an initialised process group;
@@ -99,6 +122,7 @@ def run_jobs_sharded(engine, prob, pt, jobs, device=None, group=None, **kw) -> L
     if device is None and dist.get_backend(group) == "nccl":
         import torch
         device = torch.device("cuda", int(getattr(engine, "device", 0)))
+    _check_same_jobs(jobs, device, group)
     costs = [max(1, j.n_steps) for j in jobs]
     blocks = balanced_blocks(costs, world)
     a, b = blocks[rank]

@@ -30,19 +30,19 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libaceqd.so")
 MAX_OVR = 6
 N_SM = 148
 
-# step kernels: persistent DMMA (state in shared memory), plain-FMA check kernel, step-synchronous DMMA
-# (state in HBM/L2, PT GEMM batched over trajectories per coupling class)
-KERNELS = {"dmma": 0, "check": 1, "stream": 2}
+# step kernels (aceqd_batch.kernel): "dmma" = the library's choice between the persistent tile kernel and the
+# small-bond kernel, "check" = plain-FMA check kernel, "colsplit" = bond-column-split cluster kernel,
+# "small" / "tile" force k_step_small / k_step_dmma
+KERNELS = {"dmma": 0, "check": 1, "colsplit": 3, "small": 4, "tile": 5}
+SMALL_MIN_TRAJ = 2048     # ACEQD_SMALL_MIN_TRAJ of include/aceqd.h
 
 
 def resolve_kernel(kernel: str, NL: int) -> str:
-    """``"auto"`` (or the ``ACEQD_KERNEL`` environment override) -> persistent kernel for small Liouville
-    spaces, step-synchronous streaming kernel for large ones (csrc/stream_kernel.cu header)."""
+    """``"auto"`` (or the ``ACEQD_KERNEL`` environment override) -> ``"dmma"``: the persistent kernels, with the
+    planner (:meth:`Engine._tile_and_cluster`) choosing tile size, cluster size and the column-split variant."""
     if kernel == "auto":
         kernel = os.environ.get("ACEQD_KERNEL", "auto")
     if kernel == "auto":
-        # measured (scripts/bench_kernels_nl16.py, DESIGN.md): the persistent kernel wins at every batch size
-        # tried, also for NL = 16; the streaming kernel stays selectable
         return "dmma"
     if kernel not in KERNELS:
         raise ValueError(f"unknown kernel {kernel!r}; choose from {sorted(KERNELS)} or 'auto'")
@@ -103,6 +103,9 @@ def load_library():
     lib.aceqd_ctx_sync.argtypes = [c_void_p]
     lib.aceqd_launch_count.argtypes = [c_void_p]
     lib.aceqd_launch_count.restype = c_longlong
+    for name in ("aceqd_last_step_kernel", "aceqd_last_opbuild_kernel", "aceqd_last_other_kernel"):
+        getattr(lib, name).argtypes = [c_void_p]
+        getattr(lib, name).restype = c_char_p
     lib.aceqd_last_timings.argtypes = [c_void_p, POINTER(c_float), POINTER(c_float)]
     lib.aceqd_pt_create.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, POINTER(c_void_p)]
@@ -333,6 +336,10 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.aceqd_launch_count(self.ctx))
 
+    def last_kernels(self) -> Dict[str, str]:
+        """Names of the kernel instantiations the last step / operator-builder / service launch used."""
+        return {k: getattr(self.lib, "aceqd_last_%s_kernel" % k)(self.ctx).decode() for k in ("step", "opbuild", "other")}
+
     def last_timings(self) -> Tuple[float, float]:
         a, b = c_float(), c_float()
         _check(self.lib.aceqd_last_timings(self.ctx, ctypes.byref(a), ctypes.byref(b)), "aceqd_last_timings")
@@ -378,7 +385,7 @@ class Engine:
         t_max = self.max_tile(NL, chi_pad)
         if t_max < 1:
             raise EngineError(f"NL={NL}, chi={chi_pad} does not fit the step kernel's shared memory")
-        T, C = self._tile_and_cluster(prob, pt, n_traj, t_max, tile_T, cluster)
+        T, C = self._tile_and_cluster(prob, pt, n_traj, t_max, tile_T, cluster, kernel)
         n_tiles = -(-n_traj // T)
         sets = np.arange(n_traj, dtype=np.int32) if sets is None else np.asarray(sets, dtype=np.int32)
         seqs = np.zeros(n_traj, dtype=SEQ_DT)
@@ -407,8 +414,10 @@ class Engine:
         return _Plan(batch=b, keep=[seqs, trajs, tile_traj, rho0], out=None,
                      out_off=trajs["out_off"], n_rows=trajs["n_steps"] + 1)
 
-    def _tile_and_cluster(self, prob, pt, n_traj, t_max, tile_T=None, cluster=None) -> Tuple[int, int]:
+    def _tile_and_cluster(self, prob, pt, n_traj, t_max, tile_T=None, cluster=None, kernel="dmma") -> Tuple[int, int]:
         hp, _ = self.problem_handle(prob, pt)
+        if kernel == "small":      # one warp per 8 trajectories: the tile list only orders the octets
+            return min(tile_T or 8, t_max), 1
         load = lambda t, c: int(self.lib.aceqd_pass_load(hp, t, c))
         if tile_T and cluster:
             return min(tile_T, t_max), cluster
@@ -580,6 +589,9 @@ class Engine:
             # a separate time origin per group keeps `step` = steps since the group's t_start
             t_start = jobs[members[0]].t_start
             step_shift = int(round((t_start - t0_ref) / dt))  # table/time bookkeeping only
+            if abs(t_start - t0_ref - step_shift * dt) > 1e-9 * max(1.0, abs(dt)):
+                raise ValueError(f"t_start={t_start} is not a whole number of steps (dt={dt}) after the earliest "
+                                 f"start {t0_ref} of the batch: run it as a separate batch")
             mto_maps = {i: self._mto_products(prob, jobs[i], mats, mcache) for i in members}
             first = {i: (min(mto_maps[i]) if mto_maps[i] else None) for i in members}
             use_fork = fork and len(members) > 1 and any(f is not None and f > 0 for f in first.values())
@@ -674,7 +686,10 @@ class Engine:
         t_max = self.max_tile(NL, common["chi_pad"])
         if t_max < 1:
             raise EngineError(f"NL={NL}, chi={common['chi_pad']} does not fit the step kernel's shared memory")
-        T, C = self._tile_and_cluster(prob, pt, len(tr), t_max, common["tile_T"], common.get("cluster"))
+        kernel = common["kernel"]
+        if kernel == "small" and len(part["snap_steps"]):
+            kernel = "tile"       # trunks write snapshots: not a small-bond kernel job
+        T, C = self._tile_and_cluster(prob, pt, len(tr), t_max, common["tile_T"], common.get("cluster"), kernel)
         n_tiles = -(-len(tr) // T)
         tile_traj = np.full(n_tiles * T, -1, dtype=np.int32)
         tile_traj[:len(tr)] = order
@@ -700,7 +715,7 @@ class Engine:
         b.n_snap_slots = part["n_slots"]
         b.out_elems, b.out = out_elems, out.ctypes.data
         b.device_resident = 0
-        b.kernel = KERNELS[common["kernel"]]
+        b.kernel = KERNELS[kernel]
         b.cluster = C
         return _Plan(batch=b, keep=[seqs, entries, trajs, tile_traj, mats, rho0, snap_steps, packed, out],
                      out=out, out_off=np.asarray(out_off_of_traj), n_rows=trajs["n_steps"] + 1)
@@ -747,7 +762,9 @@ class Engine:
         if not self.record_timings:
             return
         step_ms, op_ms = self.last_timings()
+        names = self.last_kernels()
         self.timing_log.append(dict(kind=kind, step_ms=step_ms, opbuild_ms=op_ms, NL=prob.NL, chi_pad=chi_pad,
+                                    step_kernel=names["step"], opbuild_kernel=names["opbuild"],
                                     kernel=int(plan.batch.kernel),
                                     n_traj=int(plan.batch.n_traj), tile_T=int(plan.batch.tile_T),
                                     cluster=int(plan.batch.cluster),

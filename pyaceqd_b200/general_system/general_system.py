@@ -254,7 +254,9 @@ def system_ace_stream(t_start, t_end, *pulses, dt=0.01, phonons=False, t_mem=20.
                                                                  temperature, threshold, t_mem, dt)
             if use_infinite:
                 # the reference name omits ae (cache-collision hazard); keep ae in ours
-                pt_file = "{}_{}nm_{}k_th{}_dt{}.pt".format(system_prefix, ae, temperature, threshold, dt)
+                # ... and t_mem: the builder truncates the memory kernel there in the infinite mode too, so a
+                # different t_mem must not silently reuse the cached tensor
+                pt_file = "{}_{}nm_{}k_th{}_tmem{}_dt{}.pt".format(system_prefix, ae, temperature, threshold, t_mem, dt)
         pt = resolve_pt(pt_file, boson_op=boson_op, dt=dt, t_mem=t_mem, ae=ae, temperature=temperature,
                         threshold=threshold, factor_ah=factor_ah, use_infinite=use_infinite,
                         boson_e_max=boson_e_max, J_file=J_file, verbose=verbose, problem=problem)
@@ -324,15 +326,23 @@ def _finish(req: Request, out: np.ndarray):
     return res
 
 
-def run_requests(reqs: List[Request]):
-    """Execute deferred requests: one GPU batch per (problem, PT, dt) group."""
+def run_requests(reqs: List[Request], distributed: Optional[bool] = None):
+    """Execute deferred requests: one GPU batch per (problem, PT, dt, drive-table grid) group.
+
+    Requests whose drives are sampled from different start times live on different table grids and run as
+    separate batches (the reference handles them independently as well).  Inside a ``torch.distributed`` job the
+    sweep is sharded over the ranks ONLY when asked for: ``distributed=True`` here, ``BatchExecutor(distributed=True)``
+    or ``ACEQD_DISTRIBUTED=1`` -- every rank must then submit the same job list in the same order (checked)."""
     from pyaceqd_b200.engine import default_engine
     eng = default_engine()
+    if distributed is None:
+        distributed = os.environ.get("ACEQD_DISTRIBUTED", "0") == "1"
     results = [None] * len(reqs)
     groups: Dict[tuple, List[int]] = {}
     for i, r in enumerate(reqs):
-        groups.setdefault((id(r.problem), id(r.pt), r.job.dt), []).append(i)
-    for (_, _, _), idx in groups.items():
+        # pulse_key[4] is the t_start the drive tables are sampled from: one table grid per batch
+        groups.setdefault((id(r.problem), id(r.pt), r.job.dt, round(r.job.t_start / r.job.dt, 6)), []).append(i)
+    for _, idx in groups.items():
         prob, pt = reqs[idx[0]].problem, reqs[idx[0]].pt
         # unify drive tables of requests that sample the same pulses from the same t_start
         by_key: Dict[tuple, List[int]] = {}
@@ -345,14 +355,21 @@ def run_requests(reqs: List[Request]):
                 for i in members:
                     reqs[i].job.tables = tabs
         plain = [i for i in idx if not reqs[i].calc_dynmap]
-        if plain:
+        # pulse files (read_pulse_file) bring their own grid: one batch per table grid
+        by_grid: Dict[tuple, List[int]] = {}
+        for i in plain:
+            g = next(((round(tb.t0, 9), round(tb.dt, 12)) for tb in reqs[i].job.tables.values() if tb is not None), None)
+            by_grid.setdefault(g, []).append(i)
+        for members in by_grid.values():
             from pyaceqd_b200 import distributed as _dist
-            jobs = [reqs[i].job for i in plain]
-            # inside a torch.distributed job the sweep shards over the ranks (one GPU each) and is
-            # all-gathered once; every rank returns the full result like wait(futures) in the reference
-            outs = _dist.run_jobs_sharded(eng, prob, pt, jobs) if (_dist.is_multi_rank() and len(jobs) > 1) \
-                else eng.run_jobs(prob, pt, jobs)
-            for i, o in zip(plain, outs):
+            jobs = [reqs[i].job for i in members]
+            if distributed and _dist.is_multi_rank() and len(jobs) > 1:
+                # the sweep shards over the ranks (one GPU each) and is all-gathered once; every rank returns the
+                # full result like wait(futures) in the reference
+                outs = _dist.run_jobs_sharded(eng, prob, pt, jobs)
+            else:
+                outs = eng.run_jobs(prob, pt, jobs)
+            for i, o in zip(members, outs):
                 results[i] = _finish(reqs[i], o)
         for i in idx:
             if reqs[i].calc_dynmap:

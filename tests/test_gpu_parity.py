@@ -138,6 +138,8 @@ def test_cluster_biexciton_fork_and_tails(engine, cluster, tile_T):
     pt = synthetic_pt(40, len(prob.cls_keys), n_slices=2, kind="unitary", scale=0.999)
     jobs = _g2_jobs(prob)
     _compare(engine, prob, pt, jobs, "dmma", cluster=cluster, tile_T=tile_T)
+    assert engine.last_kernels()["step"] == "k_step_dmma<1,4> T=%d cluster=%d segments=0" % (tile_T, cluster)
+    assert engine.last_kernels()["opbuild"] == "k_opbuild_dmma<2>"
     tails = engine.run_jobs(prob, pt, _g2_jobs(prob, tail=5), cluster=cluster, tile_T=tile_T)
     full = engine.run_jobs(prob, pt, jobs, cluster=1, tile_T=tile_T)
     assert max(np.abs(f[:, -5:] - t).max() for f, t in zip(full, tails)) < 1e-12
@@ -181,69 +183,57 @@ def test_planner_picks_clusters_for_small_batches(engine):
     assert engine._tile_and_cluster(tls, ptt, 4096, engine.max_tile(4, 128)) == (16, 1)
 
 
-# ------------------------------------------------------------------ step-synchronous streaming kernel
-def test_stream_kernel_biexciton_fork_tails_and_sixlevel(engine):
-    prob = biexciton_problem(outputs=["|1><1|_4", "(|3><1|_4*|1><1|_4*|1><3|_4)", "|0><3|_4"])
-    pt = synthetic_pt(40, len(prob.cls_keys), n_slices=2, kind="unitary", scale=0.999)
-    jobs = _g2_jobs(prob)
-    _compare(engine, prob, pt, jobs, "stream")
-    tails = engine.run_jobs(prob, pt, _g2_jobs(prob, tail=5), kernel="stream")
-    full = engine.run_jobs(prob, pt, jobs, kernel="dmma")
-    assert max(np.abs(f[:, -5:] - t).max() for f, t in zip(full, tails)) < 1e-12
-    _compare(engine, prob, pt, jobs, "stream", fork=False)
-    six = sixls_problem()
-    pt6 = synthetic_pt(24, len(six.cls_keys), kind="unitary", scale=0.999)
-    p6 = ChirpedPulse(tau_0=1.0, e_start=-1.0, alpha=0, t0=2.0, e0=3.0, polar_x=0.7)
-    jobs6 = [Job(0.0, 3.0, 0.1, tables=make_tables([p6], 0.0, 3.0, 0.1)) for _ in range(3)]
-    _compare(engine, six, pt6, jobs6, "stream")
-    pt128 = synthetic_pt(128, len(prob.cls_keys), kind="unitary", scale=0.999)
-    _compare(engine, prob, pt128, _g2_jobs(prob, n_t=8, tau_max=2.0), "stream")
-
-
-def test_stream_kernel_tls_growing_pt_ragged_and_sweep(engine):
+def test_more_tiles_than_sms_segments_waves_and_copy_overlap(engine, monkeypatch):
+    """More tiles than SMs on the tile kernel (chi = 40 > 32, so the small-bond kernel cannot take the batch), through
+    host buffers: (a) the default segment schedule (tiles cut into one piece of steps per SM, bond states handed over
+    through HBM), (b) ACEQD_SEGMENTS=0: the partial wave first, operators of the later waves built on a side stream,
+    (c) pageable outputs: finished waves copied while the last wave runs.  Results must not depend on any of it."""
     prob = tls_problem()
-    pt = synthetic_growing_pt(24, len(prob.cls_keys), n_initial=5, n_repeat=3)
-    p = ChirpedPulse(tau_0=1, e_start=0.5, alpha=0, t0=3, e0=2)
-    jobs = [Job(0.0, te, 0.1, tables=make_tables([p], 0.0, te, 0.1)) for te in (0.0, 0.1, 0.3, 1.0, 2.7, 5.0)]
-    _compare(engine, prob, pt, jobs, "stream")
-    pt2 = synthetic_pt(64, len(prob.cls_keys), n_slices=2, kind="unitary", scale=0.999)
-    _compare(engine, prob, pt2, sweep_jobs(9, 9, t_end=3.0), "stream")
-    _compare(engine, tls_problem(phonons=False), trivial_pt(4), jobs[:3], "stream")
-
-
-def test_wave_split_copy_overlap_path(engine):
-    """More tiles than SMs through host buffers: full waves and the last wave are separate launches and the
-    finished waves' outputs are copied while the last wave runs -- results must not depend on it."""
-    prob = tls_problem()
-    pt = synthetic_pt(8, len(prob.cls_keys), kind="unitary", scale=0.999)
+    pt = synthetic_pt(40, len(prob.cls_keys), kind="unitary", scale=0.999)
     jobs = sweep_jobs(20, 30, t_end=2.0)                          # 600 trajectories
-    split = engine.run_jobs(prob, pt, jobs, kernel="dmma", tile_T=2)      # 300 tiles > 148 SMs
-    whole = engine.run_jobs(prob, pt, jobs, kernel="dmma", tile_T=16)     # 38 tiles: single launch
-    assert max(np.abs(a - b).max() for a, b in zip(split, whole)) < 1e-12
+    whole = engine.run_jobs(prob, pt, jobs, kernel="dmma", tile_T=16, cluster=1)     # 38 tiles: single launch
+    assert engine.last_kernels()["step"] == "k_step_dmma<1,1> T=16 cluster=1 segments=0"
     for k in (0, 147 * 2, 148 * 2, 599):                          # around the wave boundary
-        assert np.abs(split[k] - oracle.propagate(prob, pt, jobs[k])).max() < TOL
+        assert np.abs(whole[k] - oracle.propagate(prob, pt, jobs[k])).max() < TOL
+    for env, seg in ((None, 1), ("0", 0)):
+        if env is None:
+            monkeypatch.delenv("ACEQD_SEGMENTS", raising=False)
+        else:
+            monkeypatch.setenv("ACEQD_SEGMENTS", env)
+        for nzc in ("0", "1"):
+            monkeypatch.setenv("ACEQD_NO_ZEROCOPY", nzc)
+            split = engine.run_jobs(prob, pt, jobs, kernel="dmma", tile_T=2, cluster=1)      # 300 tiles > 148 SMs
+            assert engine.last_kernels()["step"] == "k_step_dmma<1,1> T=2 cluster=1 segments=%d" % seg
+            assert max(np.abs(a - b).max() for a, b in zip(split, whole)) < 1e-12, (env, nzc)
+    monkeypatch.delenv("ACEQD_SEGMENTS", raising=False)
+    monkeypatch.delenv("ACEQD_NO_ZEROCOPY", raising=False)
 
 
 # ------------------------------------------------------------------ small-bond kernel (one warp per 8 trajectories)
 @pytest.mark.parametrize("chi", [5, 8, 16, 20, 32])
-def test_small_bond_kernel_matches_oracle_and_tile_kernel(engine, chi, monkeypatch):
-    """NL = 4, chi_pad <= 32 runs on k_step_small (PT resident in shared memory, warp-private state).  Ragged
-    lengths, multi-slice PTs, MTO rows (override entries), tails and a forked batch (branches start from snapshots
-    written by the tile kernel's trunk)."""
+def test_small_bond_kernel_matches_oracle_and_tile_kernel(engine, chi):
+    """NL = 4, chi_pad <= 32 on k_step_small<chi_pad/8> (PT resident in shared memory, warp-private state), forced with
+    kernel="small" and PROVEN by the library's record of the kernel it launched.  Ragged lengths and octets,
+    multi-slice PTs, MTO rows (override entries), tails, more outputs than lanes of a quad, and a forked batch whose
+    branches start from snapshots written by the tile kernel's trunk."""
     from pyaceqd_b200.opparser import parse_operator
     prob = tls_problem()
     pt = synthetic_pt(chi, len(prob.cls_keys), n_slices=2, kind="unitary", scale=0.999)
+    nt = -(-chi // 8)
+    small = "k_step_small<%d>" % nt
+
+    def ran_small():
+        assert engine.last_kernels()["step"].startswith(small), engine.last_kernels()
+
     jobs = sweep_jobs(7, 9, t_end=6.0)                      # 63 trajectories: octets with a ragged tail
-    monkeypatch.setenv("ACEQD_SMALL", "1")
-    n0 = engine.launch_count()
-    got = engine.run_jobs(prob, pt, jobs, kernel="dmma")
+    got = engine.run_jobs(prob, pt, jobs, kernel="small")
+    ran_small()
     for k in range(0, len(jobs), 5):
         assert np.abs(got[k] - oracle.propagate(prob, pt, jobs[k])).max() < TOL
-    monkeypatch.setenv("ACEQD_SMALL", "0")
-    ref = engine.run_jobs(prob, pt, jobs, kernel="dmma")
+    ref = engine.run_jobs(prob, pt, jobs, kernel="tile")
+    assert engine.last_kernels()["step"].startswith("k_step_dmma<1,1>")
     assert max(np.abs(a - b).max() for a, b in zip(got, ref)) < 1e-12
-    monkeypatch.setenv("ACEQD_SMALL", "1")
-    # ragged lengths + MTOs at several times + tails
+    # ragged lengths + MTOs at several times (override rows)
     p = ChirpedPulse(tau_0=1.0, e_start=0.3, alpha=0, t0=2.0, e0=1.5)
     s = parse_operator("|0><1|_2", 2)
     rag = []
@@ -253,18 +243,48 @@ def test_small_bond_kernel_matches_oracle_and_tile_kernel(engine, chi, monkeypat
         if te >= 1.0:
             mt += [MTO(prob.mto_superop(s.conj().T, "_left"), 0.5, True), MTO(prob.mto_superop(s, "_right"), 0.5, False)]
         rag.append(Job(0.0, te, 0.1, tables=tabs, mtos=mt))
-    _compare(engine, prob, pt, rag, "dmma", fork=False)
+    _compare(engine, prob, pt, rag, "small", fork=False)
+    ran_small()
     # forked G1-style batch: trunk (tile kernel, snapshots) + branches (small kernel, init from snapshots)
     tabs = make_tables([p], 0.0, 12.0, 0.1)
     fj = []
     for t1 in np.arange(0.5, 5.0, 0.5):
         mt = prob.parse_mtos([{"operator": "|0><1|_2", "applyFrom": "_left", "time": float(t1)}])
         fj.append(Job(0.0, float(t1 + 3.0), 0.1, tables=tabs, mtos=mt))
-    _compare(engine, prob, pt, fj, "dmma", fork=True)
+    engine.record_timings = True
+    engine.timing_log.clear()
+    try:
+        _compare(engine, prob, pt, fj, "small", fork=True)
+        kinds = {l["kind"]: l["step_kernel"] for l in engine.timing_log}
+    finally:
+        engine.record_timings = False
+    assert kinds["trunk"].startswith("k_step_dmma") and kinds["main"].startswith(small), kinds
     # more output functionals than lanes of a quad (full density matrix + two products)
     prob6 = tls_problem(outputs=["|0><0|_2", "|1><1|_2", "|0><1|_2", "|1><0|_2", "(|1><0|_2*|0><1|_2)", "|0><0|_2+|1><1|_2"])
-    _compare(engine, prob6, pt, sweep_jobs(3, 5, t_end=3.0), "dmma")
+    _compare(engine, prob6, pt, sweep_jobs(3, 5, t_end=3.0), "small")
+    ran_small()
     tails = engine.run_jobs(prob, pt, [Job(j.t_start, j.t_end, j.dt, tables=j.tables, mtos=j.mtos, tail_rows=11)
-                                       for j in fj], kernel="dmma")
-    full = engine.run_jobs(prob, pt, fj, kernel="dmma")
+                                       for j in fj], kernel="small")
+    ran_small()
+    full = engine.run_jobs(prob, pt, fj, kernel="tile")
     assert max(np.abs(f[:, -11:] - t).max() for f, t in zip(full, tails)) < 1e-12
+
+
+def test_kernel_choice_of_the_library(engine):
+    """kernel 0 takes k_step_small only for batches that can fill the sub-partitions; small batches stay on tiles
+    (shared by clusters).  Ineligible batches forced onto the small kernel fail loudly."""
+    from pyaceqd_b200.engine import SMALL_MIN_TRAJ, EngineError
+    prob = tls_problem()
+    pt = synthetic_pt(16, len(prob.cls_keys), kind="unitary", scale=0.999)
+    jobs = sweep_jobs(6, 6, t_end=1.0)
+    engine.run_jobs(prob, pt, jobs)
+    assert engine.last_kernels()["step"].startswith("k_step_dmma<1,1>")
+    p = ChirpedPulse(tau_0=1.0, e_start=0.3, alpha=0, t0=0.5, e0=1.5)
+    tabs = make_tables([p], 0.0, 1.0, 0.1)
+    many = [Job(0.0, 1.0, 0.1, tables=tabs) for _ in range(SMALL_MIN_TRAJ)]
+    out = engine.run_jobs(prob, pt, many)
+    assert engine.last_kernels()["step"].startswith("k_step_small<2>")
+    assert engine.last_kernels()["opbuild"] == "k_opbuild_reg<4>"
+    assert np.abs(out[-1] - oracle.propagate(prob, pt, many[-1])).max() < TOL
+    with pytest.raises(EngineError):
+        engine.run_jobs(prob, synthetic_pt(40, len(prob.cls_keys), kind="unitary"), jobs, kernel="small")

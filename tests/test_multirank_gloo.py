@@ -61,6 +61,12 @@ def _worker(rank, world, port, q):
         jobs = [_Job(n) for n in (3, 9, 1, 4, 4, 7)]
         res = run_jobs_sharded(_Eng(), _Prob(), None, jobs)
         ok2 = all(r.shape == (2, j.n_steps + 1) and np.all(r == j.n_steps + 0.5j) for r, j in zip(res, jobs))
+        # ranks that submit different job lists are caught before the gather (no hang, no misassembled result)
+        try:
+            run_jobs_sharded(_Eng(), _Prob(), None, jobs[:5] if rank else jobs)
+            ok2 = False
+        except RuntimeError as exc:
+            ok2 = ok2 and "different job lists" in str(exc)
         # a whole workflow inside the process group: the G2 sweep shards over the ranks (oracle backend)
         import sys
         sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
@@ -72,6 +78,12 @@ def _worker(rank, world, port, q):
         p = ChirpedPulse(tau_0=0.5, e_start=0, alpha=0, t0=1.5, e0=2.0)
         with oracle_backend() as eng:
             eng.device = 0
+            # sharding is opt-in: without it every rank computes the whole sweep and meets no collective
+            three_op_two_time(tls, np.round(np.arange(0.0, 3.0, 0.5), 6), p, tau_max=2.0, dt=0.25,
+                              options={"lindblad": True, "phonons": False, "gamma_e": 0.2})
+            ok2 = ok2 and sum(c[0] for c in eng.calls) == 6
+            eng.calls.clear()
+            os.environ["ACEQD_DISTRIBUTED"] = "1"
             t1, tau, G = three_op_two_time(tls, np.round(np.arange(0.0, 3.0, 0.5), 6), p, tau_max=2.0, dt=0.25,
                                            options={"lindblad": True, "phonons": False, "gamma_e": 0.2})
             shard_sizes = [c[0] for c in eng.calls]
