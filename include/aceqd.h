@@ -100,6 +100,10 @@ typedef struct {
     int32_t sb;       /* index into mto_mats applied BEFORE the output row (applyBefore), or -1 */
     int32_t sa;       /* index into mto_mats applied AFTER the output row, or -1               */
     int32_t has_prev; /* a half step precedes this row                                         */
+    int32_t clamp;    /* > 0: this row's drive ends after `clamp` samples (end value held beyond):     */
+                      /* the reference writes one pulse file PER run on np.arange(t_start, t_end, dt)  */
+                      /* (general_system.py:55-71,213), so the last step of a run that shares a longer */
+                      /* table with other runs must not see samples past its own t_end - dt            */
 } aceqd_entry;
 
 #define ACEQD_MAX_OVR 6
@@ -166,7 +170,7 @@ typedef struct {
                                /*    (k_step_dmma) and, for NL = 4 / chi_pad <= 32 batches of at least    */
                                /*    ACEQD_SMALL_MIN_TRAJ trajectories, the small-bond kernel k_step_small */
                                /* 1: plain-FMA check kernel (tests)                                        */
-                               /* 3: bond-column-split cluster kernel k_step_colsplit: `cluster` CTAs hold */
+                               /* 3: split-K cluster kernel k_step_splitk: `cluster` CTAs hold             */
                                /*    chi_pad/cluster bond columns each of tile_T trajectories (large NL)   */
                                /* 4: k_step_small or ACEQD_ERR_CAPACITY;  5: k_step_dmma always            */
     int32_t cluster;           /* CTAs per tile (0/1, 2, 4 or 8): a thread-block cluster shares one tile.  */
@@ -236,6 +240,10 @@ void aceqd_struct_sizes(int32_t out[4]);
 /* Largest trajectories-per-tile T for which (NL, chi_pad) fits the step kernel's shared
  * memory budget (0 if even T=1 does not fit). */
 int aceqd_max_tile(int NL, int chi_pad);
+
+/* Planner helper for aceqd_batch.kernel = 3: shared-memory bytes the split-K cluster kernel needs for tile_T = G
+ * trajectories on a cluster of C CTAs (0: unsupported combination or does not fit). */
+long long aceqd_splitk_fit(int NL, int chi_pad, int G, int C);
 
 /* With more tiles than SMs the step kernel does not run in waves: the tiles are laid end to end and cut into
  * one equal piece of steps per SM; a tile that straddles a cut is started by one CTA and finished by the next

@@ -38,13 +38,14 @@ def n_steps_of(job) -> int:
     return int(round((job.t_end - job.t_start) / job.dt))
 
 
-def sample_field(table, t: float) -> complex:
+def sample_field(table, t: float, n_valid: int = 0) -> complex:
     """Value of a tabulated drive at time ``t``: linear interpolation between the samples of
     the pulse file (general_system.py:55-71 writes them on ``t0 + j*dt``), end values held
-    outside the table."""
+    outside the table.  ``n_valid`` > 0: only the first ``n_valid`` samples belong to this run's
+    own pulse file (the reference writes it on np.arange(t_start, t_end, dt), :213)."""
     x = (t - table.t0) / table.dt
     v = table.values
-    n = len(v)
+    n = len(v) if n_valid <= 0 else min(len(v), n_valid)
     if n == 0:
         return 0.0 + 0.0j
     if x <= 0:
@@ -64,7 +65,7 @@ def liouvillian_at(problem, job, t: float) -> np.ndarray:
         tab = job.tables.get(pol)
         if tab is None:
             continue
-        f = sample_field(tab, t)
+        f = sample_field(tab, t, getattr(job, "table_len", 0))
         L += f * problem.LA[k] + np.conj(f) * problem.LB[k]
     return L
 

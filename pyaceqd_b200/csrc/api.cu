@@ -72,7 +72,7 @@ struct aceqd_ctx {
     LaunchLog log;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // step, opbuild, tlmap start/stop
     bool have_step = false, have_op = false, have_tl = false;
-    DevBuf W, OV, tables, seqs, seq_base, entries, mto, rho0s, trajs, tiles, snap_steps, snaps,
+    DevBuf W, OV, tables, seqs, seq_base, entries, mto, rho0s, trajs, tiles, snap_steps, snaps, snap_r,
         out, passes, scratch, misc, octets, segs, seg_off, seg_state, seg_flags, opscratch, tl_pool, tl_v0, tl_segoff, tl_segs, tl_w, tl_out, tl_final;
     long long* ticks = nullptr;           // debug phase clock of the step kernel (aceqd_debug_phase_ticks)
     // layout of the operators currently in the workspace
@@ -83,6 +83,7 @@ struct aceqd_pt {
     aceqd_ctx* ctx = nullptr;
     PtDev d{};
     void *blob = nullptr, *closure = nullptr, *kin = nullptr, *nout = nullptr, *off = nullptr;
+    void *pblob = nullptr, *poff = nullptr;   // panel-ordered copy for the split-K kernel (chi_pad > PANEL only)
     long long blob_doubles = 0;
 };
 
@@ -145,7 +146,7 @@ void aceqd_ctx_destroy(aceqd_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->W, &c->OV, &c->tables, &c->seqs, &c->seq_base, &c->entries, &c->mto,
-                      &c->rho0s, &c->trajs, &c->tiles, &c->snap_steps, &c->snaps, &c->out,
+                      &c->rho0s, &c->trajs, &c->tiles, &c->snap_steps, &c->snaps, &c->snap_r, &c->out,
                       &c->passes, &c->scratch, &c->misc, &c->octets, &c->segs, &c->seg_off, &c->seg_state, &c->seg_flags, &c->opscratch, &c->tl_pool, &c->tl_v0, &c->tl_segoff,
                       &c->tl_segs, &c->tl_w, &c->tl_out, &c->tl_final})
         b->release();
@@ -264,6 +265,35 @@ int aceqd_pt_create(aceqd_ctx* c, int n_cls, int n_slices, int n_initial, const 
     PT_UP(pt->kin, kin);
     PT_UP(pt->nout, nout);
     PT_UP(pt->off, off);
+    // chi_pad > PANEL: a second copy cut into panels of PANEL output columns, [slice][cls][panel][chunk], row stride
+    // PANEL + 4 (what one split-K GEMM pass streams)
+    const int n_panels = (chi_pad + PANEL - 1) / PANEL;
+    std::vector<double> pblob;
+    std::vector<long long> poff(n_slices, 0);
+    if (chi_pad > PANEL) {
+        const int pstride = PANEL + 4, pchunk = 2 * KC * pstride;
+        long long ptotal = 0;
+        for (int s = 0; s < n_slices; ++s) {
+            poff[s] = ptotal;
+            ptotal += (long long)n_cls * n_panels * (kin[s] / KC) * pchunk;
+        }
+        pblob.assign((size_t)ptotal, 0.0);
+        for (int s = 0; s < n_slices; ++s) {
+            const int din = chi_in[s], dout = chi_out[s], nch = kin[s] / KC;
+            for (int b = 0; b < n_cls; ++b) {
+                const double* src = slices[s] + (size_t)b * din * dout * 2;
+                for (int d1 = 0; d1 < din; ++d1)
+                    for (int d2 = 0; d2 < dout; ++d2) {
+                        const int q = d2 / PANEL, c = d2 - q * PANEL;
+                        double* ch = pblob.data() + poff[s] + (((size_t)b * n_panels + q) * nch + d1 / KC) * pchunk;
+                        ch[(size_t)(d1 % KC) * pstride + c] = src[((size_t)d1 * dout + d2) * 2];
+                        ch[(size_t)KC * pstride + (size_t)(d1 % KC) * pstride + c] = src[((size_t)d1 * dout + d2) * 2 + 1];
+                    }
+            }
+        }
+        PT_UP(pt->pblob, pblob);
+        PT_UP(pt->poff, poff);
+    }
 #undef PT_UP
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
         set_error("aceqd_pt_create: sync failed");
@@ -283,6 +313,9 @@ int aceqd_pt_create(aceqd_ctx* c, int n_cls, int n_slices, int n_initial, const 
     d.off = (const long long*)pt->off;
     d.blob = (const double*)pt->blob;
     d.closure = (const double*)pt->closure;
+    d.pblob = (const double*)pt->pblob;
+    d.poff = (const long long*)pt->poff;
+    d.n_panels = pt->pblob ? n_panels : 1;
     *out = pt;
     return ACEQD_OK;
 }
@@ -290,7 +323,7 @@ int aceqd_pt_create(aceqd_ctx* c, int n_cls, int n_slices, int n_initial, const 
 void aceqd_pt_destroy(aceqd_pt* pt) {
     if (!pt) return;
     if (pt->ctx) cudaSetDevice(pt->ctx->device);
-    for (void* p : {pt->blob, pt->closure, pt->kin, pt->nout, pt->off})
+    for (void* p : {pt->blob, pt->closure, pt->kin, pt->nout, pt->off, pt->pblob, pt->poff})
         if (p) cudaFree(p);
     delete pt;
 }
@@ -718,6 +751,16 @@ int aceqd_debug_phase_ticks(aceqd_ctx* c, int enable, long long* out8) {
     return ACEQD_OK;
 }
 
+/* Shared-memory bytes of the split-K cluster kernel for G trajectories on a cluster of C CTAs (deepest chunk ring
+ * that fits; 0 if the combination is unsupported or does not fit). */
+long long aceqd_splitk_fit(int NL, int chi_pad, int G, int C) {
+    for (int st = MAX_STAGES; st >= 2; --st) {
+        const size_t smem = splitk_smem_bytes(NL, chi_pad, G, C, st);
+        if (smem && smem <= (size_t)SMEM_BUDGET) return (long long)smem;
+    }
+    return 0;
+}
+
 int aceqd_max_tile(int NL, int chi_pad) {
     for (int T = MAX_TILE_T; T >= 1; T >>= 1)
         if (step_smem_bytes(NL, chi_pad, T, 2, 0, 1) <= (size_t)SMEM_BUDGET) return T;
@@ -783,6 +826,8 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
         // growing discards old snapshots; writers re-create them in this call
         if ((rc = c->snaps.reserve((size_t)b->n_snap_slots * pd.NL * chi_pad * 16))) return rc;
     }
+    // closures of the snapshot rows (same slots); kept as large as the snapshot pool
+    if (c->snaps.cap > 0 && (rc = c->snap_r.reserve(c->snaps.cap / (size_t)chi_pad + 64))) return rc;
     double* out_dev = nullptr;
     bool zero_copy = false;   // page-locked host output: the kernel writes its rows straight through PCIe
     if (b->device_resident) {
@@ -811,6 +856,7 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
     sp.rho0s = (const double*)c->rho0s.p;
     sp.snap_steps = (const int*)c->snap_steps.p;
     sp.snaps = (double*)c->snaps.p;
+    sp.snap_r = (double*)c->snap_r.p;
     sp.out = out_dev;
     sp.ticks = c->ticks;
     if (const char* tc = getenv("ACEQD_TICK_CLUSTER"))   // debug clock only for launches of this cluster size
@@ -898,6 +944,52 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
                 }
                 return ACEQD_OK;
             }
+        }
+        if (b->kernel == 3) {
+            // ---- split-K cluster kernel: `cluster` CTAs hold chi_pad/cluster bond columns each of T trajectories
+            int stages = 0;
+            size_t smem = 0;
+            for (int st = MAX_STAGES; st >= 2; --st) {
+                smem = splitk_smem_bytes(pd.NL, chi_pad, T, cluster, st);
+                if (smem && smem <= (size_t)SMEM_BUDGET) {
+                    stages = st;
+                    break;
+                }
+            }
+            if (!stages) {
+                set_error("split-K kernel: NL=%d chi_pad=%d T=%d cluster=%d is not supported or does not fit %d B of "
+                          "shared memory", pd.NL, chi_pad, T, cluster, SMEM_BUDGET);
+                return ACEQD_ERR_CAPACITY;
+            }
+            std::vector<PassDesc> passes;
+            if ((rc = build_passes(prob, T, 1, passes))) return rc;
+            UP(c->passes, passes.data(), passes.size() * sizeof(PassDesc));
+            UP(c->tiles, b->tile_traj, (size_t)b->n_tiles * T * sizeof(int32_t));
+            sp.T = T;
+            sp.n_pass = (int)passes.size();
+            sp.stages = stages;
+            sp.n_tiles = b->n_tiles;
+            sp.cluster = cluster;
+            sp.NR = splitk_columns(chi_pad, cluster);
+            sp.rslots = chi_pad > PANEL ? 1 : 2;   // with panels the two panels of a row block alternate on one slot
+            sp.passes = (const PassDesc*)c->passes.p;
+            sp.tile_traj = (const int*)c->tiles.p;
+            if (c->split_ops_pending) {
+                ACEQD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_built, 0));
+                c->split_ops_pending = false;
+            }
+            c->split_tiles = 0;
+            ACEQD_CUDA(cudaEventRecord(c->ev[0], c->stream));
+            if ((rc = launch_step_splitk(sp, smem, c->stream, &c->log))) return rc;
+            ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
+            c->have_step = true;
+            if (!b->device_resident) {
+                if (!zero_copy)
+                    ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)b->out_elems * 16, cudaMemcpyDeviceToHost,
+                                               c->stream));
+                ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+            }
+            return ACEQD_OK;
         }
         std::vector<PassDesc> passes;
         if ((rc = build_passes(prob, T, cluster, passes))) return rc;

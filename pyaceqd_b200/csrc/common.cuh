@@ -15,7 +15,13 @@ namespace aceqd {
 constexpr int KC = 8;             // k rows of one PT chunk (two DMMA k-steps)
 constexpr int MC = 2;             // m-tiles (8 rows each) accumulated per pass
 constexpr int N_COMPUTE_WARPS = 8;
-constexpr int STEP_THREADS = (N_COMPUTE_WARPS + 1) * 32;  // + 1 TMA producer warp
+// A thread that issues a cp.async.bulk right after mbarrier traffic pays ~450 cycles before its next copy can go
+// out (scripts/micro/l2_ingest.cu: one chunk per 257 ns whatever its size or the ring depth), while copies of
+// DIFFERENT warps overlap (scripts/micro/bulk_latency.cu: 67 B/clk per SM with 64+ KB in flight).  So the PT chunk
+// ring is fed by several producer warps (chunk c belongs to producer c mod P) and the per-row operators by their own.
+constexpr int N_CHUNK_PRODUCERS = 1;   // measured: more producers do not speed up the tile kernel (profiles/r05c_*)
+constexpr int N_PRODUCER_WARPS = N_CHUNK_PRODUCERS + 1;   // + the W|OV stager
+constexpr int STEP_THREADS = (N_COMPUTE_WARPS + N_PRODUCER_WARPS) * 32;
 constexpr int MAX_NL = 64;
 constexpr int MAX_PASSES = 96;
 constexpr int MAX_TILE_T = 16;
@@ -58,7 +64,14 @@ struct PtDev {
     const long long* off;    // [n_slices] offset (doubles) of chunk (cls 0, j 0)
     const double* blob;      // chunks ordered [slice][cls][chunk]
     const double* closure;   // [n_slices][2*chi_pad] interleaved complex, zero padded
+    // the same slices cut into panels of PANEL output columns (split-K cluster kernel, chi_pad > PANEL only):
+    // chunks ordered [slice][cls][panel][chunk], row stride PANEL + 4
+    const double* pblob;
+    const long long* poff;   // [n_slices]
+    int n_panels;            // panels of the widest slice (1 when pblob is null)
+    int pad2_;
 };
+constexpr int PANEL = 128;        // output columns of one split-K GEMM pass (8 warps x 2 n-tiles)
 
 // ---------------------------------------------------------------- device-side problem
 struct ProbDev {
@@ -120,6 +133,10 @@ struct StepParams {
     unsigned seg_epoch;
     int n_ctas;               // grid size with a segment schedule
     long long* ticks;         // debug: [8] phase cycle counters of CTA 0 (null = off)
+    double* snap_r;           // [slots][NL] complex: closure rho of the snapshot row (written with every snapshot)
+    // split-K cluster kernel (splitk_kernel.cu): `cluster` CTAs hold NR bond columns each of T trajectories
+    int NR;                   // bond columns per CTA (multiple of 8)
+    int rslots;               // receive-ring depth for the partial products (2)
 };
 
 // ---------------------------------------------------------------- operator builder
@@ -152,6 +169,11 @@ int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, Lau
 int launch_step_check(const StepParams& p, double* scratch, cudaStream_t s, LaunchLog* log);
 size_t step_smem_bytes(int NL, int chi_pad, int T, int stages, int wov_doubles, int wbufs);
 size_t step_seg_slot_doubles(int NL, int chi_pad, int T);
+// split-K cluster kernel: shared-memory bytes for (NL, chi_pad, n_out) with G trajectories on a cluster of C CTAs and
+// `stages` PT chunk stages (0 if the combination is not supported)
+size_t splitk_smem_bytes(int NL, int chi_pad, int G, int C, int stages);
+int splitk_columns(int chi_pad, int C);   // NR
+int launch_step_splitk(const StepParams& p, size_t smem_bytes, cudaStream_t s, LaunchLog* log);
 // small-bond kernel (small_kernel.cu): one warp per 8 trajectories, process tensor resident in shared memory
 size_t small_smem_bytes(long long pt_doubles, int n_slices, int chi_pad, int n_out, int warps);
 int launch_step_small(const StepParams& p, long long pt_doubles, int warps_per_cta, size_t smem_bytes, cudaStream_t s,

@@ -220,7 +220,7 @@ __device__ __forceinline__ double2 sample_table(const double2* v, int n, double 
 // A = (L0 + sum_k f_k LA_k + conj(f_k) LB_k) * delta   at time t, drive set `set`
 template <int G>
 __device__ void assemble(double2* A, const OpBuildParams& p, int set, double t, double delta,
-                         int tid, int gid) {
+                         int tid, int gid, int ns) {
     const int n = p.prob.NL, n2 = n * n;
     const double2* L0 = reinterpret_cast<const double2*>(p.prob.L0);
     const double2* LA = reinterpret_cast<const double2*>(p.prob.LA);
@@ -233,7 +233,7 @@ __device__ void assemble(double2* A, const OpBuildParams& p, int set, double t, 
             const int tb = p.prob.field_table[k];
             if (tb < 0 || tb >= p.n_tables) continue;
             const double2 f =
-                sample_table(tabs + ((size_t)set * p.n_tables + tb) * p.n_samples, p.n_samples, x);
+                sample_table(tabs + ((size_t)set * p.n_tables + tb) * p.n_samples, ns, x);
             cfma(acc, f, LA[(size_t)k * n2 + e]);
             cfma(acc, make_double2(f.x, -f.y), LB[(size_t)k * n2 + e]);
         }
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(256) k_opbuild(OpBuildParams p) {
     const double half = 0.5 * p.dt;
     for (long long e = p.e_begin + (long long)blockIdx.x * groups + gid; e < total;
          e += (long long)gridDim.x * groups) {
-        int set, step, sb = -1, sa = -1, has_prev;
+        int set, step, sb = -1, sa = -1, has_prev, ns = p.n_samples;
         if (e < p.n_seq_entries) {
             int lo = 0, hi = p.n_seq;  // seq_base[lo] <= e < seq_base[hi]
             while (hi - lo > 1) {
@@ -275,13 +275,14 @@ __global__ void __launch_bounds__(256) k_opbuild(OpBuildParams p) {
         } else {
             const aceqd_entry en = p.entries[e - p.n_seq_entries];
             set = en.set; step = en.step; sb = en.sb; sa = en.sa; has_prev = en.has_prev;
+            if (en.clamp > 0) ns = min(en.clamp, p.n_samples);   // this row sees only the first `clamp` samples of its drive
         }
         const double t_n = p.t0 + (double)step * p.dt;
         const double2* mto = reinterpret_cast<const double2*>(p.mto_mats);
 
         // ---- V = Sb * M2_{n-1}
         if (has_prev) {
-            assemble<G>(A, p, set, t_n - p.dt + p.eval_off2 * p.dt, half, tid, gid);
+            assemble<G>(A, p, set, t_n - p.dt + p.eval_off2 * p.dt, half, tid, gid, ns);
             double2* M2 = expm_group<G, BLK>(A, red, n, tid, gid);
             if (sb >= 0) {
                 gmm<G, BLK>(V, mto + (size_t)sb * n2, M2, n, tid, gid, 1.0, false);
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(256) k_opbuild(OpBuildParams p) {
             Xp = X;
         }
         // ---- W = M1_n * X   (zero padded to [NLp8][NLp4])
-        assemble<G>(A, p, set, t_n + p.eval_off1 * p.dt, half, tid, gid);
+        assemble<G>(A, p, set, t_n + p.eval_off1 * p.dt, half, tid, gid, ns);
         double2* M1 = expm_group<G, BLK>(A, red, n, tid, gid);
         {
             double2* w = reinterpret_cast<double2*>(p.W + (size_t)e * p.prob.w_doubles);
@@ -402,7 +403,7 @@ __device__ __forceinline__ void expm_reg(double2 (&A)[N][N], double2 (&P)[N][N])
 
 template <int N>
 __device__ __forceinline__ void assemble_reg(double2 (&A)[N][N], const OpBuildParams& p, int set, double t,
-                                             double delta) {
+                                             double delta, int ns) {
     const double2* L0 = reinterpret_cast<const double2*>(p.prob.L0);
     const double2* LA = reinterpret_cast<const double2*>(p.prob.LA);
     const double2* LB = reinterpret_cast<const double2*>(p.prob.LB);
@@ -415,7 +416,7 @@ __device__ __forceinline__ void assemble_reg(double2 (&A)[N][N], const OpBuildPa
     for (int k = 0; k < p.prob.n_fields; ++k) {
         const int tb = p.prob.field_table[k];
         if (tb < 0 || tb >= p.n_tables) continue;
-        const double2 f = sample_table(tabs + ((size_t)set * p.n_tables + tb) * p.n_samples, p.n_samples, x);
+        const double2 f = sample_table(tabs + ((size_t)set * p.n_tables + tb) * p.n_samples, ns, x);
         const double2 fc = make_double2(f.x, -f.y);
 #pragma unroll
         for (int i = 0; i < N; ++i)
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(OPREG_THREADS) k_opbuild_reg(OpBuildParams p) 
     const int ld = p.prob.NLp4, n_out = p.prob.n_out;
     for (long long e = p.e_begin + (long long)blockIdx.x * OPREG_THREADS + threadIdx.x; e < total;
          e += (long long)gridDim.x * OPREG_THREADS) {
-        int set, step, sb = -1, sa = -1, has_prev;
+        int set, step, sb = -1, sa = -1, has_prev, ns = p.n_samples;
         if (e < p.n_seq_entries) {
             int lo = 0, hi = p.n_seq;  // seq_base[lo] <= e < seq_base[hi]
             while (hi - lo > 1) {
@@ -461,12 +462,13 @@ __global__ void __launch_bounds__(OPREG_THREADS) k_opbuild_reg(OpBuildParams p) 
         } else {
             const aceqd_entry en = p.entries[e - p.n_seq_entries];
             set = en.set; step = en.step; sb = en.sb; sa = en.sa; has_prev = en.has_prev;
+            if (en.clamp > 0) ns = min(en.clamp, p.n_samples);   // this row sees only the first `clamp` samples of its drive
         }
         const double t_n = p.t0 + (double)step * p.dt;
         double2 A[N][N], P[N][N];
         // ---- V = Sb * M2_{n-1}
         if (has_prev) {
-            assemble_reg<N>(A, p, set, t_n - p.dt + p.eval_off2 * p.dt, half);
+            assemble_reg<N>(A, p, set, t_n - p.dt + p.eval_off2 * p.dt, half, ns);
             expm_reg<N>(A, P);
         } else {
 #pragma unroll
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(OPREG_THREADS) k_opbuild_reg(OpBuildParams p) 
                 for (int j = 0; j < N; ++j) mine[(i * N + j) * OPREG_THREADS] = P[i][j];
         }
         // ---- W = M1_n * X   (zero padded to [NLp8][NLp4])
-        assemble_reg<N>(A, p, set, t_n + p.eval_off1 * p.dt, half);
+        assemble_reg<N>(A, p, set, t_n + p.eval_off1 * p.dt, half, ns);
         expm_reg<N>(A, P);
         double2* w = reinterpret_cast<double2*>(p.W + (size_t)e * p.prob.w_doubles);
 #pragma unroll
@@ -696,7 +698,7 @@ __device__ int expm_warp(WMat<NP>* M, int n, int lane, const LaneOffs& lo) {
 // Lsm: L0 | LA[0..n_fields) | LB[0..n_fields) as row-major complex n x n (shared memory copy, or the global arrays)
 template <int NP>
 __device__ void assemble_warp(WMat<NP> A, const OpBuildParams& p, const double2* L0, const double2* LA,
-                              const double2* LB, int set, double t, double delta, int lane) {
+                              const double2* LB, int set, double t, double delta, int lane, int ns) {
     constexpr int LD = WMat<NP>::LD;
     const int n = p.prob.NL, n2 = n * n, nf = p.prob.n_fields;
     const double2* tabs = reinterpret_cast<const double2*>(p.tables);
@@ -706,7 +708,7 @@ __device__ void assemble_warp(WMat<NP> A, const OpBuildParams& p, const double2*
     if (lane < nf) {
         const int tb = p.prob.field_table[lane];
         if (tb >= 0 && tb < p.n_tables)
-            fl = sample_table(tabs + ((size_t)set * p.n_tables + tb) * p.n_samples, p.n_samples, x);
+            fl = sample_table(tabs + ((size_t)set * p.n_tables + tb) * p.n_samples, ns, x);
     }
     for (int e0 = 0; e0 < n2; e0 += 32) {          // warp-uniform trip count: the shuffles below need every lane
         const int e = e0 + lane;
@@ -792,7 +794,7 @@ __global__ void __launch_bounds__(128) k_opbuild_dmma(OpBuildParams p, int warps
     const double2* mto = reinterpret_cast<const double2*>(p.mto_mats);
     for (long long e = p.e_begin + (long long)blockIdx.x * warps_per_cta + warp; e < total;
          e += (long long)gridDim.x * warps_per_cta) {
-        int set, step, sb = -1, sa = -1, has_prev;
+        int set, step, sb = -1, sa = -1, has_prev, ns = p.n_samples;
         if (e < p.n_seq_entries) {
             int lo = 0, hi = p.n_seq;  // seq_base[lo] <= e < seq_base[hi]
             while (hi - lo > 1) {
@@ -807,11 +809,12 @@ __global__ void __launch_bounds__(128) k_opbuild_dmma(OpBuildParams p, int warps
         } else {
             const aceqd_entry en = p.entries[e - p.n_seq_entries];
             set = en.set; step = en.step; sb = en.sb; sa = en.sa; has_prev = en.has_prev;
+            if (en.clamp > 0) ns = min(en.clamp, p.n_samples);   // this row sees only the first `clamp` samples of its drive
         }
         const double t_n = p.t0 + (double)step * p.dt;
         // ---- V = Sb * M2_{n-1}
         if (has_prev) {
-            assemble_warp<NP>(M[0], p, L0, LA, LB, set, t_n - p.dt + p.eval_off2 * p.dt, half, lane);
+            assemble_warp<NP>(M[0], p, L0, LA, LB, set, t_n - p.dt + p.eval_off2 * p.dt, half, lane, ns);
             const int r = expm_warp<NP>(M, n, lane, lo);
             if (sb >= 0) {
                 load_global(M[0], mto + (size_t)sb * n2);
@@ -848,7 +851,7 @@ __global__ void __launch_bounds__(128) k_opbuild_dmma(OpBuildParams p, int warps
             Xp = X;
         }
         // ---- W = M1_n * X   (zero padded to [NLp8][NLp4])
-        assemble_warp<NP>(M[0], p, L0, LA, LB, set, t_n + p.eval_off1 * p.dt, half, lane);
+        assemble_warp<NP>(M[0], p, L0, LA, LB, set, t_n + p.eval_off1 * p.dt, half, lane, ns);
         const int r1 = expm_warp<NP>(M, n, lane, lo);
         WMat<NP> Wm = M[r1 == 4 ? 5 : 4];
         wmm<NP>(Wm, M[r1], Xp, lane, zero);

@@ -53,6 +53,21 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {  // sam
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// One cluster-scope release fence followed by RELAXED remote arrivals: a `mbarrier.arrive.release.cluster` per peer
+// pays a cluster-scope fence each time (measured: ~1.5k cycles per arrive, 16 serialised arrives per GEMM pass made
+// the split-K kernel 5x slower than the tile kernel; profiles/r05e_*).  Call from lanes 0..C-1 of ONE warp after a CTA
+// barrier: the fence executes once for the warp, every lane signals one peer.
+__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Remote store that completes on the DESTINATION CTA's mbarrier (tx-count): data and signal travel together through
+// the async proxy, so neither side needs a cluster-scope fence (which costs ~2k cycles: profiles/r05i_splitk_ticks.txt).
+__device__ __forceinline__ void st_async_v2(uint32_t dst_cluster, double a, double b, uint32_t mbar_cluster) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(dst_cluster),
+                 "d"(a), "d"(b), "r"(mbar_cluster)
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"

@@ -19,7 +19,7 @@ namespace aceqd {
 namespace {
 
 struct SmemLayout {
-    size_t bar, traj, pass, pos, r, rall, own, q, snapn, meta, wov, state, chunks, total;
+    size_t bar, traj, pass, pos, r, rall, own, brow, q, snapn, meta, wov, state, chunks, total;
     size_t plane;  // doubles per state plane
 };
 
@@ -43,6 +43,7 @@ __host__ __device__ inline SmemLayout make_layout(int NL, int chi_pad, int T, in
     L.r = o;     o += align_up(16 * R * N_COMPUTE_WARPS, 16);   // per-warp partial closures
     L.rall = o;  o += align_up(16 * R, 16);                     // closure rho[row] of the current output row
     L.own = o;   o += align_up(sizeof(int) * MAX_NL, 16);       // alpha position computed by this CTA?
+    L.brow = o;  o += align_up(sizeof(int) * (MAX_NL + 8), 16); // the alphas whose rows this CTA computes, in m-tiles of 8
     L.meta = o;  o += align_up(sizeof(int) * 2 * META_SLICES, 16);
     L.q = o;     o += align_up(16 * (size_t)chi_pad, 16);
     o = align_up(o, 128);
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     double2* rpart = reinterpret_cast<double2*>(smem_raw + L.r);   // [warp][row]
     double2* rall = reinterpret_cast<double2*>(smem_raw + L.rall); // [row]
     int* own_pos = reinterpret_cast<int*>(smem_raw + L.own);       // [alpha position] rows computed here?
+    int* brow = reinterpret_cast<int*>(smem_raw + L.brow);         // [m-tile of the system product][8] alpha or -1
     double2* qbuf = reinterpret_cast<double2*>(smem_raw + L.q);
     int* smeta = reinterpret_cast<int*>(smem_raw + L.meta);
     double* Wst = reinterpret_cast<double*>(smem_raw + L.wov);
@@ -92,6 +94,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     const int C = p.cluster;
     const uint32_t crank = C > 1 ? cluster_ctarank() : 0u;
     const uint32_t bar_y = smem_u32(bars + 2 * MAX_STAGES + 4), bar_free = smem_u32(bars + 2 * MAX_STAGES + 5);
+    // "the rows I pushed in the previous step have landed in every peer": the bulk copies read their SOURCE rows
+    // asynchronously, and the next system product overwrites those rows in place -- it must not start before every
+    // peer has seen its exchange barrier complete (found with NL = 36, T = 1 on 8-CTA clusters: 14 copies of 17 KB
+    // were still being read when the next step began)
+    const uint32_t bar_landed = smem_u32(bars + 2 * MAX_STAGES + 6);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
     const uint32_t bar_wfull = smem_u32(bars + 2 * MAX_STAGES), bar_wempty = smem_u32(bars + 2 * MAX_STAGES + 2);
     // offset (doubles) of state row (pos, j) inside a plane; rows are alpha-major with a skew
@@ -120,20 +127,29 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             mbar_init(bar_wfull + 8 * s, 1);
             mbar_init(bar_wempty + 8 * s, N_COMPUTE_WARPS);
         }
-        mbar_init(bar_y, (uint32_t)C);                       // own expect_tx arrival + one arrival per peer
+        mbar_init(bar_y, 1);                                 // own expect_tx; rows (bulk copies) and closures (st.async) count bytes
         mbar_init(bar_free, (uint32_t)(C > 1 ? C - 1 : 1));  // "I have read your rows" from every peer
+        mbar_init(bar_landed, (uint32_t)(C > 1 ? C - 1 : 1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
     // which alpha positions (blocks of T rows) this CTA computes, and how many bytes its peers push per step
     // (T divides the 8-row m-tile or is a multiple of it, so an alpha block never straddles two passes)
-    auto pass_push_bytes = [&](const PassDesc& pd) -> uint32_t {
-        uint32_t b = 0;
+    // the rows of a pass are consecutive in a plane (alpha blocks of T rows separated by SKEW doubles of padding), so a
+    // pass travels as ONE bulk copy per plane and peer, padding included
+    auto pass_rows = [&](const PassDesc& pd) -> int {
+        int n = 0;
 #pragma unroll
-        for (int mc = 0; mc < MC; ++mc) b += (uint32_t)pd.nvalid[mc] * (uint32_t)strideA * 16u;  // re + im planes
-        return b;
+        for (int mc = 0; mc < MC; ++mc) n += pd.nvalid[mc];
+        return n;
     };
+    auto pass_plane_bytes = [&](const PassDesc& pd) -> uint32_t {
+        const int r0 = pd.row0[0], r1 = r0 + pass_rows(pd) - 1;
+        return (uint32_t)(((size_t)r1 * strideA + (size_t)(r1 / T) * SKEW + strideA) -
+                          ((size_t)r0 * strideA + (size_t)(r0 / T) * SKEW)) * 8u;
+    };
+    auto pass_push_bytes = [&](const PassDesc& pd) -> uint32_t { return 2u * pass_plane_bytes(pd); };   // re + im planes
     uint32_t rx_bytes = 0;
     for (int ps = 0; ps < p.n_pass; ++ps) {
         const PassDesc& pd = passes[ps];
@@ -142,11 +158,23 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 for (int mc = 0; mc < MC; ++mc)
                     for (int r = pd.row0[mc]; r < pd.row0[mc] + pd.nvalid[mc]; r += 1) own_pos[r / T] = 1;
         } else {
-            rx_bytes += pass_push_bytes(pd);
+            rx_bytes += pass_push_bytes(pd) + 16u * (uint32_t)pass_rows(pd);   // rows + their closures
         }
     }
     if (C > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
     else __syncthreads();
+    // system product: a CTA of a cluster needs X only for the rows it multiplies itself.  Its alphas are gathered into
+    // consecutive m-tiles (rows of W are read through this table), so that C CTAs share the product instead of each
+    // computing nearly all of it (own alphas are scattered over the natural 8-row groups).
+    if (tid == 0) {
+        int k = 0;
+        for (int a = 0; a < NL; ++a)
+            if (C == 1 || own_pos[pos[a]]) brow[k++] = a;
+        while (k & 7) brow[k++] = -1;
+        brow[MAX_NL + 7] = k / 8;     // m-tiles of this CTA's system product
+    }
+    __syncthreads();
+    const int MTB = brow[MAX_NL + 7];
 
     // A CTA works through a list of SEGMENTS (tile, step range): with more tiles than SMs the host lays
     // the tiles end to end and cuts the line into equal pieces, one per CTA (wrap-around rule), so a tile
@@ -157,6 +185,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     // pipeline positions persist across segments (producer and consumers advance identically)
     int stage = 0;
     uint32_t phase = 0, wph0 = 0u, wph1 = 0u;
+    unsigned chunk_ctr = 0u;   // producers: chunks issued by all producers together so far
     for (int si = 0; si < n_seg; ++si) {
     SegDesc sg;
     if (p.segs) {
@@ -253,12 +282,39 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
     }
     __syncthreads();
 
-    // ------------------------------------------------------------------ producer warp
-    if (warp == N_COMPUTE_WARPS) {
-        if (lane == 0) {
+    // ------------------------------------------------------------------ producer warps
+    // warps 8 .. 8+P-1 feed the PT chunk ring: chunk number c (counted over passes, steps and segments) goes to
+    // stage c mod S and is issued by producer c mod P, P <= S (with P <= S a producer can never be two ring
+    // generations ahead of the consumers, so the parity wait on the stage's empty barrier is unambiguous);
+    // the last producer warp stages the per-row operators W_n | OV_n.
+    if (warp >= N_COMPUTE_WARPS) {
+        const int pw = warp - N_COMPUTE_WARPS;
+        const int P = min(N_CHUNK_PRODUCERS, stages);
+        if (lane == 0 && pw < P) {
             const uint32_t bytes = (uint32_t)p.pt.chunk_doubles * 8u;
+            for (int n = n_lo; n < n_hi; ++n) {
+                const int s = slice_of(p.pt, n);
+                const int nch = (s < META_SLICES ? smeta[2 * s] : p.pt.kin_pad[s]) / KC;
+                const double* sl = p.pt.blob + p.pt.off[s];
+                for (int ps = 0; ps < p.n_pass; ++ps) {
+                    if (passes[ps].owner != (int)crank) continue;
+                    const double* src = sl + (size_t)passes[ps].blk * nch * p.pt.chunk_doubles;
+                    for (int j = (int)((pw + P - chunk_ctr % P) % P); j < nch; j += P) {
+                        const unsigned c = chunk_ctr + (unsigned)j;
+                        const int st = (int)(c % (unsigned)stages);
+                        const uint32_t ph = (c / (unsigned)stages) & 1u;
+                        mbar_wait(bar_empty + 8 * st, ph ^ 1u);
+                        mbar_expect_tx(bar_full + 8 * st, bytes);
+                        bulk_g2s(smem_u32(chunks + (size_t)st * p.pt.chunk_doubles),
+                                 src + (size_t)j * p.pt.chunk_doubles, bytes, bar_full + 8 * st);
+                    }
+                    chunk_ctr += (unsigned)nch;
+                }
+            }
+        } else if (lane == 0 && pw == N_CHUNK_PRODUCERS && wsm) {
             const uint32_t w_bytes = (uint32_t)p.prob.w_doubles * 8u, ov_bytes = (uint32_t)p.prob.ov_doubles * 8u;
-            // stage the per-row operators W_n | OV_n of every active trajectory into buffer n & 1
+            // stage the per-row operators W_n | OV_n of every active trajectory into buffer n & 1 (or the single
+            // buffer, which the consumers hand back after the system product of row n)
             auto issue_wov = [&](int n) {
                 const int buf = wbufs == 2 ? (n & 1) : 0;
                 mbar_wait(bar_wempty + 8 * buf, (buf ? wph1 : wph0) ^ 1u);
@@ -279,64 +335,32 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                              bar_wfull + 8 * buf);
                 }
             };
-            if (wsm) issue_wov(n_lo);
-            for (int n = n_lo; n < n_hi; ++n) {
-                bool w_next = wsm && (n + 1 < n_hi || final_seg);   // row n_hi of an unfinished tile belongs to the next segment
-                if (w_next && wbufs == 2) {
-                    issue_wov(n + 1);
-                    w_next = false;
-                }
-                const int s = slice_of(p.pt, n);
-                const int nch = (s < META_SLICES ? smeta[2 * s] : p.pt.kin_pad[s]) / KC;
-                const double* sl = p.pt.blob + p.pt.off[s];
-                for (int ps = 0; ps < p.n_pass; ++ps) {
-                    if (passes[ps].owner != (int)crank) continue;
-                    const double* src = sl + (size_t)passes[ps].blk * nch * p.pt.chunk_doubles;
-                    for (int j = 0; j < nch; ++j) {
-                        mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-                        mbar_expect_tx(bar_full + 8 * stage, bytes);
-                        bulk_g2s(smem_u32(chunks + (size_t)stage * p.pt.chunk_doubles),
-                                 src + (size_t)j * p.pt.chunk_doubles, bytes, bar_full + 8 * stage);
-                        if (++stage == stages) { stage = 0; phase ^= 1u; }
-                    }
-                    if (w_next) {   // single buffer: the consumers are in phase C now, W(n) has been released
-                        issue_wov(n + 1);
-                        w_next = false;
-                    }
-                }
-                if (w_next) issue_wov(n + 1);   // this CTA owns no pass
-            }
+            issue_wov(n_lo);
+            for (int n = n_lo; n < n_hi; ++n)
+                if (n + 1 < n_hi || final_seg) issue_wov(n + 1);   // row n_hi of an unfinished tile belongs to the next segment
         }
         continue;   // next segment (all lanes meet the compute warps at its first barrier)
     }
 
     // ------------------------------------------------------------------ compute warps
     const int g = lane >> 2, tq = lane & 3;  // DMMA fragment coordinates
-    uint32_t yph = 0u, fph = 0u;             // phases of the row-exchange barriers
+    uint32_t yph = 0u, fph = 0u, lph = 0u;   // phases of the row-exchange barriers
     bool free_waited = false;
     // push the freshly computed rows of one pass into every peer's copy of the state (tid 0 only)
     auto push_pass = [&](const PassDesc& pd) {
         if (!free_waited) {              // peers have finished reading the previous contents
-            mbar_wait_cluster(bar_free, fph);
+            mbar_wait(bar_free, fph);
             free_waited = true;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#pragma unroll
-        for (int mc = 0; mc < MC; ++mc) {
-            int r = pd.row0[mc];
-            const int r_end = r + pd.nvalid[mc];
-            while (r < r_end) {          // rows of one alpha block are contiguous in a plane
-                const int m = min((r / T + 1) * T, r_end) - r;
-                const size_t off = (size_t)r * strideA + (size_t)(r / T) * SKEW;
-                const uint32_t bytes = (uint32_t)m * (uint32_t)strideA * 8u;
-                for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) {
-                    if (peer == crank) continue;
-                    const uint32_t rb = mapa(bar_y, peer);
-                    bulk_s2s(mapa(smem_u32(Xre + off), peer), smem_u32(Xre + off), bytes, rb);
-                    bulk_s2s(mapa(smem_u32(Xim + off), peer), smem_u32(Xim + off), bytes, rb);
-                }
-                r += m;
-            }
+        const int r0 = pd.row0[0];
+        const size_t off = (size_t)r0 * strideA + (size_t)(r0 / T) * SKEW;
+        const uint32_t bytes = pass_plane_bytes(pd);
+        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) {
+            if (peer == crank) continue;
+            const uint32_t rb = mapa(bar_y, peer);
+            bulk_s2s(mapa(smem_u32(Xre + off), peer), smem_u32(Xre + off), bytes, rb);
+            bulk_s2s(mapa(smem_u32(Xim + off), peer), smem_u32(Xim + off), bytes, rb);
         }
     };
     const int NT = chi_pad / 8;
@@ -360,8 +384,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         const int buf = wbufs == 2 ? (n & 1) : 0;
         if (C > 1) {
             if (n > n_lo) {           // rows and closures computed by the peers in step n-1 have landed
-                mbar_wait_cluster(bar_y, yph);
+                mbar_wait(bar_y, yph);
                 yph ^= 1u;
+                // tell every peer that ITS rows have landed here (a pure signal: no data travels with it)
+                if (warp == 0 && lane < C && (uint32_t)lane != crank) mbar_arrive_remote_relaxed(mapa(bar_landed, (uint32_t)lane));
             }
             if (n < n_end && tid == 0) mbar_expect_tx(bar_y, rx_bytes);   // arm this step's exchange
         }
@@ -444,6 +470,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                     const size_t o = rowoff(pos[a], j) + d;
                     dst[e] = make_double2(Xre[o], Xim[o]);
                 }
+                // the closure of this row travels with the snapshot (column-distributed kernels start from it)
+                if (p.snap_r)
+                    for (int a = tid; a < NL; a += N_COMPUTE_WARPS * 32)
+                        reinterpret_cast<double2*>(p.snap_r)[(size_t)(t.snap_slot0 + snapn[j]) * NL + a] = rall[pos[a] * T + j];
             }
         }
         if (n == n_end) {
@@ -465,6 +495,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             }
         }
 
+        if (C > 1 && n > n_lo) {      // my pushes of step n-1 have been read out of my rows: they may be overwritten
+            mbar_wait(bar_landed, lph);
+            lph ^= 1u;
+        }
         TICK(2);
         // ---------------- phase B: X = W_n Y.  Warp w owns bond columns of its n-tiles for every
         // trajectory (column-local, in place, no block barrier); JU trajectories x NBB n-tiles are
@@ -581,12 +615,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                         }
                     }
                 __syncwarp();
-                for (int mt = 0; mt < MTU; ++mt) {
-                    if (C > 1) {     // only the rows this CTA feeds into its own GEMM passes are needed
-                        bool need = false;
-                        for (int a8 = 8 * mt; a8 < min(8 * mt + 8, NL); ++a8) need |= own_pos[pos[a8]] != 0;
-                        if (!need) continue;
-                    }
+                for (int mt = 0; mt < MTB; ++mt) {     // m-tiles of the rows this CTA feeds into its own GEMM passes
+                    const int arow = brow[8 * mt + g];  // alpha of this lane's W row (and output row), -1 = padding
                     double cr[JU][NBB][2], ci[JU][NBB][2];
 #pragma unroll
                     for (int jj = 0; jj < JU; ++jj)
@@ -600,8 +630,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
 #pragma unroll
                             for (int jj = 0; jj < JU; ++jj) {
                                 w[jj] = make_double2(0.0, 0.0);
-                                if (act[jj]) {
-                                    const double2* wp = Wp[jj] + (size_t)(8 * mt + g) * NLp4 + tq + 4 * ks;
+                                if (act[jj] && arow >= 0) {
+                                    const double2* wp = Wp[jj] + (size_t)arow * NLp4 + tq + 4 * ks;
                                     w[jj] = wsm ? *wp : __ldg(wp);
                                 }
                             }
@@ -623,8 +653,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                                     }
                         }
                     }
-                    const int a = 8 * mt + g;
-                    if (a < NL && (C == 1 || own_pos[pos[a]])) {
+                    const int a = arow;
+                    if (a >= 0) {
 #pragma unroll
                         for (int jj = 0; jj < JU; ++jj)
 #pragma unroll
@@ -647,10 +677,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         }
         compute_bar();
         TICK(3);
-        if (C > 1 && tid == 0) {   // every warp of this CTA has read the peers' rows: they may overwrite them
-            for (uint32_t peer = 0; peer < (uint32_t)C; ++peer)
-                if (peer != crank) mbar_arrive_remote(mapa(bar_free, peer));
-        }
+        // every warp of this CTA has read the peers' rows (their values are in registers): they may overwrite them
+        if (C > 1 && warp == 0 && lane < C && (uint32_t)lane != crank) mbar_arrive_remote_relaxed(mapa(bar_free, (uint32_t)lane));
 
         // ---------------- phase C: PT slice, Y = X A_n[beta]
         const int s = slice_of(p.pt, n);
@@ -710,6 +738,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 pi[mc] += __shfl_xor_sync(0xffffffffu, pi[mc], 2);
                 if (wr[mc] && tq == 0) rpart[warp * R + row[mc]] = make_double2(pr[mc], pi[mc]);
             }
+            // the rows written above are read by the bulk-copy engine (async proxy) when they are pushed to the peers
+            if (C > 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         };
         for (int ps = 0; ps < p.n_pass; ++ps) {
             const PassDesc pd = passes[ps];
@@ -783,16 +813,14 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 r.y += r2.y;
             }
             rall[row] = r;
-            for (uint32_t peer = 0; C > 1 && peer < (uint32_t)C; ++peer)
-                if (peer != crank) st_cluster_c128(mapa(smem_u32(rall + row), peer), r);
+            for (uint32_t peer = 0; C > 1 && peer < (uint32_t)C; ++peer)   // counted by the peer's exchange barrier
+                if (peer != crank) st_async_v2(mapa(smem_u32(rall + row), peer), r.x, r.y, mapa(bar_y, peer));
         }
         compute_bar();
         TICK(6);
         if (C > 1 && tid == 0) {
             if (pending_push >= 0) push_pass(passes[pending_push]);
-            if (!free_waited) mbar_wait_cluster(bar_free, fph);   // keep the phase in step without own passes
-            for (uint32_t peer = 0; peer < (uint32_t)C; ++peer)   // release: closures above are visible first
-                if (peer != crank) mbar_arrive_remote(mapa(bar_y, peer));
+            if (!free_waited) mbar_wait(bar_free, fph);   // keep the phase in step without own passes
         }
         fph ^= 1u;
     }
@@ -872,6 +900,9 @@ __global__ void __launch_bounds__(256) k_step_check(const StepParams p, double* 
         if (snapn < t.snap_cnt && p.snap_steps[t.snap_off + snapn] == i) {
             double2* dst = reinterpret_cast<double2*>(p.snaps) + (size_t)(t.snap_slot0 + snapn) * tot;
             for (int e = tid; e < tot; e += blockDim.x) dst[e] = Y[e];
+            if (p.snap_r)
+                for (int a = tid; a < NL; a += blockDim.x)
+                    reinterpret_cast<double2*>(p.snap_r)[(size_t)(t.snap_slot0 + snapn) * NL + a] = r[a];
             ++snapn;
         }
         if (i == t.n_steps) break;

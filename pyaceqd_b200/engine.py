@@ -31,9 +31,9 @@ MAX_OVR = 6
 N_SM = 148
 
 # step kernels (aceqd_batch.kernel): "dmma" = the library's choice between the persistent tile kernel and the
-# small-bond kernel, "check" = plain-FMA check kernel, "colsplit" = bond-column-split cluster kernel,
-# "small" / "tile" force k_step_small / k_step_dmma
-KERNELS = {"dmma": 0, "check": 1, "colsplit": 3, "small": 4, "tile": 5}
+# small-bond kernel (and, for large Liouville spaces, the planner's choice of the split-K cluster kernel), "check" =
+# plain-FMA check kernel, "splitk" = split-K cluster kernel, "small" / "tile" force k_step_small / k_step_dmma
+KERNELS = {"dmma": 0, "check": 1, "splitk": 3, "small": 4, "tile": 5}
 SMALL_MIN_TRAJ = 2048     # ACEQD_SMALL_MIN_TRAJ of include/aceqd.h
 
 
@@ -51,8 +51,8 @@ def resolve_kernel(kernel: str, NL: int) -> str:
 T_EVAL = {"half_mid": (0.25, 0.75), "step_mid": (0.5, 0.5), "start": (0.0, 0.5)}
 
 SEQ_DT = np.dtype([("set", "<i4"), ("step0", "<i4"), ("len", "<i4"), ("first_has_prev", "<i4")], align=True)
-ENTRY_DT = np.dtype([("set", "<i4"), ("step", "<i4"), ("sb", "<i4"), ("sa", "<i4"), ("has_prev", "<i4")],
-                    align=True)
+ENTRY_DT = np.dtype([("set", "<i4"), ("step", "<i4"), ("sb", "<i4"), ("sa", "<i4"), ("has_prev", "<i4"),
+                     ("clamp", "<i4")], align=True)
 TLSEG_DT = np.dtype([("start", "<i4"), ("count", "<i4"), ("emit", "<i4"), ("stride", "<i4")], align=True)
 TRAJ_DT = np.dtype([("ent0", "<i8"), ("out_off", "<i8"), ("step0", "<i4"), ("n_steps", "<i4"),
                     ("init_kind", "<i4"), ("init_index", "<i4"), ("n_ovr", "<i4"),
@@ -125,6 +125,8 @@ def load_library():
                                     c_int, c_void_p, c_int, c_void_p, c_void_p]
     lib.aceqd_tlmap_last_ms.argtypes = [c_void_p, POINTER(c_float)]
     lib.aceqd_max_tile.argtypes = [c_int, c_int]
+    lib.aceqd_splitk_fit.argtypes = [c_int, c_int, c_int, c_int]
+    lib.aceqd_splitk_fit.restype = c_longlong
     lib.aceqd_pass_load.argtypes = [c_void_p, c_int, c_int]
     lib.aceqd_fp64_peak.argtypes = [c_void_p, c_int, c_int, POINTER(c_double)]
     lib.aceqd_host_alloc.argtypes = [ctypes.c_size_t, POINTER(c_void_p)]
@@ -175,6 +177,7 @@ def choose_tile(n_traj: int, rows_per_block: Sequence[int], t_max: int, n_sm: in
 
 
 CLUSTER_CAPACITY = {1: N_SM, 2: N_SM, 4: 132, 8: 128}   # co-resident CTAs per cluster size (GPC packing)
+SPLITK_PASS_OVERHEAD = 128.0   # split-K planner: per-pass exchange cost in units of (m-tile x PT k-row)
 
 
 def choose_tile_cluster(n_traj: int, pass_load, t_max: int, clusters: Sequence[int] = (1, 2, 4, 8)) -> Tuple[int, int]:
@@ -383,8 +386,8 @@ class Engine:
         _, blk_of_alpha = self.problem_handle(prob, pt)
         chi_pad = -(-pt.chi_max // 8) * 8
         t_max = self.max_tile(NL, chi_pad)
-        if t_max < 1:
-            raise EngineError(f"NL={NL}, chi={chi_pad} does not fit the step kernel's shared memory")
+        if t_max < 1 and kernel in ("dmma", "tile"):
+            kernel = "splitk"     # one trajectory does not fit a CTA: spread its bond columns over a cluster
         T, C = self._tile_and_cluster(prob, pt, n_traj, t_max, tile_T, cluster, kernel)
         n_tiles = -(-n_traj // T)
         sets = np.arange(n_traj, dtype=np.int32) if sets is None else np.asarray(sets, dtype=np.int32)
@@ -418,6 +421,8 @@ class Engine:
         hp, _ = self.problem_handle(prob, pt)
         if kernel == "small":      # one warp per 8 trajectories: the tile list only orders the octets
             return min(tile_T or 8, t_max), 1
+        if kernel == "splitk":
+            return self._splitk_tile(prob, pt, n_traj, tile_T, cluster)[:2]
         load = lambda t, c: int(self.lib.aceqd_pass_load(hp, t, c))
         if tile_T and cluster:
             return min(tile_T, t_max), cluster
@@ -425,6 +430,40 @@ class Engine:
             t = min(tile_T, t_max)
             return t, choose_tile_cluster(n_traj, lambda tt, c: load(t, c) if tt == t else 0, t)[1]
         return choose_tile_cluster(n_traj, load, t_max, clusters=(cluster,) if cluster else (1, 2, 4, 8))
+
+    def _splitk_tile(self, prob, pt, n_traj, tile_T=None, cluster=None):
+        """(G, C, cost) of the split-K cluster kernel: G trajectories per tile on a cluster of C CTAs that hold
+        chi_pad/C bond columns each.  Cost model, calibrated on the cfg3 branch launch (profiles/r05j_gc_sweep.txt):
+        CTA-time per trajectory-step = C x sum over the passes of a tile (row blocks of <= 16 rows that share a PT
+        block, per panel of 128 output columns) of (m-tiles x k-rows of this CTA + a fixed cost of the partial-product
+        exchange, which doubles on 8-CTA clusters), times the waves of clusters."""
+        if os.environ.get("ACEQD_SPLITK_GC") and not (tile_T or cluster):     # experiments: "G,C"
+            tile_T, cluster = (int(x) for x in os.environ["ACEQD_SPLITK_GC"].split(","))
+        _, blk_of_alpha = self.problem_handle(prob, pt)
+        rows = np.bincount(blk_of_alpha)
+        rows = rows[rows > 0]
+        chi_pad = -(-pt.chi_max // 8) * 8
+        n_pan = -(-chi_pad // 128)
+        best = None
+        for c in ((cluster,) if cluster else (2, 4, 8)):
+            ovh = SPLITK_PASS_OVERHEAD * (2.0 if c == 8 else 1.0)
+            for g in ((tile_T,) if tile_T else range(1, 17)):
+                if g > max(1, n_traj) and not tile_T:
+                    continue
+                if not self.lib.aceqd_splitk_fit(prob.NL, chi_pad, g, c):
+                    continue
+                work = 0.0
+                for r in rows:
+                    mt = -(-(g * r) // 8)
+                    work += n_pan * (mt * chi_pad / c + -(-mt // 2) * ovh)
+                tiles = -(-n_traj // g)
+                waves = -(-(tiles * c) // CLUSTER_CAPACITY[c])
+                cost = waves * c * work / min(g, max(1, n_traj))
+                if best is None or cost < best[2] - 1e-9:
+                    best = (g, c, cost)
+        if best is None:
+            raise EngineError(f"NL={prob.NL}, chi={chi_pad}: no (tile, cluster) of the split-K kernel fits shared memory")
+        return best
 
     def run_sweep(self, prob: Problem, pt: Optional[ProcessTensor], tables: np.ndarray,
                   grid: Tuple[float, float], t_start: float, n_steps: int, dt: float, *,
@@ -538,7 +577,7 @@ class Engine:
 
     def plan(self, prob: Problem, pt: ProcessTensor, jobs: Sequence[Job], *, kernel: str = "auto",
              t_eval: str = "half_mid", fork: bool = True, tile_T: Optional[int] = None,
-             cluster: Optional[int] = None):
+             cluster: Optional[int] = None, trunk_kernel: Optional[str] = None):
         """Build the trunk batch (may be None) and the main batch for `jobs`."""
         if not jobs:
             raise ValueError("no jobs")
@@ -546,8 +585,8 @@ class Engine:
         for jb in jobs:
             if abs(jb.dt - dt) > 1e-15:
                 raise ValueError("all jobs of one batch must share dt")
-            if len({jb.mto_step(m) for m in jb.mtos}) > MAX_OVR:
-                raise ValueError(f"more than {MAX_OVR} distinct multitime-operator times in one job")
+            if len({jb.mto_step(m) for m in jb.mtos}) > MAX_OVR - 2:
+                raise ValueError(f"more than {MAX_OVR - 2} distinct multitime-operator times in one job")
         packed, set_of_job, grid = self._tables_of(jobs)
         chi_pad = -(-pt.chi_max // 8) * 8
         NL, n_out = prob.NL, prob.n_out
@@ -593,7 +632,20 @@ class Engine:
                 raise ValueError(f"t_start={t_start} is not a whole number of steps (dt={dt}) after the earliest "
                                  f"start {t0_ref} of the batch: run it as a separate batch")
             mto_maps = {i: self._mto_products(prob, jobs[i], mats, mcache) for i in members}
-            first = {i: (min(mto_maps[i]) if mto_maps[i] else None) for i in members}
+            # a run that shares a longer drive table with others must not see samples past its own last one (the
+            # reference writes the pulse file of every run on np.arange(t_start, t_end, dt)): the rows whose half
+            # steps reach beyond it -- the last two -- get explicit entries evaluated on the truncated table
+            clamp_of = {}
+            for i in members:
+                jb = jobs[i]
+                n_tab = max([len(tb.values) for tb in jb.tables.values() if tb is not None] + [0])
+                if 0 < jb.table_len < n_tab:
+                    clamp_of[i] = int(jb.table_len)
+                    for k in (jb.n_steps - 1, jb.n_steps):
+                        if k >= 0:
+                            mto_maps[i].setdefault(k, (-1, -1))
+            first = {i: (min(mto_rows) if (mto_rows := [k for k, v in mto_maps[i].items() if v != (-1, -1)]) else None)
+                     for i in members}
             use_fork = fork and len(members) > 1 and any(f is not None and f > 0 for f in first.values())
             if use_fork:
                 fork_steps = sorted({f for f in first.values() if f is not None and f > 0})
@@ -617,7 +669,8 @@ class Engine:
                     ovr = []
                     for k, (sb, sa) in sorted(mto_maps[i].items()):
                         ovr.append((k, len(entries)))
-                        entries.append((sset, step_shift + k, sb, sa, 1 if k > 0 else 0))
+                        entries.append((sset, step_shift + k, sb, sa, 1 if k > 0 else 0,
+                                        clamp_of.get(i, 0) if k >= jb.n_steps - 1 else 0))
                     if f is None or f == 0:
                         trajs.append(dict(job=i, seq=q_main, off=0, step0=0, n_steps=jb.n_steps, init_kind=0,
                                           init_index=r0, ovr=ovr, row0=0, out_from=int(g0[i])))
@@ -638,12 +691,13 @@ class Engine:
                     ovr = []
                     for k, (sb, sa) in sorted(mto_maps[i].items()):
                         ovr.append((k, len(entries)))
-                        entries.append((sset, step_shift + k, sb, sa, 1 if k > 0 else 0))
+                        entries.append((sset, step_shift + k, sb, sa, 1 if k > 0 else 0,
+                                        clamp_of.get(i, 0) if k >= jb.n_steps - 1 else 0))
                     trajs.append(dict(job=i, seq=q, off=0, step0=0, n_steps=jb.n_steps, init_kind=0,
                                       init_index=r0, ovr=ovr, row0=0, out_from=int(g0[i])))
 
         common = dict(prob=prob, pt=pt, dt=dt, t0=t0_ref, off=(off1, off2), packed=packed, grid=grid,
-                      mats=mats, chi_pad=chi_pad, kernel=kernel, tile_T=tile_T, cluster=cluster,
+                      mats=mats, chi_pad=chi_pad, kernel=kernel, tile_T=tile_T, cluster=cluster, trunk_kernel=trunk_kernel,
                       rho0s=np.asarray(rho0s))
         main = dict(seqs=seqs, entries=entries, trajs=trajs, snap_steps=[], n_slots=0)
         trunk = None
@@ -684,11 +738,15 @@ class Engine:
         blk_of_alpha = self.problem_handle(prob, pt)[1]
         rows_per_block = np.bincount(blk_of_alpha).tolist()
         t_max = self.max_tile(NL, common["chi_pad"])
-        if t_max < 1:
-            raise EngineError(f"NL={NL}, chi={common['chi_pad']} does not fit the step kernel's shared memory")
         kernel = common["kernel"]
-        if kernel == "small" and len(part["snap_steps"]):
-            kernel = "tile"       # trunks write snapshots: not a small-bond kernel job
+        if len(part["snap_steps"]) and kernel in ("small", "splitk"):
+            # trunks (few trajectories that write snapshots): not a small-bond kernel job, and a single trajectory is
+            # faster on the tile kernel's pass-split cluster than on the split-K cluster
+            kernel = common.get("trunk_kernel") or "tile"
+        if t_max < 1 and kernel in ("dmma", "tile"):
+            kernel = "splitk"     # one trajectory does not fit a CTA: spread its bond columns over a cluster
+        if t_max < 1 and kernel != "splitk":
+            raise EngineError(f"NL={NL}, chi={common['chi_pad']} does not fit the step kernel's shared memory")
         T, C = self._tile_and_cluster(prob, pt, len(tr), t_max, common["tile_T"], common.get("cluster"), kernel)
         n_tiles = -(-len(tr) // T)
         tile_traj = np.full(n_tiles * T, -1, dtype=np.int32)
@@ -723,14 +781,16 @@ class Engine:
     # -------------------------------------------------------------- running
     def run_jobs(self, prob: Problem, pt: Optional[ProcessTensor], jobs: Sequence[Job], *,
                  kernel: str = "auto", t_eval: str = "half_mid", fork: bool = True,
-                 tile_T: Optional[int] = None, cluster: Optional[int] = None) -> List[np.ndarray]:
+                 tile_T: Optional[int] = None, cluster: Optional[int] = None,
+                 trunk_kernel: Optional[str] = None) -> List[np.ndarray]:
         """Propagate `jobs`; returns one ``[n_out, n_steps+1]`` complex array per job."""
         if pt is None:
             pt = self._trivial(prob)
         hp, _ = self.problem_handle(prob, pt)
         hpt = self.pt_handle(pt)
         common, trunk, main, (out_off, n_rows, out_elems, copy_list) = self.plan(
-            prob, pt, jobs, kernel=kernel, t_eval=t_eval, fork=fork, tile_T=tile_T, cluster=cluster)
+            prob, pt, jobs, kernel=kernel, t_eval=t_eval, fork=fork, tile_T=tile_T, cluster=cluster,
+            trunk_kernel=trunk_kernel)
         n_out = prob.n_out
         trunk_out = None
         if trunk is not None:

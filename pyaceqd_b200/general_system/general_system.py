@@ -133,6 +133,7 @@ class Request:
     table_maker: object       # callable(t_end) -> tables dict, used when tables are unified
     calc_dynmap: bool = False
     result: Optional[np.ndarray] = None
+    sampled: bool = True      # drives sampled from pulse objects on np.arange(t_start, t_end, dt) (not read from files)
 
 
 def _problem_for(**kw) -> Problem:
@@ -312,7 +313,8 @@ def system_ace_stream(t_start, t_end, *pulses, dt=0.01, phonons=False, t_mem=20.
               tables={} if (sink is not None and not calc_dynmap) else make_tables(t_end),
               mtos=problem.parse_mtos(multitime_op))
     req = Request(problem=problem, pt=pt, job=job, pulse_key=pulse_key, table_maker=make_tables,
-                  calc_dynmap=calc_dynmap)
+                  calc_dynmap=calc_dynmap,
+                  sampled=(rf_op is not None and rf_file is None) or (rf_op is None and pulse_file_x is None))
     if sink is not None and not calc_dynmap:
         sink.append(req)
         return req      # BatchExecutor resolves it
@@ -354,6 +356,9 @@ def run_requests(reqs: List[Request], distributed: Optional[bool] = None):
                 tabs = reqs[members[0]].table_maker(te)
                 for i in members:
                     reqs[i].job.tables = tabs
+                    # ... but every run sees only the samples of its OWN pulse file (reference :213), end value held
+                    if reqs[i].sampled:
+                        reqs[i].job.table_len = len(np.arange(reqs[i].job.t_start, reqs[i].job.t_end, step=reqs[i].job.dt))
         plain = [i for i in idx if not reqs[i].calc_dynmap]
         # pulse files (read_pulse_file) bring their own grid: one batch per table grid
         by_grid: Dict[tuple, List[int]] = {}

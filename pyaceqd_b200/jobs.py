@@ -35,6 +35,8 @@ class Job:
     mtos: List[MTO] = field(default_factory=list)
     tail_rows: int = 0   # > 0: only the last `tail_rows` output rows are needed (0 = all)
     rho0: Optional[np.ndarray] = None   # initial vectorised state overriding the problem's (dynamical maps)
+    table_len: int = 0   # > 0: this run's own drive has only this many samples (end value held beyond): the reference
+                         # samples the pulse file of every run on np.arange(t_start, t_end, dt); 0 = the whole table
 
     @property
     def n_steps(self) -> int:

@@ -28,21 +28,27 @@ peak = eng.fp64_peak("dmma", 20000)
 shapes = [("biexciton", biexciton_problem(outputs=["|1><1|_4", "|3><3|_4"]), 128, 2048, 100, 0.25),
           ("sixls", sixls_problem(), 128, 1184, 60, 0.1),
           ("fivels", fivels_problem(), 256, 592, 60, 0.1)]
-if len(sys.argv) > 1:
-    shapes = [s for s in shapes if s[0] in sys.argv[1:]]
+kernel = "dmma"
+args = [a for a in sys.argv[1:]]
+for a in list(args):
+    if a.startswith("--kernel="):
+        kernel = a.split("=", 1)[1]
+        args.remove(a)
+if args:
+    shapes = [s for s in shapes if s[0] in args]
 for name, prob, chi, n_traj, n_steps, dt in shapes:
     pt = synthetic_pt(chi, len(prob.cls_keys), kind="unitary", scale=0.999)
     jobs = []
     for a in np.linspace(0.5, 12.0, n_traj):
         p = ChirpedPulse(tau_0=3.0, e_start=-2.0, alpha=0, t0=4.0, e0=a, polar_x=0.8)
         jobs.append(Job(0.0, n_steps * dt, dt, tables=make_tables([p], 0.0, n_steps * dt, dt), tail_rows=1))
-    eng.run_jobs(prob, pt, jobs, kernel="dmma")
+    eng.run_jobs(prob, pt, jobs, kernel=kernel)
     eng.timing_log.clear()
-    t = time.perf_counter(); out = eng.run_jobs(prob, pt, jobs, kernel="dmma"); wall = time.perf_counter() - t
+    t = time.perf_counter(); out = eng.run_jobs(prob, pt, jobs, kernel=kernel); wall = time.perf_counter() - t
     l = eng.timing_log[-1]
     NL = prob.NL
     fl = 8.0 * NL * chi * (2 * NL + chi) * n_traj * n_steps
-    print(json.dumps(dict(shape=name, NL=NL, chi=chi, n_cls=len(prob.cls_keys), n_traj=n_traj, n_steps=n_steps,
+    print(json.dumps(dict(shape=name, kernel=l['step_kernel'], opbuild_kernel=l['opbuild_kernel'], NL=NL, chi=chi, n_cls=len(prob.cls_keys), n_traj=n_traj, n_steps=n_steps,
                           tile_T=l["tile_T"], cluster=l["cluster"], step_ms=l["step_ms"], opbuild_ms=l["opbuild_ms"],
                           wall_ms=1e3 * wall, tflops=fl / (l["step_ms"] * 1e-3) / 1e12,
                           frac_of_dmma_peak=fl / (l["step_ms"] * 1e-3) / 1e12 / peak, dmma_peak=peak,

@@ -80,10 +80,11 @@ def test_three_op_two_time_g2_grid():
     for j, t1_j in enumerate(t_axis):
         mtos = [{"operator": "|1><0|_2", "applyFrom": "_right", "applyBefore": "false", "time": t1_j},
                 {"operator": "|0><1|_2", "applyFrom": "_left", "applyBefore": "false", "time": t1_j}]
-        # the workflow shares one drive table (longest job) across all t1; mirror that here
+        # like the reference, every run sees its OWN pulse file: samples on np.arange(0, t_end, dt), end value held
+        # (general_system.py:213) -- although the engine shares one table and one trunk across all t1
         prob = build_problem(initial="|0><0|_2", lindblad_ops=[["|0><1|_2", 0.05]],
                              interaction_ops=[["|1><0|_2", "x"]], output_ops=outs)
-        tt = np.arange(0.0, t_axis[-1] + 5.0, 0.1)
+        tt = np.arange(0.0, float(t1_j + 5.0), 0.1)
         px, _ = gs.sample_pulses(tt, [p])
         job = Job(0.0, float(t1_j + 5.0), 0.1, tables={"x": FieldTable(0.0, 0.1, px)}, mtos=prob.parse_mtos(mtos))
         ref = oracle.propagate(prob, trivial_pt(1), job)

@@ -50,7 +50,7 @@ def _check(engine, prob, pt, jobs, sample, min_signal=1e-2, **kw):
     return got
 
 
-@pytest.mark.parametrize("kernel", ["dmma", "colsplit"])
+@pytest.mark.parametrize("kernel", ["dmma", "splitk"])
 def test_cfg3_full_grid_256_branches_x_256_steps(engine, kernel):
     prob = biexciton_problem(outputs=["|1><1|_4", "(|3><1|_4*|1><1|_4*|1><3|_4)"])
     pt = synthetic_pt(128, len(prob.cls_keys), kind="unitary", scale=0.999)
@@ -72,11 +72,11 @@ def test_cfg3_full_grid_256_branches_x_256_steps(engine, kernel):
     finally:
         engine.record_timings = False
     assert log["main"]["n_traj"] == n_t and log["trunk"]["n_traj"] == 1
-    want = "k_step_colsplit" if kernel == "colsplit" else "k_step_dmma<2,4>"
+    want = "k_step_splitk" if kernel == "splitk" else "k_step_dmma<2,4>"
     assert log["main"]["step_kernel"].startswith(want), log["main"]
 
 
-@pytest.mark.parametrize("kernel", ["dmma", "colsplit"])
+@pytest.mark.parametrize("kernel", ["dmma", "splitk"])
 def test_cfg4_sixlevel_nl36_chi128_g2_reuse_pattern(engine, kernel):
     prob = sixls_problem()
     pt = synthetic_pt(128, len(prob.cls_keys), n_slices=2, kind="unitary", scale=0.999)
@@ -92,7 +92,7 @@ def test_cfg4_sixlevel_nl36_chi128_g2_reuse_pattern(engine, kernel):
     _check(engine, prob, pt, jobs, range(len(jobs)), min_signal=1e-3, kernel=kernel)
 
 
-@pytest.mark.parametrize("kernel", ["dmma", "colsplit"])
+@pytest.mark.parametrize("kernel", ["dmma", "splitk"])
 def test_cfg5_fivelevel_nl25_chi256_three_mtos(engine, kernel):
     prob = fivels_problem()
     pt = synthetic_pt(256, len(prob.cls_keys), kind="unitary", scale=0.999)
@@ -132,4 +132,4 @@ def test_physical_pts_from_the_host_builder_on_the_gpu(engine):
             [{"operator": "|3><1|_4", "applyFrom": "_right", "time": t1},
              {"operator": "|1><3|_4", "applyFrom": "_left", "time": t1}])))
     _check(engine, bx, ptb, jb, range(len(jb)), min_signal=1e-3)
-    _check(engine, bx, ptb, jb, range(len(jb)), min_signal=1e-3, kernel="colsplit")
+    _check(engine, bx, ptb, jb, range(len(jb)), min_signal=1e-3, kernel="splitk")
