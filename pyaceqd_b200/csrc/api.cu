@@ -578,14 +578,25 @@ static int build_passes(const aceqd_problem* prob, int T, int cluster, std::vect
         for (int mc = 0; mc < MC; ++mc) w += passes[i].nvalid[mc] > 0;
         return w;
     };
+    // ties in m-tiles go to the CTA with fewer ROWS so far: the system product of a CTA costs ceil(own alphas / 8)
+    // m-tiles per trajectory, and an uneven split (10 + 6 alphas for the biexciton at T = 4) doubles it on one CTA
+    auto rows_of = [&](int i) {
+        int r = 0;
+        for (int mc = 0; mc < MC; ++mc) r += passes[i].nvalid[mc];
+        return r;
+    };
+    std::vector<int> rows(load.size(), 0);
     for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weight(a) > weight(b); });
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return weight(a) != weight(b) ? weight(a) > weight(b) : rows_of(a) > rows_of(b);
+    });
     for (int i : order) {
         int best = 0;
         for (int r = 1; r < (int)load.size(); ++r)
-            if (load[r] < load[best]) best = r;
+            if (load[r] < load[best] || (load[r] == load[best] && rows[r] < rows[best])) best = r;
         passes[i].owner = best;
         load[best] += weight(i);
+        rows[best] += rows_of(i);
     }
     return ACEQD_OK;
 }

@@ -14,7 +14,7 @@ n_t, dt = 256, 0.25
 eng = default_engine(0)
 lib = eng.lib
 lib.aceqd_debug_phase_ticks.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
-pt = synthetic_pt(128, 9, dt=dt, seed=1234)
+pt = synthetic_pt(128, 9, dt=dt, seed=1234, kind="unitary", scale=0.999)
 f = os.path.join(tempfile.mkdtemp(), "pt.pt"); pt.save(f)
 pulse = ChirpedPulse(tau_0=5.0, e_start=-2.0, alpha=0, t0=20.0, e0=5.0, polar_x=1.0)
 t_axis = np.round(dt * np.arange(n_t), 6)
