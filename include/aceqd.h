@@ -177,7 +177,13 @@ typedef struct {
                                /* kernel 0/5: its GEMM passes are split, rows exchanged through            */
                                /* distributed shared memory, every CTA keeps the full bond state;          */
                                /* kernel 3: the bond columns are split (see above)                         */
-    int32_t pad_;
+    int32_t n_reduce;          /* > 0: fused tail reduction (workflow-level fusion, pol_entanglement/G2.py:507-533):   */
+                               /* the outputs stay in HBM and only, per trajectory and pair p, the trapezoid over its   */
+                               /* kept rows   s * (f_0/2 + f_1 + ... + f_{m-1} + f_m/2),   f_0 = out[row 0][zero_p],     */
+                               /* f_k = out[row k][tau_p]   comes back (the tau integral of G2(t, tau) per t)            */
+    const int32_t* reduce_ch;  /* [n_reduce][2] = (tau_p, zero_p) output channels                                       */
+    double reduce_spacing;     /* s: spacing of the tau axis                                                            */
+    double* reduce_out;        /* host [n_traj][n_reduce] complex                                                       */
 } aceqd_batch;
 
 /*

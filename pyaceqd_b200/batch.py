@@ -39,7 +39,7 @@ class BatchFuture:
 class BatchExecutor:
     """Drop-in for ``concurrent.futures.ThreadPoolExecutor`` around ``system(...)`` calls."""
 
-    def __init__(self, max_workers=None, tail_rows=0, distributed=None, **_ignored):
+    def __init__(self, max_workers=None, tail_rows=0, distributed=None, tail_reduce=None, **_ignored):
         """``tail_rows`` > 0: every deferred job returns only its last ``tail_rows`` output rows
         (the workflows index results from the end, e.g. ``res[1][-n_tau:]``
         ``two_time/correlations.py:182-183``), which bounds the device->host volume of a sweep."""
@@ -48,6 +48,9 @@ class BatchExecutor:
         # jobs in the same order); None: only if ACEQD_DISTRIBUTED=1.  Never implicit: a script that already
         # splits its sweep per rank, or runs it on rank 0 only, must not meet a collective here.
         self.distributed = distributed
+        # (pairs, spacing): every deferred job returns the trapezoid over its kept rows per output pair, reduced on the
+        # device (Engine.run_jobs) -- the tau integrals of the G2 workflows without shipping the (t, tau) map
+        self.tail_reduce = tail_reduce
         self.tail_rows = int(tail_rows or 0)
         self._requests = []     # (Request | immediate result, post-processing)
         self._results: list = []
@@ -108,7 +111,7 @@ class BatchExecutor:
         pending = [(i, r) for (i, r) in self._requests if self._results[i] is None]
         if not pending:
             return
-        res = _gs.run_requests([r for _, r in pending], distributed=self.distributed)
+        res = _gs.run_requests([r for _, r in pending], distributed=self.distributed, tail_reduce=self.tail_reduce)
         for (i, _), out in zip(pending, res):
             self._results[i] = out
             for cb in self._futures[i]._callbacks:

@@ -778,6 +778,27 @@ int aceqd_max_tile(int NL, int chi_pad) {
     return 0;
 }
 
+// End of a launch with host buffers: either the outputs go back (staged copy unless the kernel wrote them straight
+// into page-locked memory), or -- fused tail reduction -- they stay in HBM and only the per-trajectory trapezoids do.
+static int finish_outputs(aceqd_ctx* c, const aceqd_batch* b, int n_out, double* out_dev, bool zero_copy, bool reduce) {
+    if (b->device_resident) return ACEQD_OK;
+    if (reduce) {
+        int rc;
+        const size_t res_bytes = (size_t)b->n_traj * b->n_reduce * 16;
+        if ((rc = c->misc.reserve(res_bytes + (size_t)b->n_reduce * 2 * sizeof(int) + 64))) return rc;
+        int* ch_dev = (int*)((char*)c->misc.p + (res_bytes + 15) / 16 * 16);
+        ACEQD_CUDA(cudaMemcpyAsync(ch_dev, b->reduce_ch, (size_t)b->n_reduce * 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        if ((rc = launch_tail_reduce((const aceqd_traj*)c->trajs.p, b->n_traj, n_out, out_dev, b->n_reduce, ch_dev,
+                                     b->reduce_spacing, (double*)c->misc.p, c->stream, &c->log)))
+            return rc;
+        ACEQD_CUDA(cudaMemcpyAsync(b->reduce_out, c->misc.p, res_bytes, cudaMemcpyDeviceToHost, c->stream));
+    } else if (!zero_copy) {
+        ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)b->out_elems * 16, cudaMemcpyDeviceToHost, c->stream));
+    }
+    ACEQD_CUDA(cudaStreamSynchronize(c->stream));
+    return ACEQD_OK;
+}
+
 int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
                     const aceqd_batch* b) {
     int rc = check_batch(prob, b);
@@ -841,7 +862,17 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
     if (c->snaps.cap > 0 && (rc = c->snap_r.reserve(c->snaps.cap / (size_t)chi_pad + 64))) return rc;
     double* out_dev = nullptr;
     bool zero_copy = false;   // page-locked host output: the kernel writes its rows straight through PCIe
-    if (b->device_resident) {
+    const bool reduce = b->n_reduce > 0 && !b->device_resident && b->reduce_ch && b->reduce_out;
+    if (reduce) {
+        for (int p = 0; p < 2 * b->n_reduce; ++p)
+            if (b->reduce_ch[p] < 0 || b->reduce_ch[p] >= pd.n_out) {
+                set_error("batch: reduce_ch[%d] = %d is not an output channel", p, b->reduce_ch[p]);
+                return ACEQD_ERR_ARG;
+            }
+        if ((rc = c->out.reserve((size_t)b->out_elems * 16))) return rc;
+        out_dev = (double*)c->out.p;      // the outputs stay in HBM
+        c->split_tiles = 0;               // (no early copy of finished waves either)
+    } else if (b->device_resident) {
         out_dev = b->out;
     } else {
         cudaPointerAttributes at{};
@@ -947,12 +978,7 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
                 if ((rc = launch_step_small(sp, pt->blob_doubles, wpc, smem, c->stream, &c->log))) return rc;
                 ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
                 c->have_step = true;
-                if (!b->device_resident) {
-                    if (!zero_copy)
-                        ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)b->out_elems * 16, cudaMemcpyDeviceToHost,
-                                                   c->stream));
-                    ACEQD_CUDA(cudaStreamSynchronize(c->stream));
-                }
+                if ((rc = finish_outputs(c, b, pd.n_out, out_dev, zero_copy, reduce))) return rc;
                 return ACEQD_OK;
             }
         }
@@ -994,12 +1020,7 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
             if ((rc = launch_step_splitk(sp, smem, c->stream, &c->log))) return rc;
             ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
             c->have_step = true;
-            if (!b->device_resident) {
-                if (!zero_copy)
-                    ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)b->out_elems * 16, cudaMemcpyDeviceToHost,
-                                               c->stream));
-                ACEQD_CUDA(cudaStreamSynchronize(c->stream));
-            }
+            if ((rc = finish_outputs(c, b, pd.n_out, out_dev, zero_copy, reduce))) return rc;
             return ACEQD_OK;
         }
         std::vector<PassDesc> passes;
@@ -1099,12 +1120,7 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
                 ACEQD_CUDA(cudaStreamSynchronize(c->copy_stream));
                 return ACEQD_OK;
             }
-            if (!b->device_resident) {
-                if (!zero_copy)
-                    ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)b->out_elems * 16, cudaMemcpyDeviceToHost,
-                                               c->stream));
-                ACEQD_CUDA(cudaStreamSynchronize(c->stream));
-            }
+            if ((rc = finish_outputs(c, b, pd.n_out, out_dev, zero_copy, reduce))) return rc;
             return ACEQD_OK;
         }
         if (c->split_ops_pending) {      // a planned split that this launch does not use: just order the streams
@@ -1115,12 +1131,7 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
         ACEQD_CUDA(cudaEventRecord(c->ev[1], c->stream));
     }
     c->have_step = true;
-    if (!b->device_resident) {
-        if (!zero_copy)
-            ACEQD_CUDA(cudaMemcpyAsync(b->out, out_dev, (size_t)b->out_elems * 16,
-                                       cudaMemcpyDeviceToHost, c->stream));
-        ACEQD_CUDA(cudaStreamSynchronize(c->stream));
-    }
+    if ((rc = finish_outputs(c, b, pd.n_out, out_dev, zero_copy, reduce))) return rc;
     return ACEQD_OK;
 }
 

@@ -181,6 +181,9 @@ int launch_step_small(const StepParams& p, long long pt_doubles, int warps_per_c
 int launch_tlmap(int NL, int n_chains, int n_w, int n_emit_max, const double* pool, const double* v0,
                  const long long* seg_off, const aceqd_tlseg* segs, const double* w, double* out,
                  double* final_v, cudaStream_t s, LaunchLog* log);
+// fused tail reduction of a batch's outputs (workflow-level fusion): result[traj][pair] = spacing * trapezoid
+int launch_tail_reduce(const aceqd_traj* trajs, int n_traj, int n_out, const double* out, int n_reduce,
+                       const int* reduce_ch, double spacing, double* result, cudaStream_t s, LaunchLog* log);
 int launch_fp64_peak(int kind, int iters, double* sink_dev, int* blocks, int* threads,
                      cudaStream_t s, LaunchLog* log);
 

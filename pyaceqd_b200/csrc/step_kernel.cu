@@ -434,28 +434,49 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
         }
         if (wsm) mbar_wait(bar_wfull + 8 * buf, buf ? wph1 : wph0);
         TICK(1);
-        for (int it = tid; it < T * n_out; it += N_COMPUTE_WARPS * 32) {
-            const int j = it / n_out, o = it - j * n_out;
-            const aceqd_traj& t = trj[j];
-            if (C > 1 && (uint32_t)(j % C) != crank) continue;   // every CTA holds all closures: split the writes
-            if (t.n_steps < 0 || n < t.step0 + t.out_from || n > t.step0 + t.n_steps) continue;
-            const int i = n - t.step0;
-            const double2* ov;
-            if (wsm) {
-                ov = reinterpret_cast<const double2*>(Wst + (size_t)(buf * T + j) * wov + p.prob.w_doubles) +
-                     (size_t)o * NL;
-            } else {
-                const long long e = entry_of(t, i, p.ovr_base);
-                ov = reinterpret_cast<const double2*>(p.OV + (size_t)e * p.prob.ov_doubles) + (size_t)o * NL;
+        // out[j][o] = OV_n[o] . rho_j: for large Liouville spaces LPO lanes share one functional (a serial sum over NL = 16
+        // or more on a handful of threads took 2.4k cycles per step of the cfg3 branch launch, profiles/r05o_*)
+        {
+            const int LPO = NL >= 16 ? 16 : 1;
+            const int items = T * n_out * LPO;
+            for (int base = 0; base < items; base += N_COMPUTE_WARPS * 32) {     // block-uniform trip count
+                const int idx = base + tid;
+                const int it = idx / LPO, l = idx - it * LPO;
+                const int j = it / n_out, o = it - j * n_out;
+                bool on = idx < items;
+                if (on && C > 1 && (uint32_t)(j % C) != crank) on = false;   // every CTA holds all closures: split the writes
+                double2 acc = make_double2(0.0, 0.0);
+                int i = 0;
+                if (on) {
+                    const aceqd_traj& t = trj[j];
+                    on = !(t.n_steps < 0 || n < t.step0 + t.out_from || n > t.step0 + t.n_steps);
+                    if (on) {
+                        i = n - t.step0;
+                        const double2* ov;
+                        if (wsm) {
+                            ov = reinterpret_cast<const double2*>(Wst + (size_t)(buf * T + j) * wov + p.prob.w_doubles) +
+                                 (size_t)o * NL;
+                        } else {
+                            const long long e = entry_of(t, i, p.ovr_base);
+                            ov = reinterpret_cast<const double2*>(p.OV + (size_t)e * p.prob.ov_doubles) + (size_t)o * NL;
+                        }
+                        for (int a = l; a < NL; a += LPO) {
+                            const double2 w = ov[a];
+                            const double2 r = rall[pos[a] * T + j];
+                            acc.x += w.x * r.x - w.y * r.y;
+                            acc.y += w.x * r.y + w.y * r.x;
+                        }
+                    }
+                }
+                for (int sh = LPO >> 1; sh > 0; sh >>= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sh);
+                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sh);
+                }
+                if (on && l == 0) {
+                    const aceqd_traj& t = trj[j];
+                    reinterpret_cast<double2*>(p.out)[t.out_off + (long long)(i - t.out_from) * n_out + o] = acc;
+                }
             }
-            double2 acc = make_double2(0.0, 0.0);
-            for (int a = 0; a < NL; ++a) {
-                const double2 w = ov[a];
-                const double2 r = rall[pos[a] * T + j];
-                acc.x += w.x * r.x - w.y * r.y;
-                acc.y += w.x * r.y + w.y * r.x;
-            }
-            reinterpret_cast<double2*>(p.out)[t.out_off + (long long)(i - t.out_from) * n_out + o] = acc;
         }
         if (any_snap && crank == 0) {
             for (int j = 0; j < T; ++j) {

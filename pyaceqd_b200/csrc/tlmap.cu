@@ -137,4 +137,57 @@ int launch_tlmap(int NL, int n_chains, int n_w, int n_emit_max, const double* po
     return ACEQD_OK;
 }
 
+// -------------------------------------------------------------------------------------------
+// Fused tail reduction: the tau integral of G2(t, tau) per t, computed where the step kernel left
+// its outputs.  Replaces the host loop of pol_entanglement/G2.py:507-533 (np.trapz over the last n_t2 + 1 rows of every
+// run) -- only n_traj x n_pairs numbers cross PCIe instead of the whole (t, tau) map.
+namespace {
+__global__ void __launch_bounds__(128) k_tail_reduce(const aceqd_traj* trajs, int n_traj, int n_out, const double2* out,
+                                                     int n_reduce, const int* reduce_ch, double spacing, double2* result) {
+    const int b = blockIdx.x;
+    if (b >= n_traj) return;
+    const aceqd_traj t = trajs[b];
+    const int rows = t.n_steps + 1 - t.out_from;            // kept rows: tau = 0 .. m
+    const double2* o = out + t.out_off;
+    __shared__ double2 part[4];
+    for (int p = 0; p < n_reduce; ++p) {
+        const int ch_tau = reduce_ch[2 * p], ch_zero = reduce_ch[2 * p + 1];
+        double2 acc = make_double2(0.0, 0.0);
+        for (int k = threadIdx.x; k < rows; k += blockDim.x) {
+            const double2 v = o[(size_t)k * n_out + (k == 0 ? ch_zero : ch_tau)];
+            const double w = (k == 0 || k == rows - 1) ? 0.5 : 1.0;
+            acc.x += w * v.x;
+            acc.y += w * v.y;
+        }
+        for (int sh = 16; sh > 0; sh >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sh);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sh);
+        }
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double2 r = part[0];
+            for (int w = 1; w < 4; ++w) {
+                r.x += part[w].x;
+                r.y += part[w].y;
+            }
+            if (rows < 2) r = make_double2(0.0, 0.0);      // a single sample spans no interval
+            result[(size_t)b * n_reduce + p] = make_double2(spacing * r.x, spacing * r.y);
+        }
+        __syncthreads();
+    }
+}
+}  // namespace
+
+int launch_tail_reduce(const aceqd_traj* trajs, int n_traj, int n_out, const double* out, int n_reduce,
+                       const int* reduce_ch, double spacing, double* result, cudaStream_t s, LaunchLog* log) {
+    if (n_traj <= 0 || n_reduce <= 0) return ACEQD_OK;
+    k_tail_reduce<<<n_traj, 128, 0, s>>>(trajs, n_traj, n_out, reinterpret_cast<const double2*>(out), n_reduce, reduce_ch,
+                                         spacing, reinterpret_cast<double2*>(result));
+    ++log->count;
+    log_name(log->other, "k_tail_reduce");
+    ACEQD_CUDA(cudaGetLastError());
+    return ACEQD_OK;
+}
+
 }  // namespace aceqd

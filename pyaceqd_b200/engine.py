@@ -74,7 +74,8 @@ class _Batch(ctypes.Structure):
         ("tile_T", c_int32), ("n_tiles", c_int32), ("tile_traj", c_void_p),
         ("n_snap_steps", c_int32), ("snap_steps", c_void_p), ("n_snap_slots", c_int32),
         ("out_elems", c_int64), ("out", c_void_p),
-        ("device_resident", c_int32), ("kernel", c_int32), ("cluster", c_int32), ("pad_", c_int32),
+        ("device_resident", c_int32), ("kernel", c_int32), ("cluster", c_int32), ("n_reduce", c_int32),
+        ("reduce_ch", c_void_p), ("reduce_spacing", c_double), ("reduce_out", c_void_p),
     ]
 
 
@@ -151,6 +152,21 @@ def _check(rc: int, what: str):
 
 def _c128(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.complex128)
+
+
+def tail_trapezoid(block: np.ndarray, pairs, spacing: float) -> np.ndarray:
+    """Host statement of the fused tail reduction: ``block[n_out, rows]`` -> ``[len(pairs)]``."""
+    out = np.zeros(len(pairs), dtype=np.complex128)
+    rows = block.shape[1]
+    if rows < 2:
+        return out
+    w = np.ones(rows)
+    w[0] = w[-1] = 0.5
+    for p, (ch_tau, ch_zero) in enumerate(pairs):
+        col = np.array(block[ch_tau], dtype=complex)
+        col[0] = block[ch_zero][0]
+        out[p] = spacing * np.sum(w * col)
+    return out
 
 
 def class_sorted_positions(block_of_alpha: np.ndarray) -> np.ndarray:
@@ -782,8 +798,14 @@ class Engine:
     def run_jobs(self, prob: Problem, pt: Optional[ProcessTensor], jobs: Sequence[Job], *,
                  kernel: str = "auto", t_eval: str = "half_mid", fork: bool = True,
                  tile_T: Optional[int] = None, cluster: Optional[int] = None,
-                 trunk_kernel: Optional[str] = None) -> List[np.ndarray]:
-        """Propagate `jobs`; returns one ``[n_out, n_steps+1]`` complex array per job."""
+                 trunk_kernel: Optional[str] = None, tail_reduce=None) -> List[np.ndarray]:
+        """Propagate `jobs`; returns one ``[n_out, n_steps+1]`` complex array per job (its last ``tail_rows`` columns
+        if the job asks for a tail).
+
+        ``tail_reduce = (pairs, spacing)`` fuses the consumer's tau integral into the launch (reference
+        ``pol_entanglement/G2.py:507-533``): ``pairs = [(ch_tau, ch_zero), ...]`` output channels; the outputs stay in
+        HBM and per job one ``[len(pairs)]`` array comes back -- ``spacing`` times the trapezoid over the job's kept rows,
+        the first row (tau = 0) read from ``ch_zero``, the others from ``ch_tau``."""
         if pt is None:
             pt = self._trivial(prob)
         hp, _ = self.problem_handle(prob, pt)
@@ -804,6 +826,21 @@ class Engine:
             trunk_out = (tp.out, t_off, t_rows)
         # branch b writes its rows at the tail of its job's block
         traj_out_off = [out_off[t["job"]] + t["row0"] * n_out for t in main["trajs"]]
+        if tail_reduce is not None and not copy_list:
+            pairs, spacing = tail_reduce
+            ch = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+            red = np.zeros((len(main["trajs"]), len(ch)), dtype=np.complex128)
+            mp = self._materialise(common, main, traj_out_off, out_elems, out_buf=red.reshape(-1))
+            mp.batch.n_reduce, mp.batch.reduce_ch = len(ch), ch.ctypes.data
+            mp.batch.reduce_spacing, mp.batch.reduce_out = float(spacing), red.ctypes.data
+            mp.batch.out_elems = out_elems
+            _check(self.lib.aceqd_propagate_batch(self.ctx, hp, hpt, ctypes.byref(mp.batch)),
+                   "aceqd_propagate_batch(tail_reduce)")
+            self._log_launch("main", prob, common["chi_pad"], mp)
+            res = [None] * len(jobs)
+            for k, t in enumerate(main["trajs"]):
+                res[t["job"]] = red[k].copy()
+            return res
         mp = self._materialise(common, main, traj_out_off, out_elems)
         _check(self.lib.aceqd_propagate_batch(self.ctx, hp, hpt, ctypes.byref(mp.batch)),
                "aceqd_propagate_batch")
@@ -816,6 +853,8 @@ class Engine:
         for i in range(len(jobs)):
             blk = out[out_off[i]: out_off[i] + n_rows[i] * n_out].reshape(n_rows[i], n_out)
             res.append(np.ascontiguousarray(blk.T))
+        if tail_reduce is not None:      # rows partly on the trunk: reduce on the host (same arithmetic)
+            return [tail_trapezoid(r, *tail_reduce) for r in res]
         return res
 
     def _log_launch(self, kind: str, prob: Problem, chi_pad: int, plan: "_Plan"):

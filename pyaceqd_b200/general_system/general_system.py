@@ -99,7 +99,13 @@ def sample_rf(t, pulses, firstonly=False):
 
 
 def read_pulse_file(path: str) -> FieldTable:
-    """ACE pulse-file reader: columns ``t Re Im`` (``general_system.py:69-70``), cached by mtime."""
+    """ACE pulse-file reader: columns ``t Re Im`` (``general_system.py:69-70``), cached by mtime.  Names registered by
+    ``PulseGenerator.generate_pulsefiles(in_memory=True)`` resolve without touching the disk."""
+    from pyaceqd_b200.pulsegenerator import memory_file
+    mem = memory_file(path)
+    if mem is not None:
+        t, values = mem
+        return FieldTable(float(t[0]), float(t[1] - t[0]) if len(t) > 1 else 1.0, values)
     key = ("file", os.path.abspath(path), os.path.getmtime(path))
     with _cache_lock:
         if key in _table_cache:
@@ -328,13 +334,15 @@ def _finish(req: Request, out: np.ndarray):
     return res
 
 
-def run_requests(reqs: List[Request], distributed: Optional[bool] = None):
+def run_requests(reqs: List[Request], distributed: Optional[bool] = None, tail_reduce=None):
     """Execute deferred requests: one GPU batch per (problem, PT, dt, drive-table grid) group.
 
     Requests whose drives are sampled from different start times live on different table grids and run as
     separate batches (the reference handles them independently as well).  Inside a ``torch.distributed`` job the
     sweep is sharded over the ranks ONLY when asked for: ``distributed=True`` here, ``BatchExecutor(distributed=True)``
-    or ``ACEQD_DISTRIBUTED=1`` -- every rank must then submit the same job list in the same order (checked)."""
+    or ``ACEQD_DISTRIBUTED=1`` -- every rank must then submit the same job list in the same order (checked).
+    ``tail_reduce = (pairs, spacing)``: every request returns the tau integral of its kept rows instead of the rows
+    (``Engine.run_jobs``), reduced on the device."""
     from pyaceqd_b200.engine import default_engine
     eng = default_engine()
     if distributed is None:
@@ -368,6 +376,11 @@ def run_requests(reqs: List[Request], distributed: Optional[bool] = None):
         for members in by_grid.values():
             from pyaceqd_b200 import distributed as _dist
             jobs = [reqs[i].job for i in members]
+            if tail_reduce is not None:
+                outs = eng.run_jobs(prob, pt, jobs, tail_reduce=tail_reduce)
+                for i, o in zip(members, outs):
+                    results[i] = o
+                continue
             if distributed and _dist.is_multi_rank() and len(jobs) > 1:
                 # the sweep shards over the ranks (one GPU each) and is all-gathered once; every rank returns the
                 # full result like wait(futures) in the reference

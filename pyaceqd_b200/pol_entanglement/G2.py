@@ -101,10 +101,10 @@ class PolarizatzionEntanglement():
     def _n_tau(self):
         return int(self.tend / self.dt)
 
-    def _sweep(self, mtos, output_ops, tend_of, tail_of):
+    def _sweep(self, mtos, output_ops, tend_of, tail_of, tail_reduce=None):
         jobs = [{"tend": tend_of(t), "mtos": [at_time(m, t) for m in mtos], "output_ops": output_ops,
                  "tail": tail_of(t)} for t in self.t1]
-        return run_sweep(self.system, jobs, options=self.options, workers=self.workers)
+        return run_sweep(self.system, jobs, options=self.options, workers=self.workers, tail_reduce=tail_reduce)
 
     def calc_timedynamics(self, output_ops=None):
         opts = dict(self.options)
@@ -163,6 +163,13 @@ class PolarizatzionEntanglement():
         outputs = list(op23s_ttau) + [op1_t + " * " + o + " * " + op4_t for o in op23s_ttau]
         mtos = [{"operator": op1_t, "applyFrom": "_right", "applyBefore": "false"},
                 {"operator": op4_t, "applyFrom": "_left", "applyBefore": "false"}]
+        if not return_full_G2:
+            # the tau integral of every t1 is taken where the trajectories end, on the device (reference :525-527 does
+            # np.trapz over the last n_t2 + 1 rows of every run on the host): only n_t1 x n_ops numbers come back
+            red = self._sweep(mtos, outputs, lambda t: self.tend, lambda t: n_tau - int(t / self.dt) + 1,
+                              tail_reduce=([(j, n_ops + j) for j in range(n_ops)], tau[1] - tau[0] if n_tau else 0.0))
+            g2 = np.array(red, dtype=complex).T.reshape(n_ops, len(self.t1))
+            return self.t1, g2, np.trapezoid(g2, self.t1, axis=1)
         res = self._sweep(mtos, outputs, lambda t: self.tend, lambda t: n_tau - int(t / self.dt) + 1)
         series = self._window_series(res, n_ops)
         g2 = np.zeros((n_ops, len(self.t1)), dtype=complex)

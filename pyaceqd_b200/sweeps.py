@@ -30,11 +30,12 @@ def at_time(mto: dict, time: float) -> dict:
     return m
 
 
-def run_sweep(system, jobs: Sequence[dict], *pulses, options: Optional[dict] = None, workers=None) -> List:
+def run_sweep(system, jobs: Sequence[dict], *pulses, options: Optional[dict] = None, workers=None, tail_reduce=None) -> List:
     """Submit ``system(t0, tend, *pulses, multitime_op=..., output_ops=..., suffix=i, **options)`` for
-    every job spec ``{"t0", "tend", "mtos", "output_ops", "tail"}`` in one batch; return results."""
+    every job spec ``{"t0", "tend", "mtos", "output_ops", "tail"}`` in one batch; return results.
+    ``tail_reduce = (pairs, spacing)``: per job the tau integrals of its tail (reduced on the device) instead."""
     opts = dict(options or {})
-    with BatchExecutor(max_workers=workers) as ex:
+    with BatchExecutor(max_workers=workers, tail_reduce=tail_reduce) as ex:
         futs = []
         for i, jb in enumerate(jobs):
             kw = dict(opts)

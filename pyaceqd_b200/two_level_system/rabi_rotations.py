@@ -5,7 +5,7 @@
 result).  The reference submits one ACE run per area to a thread pool (``:172-198``); here the
 whole sweep is one GPU batch.  ``_AreaSweep`` is shared with
 :class:`pyaceqd_b200.four_level_system.tpe_rotations.TPERotations`.  Plotting and the FFT pulse
-carving (``pulsegenerator.py``) are out of scope: pass ready-made ``pulse_files`` instead.
+carving runs through :mod:`pyaceqd_b200.pulsegenerator` (fields handed over in memory, no pulse files on disk).
 """
 from __future__ import annotations
 
@@ -82,13 +82,17 @@ class _AreaSweep():
                           plotlims=None, lindblad=True, carve_pulse=False, pulse_args=None, filter_width=0.14,
                           pulse_file=None):
         """Full time dynamics for one pulse (reference ``:80-118``); returns ``t.real`` and the outputs."""
-        if carve_pulse:
-            raise NotImplementedError("FFT pulse carving is out of scope; pass pulse_file=<sampled field file>")
         p = ChirpedPulse(tau_0=tau, e_start=detuning, alpha=0, e0=area, polar_x=1.0, t0=4 * tau)
         if tend is None:
             tend = np.round(10 / self.gamma_e) + 100
         self._ensure_pt()
         kw = dict(self.options)
+        if carve_pulse and pulse_file is None:
+            # a Gaussian carved out of a broader spectrum by a band pass with soft edges (reference :94-98)
+            shaped = self._carved_pulse(area, 100, np.round(10 / self.gamma_e), pulse_args or {"width_t": 4, "central_f": 0},
+                                        filter_width, 0.01)
+            pulse_file, _ = shaped.generate_pulsefiles(suffix="timedynamics", temp_dir=self.options.get("temp_dir", ""),
+                                                       in_memory=True)
         if pulse_file is not None:
             kw[self._pulse_file_kw()] = pulse_file
         res = self._system(0, tend, p, lindblad=lindblad, **kw)
@@ -96,6 +100,16 @@ class _AreaSweep():
             export_csv(path + "timedynamics_{:.2f}ps_{:.2f}pi.csv".format(tau, area), res[0].real,
                        *[r.real for r in res[2:]])
         return (res[0].real,) + tuple(res[1:])
+
+    @staticmethod
+    def _carved_pulse(area, t0, t_window, pulse_args, filter_width, rise_f):
+        """``PulseGenerator`` holding one spectrally carved pulse (reference ``rabi_rotations.py:94-97,176-183``)."""
+        from pyaceqd_b200.pulsegenerator import PulseGenerator
+        pulse = PulseGenerator(0, t_window, 0.02)
+        pulse.add_gaussian_time(t0=t0, sig_or_fwhm='fwhm', field_or_intesity='int', area_time=area, **pulse_args)
+        pulse.add_filter_double_erf(central_f=0, width_f=filter_width, rise_f=rise_f)
+        pulse.apply_frequency_filter()
+        return pulse
 
     def _filename(self, path, carve_pulse, pulse_args, filter_width):
         name = path + self.prefix
@@ -116,8 +130,17 @@ class _AreaSweep():
         if os.path.exists(filename + ".csv"):
             data = np.loadtxt(filename + ".csv", delimiter=",")
             return (data[:, 0], data[:, 1]) if self.n_columns == 1 else (data[:, 0],) + tuple(data[:, 1:].T)
+        t_end_add = 0
         if carve_pulse and pulse_files is None:
-            raise NotImplementedError("FFT pulse carving is out of scope; pass pulse_files=[...] (one per area)")
+            # one carved pulse per area; the area that survives the filter replaces the nominal one (reference :176-187)
+            t_end_add = 400
+            pulse_files = []
+            self.areas = np.array(self.areas, dtype=float)
+            for i in range(len(self.areas)):
+                shaped = self._carved_pulse(self.areas[i], 200, np.round(10 / self.gamma_e), pulse_args, filter_width, rise_f)
+                pulse_files.append(shaped.generate_pulsefiles(suffix=str(i), temp_dir=self.options.get("temp_dir", ""),
+                                                              in_memory=True)[0])
+                self.areas[i] = np.sqrt(shaped.pulse_power)
         self._ensure_pt()
         with BatchExecutor(max_workers=workers) as ex:
             futs = []
@@ -127,10 +150,10 @@ class _AreaSweep():
                 if pulse_files is not None:
                     kw[self._pulse_file_kw()] = pulse_files[i]
                 if integrate:
-                    tend = np.round(self.integrate_window_factor / self.gamma_e) + self.integrate_extra
+                    tend = np.round(self.integrate_window_factor / self.gamma_e) + self.integrate_extra + t_end_add
                     futs.append(ex.submit(self._system, 0, tend, p, lindblad=True, suffix=i, **kw))
                 else:
-                    futs.append(ex.submit(self._system, 0, 8 * self.tau, p, lindblad=False, suffix=i, **kw))
+                    futs.append(ex.submit(self._system, 0, 8 * self.tau + t_end_add, p, lindblad=False, suffix=i, **kw))
             wait(futs)
         results = np.zeros((self.n_columns, len(self.areas)))
         for i, f in enumerate(futs):

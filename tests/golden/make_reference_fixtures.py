@@ -115,6 +115,50 @@ for name in sorted(os.listdir(tmp)):
     files[name] = open(tmp + name).read().replace(tmp, "<TMP>")
 out["prepare_only_files"] = files
 
+# --- pulse shaper (pulsegenerator.py): fields built in time / frequency, filters, power, rotating frame, files
+import pyaceqd.pulsegenerator as rpg  # noqa: E402
+
+
+def _pg_state(g):
+    return dict(tx=cplx(g.temporal_representation_x), ty=cplx(g.temporal_representation_y),
+                fx=cplx(g.frequency_representation_x), fy=cplx(g.frequency_representation_y),
+                filt_x=cplx(g.frequency_filter_x), filt_y=cplx(g.frequency_filter_y), power=float(g.pulse_power),
+                actions=int(g.action_counter), central_wavelength=float(g.central_wavelength))
+
+
+pg_out = {}
+g = rpg.PulseGenerator(0, 60, 0.25, central_wavelength=800)
+pg_out["grid"] = dict(time=g.time.tolist(), frequencies=g.frequencies.tolist(), energies=g.energies.tolist(),
+                      wavelengths=g.wavelengths.tolist())
+g.add_gaussian_time(width_t=4, central_f=0.1, t0=30, area_time=3.0, sig_or_fwhm='fwhm', field_or_intesity='int',
+                    polarisation=[1, 0.5], phase=0.2)
+pg_out["gauss_time"] = _pg_state(g)
+g.add_filter_double_erf(central_f=0, width_f=0.14, rise_f=0.01)
+g.apply_frequency_filter()
+pg_out["double_erf_applied"] = _pg_state(g)
+g.set_pulse_power(2.5)
+pg_out["set_power"] = _pg_state(g)
+h = rpg.PulseGenerator(0, 60, 0.25, central_wavelength=800)
+h.add_gaussian_freq(width_f=0.5, central_f=-1.0, area_time=2.0, phase_taylor=[0.3, 0.0, 20.0], shift_time=25.0, unit='meV',
+                    polarisation=[0, 1])
+h.add_filter_gaussian(central_f=-0.2, width_f=0.3, transmission=0.8, sig_fwhm='fwhm', unit='meV', polarisation='y')
+h.add_filter_sigmoid(central_f=0.05, width_f=0.2, rise_f=0.01, transmission=0.6, merging='m')
+h.add_filter_rectangle(central_f=0.0, width_f=0.6, transmission=0.9, merging='*')
+h.add_phase_filter(central_f=0.0, phase_taylor=[0.0, 1.5, -8.0])
+pg_out["freq_filters"] = _pg_state(h)
+h.apply_frequency_filter('y')
+pg_out["freq_filters_applied"] = _pg_state(h)
+h.set_rotating_frame(799.0)
+pg_out["rotating_frame"] = _pg_state(h)
+g.merge_pulses(h)
+pg_out["merged"] = _pg_state(g)
+pg_tmp = tempfile.mkdtemp() + "/"
+fx, fy = g.generate_pulsefiles(temp_dir=pg_tmp, suffix="7")
+pg_out["files"] = {os.path.basename(fx): open(fx).read(), os.path.basename(fy): open(fy).read()}
+pg_out["units"] = {k: float(g._Units(v, u)) for k, (v, u) in
+                   {"meV": (1.3, "meV"), "nm_abs": (801.0, "nm"), "nm_rel": (-0.7, "nm"), "hz": (0.4, "Hz")}.items()}
+out["pulsegenerator"] = pg_out
+
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_host.json"), "w") as fh:
     json.dump(out, fh, default=lambda o: o.item() if hasattr(o, "item") else o.tolist())
 print("wrote reference_host.json")

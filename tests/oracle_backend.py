@@ -29,6 +29,9 @@ class OracleEngine:
                 pj.rho0 = np.asarray(j.rho0, dtype=complex).reshape(-1)
             full = oracle.propagate(pj, pt, j, t_eval=kw.get("t_eval", "half_mid"))
             out.append(np.ascontiguousarray(full[:, -j.tail_rows:]) if j.tail_rows else full)
+        if kw.get("tail_reduce") is not None:      # host statement of the fused tail reduction
+            from pyaceqd_b200.engine import tail_trapezoid
+            return [tail_trapezoid(o, *kw["tail_reduce"]) for o in out]
         return out
 
     def expm(self, mats):

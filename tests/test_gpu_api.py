@@ -132,3 +132,29 @@ def test_calc_dynmap_and_get_M_t():
     assert M.shape == (4, 4) and np.abs(np.ones(4) @ np.eye(2).reshape(-1)[:, None] * 0).max() == 0
     tr = np.eye(2).reshape(-1)
     assert np.abs(tr @ M - tr).max() < 1e-12                 # trace preserving propagator
+
+
+def test_fused_tail_reduction_equals_host_trapezoid(engine):
+    """Workflow-level fusion: the tau integral of every run's tail is taken on the device
+    (k_tail_reduce) where the step kernel left its outputs -- same numbers as np.trapz over the shipped rows."""
+    from helpers import biexciton_problem, make_tables
+    from pyaceqd_b200.engine import tail_trapezoid
+    from pyaceqd_b200.process_tensor import synthetic_pt
+    prob = biexciton_problem(outputs=["|1><1|_4", "|3><3|_4", "(|3><1|_4*|1><1|_4*|1><3|_4)", "(|3><1|_4*|3><3|_4*|1><3|_4)"])
+    pt = synthetic_pt(24, len(prob.cls_keys), kind="unitary", scale=0.999)
+    dt, tend = 0.25, 9.0
+    p = ChirpedPulse(tau_0=1.0, e_start=-2.0, alpha=0, t0=3.0, e0=4.0, polar_x=0.8)
+    tabs = make_tables([p], 0.0, tend, dt)
+    jobs = []
+    for t1 in (0.0, 1.0, 2.5, 4.0, 8.75, 9.0):
+        mt = prob.parse_mtos([{"operator": "|3><1|_4", "applyFrom": "_right", "time": t1},
+                              {"operator": "|1><3|_4", "applyFrom": "_left", "time": t1}])
+        jobs.append(Job(0.0, tend, dt, tables=tabs, mtos=mt, tail_rows=int(round((tend - t1) / dt)) + 1))
+    pairs = [(0, 2), (1, 3)]
+    full = engine.run_jobs(prob, pt, jobs)
+    fused = engine.run_jobs(prob, pt, jobs, tail_reduce=(pairs, dt))
+    assert engine.last_kernels()["other"] == "k_tail_reduce"
+    for f, r, jb in zip(full, fused, jobs):
+        want = tail_trapezoid(f, pairs, dt)
+        assert r.shape == (2,) and np.abs(r - want).max() < 1e-12, jb.tail_rows
+    assert np.abs(fused[-1]).max() == 0.0 and max(np.abs(r).max() for r in fused) > 1e-3    # one sample spans no interval
