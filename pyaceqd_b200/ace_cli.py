@@ -163,8 +163,25 @@ def _generate_pt(params, path):
     """Process-tensor generation file (``:162-190``): QDPhonon bath for the diagonal ``Boson_SysOp``."""
     from pyaceqd_b200.opparser import parse_operator
     from pyaceqd_b200.pt_builder import build_qd_phonon_pt
+    from pyaceqd_b200.pt_builder import build_pt_from_spectral_density_file, write_spectral_density
+    if "Boson_J_print" in params:          # <file> e_min e_max n
+        w = params["Boson_J_print"][0][0]
+        a_e_, a_h_ = float(_one(params, "Boson_J_a_e", 5.0)), _one(params, "Boson_J_a_h")
+        write_spectral_density(w[0], a_e=a_e_, a_h=None if a_h_ is None else float(a_h_), e_min=float(w[1]) if len(w) > 1 else 0.0,
+                               e_max=float(w[2]) if len(w) > 2 else 15.0, n=int(w[3]) if len(w) > 3 else 2000)
     if "Boson_J_from_file" in params:
-        raise NotImplementedError("Boson_J_from_file is not supported by the PT builder yet")
+        # the reference writes no Boson_SysOp in this mode (general_system.py:178-179): a two-level |1><1| coupling
+        op = parse_operator(params["Boson_SysOp"][0][1][0]) if "Boson_SysOp" in params else np.diag([0.0, 1.0])
+        dt = float(_one(params, "dt"))
+        t_mem = float(_one(params, "t_mem", float(_one(params, "te", 2 * 20.48)) / 2))
+        pt = build_pt_from_spectral_density_file(_one(params, "Boson_J_from_file"), np.real(np.diag(op)), dt, t_mem,
+                                                 float(_one(params, "temperature", 4)), threshold=float(_one(params, "threshold", 1e-8)),
+                                                 e_max=float(_one(params, "Boson_E_max", 7)))
+        target = _one(params, "write_PT")
+        pt.save(target)
+        with open(target + "_initial", "w") as fh:
+            fh.write("aceqd-b200 process tensor: see {}\n".format(os.path.basename(target)))
+        return target
     op = parse_operator(params["Boson_SysOp"][0][1][0])
     a_e = float(_one(params, "Boson_J_a_e", 5.0))
     a_h = _one(params, "Boson_J_a_h")

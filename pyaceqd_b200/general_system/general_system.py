@@ -174,13 +174,16 @@ def resolve_pt(pt_file: str, *, boson_op, dt, t_mem, ae, temperature, threshold,
                 "{}_initial is an ACE-format process tensor; its binary layout is undocumented "
                 "(SURVEY App. E, R2). Rebuild it with this engine (delete the ACE files).".format(pt_file))
         print("{} not found. Calculating...".format(pt_file))
-        from pyaceqd_b200.pt_builder import build_qd_phonon_pt
-        if J_file is not None:
-            raise NotImplementedError("Boson_J_from_file is not supported by the PT builder yet")
-        pt = build_qd_phonon_pt(coupling_diag=problem.meta["coupling_diag"], dt=float(dt), t_mem=float(t_mem),
-                                a_e=float(ae), a_h=None if factor_ah is None else float(ae) / float(factor_ah),
-                                temperature=float(temperature), threshold=10.0 ** (-int(threshold)),
-                                e_max=float(boson_e_max), use_infinite=bool(use_infinite), verbose=verbose)
+        from pyaceqd_b200.pt_builder import build_pt_from_spectral_density_file, build_qd_phonon_pt
+        if J_file is not None:      # Boson_J_from_file (reference :178-179): tabulated spectral density
+            pt = build_pt_from_spectral_density_file(J_file, problem.meta["coupling_diag"], float(dt), float(t_mem),
+                                                     float(temperature), threshold=10.0 ** (-int(threshold)),
+                                                     e_max=float(boson_e_max), verbose=verbose)
+        else:
+            pt = build_qd_phonon_pt(coupling_diag=problem.meta["coupling_diag"], dt=float(dt), t_mem=float(t_mem),
+                                    a_e=float(ae), a_h=None if factor_ah is None else float(ae) / float(factor_ah),
+                                    temperature=float(temperature), threshold=10.0 ** (-int(threshold)),
+                                    e_max=float(boson_e_max), use_infinite=bool(use_infinite), verbose=verbose)
         try:
             pt.save(pt_file)
         except OSError:
@@ -248,6 +251,9 @@ def system_ace_stream(t_start, t_end, *pulses, dt=0.01, phonons=False, t_mem=20.
         print("prepared file {}, exiting.".format(stem + ".param"))
         return [np.array([0, 0]) for _ in range(1 + len(output_ops))]
 
+    if J_to_file is not None and phonons:      # Boson_J_print <file> 0 15 2000 (reference :186-187)
+        from pyaceqd_b200.pt_builder import write_spectral_density
+        write_spectral_density(J_to_file, a_e=float(ae), a_h=None if factor_ah is None else float(ae) / float(factor_ah))
     problem = _problem_for(system_op=system_op, boson_op=boson_op if phonons else None, initial=initial,
                            lindblad_ops=lindblad_ops, interaction_ops=interaction_ops, output_ops=output_ops,
                            rf_op=rf_op, rho0=rho0, dict_zero=dict_zero)

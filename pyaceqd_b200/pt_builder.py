@@ -22,6 +22,7 @@ gauge-fixed so that the initial bond state is ``e_0``.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -222,3 +223,40 @@ def build_qd_phonon_pt(coupling_diag: Sequence[float], dt: float, t_mem: float, 
     if verbose:
         print(f"QD phonon PT: dt={dt} ps, memory {t_mem} ps, T={temperature} K, chi={pt.chi_max}")
     return pt
+
+
+# ---------------------------------------------------------------------------------------------- spectral-density files
+def write_spectral_density(path: str, a_e: float = 5.0, a_h: Optional[float] = None, e_min: float = 0.0,
+                           e_max: float = 15.0, n: int = 2000) -> None:
+    """``Boson_J_print <file> 0 15 2000`` (reference ``general_system.py:186-187``): two columns, ``hbar w`` in meV and
+    ``J(w)`` in 1/ps, ``n`` rows.  (ACE's own print format cannot be checked here; this is the format
+    :func:`read_spectral_density` reads back.)"""
+    e = np.linspace(e_min, e_max, n)
+    J = qd_phonon_spectral_density(e / constants.hbar, a_e, a_h)
+    np.savetxt(path, np.column_stack([e, J]), fmt="%.12e", delimiter=" ")
+
+
+def read_spectral_density(path: str):
+    """Tabulated spectral density (``Boson_J_from_file``, reference ``general_system.py:178-179``): columns ``hbar w``
+    (meV) and ``J`` (1/ps).  Returns ``(w [1/ps], J [1/ps])`` on the file's grid."""
+    data = np.loadtxt(path, ndmin=2)
+    if data.shape[1] < 2 or len(data) < 2:
+        raise ValueError("{}: expected two columns (energy in meV, J in 1/ps)".format(path))
+    order = np.argsort(data[:, 0])
+    return data[order, 0] / constants.hbar, data[order, 1]
+
+
+def build_pt_from_spectral_density_file(path: str, coupling_diag: Sequence[float], dt: float, t_mem: float,
+                                        temperature: float, threshold: float = 1e-8, e_max: Optional[float] = None,
+                                        n_w: int = 20001, chi_max: int = 512, verbose: bool = False) -> ProcessTensor:
+    """PT of the bath whose spectral density is tabulated in ``path``; the table is interpolated linearly onto the
+    builder's frequency grid and cut at ``e_max`` (meV, ``Boson_E_max``) or at the end of the table."""
+    w_tab, j_tab = read_spectral_density(path)
+    w_hi = w_tab[-1] if e_max is None else min(w_tab[-1], e_max / constants.hbar)
+    w = np.linspace(0.0, w_hi, n_w)
+    J = np.interp(w, w_tab, j_tab, left=0.0, right=0.0)
+    pt = build_gaussian_pt(coupling_diag, J, w, dt, t_mem, temperature, threshold=threshold, subtract_polaron_shift=True,
+                           chi_max=chi_max, verbose=verbose)
+    pt.meta.update({"J_file": os.path.basename(path), "temperature": temperature, "t_mem": t_mem})
+    return pt
+

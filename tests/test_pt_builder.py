@@ -113,3 +113,28 @@ def test_pt_save_load_roundtrip(tmp_path):
     assert back.block_of_class(keys).tolist() == list(range(9))
     with pytest.raises(ValueError):
         back.block_of_class(np.array([[0.0, 3.0]]))
+
+
+def test_spectral_density_file_round_trip(tmp_path):
+    """Boson_J_print / Boson_J_from_file (reference general_system.py:178-179,186-187): a PT built from the printed
+    QDPhonon spectral density equals the PT built from the analytic one (up to the table's interpolation error)."""
+    from pyaceqd_b200.pt_builder import (build_pt_from_spectral_density_file, build_qd_phonon_pt, read_spectral_density,
+                                         write_spectral_density)
+    f = str(tmp_path / "J_omega.dat")
+    write_spectral_density(f, a_e=5.0)
+    w, J = read_spectral_density(f)
+    assert len(w) == 2000 and abs(w[-1] * 0.6582119569 - 15.0) < 1e-9 and J[0] == 0.0 and J.max() > 0.05
+    a = build_qd_phonon_pt([0.0, 1.0], dt=0.2, t_mem=4.0, a_e=5.0, temperature=4.0, threshold=1e-7)
+    b = build_pt_from_spectral_density_file(f, [0.0, 1.0], dt=0.2, t_mem=4.0, temperature=4.0, threshold=1e-7, e_max=7.0)
+    assert abs(a.chi_max - b.chi_max) <= 1
+    # compare what the tensors DO: dephasing of the coherence class over 30 steps
+    def decay(pt):
+        k = pt.block_of_class(np.array([[1.0, 0.0]]))[0]
+        v = np.zeros(pt.chi_max, dtype=complex)
+        v[0] = 1.0
+        out = []
+        for _ in range(30):
+            v = v @ pt.slices[0][k]
+            out.append(v @ pt.closures[0])
+        return np.array(out)
+    assert np.abs(decay(a) - decay(b)).max() < 2e-5
