@@ -15,3 +15,7 @@ mto_right_transposed = False
 # DynamicalMap.E layout: the reference's consumers treat dm[0] as E_{t1,t0} (tools.py:470-479), so the
 # identity at t0 is not returned by default.
 dynmap_includes_t0 = False
+# two_time/propagate_tau.f90:492,524 return to the maps of the period start when ``j + j_start == n_tb + 1``, one step
+# BEFORE the period boundary (the phonon-free routine, :286, resets at the boundary).  False keeps the reference's
+# numbers; True resets at the boundary, which is what the direct multi-time-operator sweeps agree with.
+phonon_block_aligned = False

@@ -322,12 +322,12 @@ def system_ace_stream(t_start, t_end, *pulses, dt=0.01, phonons=False, t_mem=20.
     sink = getattr(_capture, "sink", None)
     # deferred calls sample their drives once per sweep in run_requests (shared, longest window)
     job = Job(float(t_start), float(t_end), float(dt),
-              tables={} if (sink is not None and not calc_dynmap) else make_tables(t_end),
+              tables={} if sink is not None else make_tables(t_end),
               mtos=problem.parse_mtos(multitime_op))
     req = Request(problem=problem, pt=pt, job=job, pulse_key=pulse_key, table_maker=make_tables,
                   calc_dynmap=calc_dynmap,
                   sampled=(rf_op is not None and rf_file is None) or (rf_op is None and pulse_file_x is None))
-    if sink is not None and not calc_dynmap:
+    if sink is not None:
         sink.append(req)
         return req      # BatchExecutor resolves it
     return run_requests([req])[0]
@@ -395,23 +395,24 @@ def run_requests(reqs: List[Request], distributed: Optional[bool] = None, tail_r
                 outs = eng.run_jobs(prob, pt, jobs)
             for i, o in zip(members, outs):
                 results[i] = _finish(reqs[i], o)
-        for i in idx:
-            if reqs[i].calc_dynmap:
-                results[i] = _run_dynmap(eng, reqs[i])
+        dyn = [i for i in idx if reqs[i].calc_dynmap]
+        if dyn:
+            for i, o in zip(dyn, _run_dynmaps(eng, [reqs[i] for i in dyn])):
+                results[i] = o
     for r, res in zip(reqs, results):
         r.result = res
     return results
 
 
-def _run_dynmap(eng, req: Request):
-    """``DynamicalMap.E`` (reference ``:328-335``): the physical run plus the NL unit vectors as
-    initial states with identity outputs, all in ONE batch.  Layout as the reference's consumers
-    expect (``tools.py:470-479``): ``E[i] = E_{t_{i+1}, t_0}``, i.e. ``E[0] rho0 = rho(t_1)`` -- the
-    identity at ``t_0`` is not part of the array unless ``constants.dynmap_includes_t0`` is set."""
+def _run_dynmaps(eng, reqs: List[Request]):
+    """``DynamicalMap.E`` (reference ``:328-335``) for requests of one (problem, PT) group: the physical runs in one
+    batch, the NL unit vectors of EVERY request as initial states with identity outputs in a second one.  Layout as
+    the reference's consumers expect (``tools.py:470-479``): ``E[i] = E_{t_{i+1}, t_0}``, i.e. ``E[0] rho0 =
+    rho(t_1)`` -- the identity at ``t_0`` is not part of the array unless ``constants.dynmap_includes_t0`` is set."""
     import copy
-    prob = req.problem
+    prob, pt = reqs[0].problem, reqs[0].pt
     NL = prob.NL
-    res = _finish(req, eng.run_jobs(prob, req.pt, [req.job])[0])
+    phys = [_finish(r, o) for r, o in zip(reqs, eng.run_jobs(prob, pt, [r.job for r in reqs]))]
     key = ("dynmap", id(prob))
     with _cache_lock:
         basis = _problem_cache.get(key)
@@ -421,14 +422,18 @@ def _run_dynmap(eng, req: Request):
             basis.meta = dict(prob.meta)
             _problem_cache[key] = basis
     jobs = []
-    for j in range(NL):
-        jb = copy.copy(req.job)
-        jb.rho0 = np.zeros(NL, dtype=complex)
-        jb.rho0[j] = 1.0
-        jb.tail_rows = 0
-        jobs.append(jb)
-    cols = eng.run_jobs(basis, req.pt, jobs)
-    E = np.empty((req.job.n_steps + 1, NL, NL), dtype=complex)
-    for j, c in enumerate(cols):
-        E[:, :, j] = c.T
-    return res, (E if getattr(constants, "dynmap_includes_t0", False) else E[1:])
+    for r in reqs:
+        for j in range(NL):
+            jb = copy.copy(r.job)
+            jb.rho0 = np.zeros(NL, dtype=complex)
+            jb.rho0[j] = 1.0
+            jb.tail_rows = 0
+            jobs.append(jb)
+    cols = eng.run_jobs(basis, pt, jobs)
+    out = []
+    for k, r in enumerate(reqs):
+        E = np.empty((r.job.n_steps + 1, NL, NL), dtype=complex)
+        for j in range(NL):
+            E[:, :, j] = cols[k * NL + j].T
+        out.append((phys[k], (E if getattr(constants, "dynmap_includes_t0", False) else E[1:])))
+    return out

@@ -44,10 +44,11 @@ def _which(pol: str) -> Tuple[bool, bool]:
 class PulseGenerator:
     def __init__(self, t0, tend=100, dt=0.5, central_wavelength=800, calibration_file=None, f0=None, fend=None, fN=1024,
                  unit='nm') -> None:
-        if calibration_file is not None:
-            raise NotImplementedError("spectrometer calibration files belong to the SLM / pulse-shaper hardware model")
-        self.calibration_file = None
-        self.central_wavelength = central_wavelength
+        self.calibration_file = calibration_file
+        if calibration_file is None:
+            self.central_wavelength = central_wavelength
+        else:                                          # the rotating frame sits on the measured exciton line
+            self._read_calibration_file(calibration_file)
         self.t0 = t0
         if f0 is not None and fend is not None:        # grid chosen from the spectral window
             self.dt = np.abs(1 / (self._Units(fend, unit) - self._Units(f0, unit)))
@@ -81,6 +82,27 @@ class PulseGenerator:
     temporal_filter_y = property(lambda s: s._filter_t[1])
 
     # ------------------------------------------------------------------ units and small helpers
+    def _read_calibration_file(self, calibration_file):
+        """Emission lines of a measured quantum dot (INI file, the one ``tools.read_calibration_file`` reads) as
+        THz offsets from the exciton line, which becomes the rotating frame (reference ``:66-86``)."""
+        import configparser
+        config = configparser.ConfigParser()
+        config.read(calibration_file)
+        self.central_wavelength = float(config['EMISSION']['exciton_wavelength'])
+        self.biexciton_wavelength = float(config['EMISSION']['biexciton_wavelength'])
+        self.dark_wavelength = float(config['EMISSION']['dark_wavelength'])
+        self.fss_bright = float(config['SPLITTING']['fss_bright'])
+        self.fss_dark = float(config['SPLITTING']['fss_dark'])
+        self.lifetime_exciton = float(config['LIFETIMES']['exciton'])
+        self.lifetime_biexciton = float(config['LIFETIMES']['biexciton'])
+        x, b, d = (self._Units(w, 'nm') for w in (self.central_wavelength, self.biexciton_wavelength, self.dark_wavelength))
+        half_bright = self._Units(self.fss_bright * 1e-3 / 2, 'mev')
+        half_dark = self._Units(self.fss_dark * 1e-3 / 2, 'mev')
+        self.exciton_x_emission, self.exciton_y_emission = x + half_bright, x - half_bright
+        self.biexciton_x_emission, self.biexciton_y_emission = b - half_bright, b + half_bright
+        self.dark_x_emission, self.dark_y_emission = d + half_dark, d - half_dark
+        self.tpe_resonance = (x + b) / 2
+
     def _Units(self, value, unit='Hz'):
         """meV or nm -> THz offset from the rotating frame ('nm' accepts absolute or relative wavelengths)."""
         u = unit.lower()[0]
@@ -287,8 +309,9 @@ class PulseGenerator:
 
     def set_rotating_frame(self, new_rf=None, unit='nm'):
         if isinstance(new_rf, str):
-            raise NotImplementedError("calibration files are not supported")
-        self.central_wavelength = self._Units_inverse(self._Units(new_rf, unit), 'nm')
+            self._read_calibration_file(new_rf)
+        else:
+            self.central_wavelength = self._Units_inverse(self._Units(new_rf, unit), 'nm')
         new_f = C_NM_THZ / self.central_wavelength
         self.central_energy = new_f * hbar * 2 * np.pi
         self._field_t *= np.exp(-1j * 2 * np.pi * (self.central_frequency - new_f) * self.time)

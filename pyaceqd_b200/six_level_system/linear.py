@@ -2,7 +2,7 @@
 ``pyaceqd/six_level_system/linear.py:20-72``): |0>=G, |1>=X, |2>=Y, |3>=S(Dx), |4>=F(Dy), |5>=B.
 In-plane field ``bx`` mixes bright and dark excitons, ``bz`` mixes within each doublet."""
 from pyaceqd_b200.general_system.general_system import system_ace_stream
-from pyaceqd_b200.tools import output_ops_dm, compose_dm
+from pyaceqd_b200.tools import output_ops_dm, compose_dm, read_calibration_file
 import pyaceqd_b200.constants as constants
 
 temp_dir = constants.temp_dir
@@ -26,10 +26,11 @@ def sixls_linear(t_start, t_end, *pulses, dt=0.5, delta_b=4, gamma_e=1/100, gamm
                  prepare_only=False, output_ops=_POPULATIONS_6, initial="|0><0|_6", t_mem=20.48,
                  output_dm=False, dressedstates=False, rf=False, rf_file=None, firstonly=False,
                  calibration_file=None, print_H=False, use_infinite=True, d0=d0, d1=d1, d2=d2):
-    if calibration_file is not None:
-        raise NotImplementedError("calibration files (tools.read_calibration_file) are not rebuilt")
-    E_X, E_Y, E_S, E_F, E_B = energies_linear(delta_B=delta_b, d0=d0, d1=d1, d2=d2)
-    gex, gez, ghx, ghz = -0.65, -0.8, -0.35, -2.2
+    if calibration_file is not None:      # measured energies, rates and g factors replace the arguments (:33-34)
+        E_X, E_Y, E_S, E_F, E_B, gamma_e, gamma_b, gamma_d, gex, ghx, gez, ghz = read_calibration_file(calibration_file)
+    else:
+        E_X, E_Y, E_S, E_F, E_B = energies_linear(delta_B=delta_b, d0=d0, d1=d1, d2=d2)
+        gex, gez, ghx, ghz = -0.65, -0.8, -0.35, -2.2
     hamiltonian = ["{}*|1><1|_6 + {}*|2><2|_6 + {}*|3><3|_6 + {}*|4><4|_6 + {}*|5><5|_6".format(
         E_X, E_Y, E_S, E_F, E_B)]
     if bx != 0:

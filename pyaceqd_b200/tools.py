@@ -297,3 +297,25 @@ def use_tl_map_mto(tl_map, dm_1, dm_2, times, rho0, t_MTO, debug=False):
         print("info on piecewise application: ", i_mto, times[i_mto], len(dm_1), len(dm_2))
     schedule = itertools.chain(dm_1[:n1], itertools.repeat(tl_map, i_mto - n1), dm_2, itertools.repeat(tl_map))
     return _chain(schedule, rho0.reshape(n * n), len(times)).reshape(len(times), n, n)
+
+
+def read_calibration_file(calibration_file):
+    """Quantum-dot parameters from an experimental calibration file (INI sections ``EMISSION``, ``SPLITTING``,
+    ``LIFETIMES``, ``G_FACTORS``; reference ``tools.py:307-344``).  Returns ``(E_X, E_Y, E_S, E_F, E_B, gamma_e,
+    gamma_b, gamma_d, g_ex, g_hx, g_ez, g_hz)``: exciton energies relative to the mean bright exciton, the binding
+    energy negative, rates in 1/ps."""
+    import configparser
+    config = configparser.ConfigParser()
+    config.read(calibration_file)
+    to_mev = lambda wavelength_nm: 1239.8 * 1e3 / wavelength_nm
+    exciton = to_mev(float(config['EMISSION']['exciton_wavelength']))
+    biexciton = to_mev(float(config['EMISSION']['biexciton_wavelength']))
+    dark = to_mev(float(config['EMISSION']['dark_wavelength']))
+    fss_bright = float(config['SPLITTING']['fss_bright']) * 1e-3
+    fss_dark = float(config['SPLITTING']['fss_dark']) * 1e-3
+    gamma_e = 1 / float(config['LIFETIMES']['exciton'])
+    gamma_b = 1 / (float(config['LIFETIMES']['biexciton']) * 2)
+    g = [float(config['G_FACTORS'][k]) for k in ('g_ex', 'g_hx', 'g_ez', 'g_hz')]
+    dark_energy = dark - exciton
+    return (fss_bright / 2, -fss_bright / 2, dark_energy + fss_dark / 2, dark_energy - fss_dark / 2,
+            -(exciton - biexciton), gamma_e, gamma_b, 0, *g)

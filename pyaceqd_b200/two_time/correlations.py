@@ -119,6 +119,34 @@ def five_op_two_time(system, t_axis, *pulses, opA="|1><0|_2", opB="|1><0|_2", op
                          debug=debug, workers=workers, n_mto=2, t_start=t_start)
 
 
+def get_spectrum(g1, tau, dir="", plot=False):
+    """Spectrum under continuous-wave excitation from ``G1(tau)`` (reference ``:322-382``): the stationary offset
+    ``g1[-1]`` is removed, negative delays are the conjugates, then an FFT.  Returns ``(s_omega, energies)`` in meV,
+    both fft-shifted."""
+    import pyaceqd_b200.constants as constants
+    g1 = np.array(g1, dtype=complex)
+    dtau = np.abs(tau[1] - tau[0])
+    g1 = g1 - g1[-1]
+    g1 = np.concatenate((np.conj(np.flip(g1[1:])), g1))
+    tau = np.concatenate((-np.flip(tau[1:]), tau))
+    s_omega = np.fft.fftshift(np.real(np.fft.fft(g1)))
+    energies = np.fft.fftshift(2 * np.pi * constants.hbar * np.fft.fftfreq(len(g1), d=dtau))
+    if plot:
+        import matplotlib.pyplot as plt
+        for name, x, y, lim, labels in (
+                ("g1_tendsymm.png", tau, np.abs(g1), (-1, 1), ("Time (ps)", "|G1(t)|")),
+                ("spectrum_log.png", energies, np.log(np.abs(s_omega)), (-3, 3), ("Frequency (meV)", "S(omega)")),
+                ("spectrum_nolog.png", energies, np.abs(s_omega), (-3, 3), ("Frequency (meV)", "S(omega)"))):
+            plt.clf()
+            plt.plot(x, y)
+            plt.xlim(*lim)
+            plt.xlabel(labels[0])
+            plt.ylabel(labels[1])
+            plt.savefig(dir + name)
+        plt.clf()
+    return s_omega, energies
+
+
 def G2_spectral_integral(t1, tau, G):
     """Time-integrated second-order correlation ``int dt int dtau G(t, tau)`` on the given axes
     (what the consumers of ``three_op_two_time`` compute, e.g. ``pol_entanglement/G2.py:292-299``)."""
@@ -214,3 +242,137 @@ def tl_three_op_two_time(system, t_axis, *pulses, t_mem=10, opA="|1><0|_2", opB=
     A, B, C = op_to_matrix(opA), op_to_matrix(opB), op_to_matrix(opC)
     return _tl_correlation(system, t_axis, pulses, C, A, B, A @ B @ C, t_mem, tau_max, dt, rho0, options, use_dm,
                            (A, B, C) if fortran_only else None)
+
+
+# ------------------------------------------------------------------------------------ time-local maps with phonons
+def _phonon_maps(system, pulses, opA, opC, t_mem, dt, rho0, options):
+    """The stationary pieces both phonon variants start from (reference ``:875-885,1022-1033``): one dynamical-map
+    run over ``4 t_mem`` with the two operators applied at ``1.2 t_mem`` -- outside the memory of the start --
+    gives the stationary map before the operators (``tl_map``), the explicit maps of the first memory time and of
+    the memory time after the operators (``blocks``; the operators are part of ``blocks[1][0]``), and the
+    stationary map after them (``tl_map2``, the last step of the run)."""
+    from pyaceqd_b200.tools import calc_tl_dynmap_pseudo, extract_dms
+    mtos = [{"operator": opC, "applyFrom": "_left", "applyBefore": "false", "time": 1.2 * t_mem},
+            {"operator": opA, "applyFrom": "_right", "applyBefore": "false", "time": 1.2 * t_mem}]
+    result, dm = system(0, 4 * t_mem, *pulses, dt=dt, rho0=rho0, multitime_op=mtos, calc_dynmap=True, **options)
+    t_sim = np.round(result[0].real, 6)
+    tl = calc_tl_dynmap_pseudo(dm, t_sim)
+    tl_map, blocks = extract_dms(tl, t_sim, t_mem, [np.round(1.2 * t_mem, 6)])
+    return tl_map, np.array(blocks, dtype=complex), tl[-1]
+
+
+def _moved(opA, opC, t):
+    return [{"operator": opC, "applyFrom": "_left", "applyBefore": "false", "time": t},
+            {"operator": opA, "applyFrom": "_right", "applyBefore": "false", "time": t}]
+
+
+def tl_three_op_two_time_phonons(system, t_axis, *pulses, t_mem=10, opA="|1><0|_2", opB="|1><1|_2", opC="|0><1|_2",
+                                 tau_max=500, dt=0.1, rho0=np.array([[1, 0], [0, 0]], dtype=complex),
+                                 options={"lindblad": True, "phonons": True}, debug=False, fortran_only=False):
+    """``<A(t) B(t + tau) C(t)>`` with a phonon memory of ``t_mem`` from time-local maps (reference ``:866-1011``).
+
+    ``rho(t)`` comes from the explicit maps of the first memory time, then powers of the stationary map; the
+    ``tau`` axis from the explicit maps after the operators -- for ``t < t_mem`` those of a run with the operators
+    AT ``t`` (the start still inside the memory), else the stationary block -- then powers of ``tl_map2``.
+    All runs below ``t_mem`` are ONE batch, all ``tau`` chains one launch of the chain kernel."""
+    from pyaceqd_b200.tlmap import Programs
+    from pyaceqd_b200.tools import calc_tl_dynmap_pseudo, extract_dms, op_to_matrix
+    if not t_axis[0] == 0:
+        raise ValueError("t_axis must start at 0.")
+    t_axis = np.round(t_axis, 6)
+    A, B, C = op_to_matrix(opA), op_to_matrix(opB), op_to_matrix(opC)
+    tl_map, blocks, tl_map2 = _phonon_maps(system, pulses, opA, opC, t_mem, dt, rho0, options)
+    n_tauc = blocks.shape[1]
+    n_tau = int(tau_max / dt)
+    tau = np.linspace(0, tau_max, n_tau + 1)
+    dim = len(rho0[0])
+    NL = dim * dim
+    inside = np.where(t_axis < t_mem)[0]
+    with BatchExecutor() as ex:
+        futs = [ex.submit(system, 0, t_axis[i] + t_mem + 10 * dt, *pulses, dt=dt, rho0=rho0,
+                          multitime_op=_moved(opA, opC, t_axis[i]), calc_dynmap=True, suffix=int(i), **options)
+                for i in inside]
+        wait(futs)
+    pr = Programs(NL)
+    off_stat, off_tl2 = pr.add(blocks[1]), pr.add(tl_map2)
+    off_own = []
+    for i, f in zip(inside, futs):
+        result, dm = f.result()
+        t_sim = np.round(result[0].real, 6)
+        _, own = extract_dms(calc_tl_dynmap_pseudo(dm, t_sim), t_sim, t_mem, [t_axis[i]])
+        off_own.append(pr.add(own[1][:n_tauc]))
+    # rho on the simulation grid: n_tauc - 1 explicit maps, then the stationary one (reference :960-972)
+    k_of = [int(np.round(t / dt, 6)) for t in t_axis]
+    states = np.empty((max(k_of) + 1, NL), dtype=complex)
+    states[0] = np.asarray(rho0, dtype=complex).reshape(NL)
+    for k in range(max(k_of)):
+        states[k + 1] = (blocks[0][k] if k < n_tauc - 1 else tl_map) @ states[k]
+    G = np.zeros((len(t_axis), n_tau + 1), dtype=complex)
+    w_abc, w_b = (A @ B @ C).T.reshape(-1), B.T.reshape(-1)
+    for i, k in enumerate(k_of):
+        G[i, 0] = w_abc @ states[k]
+        first = off_own[i] if i < len(inside) else off_stat
+        n1 = min(n_tauc, n_tau)
+        pr.chain(states[k], [(first, n1, 1, 1), (off_tl2, n_tau - n1, 1, 0)])
+    out_vals, _ = pr.run(w=w_b[None])
+    G[:, 1:] = out_vals[:, :n_tau, 0]
+    return t_axis, tau, G
+
+
+def tl_threeoptwotime_phonons_dm(system, t_axis, *pulses, t_mem=10, opA="|1><0|_2", opB="|1><1|_2", opC="|0><1|_2",
+                                 tau_max=500, dt=0.1, rho0=np.array([[1, 0], [0, 0]], dtype=complex),
+                                 options={"lindblad": True, "phonons": True}, debug=False, fortran_only=False):
+    """As :func:`tl_three_op_two_time_phonons`, but for ``t <= t_mem`` the first ``t_mem`` of the ``tau`` axis is
+    the full dynamical map of a run with the operators at ``t`` applied to ``rho0`` (reference ``:1013-1185``) --
+    i.e. the trajectory itself, which is what is run here (one job per ``t``, ONE batch, instead of the NL + 1 of
+    a map) -- and, beyond ``t_mem``, ALL explicit maps of the first memory time before the stationary one."""
+    from pyaceqd_b200.tlmap import Programs
+    from pyaceqd_b200.tools import op_to_matrix
+    if not t_axis[0] == 0:
+        raise ValueError("t_axis must start at 0.")
+    t_axis = np.round(t_axis, 6)
+    A, B, C = op_to_matrix(opA), op_to_matrix(opB), op_to_matrix(opC)
+    tl_map, blocks, tl_map2 = _phonon_maps(system, pulses, opA, opC, t_mem, dt, rho0, options)
+    n_tauc = blocks.shape[1]
+    n_tau = int(tau_max / dt)
+    tau = np.linspace(0, tau_max, n_tau + 1)
+    dim = len(rho0[0])
+    NL = dim * dim
+    inside = np.where(t_axis <= t_mem)[0]
+    opts = dict(options)
+    opts["output_ops"] = [_product(opA, opB, opC)] + ["|%d><%d|_%d" % (c, r, dim) for r in range(dim) for c in range(dim)]
+    with BatchExecutor() as ex:
+        futs = [ex.submit(system, 0, t_axis[i] + t_mem, *pulses, dt=dt, rho0=rho0,
+                          multitime_op=_moved(opA, opC, t_axis[i]), suffix=int(i), **opts) for i in inside]
+        wait(futs)
+    pr = Programs(NL)
+    off_stat, off_tl2 = pr.add(blocks[1]), pr.add(tl_map2)
+    G = np.zeros((len(t_axis), n_tau + 1), dtype=complex)
+    w_abc, w_b = (A @ B @ C).T.reshape(-1), B.T.reshape(-1)
+    for i, f in zip(inside, futs):
+        res = f.result()
+        k = int(np.round(t_axis[i] / dt, 6))
+        rho = res[2:2 + NL].T                      # rho[k] = vec(rho(t_k)), row-major (output |c><r| reads rho_rc)
+        G[i, 0] = res[1][k]                        # the operator product at the operator time (before they act)
+        n_map = min(rho.shape[0] - 1 - k, n_tau)
+        G[i, 1:1 + n_map] = rho[k + 1:k + 1 + n_map] @ w_b
+        pr.chain(rho[k + n_map], [(off_tl2, n_tau - n_map, 1, 0)])
+    v = np.asarray(rho0, dtype=complex).reshape(NL)
+    for m in blocks[0]:
+        v = m @ v
+    k_done = n_tauc
+    for i in range(len(inside), len(t_axis)):
+        k = int(np.round(t_axis[i] / dt, 6))
+        v = np.linalg.matrix_power(tl_map, k - k_done) @ v
+        k_done = k
+        G[i, 0] = w_abc @ v
+        n1 = min(n_tauc, n_tau)
+        pr.chain(v, [(off_stat, n1, 1, 1), (off_tl2, n_tau - n1, 1, 0)])
+    out_vals, _ = pr.run(w=w_b[None])
+    for i in range(len(t_axis)):
+        if i < len(inside):
+            n_map = min(int(np.round((t_axis[i] + t_mem) / dt, 6)) - int(np.round(t_axis[i] / dt, 6)), n_tau)
+            G[i, 1 + n_map:] = out_vals[i, :n_tau - n_map, 0]
+        else:
+            G[i, 1:] = out_vals[i, :n_tau, 0]
+    return t_axis, tau, G

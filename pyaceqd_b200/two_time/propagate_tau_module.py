@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import numpy as np
 
+import pyaceqd_b200.constants as constants
 from pyaceqd_b200.tlmap import Programs, left_superop, maps_first, right_superop, rle, trace_functional
 
 
@@ -120,9 +121,10 @@ def calc_twotime_phonon_block(dm_taucs2, dm_sep1, dm_sep2, dm_s, rho_init, n_tb,
     o_t = pr.add(np.ascontiguousarray(np.transpose(taucs, (2, 3, 0, 1)).reshape(n_tauc * n_map, NL, NL))) \
         if n_tauc else 0
     steps = np.arange(K)
+    align = 1 if constants.phonon_block_aligned else 0      # see constants.py: the Fortran resets one step early
     for i, (v, j) in enumerate(zip(states, js)):
         j1 = int(j) + 1                                     # Fortran's 1-based j_array(i)
-        first = n_tb - j1                                   # steps before `j + j_start == n_tb + 1` fires
+        first = n_tb - j1 + align                           # steps before `j + j_start == n_tb + 1` fires
         if first >= 1:
             pos = np.where(steps < first, steps + 1, (steps - first) % n_tb + 1)
             own = steps < first

@@ -14,13 +14,14 @@ Two computation routes, as in the reference:
   the (t, tau) grid is filled by matrix-vector chains -- the reference's Fortran helper
   (``calc_onetime_parallel_block``, ``:741,770``), here the chain kernel of ``csrc/tlmap.cu``.
 
-The phonon variants of the time-local route (``G1_tl_phonons`` / ``G2_tl_phonons`` ``:513-713``)
-are not rebuilt yet; their kernel (``calc_twotime_phonon_block``) is.
+With phonons the time-local route (``G1_tl_phonons`` / ``G2_tl_phonons`` ``:513-713``) needs one dynamical-map
+run per ``t`` inside the memory time: all of them are ONE GPU batch here, then ``calc_twotime_phonon_block``.
 """
 from __future__ import annotations
 
 import numpy as np
 
+from pyaceqd_b200.batch import BatchExecutor, wait
 from pyaceqd_b200.pulses import PulseTrain
 from pyaceqd_b200.sweeps import at_time, run_sweep
 from pyaceqd_b200.timebin.timebin import TimeBin
@@ -216,14 +217,133 @@ class Indistinguishability(Purity):
         tau, grid = self._tl_grid(np.identity(self.dim), self.sigma_xdag_mat, self.sigma_x_mat)
         return tau, np.trapezoid(np.abs(grid) ** 2, self.t_axis_complete, axis=0)
 
+    # ------------------------------------------------------------------ time-local route with phonons
+    def get_tl_phonons(self, mtos=[], t_mtos=[]):
+        """Stationary map and explicit blocks of ``gaussian_t + t_mem`` length at the start and after every
+        operator time of one run over ``2.1 (gaussian_t + t_mem)`` (reference ``:415-424``)."""
+        tmem = self.gaussian_t + self.t_mem
+        result, dm = self.system(0, 2.1 * tmem, multitime_op=mtos, calc_dynmap=True, **self.options)
+        t = np.round(result[0].real, 6)
+        tl_map, pieces = extract_dms(calc_tl_dynmap_pseudo(dm, t), t, tmem, t_MTOs=t_mtos)
+        if any(len(b) != len(pieces[0]) for b in pieces):
+            raise ValueError("the run over 2.1 (gaussian_t + t_mem) ends before the memory after the operators does: "
+                             "0.1 (gaussian_t + t_mem) must cover 6 time steps")
+        return tl_map, np.array(pieces, dtype=complex)
+
+    def _periodic_states(self, block, tl_map):
+        periods = self.factor_t + self.factor_tau
+        n_tb = int(self.tb / self.dt)
+        t_total = np.linspace(0, periods * self.tb, periods * n_tb + 1)
+        rho = np.zeros((len(t_total), self.dim ** 2), dtype=complex)
+        rho[0, 0] = 1.0
+        n_explicit = len(block)
+        for k in range(len(t_total) - 1):
+            i = k % n_tb                       # explicit map i for i < len(block) - 1, as in the reference loops
+            rho[k + 1] = (block[i] if i < n_explicit - 1 else tl_map) @ rho[k]
+        return t_total, rho
+
+    def calc_timedynamics_tl_phonons(self):
+        """Reference ``:426-447``."""
+        tl_map, pieces = self.get_tl_phonons(mtos=[], t_mtos=[])
+        t_total, rho = self._periodic_states(pieces[0], tl_map)
+        return t_total, rho.reshape(len(t_total), self.dim, self.dim)
+
+    def simple_propagation_tl_phonons(self, return_whole=False):
+        """``G0(tau)`` from the per-period maps of the phonon run (reference ``:350-393``)."""
+        tl_map, pieces = self.get_tl_phonons(mtos=[], t_mtos=[])
+        _, rho = self._periodic_states(pieces[0], tl_map)
+        rho = rho.reshape(-1, self.dim, self.dim)
+        n_tau = self._n_tau()
+        t2 = np.linspace(0, self.factor_tau * self.tb, n_tau + 1)
+        t1 = np.linspace(0, self.factor_t * self.tb, int(self.factor_t * self.tb / self.dt) + 1)
+        val = np.real(np.einsum("ab,tba->t", self.sigma_xdag_mat @ self.sigma_x_mat, rho))
+        return t2, self._uncorrelated(val, len(t1), t1, len(t2))
+
+    def _moved(self, mtos, t_mto):
+        out = []
+        for m in mtos:
+            m = dict(m)
+            m["time"] = t_mto
+            out.append(m)
+        return out
+
+    def get_dm2_phonons(self, mtos, t_mto, suffix=1):
+        """Explicit maps of the ``gaussian_t + t_mem`` after operators applied at ``t_mto`` (reference ``:475-486``)."""
+        tmem = self.gaussian_t + self.t_mem
+        result, dm = self.system(0, t_mto + tmem + 2 * self.dt, multitime_op=self._moved(mtos, t_mto),
+                                 calc_dynmap=True, suffix=suffix, **self.options)
+        t = np.round(result[0].real, 6)
+        return extract_dms(calc_tl_dynmap_pseudo(dm, t), t, tmem, t_MTOs=[t_mto])[1][1]
+
+    def _dm2_advanced_run(self, submit, mtos, t_mto, suffix):
+        return submit(self.system, 0, self.gaussian_t + 2 * self.t_mem + 2 * self.dt,
+                      multitime_op=self._moved(mtos, t_mto), calc_dynmap=True, suffix=suffix, **self.options)
+
+    def _dm2_advanced_maps(self, run, t_mto):
+        result, dm = run
+        t = np.round(result[0].real, 6)
+        memory = np.max([self.gaussian_t + self.t_mem - t_mto, self.t_mem])
+        return extract_dms(calc_tl_dynmap_pseudo(dm, t), t, memory, t_MTOs=[t_mto])[1][1]
+
+    def get_dm2_phonons_advanced(self, mtos, t_mto, suffix=1):
+        """As :meth:`get_dm2_phonons` with the shortest run that still covers the memory: it ends at ``gaussian_t +
+        2 t_mem`` and keeps ``max(gaussian_t + t_mem - t_mto, t_mem)`` of maps (reference ``:488-511``)."""
+        return self._dm2_advanced_maps(self._dm2_advanced_run(lambda f, *a, **k: f(*a, **k), mtos, t_mto, suffix), t_mto)
+
+    def _tl_phonon_grid(self, mtos, opa, opb, opc):
+        """Shared body of :meth:`G1_tl_phonons` / :meth:`G2_tl_phonons` (reference ``:513-644,646-712``): the
+        stationary blocks from a run with the operators beyond all memory, one dynamical-map run per ``t1`` inside
+        the memory -- ALL of them in one GPU batch -- and the (t, tau) grid as chains on the chain kernel."""
+        t_apply = self.gaussian_t + self.t_mem + 5 * self.dt
+        tl_map, pieces = self.get_tl_phonons(mtos=self._moved(mtos, t_apply), t_mtos=[np.round(t_apply, 6)])
+        tau_max = self.tb * self.factor_tau
+        n_tau = int(tau_max / self.dt)
+        inside = np.where(self.t1 <= (self.gaussian_t + self.t_mem))[0]
+        own = np.zeros((len(inside),) + pieces[0].shape, dtype=complex)
+        own[:, :] = tl_map                       # shorter blocks are padded with the stationary map (:527-529)
+        with BatchExecutor(max_workers=self.workers) as ex:
+            runs = [self._dm2_advanced_run(ex.submit, mtos, np.round(self.t1[i], 6), int(i)) for i in range(len(inside))]
+            wait(runs)
+        for i, f in enumerate(runs):
+            part = self._dm2_advanced_maps(f.result(), np.round(self.t1[i], 6))
+            own[i, :len(part)] = part
+        t_end = self.t_axis_complete[-1] + tau_max
+        t_axis = np.linspace(0, t_end, int(t_end / self.dt) + 1)
+        rho0 = np.zeros(self.dim ** 2, dtype=complex)
+        rho0[0] = 1.0
+        grid = propagate_tau_module.calc_twotime_phonon_block(
+            dm_taucs2=np.asfortranarray(own.transpose(2, 3, 0, 1)),
+            dm_sep1=np.asfortranarray(pieces[0].transpose(1, 2, 0)),
+            dm_sep2=np.asfortranarray(pieces[1].transpose(1, 2, 0)), dm_s=tl_map, rho_init=rho0,
+            n_tb=int(self.tb / self.dt), nx_tau=self.factor_tau, dim=self.dim, opa=opa, opb=opb, opc=opc,
+            time=t_axis, time_sparse=self.t_axis_complete)
+        return np.linspace(0, tau_max, n_tau + 1), grid
+
+    def G1_tl_phonons(self):
+        """Reference ``:513-644``."""
+        mtos = [{"operator": self.sigma_x, "applyFrom": "_left", "applyBefore": "false"}]
+        tau, grid = self._tl_phonon_grid(mtos, np.identity(self.dim), self.sigma_xdag_mat, self.sigma_x_mat)
+        return tau, np.trapezoid(np.abs(grid) ** 2, self.t_axis_complete, axis=0)
+
+    def G2_tl_phonons(self):
+        """Reference ``:646-712``."""
+        mtos = [{"operator": self.sigma_x, "applyFrom": "_left", "applyBefore": "false"},
+                {"operator": self.sigma_xdag, "applyFrom": "_right", "applyBefore": "false"}]
+        a, c = self.sigma_xdag_mat, self.sigma_x_mat
+        tau, grid = self._tl_phonon_grid(mtos, a, a @ c, c)
+        return tau, np.trapezoid(np.abs(grid), self.t_axis_complete, axis=0)
+
     def calc_indistinguishability(self):
         """Returns ``(indistinguishability, single-photon purity)`` (reference ``:776-822``)."""
-        if self.dm and self.options.get("phonons"):
-            raise NotImplementedError("time-local route with phonons (G1_tl_phonons / G2_tl_phonons) is not rebuilt "
-                                      "yet; use dm=False (direct route) with phonons")
-        t1, g1 = self.G1_tl() if self.dm else self.G1()
-        t2, g2 = self.G2_tl() if self.dm else self.G2()
-        t0, g0 = self.simple_propagation_tl() if self.dm else self.simple_propagation()
+        phonons = bool(self.dm and self.options.get("phonons"))
+        if phonons:
+            t1, g1 = self.G1_tl_phonons()
+            t2, g2 = self.G2_tl_phonons()
+            t0, g0 = self.simple_propagation_tl_phonons()
+        else:
+            t1, g1 = self.G1_tl() if self.dm else self.G1()
+            t2, g2 = self.G2_tl() if self.dm else self.G2()
+            t0, g0 = self.simple_propagation_tl() if self.dm else self.simple_propagation()
         g11, g12 = _ratio_first_to_second_peak(t1, g1, self.tb, self.dt)
         g21, g22 = _ratio_first_to_second_peak(t2, g2, self.tb, self.dt)
         g01, g02 = _ratio_first_to_second_peak(t0, g0, self.tb, self.dt)

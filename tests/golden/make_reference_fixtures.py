@@ -159,6 +159,49 @@ pg_out["units"] = {k: float(g._Units(v, u)) for k, (v, u) in
                    {"meV": (1.3, "meV"), "nm_abs": (801.0, "nm"), "nm_rel": (-0.7, "nm"), "hz": (0.4, "Hz")}.items()}
 out["pulsegenerator"] = pg_out
 
+# --- measured-dot calibration files (tools.py:307-344, pulsegenerator.py:66-86, six_level_system/linear.py:33-34)
+CALIBRATION = """[EMISSION]
+exciton_wavelength = 795.1
+biexciton_wavelength = 796.2
+dark_wavelength = 795.9
+[SPLITTING]
+fss_bright = 12.0
+fss_dark = 2.0
+[LIFETIMES]
+exciton = 180
+biexciton = 110
+dark = 5000
+[G_FACTORS]
+g_ex = -0.6
+g_hx = -0.3
+g_ez = -0.75
+g_hz = -2.1
+"""
+cal_tmp = tempfile.mkdtemp() + "/"
+with open(cal_tmp + "dot.ini", "w") as fh:
+    fh.write(CALIBRATION)
+cal = {"text": CALIBRATION, "values": [float(v) for v in rt.read_calibration_file(cal_tmp + "dot.ini")]}
+gc = rpg.PulseGenerator(0, 50, 0.5, calibration_file=cal_tmp + "dot.ini")
+names = ("central_wavelength", "exciton_x_emission", "exciton_y_emission", "biexciton_x_emission", "biexciton_y_emission",
+         "dark_x_emission", "dark_y_emission", "tpe_resonance")
+cal["pulsegenerator"] = {n: float(getattr(gc, n)) for n in names}
+gc.set_rotating_frame(800.0)
+gc.set_rotating_frame(cal_tmp + "dot.ini")
+cal["pulsegenerator_after_rf"] = {n: float(getattr(gc, n)) for n in names + ("central_energy", "central_frequency")}
+from pyaceqd.six_level_system.linear import sixls_linear as ref_sixls  # noqa: E402
+ref_sixls(0, 4.0, pc, dt=0.25, lindblad=True, bx=1.5, bz=0.5, temp_dir=cal_tmp, suffix="cal", prepare_only=True,
+          calibration_file=cal_tmp + "dot.ini")
+cal["sixls_param"] = {n: open(cal_tmp + n).read().replace(cal_tmp, "<TMP>") for n in sorted(os.listdir(cal_tmp))
+                      if n.endswith(".param")}
+out["calibration"] = cal
+
+# --- CW spectrum from G1(tau) (two_time/correlations.py:322-382)
+import pyaceqd.two_time.correlations as rc  # noqa: E402
+tau_s = np.linspace(0, 40.0, 161)
+g1_s = (0.3 * np.exp(-0.1 * tau_s) * np.exp(-1j * 0.8 * tau_s) + 0.1 * np.exp(-0.02 * tau_s) + 0.05).astype(complex)
+s_om, e_om = rc.get_spectrum(g1_s, tau_s)
+out["get_spectrum"] = dict(tau=tau_s.tolist(), g1=cplx(g1_s), s=np.asarray(s_om).tolist(), e=np.asarray(e_om).tolist())
+
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_host.json"), "w") as fh:
     json.dump(out, fh, default=lambda o: o.item() if hasattr(o, "item") else o.tolist())
 print("wrote reference_host.json")

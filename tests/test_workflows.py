@@ -10,6 +10,8 @@ from oracle_backend import oracle_backend
 from pyaceqd_b200.pulses import ChirpedPulse
 
 TOL = 1e-10
+# pseudo-inverses of maps that lost rank to an operator amplify the 1e-13 engine-vs-oracle difference
+WORKFLOW_TOL = {"tl_corr_phonons": 1e-7, "purity_phonons": 1e-7}
 
 
 # ------------------------------------------------------------------------------------ scenarios
@@ -139,6 +141,65 @@ def scenario_tl_correlations(tmp):
     return {"tau": tau, "g1_tl": g1_tl, "g2_tl": g2_tl, "g2_f": g2_f, "g1": g1, "g2": g2, "g2_stat": g2_stat}
 
 
+PHONON_OPTS = {"lindblad": True, "phonons": True, "t_mem": 1.0, "ae": 5.0, "temperature": 20, "threshold": 6,
+               "use_infinite": True}
+
+
+def scenario_tl_correlations_phonons(tmp):
+    """Phonon variants of the time-local G2 (reference correlations.py:866-1185) next to the direct MTO sweep: a
+    CW-driven emitter coupled to a QD phonon bath whose process tensor remembers 1 ps."""
+    from pyaceqd_b200.pulses import CWLaser
+    from pyaceqd_b200.two_level_system.tls import tls
+    from pyaceqd_b200.two_time.correlations import (three_op_two_time, tl_three_op_two_time_phonons,
+                                                    tl_threeoptwotime_phonons_dm)
+    p = CWLaser(e0=0.6)
+    opts = dict(PHONON_OPTS, gamma_e=0.3, temp_dir=tmp, pt_file=tmp + "cw.pt")
+    t_axis = np.round(np.arange(0, 4.01, 0.5), 6)
+    rho0 = np.array([[1, 0], [0, 0]], dtype=complex)
+    _, tau, g2 = three_op_two_time(tls, t_axis, p, tau_max=3.0, dt=0.1, options=dict(opts))
+    _, _, g2_tl = tl_three_op_two_time_phonons(tls, t_axis, p, t_mem=1.5, tau_max=3.0, dt=0.1, rho0=rho0,
+                                               options=dict(opts))
+    _, _, g2_dm = tl_threeoptwotime_phonons_dm(tls, t_axis, p, t_mem=1.5, tau_max=3.0, dt=0.1, rho0=rho0,
+                                               options=dict(opts))
+    free = dict(opts, phonons=False)
+    free.pop("pt_file")
+    _, _, g2_free = three_op_two_time(tls, t_axis, p, tau_max=3.0, dt=0.1, options=free)
+    return {"tau": tau, "g2": g2, "g2_tl": g2_tl, "g2_dm": g2_dm, "g2_free": g2_free}
+
+
+def _indist_phonons(tmp, dm):
+    from pyaceqd_b200.two_level_system.tls import tls
+    from pyaceqd_b200.two_time.purity import Indistinguishability
+    p = ChirpedPulse(tau_0=0.15, e_start=0, alpha=0, t0=0.8, e0=1.0)
+    opts = dict(PHONON_OPTS, gamma_e=1.5, temp_dir=tmp, pt_file=tmp + "train.pt")
+    return Indistinguishability(tls, "|0><1|_2", "|1><0|_2", p, dt=0.05, tb=4.0, dt_small=0.05, gaussian_t=2.5,
+                                simple_exp=False, dt_big=0.5, options=opts, dm=dm, t_mem=1.0)
+
+
+def scenario_purity_phonons(tmp):
+    """Indistinguishability with phonons: direct route, the time-local route as the reference's Fortran walks the
+    periods (purity.py:513-712) and the same with the period boundary aligned (constants.phonon_block_aligned)."""
+    import pyaceqd_b200.constants as constants
+    direct = _indist_phonons(tmp, dm=False)
+    ind, pur = direct.calc_indistinguishability()
+    _, _, grid = direct.G2(return_whole=True)
+    tl = _indist_phonons(tmp, dm=True)
+    ind_tl, pur_tl = tl.calc_indistinguishability()
+    mtos = [{"operator": tl.sigma_x, "applyFrom": "_left", "applyBefore": "false"},
+            {"operator": tl.sigma_xdag, "applyFrom": "_right", "applyBefore": "false"}]
+    a, c = tl.sigma_xdag_mat, tl.sigma_x_mat
+    constants.phonon_block_aligned = True
+    try:
+        _, grid_al = tl._tl_phonon_grid(mtos, a, a @ c, c)
+        ind_al, pur_al = tl.calc_indistinguishability()
+    finally:
+        constants.phonon_block_aligned = False
+    _, rho = tl.calc_timedynamics_tl_phonons()
+    occ = direct.calc_timedynamics()[2]
+    return {"ind": ind, "pur": pur, "ind_tl": ind_tl, "pur_tl": pur_tl, "ind_al": ind_al, "pur_al": pur_al,
+            "grid": grid, "grid_al": np.abs(grid_al), "occ_tl": rho[:, 1, 1].real, "occ": occ.real}
+
+
 def scenario_timebin_tl(tmp):
     """Time-local route of the time-bin density matrix next to the direct (multi-time-operator) route."""
     from pyaceqd_b200.four_level_system.linear import biexciton
@@ -176,7 +237,7 @@ def scenario_adapters(tmp):
             "dark4": darkmodel(0, 5, p, delta_xd=0.5, **kw), "dark3": darkmodel3(0, 5, p, delta_xd=0.5, **kw)}
 
 
-SCENARIOS = {"adapters": scenario_adapters, "timebin_tl": scenario_timebin_tl, "tl_corr": scenario_tl_correlations, "dynmap": scenario_dynmap, "purity": scenario_purity, "g1": scenario_g1, "polent": scenario_polent, "timebin": scenario_timebin,
+SCENARIOS = {"tl_corr_phonons": scenario_tl_correlations_phonons, "purity_phonons": scenario_purity_phonons, "adapters": scenario_adapters, "timebin_tl": scenario_timebin_tl, "tl_corr": scenario_tl_correlations, "dynmap": scenario_dynmap, "purity": scenario_purity, "g1": scenario_g1, "polent": scenario_polent, "timebin": scenario_timebin,
              "onephoton": scenario_onephoton, "rabi": scenario_rabi}
 
 
@@ -317,6 +378,30 @@ def test_tl_correlations_equal_direct_sweeps(tmp_path):
     assert np.allclose(g[:, 0], 0) and np.all(np.abs(g[:, 1:]) < 1e-12)    # G2 of a single emitter stays 0 undriven
 
 
+def test_tl_correlations_with_phonons_follow_direct_sweeps(tmp_path):
+    """With a bath memory the time-local routes are exact up to the memory cut (1.5 ps here for a PT that remembers
+    1 ps): they follow the direct sweeps far closer than the phonon-free dynamics do."""
+    out, eng = _run_oracle("tl_corr_phonons", tmp_path)
+    assert np.abs(out["g2_tl"] - out["g2"]).max() < 5e-5
+    assert np.abs(out["g2_dm"] - out["g2"]).max() < 5e-5
+    assert np.abs(out["g2_free"] - out["g2"]).max() > 5e-3            # the bath matters in this scenario
+    # the dynamical-map runs inside the memory time are ONE batch of runs plus one of their NL unit vectors
+    assert any(c[0] == 3 * 4 for c in eng.calls)
+
+
+def test_indistinguishability_with_phonons(tmp_path):
+    out, eng = _run_oracle("purity_phonons", tmp_path)
+    # per-period maps reproduce the pulse-train dynamics
+    n = min(len(out["occ"]), len(out["occ_tl"]))
+    assert np.abs(out["occ"][:n] - out["occ_tl"][:n]).max() < 2e-3
+    # aligned at the period boundary, the map route fills the same (t, tau) grid as the direct one (the last t sits
+    # ON the boundary and is left out); the reference's own walk returns to the period start one step early
+    assert np.abs(out["grid"][:-1] - out["grid_al"][:-1]).max() < 1e-3
+    assert abs(out["pur_al"] - out["pur"]) < 2e-3 and abs(out["ind_al"] - out["ind"]) < 2e-3
+    assert abs(out["pur_tl"] - out["pur"]) < 1e-2 and abs(out["ind_tl"] - out["ind"]) < 1e-2
+    assert any(c[0] == 17 * 4 for c in eng.calls)                     # all t inside the memory: one batch of maps
+
+
 def test_purity_and_indistinguishability_routes(tmp_path):
     out, eng = _run_oracle("purity", tmp_path)
     assert abs(out["pur"] - out["pur2"]) < 1e-13
@@ -359,7 +444,7 @@ def test_workflow_gpu_equals_oracle_backend(name, tmp_path):
     assert sorted(got) == sorted(want)
     for k in want:
         d = np.abs(np.asarray(got[k]) - np.asarray(want[k])).max()
-        assert d < TOL, (name, k, d)
+        assert d < WORKFLOW_TOL.get(name, TOL), (name, k, d)
 
 
 @pytest.mark.gpu
