@@ -139,3 +139,45 @@ def run_jobs_sharded(engine, prob, pt, jobs, device=None, group=None, **kw) -> L
         out.append(np.ascontiguousarray(full[off:off + r].T))
         off += r
     return out
+
+
+def run_arrays_sharded(engine, prob, pt, arr, device=None, group=None, **kw):
+    """:func:`run_jobs_sharded` for the array route (``Engine.run_arrays``): contiguous, step-count-balanced row
+    blocks of the job table per rank, one all-gather of the kept rows.  Returns ``(out, out_off, n_rows)`` of the
+    WHOLE sweep on every rank."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return engine.run_arrays(prob, pt, arr, **kw)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if device is None and dist.get_backend(group) == "nccl":
+        device = torch.device("cuda", int(getattr(engine, "device", 0)))
+    h = hashlib.sha256()
+    for a in (arr.n_steps, arr.tail, arr.n_ev, arr.ev_step, arr.shift):
+        h.update(np.ascontiguousarray(a, dtype=np.int64).tobytes())
+    mine = torch.from_numpy(np.frombuffer(h.digest()[:16], dtype=np.int64).copy())
+    if device is not None:
+        mine = mine.to(device)
+    allv = torch.empty(world * 2, dtype=torch.int64, device=mine.device)
+    dist.all_gather_into_tensor(allv, mine, group=group)
+    allv = allv.cpu().numpy().reshape(world, 2)
+    if not (allv == allv[0]).all():
+        raise RuntimeError("run_arrays_sharded: the ranks submitted different job lists (count / lengths / order); "
+                           "distributed sharding needs the same sweep on every rank")
+    n_out = prob.n_out
+    n_steps = arr.n_steps.astype(np.int64)
+    n_rows = np.where(arr.tail > 0, np.minimum(n_steps + 1, arr.tail), n_steps + 1).astype(np.int64)
+    blocks = balanced_blocks(np.maximum(1, n_steps), world)
+    a, b = blocks[rank]
+    if b > a:
+        out, _, _ = engine.run_arrays(prob, pt, arr.rows(a, b), **kw)
+        local = np.ascontiguousarray(out).reshape(-1, n_out)
+    else:
+        local = np.zeros((0, n_out), complex)
+    counts = [int(n_rows[x:y].sum()) for (x, y) in blocks]
+    full = all_gather_blocks(local, counts, device=device, group=group)
+    out_off = np.zeros(len(n_rows), dtype=np.int64)
+    out_off[1:] = np.cumsum(n_rows[:-1] * n_out)
+    return np.ascontiguousarray(full).reshape(-1), out_off, n_rows

@@ -21,6 +21,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
+from . import planner
 from .jobs import FieldTable, Job
 from .problem import Problem
 from .process_tensor import ProcessTensor, trivial_pt
@@ -527,235 +528,45 @@ class Engine:
         _check(self.lib.aceqd_ctx_sync(self.ctx), "aceqd_ctx_sync")
 
     # -------------------------------------------------------------- planning
-    @staticmethod
-    def _tables_of(jobs: Sequence[Job]):
-        """Pack the jobs' drive tables into [n_sets, 3, n_samples]; identical table objects share
-        a set.  All tables of one batch must live on one sampling grid."""
-        set_of_job, sets, key_to_set = [], [], {}
-        grid = None
-        nmax = 1
-        for jb in jobs:
-            key = tuple(id(jb.tables.get(p)) if jb.tables.get(p) is not None else 0 for p in ("x", "y", "rf"))
-            if key not in key_to_set:
-                key_to_set[key] = len(sets)
-                sets.append(jb.tables)
-                for tb in jb.tables.values():
-                    if tb is None:
-                        continue
-                    g = (float(tb.t0), float(tb.dt))
-                    if grid is None:
-                        grid = g
-                    elif abs(grid[0] - g[0]) > 1e-12 or abs(grid[1] - g[1]) > 1e-15:
-                        raise ValueError("all drive tables of one batch must share t0 and dt")
-                    nmax = max(nmax, len(tb.values))
-            set_of_job.append(key_to_set[key])
-        if grid is None:
-            grid = (0.0, 1.0)
-        packed = np.zeros((len(sets), 3, nmax), dtype=np.complex128)
-        for s, tabs in enumerate(sets):
-            for k, pol in enumerate(("x", "y", "rf")):
-                tb = tabs.get(pol)
-                if tb is None or len(tb.values) == 0:
-                    continue
-                n = len(tb.values)
-                packed[s, k, :n] = tb.values
-                packed[s, k, n:] = tb.values[-1]  # end value held (oracle.sample_field)
-        return packed, np.asarray(set_of_job, dtype=np.int32), grid
-
-    def _mto_products(self, prob: Problem, job: Job, mats: list, cache: dict):
-        """Group a job's MTOs by step; returns {step: (sb_id, sa_id)} with matrix-pool ids."""
-        by_step: Dict[int, Tuple[list, list]] = {}
-        for m in job.mtos:
-            k = job.mto_step(m)
-            by_step.setdefault(k, ([], []))[0 if m.before else 1].append(m.superop)
-        out = {}
-        for k, (bef, aft) in by_step.items():
-            ids = []
-            for lst in (bef, aft):
-                if not lst:
-                    ids.append(-1)
-                    continue
-                idkey = tuple(id(s) for s in lst)   # superoperators are cached objects (Problem.parse_mtos)
-                if idkey in cache:
-                    ids.append(cache[idkey][0])
-                    continue
-                prod = np.eye(prob.NL, dtype=complex)
-                for s in lst:  # file order: first listed acts first
-                    prod = s @ prod
-                key = prod.tobytes()
-                if key not in cache:
-                    cache[key] = len(mats)
-                    mats.append(_c128(prod))
-                cache[idkey] = (cache[key], lst)   # keeps the operands alive so the ids stay unique
-                ids.append(cache[key])
-            out[k] = (ids[0], ids[1])
-        return out
-
     def plan(self, prob: Problem, pt: ProcessTensor, jobs: Sequence[Job], *, kernel: str = "auto",
              t_eval: str = "half_mid", fork: bool = True, tile_T: Optional[int] = None,
              cluster: Optional[int] = None, trunk_kernel: Optional[str] = None):
-        """Build the trunk batch (may be None) and the main batch for `jobs`."""
-        if not jobs:
-            raise ValueError("no jobs")
-        dt = float(jobs[0].dt)
-        for jb in jobs:
-            if abs(jb.dt - dt) > 1e-15:
-                raise ValueError("all jobs of one batch must share dt")
-            if len({jb.mto_step(m) for m in jb.mtos}) > MAX_OVR - 2:
-                raise ValueError(f"more than {MAX_OVR - 2} distinct multitime-operator times in one job")
-        packed, set_of_job, grid = self._tables_of(jobs)
+        """Levels of trajectory descriptors for ``jobs`` (:mod:`pyaceqd_b200.planner`): ``(common, plan)``."""
+        return self.plan_arrays(prob, pt, planner.arrays_from_jobs(prob, jobs), kernel=kernel, t_eval=t_eval, fork=fork,
+                                tile_T=tile_T, cluster=cluster, trunk_kernel=trunk_kernel)
+
+    def plan_arrays(self, prob: Problem, pt: ProcessTensor, arr: "planner.JobArrays", *, kernel: str = "auto",
+                    t_eval: str = "half_mid", fork: bool = True, tile_T: Optional[int] = None,
+                    cluster: Optional[int] = None, trunk_kernel: Optional[str] = None):
         chi_pad = -(-pt.chi_max // 8) * 8
-        NL, n_out = prob.NL, prob.n_out
-        kernel = resolve_kernel(kernel, NL)
-        off1, off2 = T_EVAL[t_eval]
+        common = dict(prob=prob, pt=pt, dt=arr.dt, t0=arr.t0, off=T_EVAL[t_eval], packed=arr.packed, grid=arr.grid,
+                      mats=arr.mats, chi_pad=chi_pad, kernel=resolve_kernel(kernel, prob.NL), tile_T=tile_T,
+                      cluster=cluster, trunk_kernel=trunk_kernel, rho0s=arr.rho0s)
+        return common, planner.plan_levels(arr, prob.n_out, fork=fork)
 
-        # ---- absolute time origin: every job starts its own PT at its t_start (ACE: ta)
-        # jobs are grouped by (drive set, t_start); absolute step 0 of a group = its t_start
-        t0_ref = min(jb.t_start for jb in jobs)
-
-        mats: list = []
-        mcache: dict = {}
-        seqs, entries, trajs = [], [], []
-        trunk_seqs, trunk_trajs, snap_steps = [], [], []
-        n_slots = 0
-        groups: Dict[Tuple[int, float, int], List[int]] = {}
-        rho0s = [_c128(prob.rho0).reshape(NL)]      # slot 0: the problem's own initial state
-        rho0_slot = {}
-        for i, jb in enumerate(jobs):
-            slot = 0
-            if jb.rho0 is not None:
-                key = _c128(jb.rho0).reshape(NL).tobytes()
-                if key not in rho0_slot:
-                    rho0_slot[key] = len(rho0s)
-                    rho0s.append(_c128(jb.rho0).reshape(NL))
-                slot = rho0_slot[key]
-            groups.setdefault((int(set_of_job[i]), round(jb.t_start / dt), slot), []).append(i)
-
-        out_off = np.zeros(len(jobs), dtype=np.int64)
-        # only the last `tail_rows` output rows of a job are kept (consumers index from the end)
-        n_rows = np.asarray([min(jb.n_steps + 1, jb.tail_rows) if jb.tail_rows else jb.n_steps + 1
-                             for jb in jobs], dtype=np.int64)
-        g0 = np.asarray([jb.n_steps + 1 for jb in jobs], dtype=np.int64) - n_rows   # first global row kept
-        out_off[1:] = np.cumsum(n_rows[:-1] * n_out)
-        out_elems = int(np.sum(n_rows * n_out))
-        copy_from_trunk = []  # (job, rows, trunk_job_index)
-
-        for (sset, _, r0), members in groups.items():
-            # a separate time origin per group keeps `step` = steps since the group's t_start
-            t_start = jobs[members[0]].t_start
-            step_shift = int(round((t_start - t0_ref) / dt))  # table/time bookkeeping only
-            if abs(t_start - t0_ref - step_shift * dt) > 1e-9 * max(1.0, abs(dt)):
-                raise ValueError(f"t_start={t_start} is not a whole number of steps (dt={dt}) after the earliest "
-                                 f"start {t0_ref} of the batch: run it as a separate batch")
-            mto_maps = {i: self._mto_products(prob, jobs[i], mats, mcache) for i in members}
-            # a run that shares a longer drive table with others must not see samples past its own last one (the
-            # reference writes the pulse file of every run on np.arange(t_start, t_end, dt)): the rows whose half
-            # steps reach beyond it -- the last two -- get explicit entries evaluated on the truncated table
-            clamp_of = {}
-            for i in members:
-                jb = jobs[i]
-                n_tab = max([len(tb.values) for tb in jb.tables.values() if tb is not None] + [0])
-                if 0 < jb.table_len < n_tab:
-                    clamp_of[i] = int(jb.table_len)
-                    for k in (jb.n_steps - 1, jb.n_steps):
-                        if k >= 0:
-                            mto_maps[i].setdefault(k, (-1, -1))
-            first = {i: (min(mto_rows) if (mto_rows := [k for k, v in mto_maps[i].items() if v != (-1, -1)]) else None)
-                     for i in members}
-            use_fork = fork and len(members) > 1 and any(f is not None and f > 0 for f in first.values())
-            if use_fork:
-                fork_steps = sorted({f for f in first.values() if f is not None and f > 0})
-                trunk_len = max(max(fork_steps),
-                                max([jobs[i].n_steps for i in members if first[i] is None] + [0]))
-                q_trunk = len(trunk_seqs)
-                trunk_seqs.append((sset, step_shift, trunk_len + 1, 0))
-                slot_of_step = {f: n_slots + k for k, f in enumerate(fork_steps)}
-                trunk_trajs.append(dict(seq=q_trunk, off=0, step0=0, n_steps=trunk_len, init_kind=0,
-                                        init_index=r0, ovr=[], snap=(len(snap_steps), len(fork_steps), n_slots),
-                                        shift=step_shift, members=members))
-                snap_steps.extend(fork_steps)
-                n_slots += len(fork_steps)
-                # main batch: one shared MTO-free sequence for the group, branches index into it
-                t_end_max = max(jobs[i].n_steps for i in members)
-                q_main = len(seqs)
-                seqs.append((sset, step_shift, t_end_max + 1, 0))
-                for i in members:
-                    jb = jobs[i]
-                    f = first[i]
-                    ovr = []
-                    for k, (sb, sa) in sorted(mto_maps[i].items()):
-                        ovr.append((k, len(entries)))
-                        entries.append((sset, step_shift + k, sb, sa, 1 if k > 0 else 0,
-                                        clamp_of.get(i, 0) if k >= jb.n_steps - 1 else 0))
-                    if f is None or f == 0:
-                        trajs.append(dict(job=i, seq=q_main, off=0, step0=0, n_steps=jb.n_steps, init_kind=0,
-                                          init_index=r0, ovr=ovr, row0=0, out_from=int(g0[i])))
-                    elif g0[i] >= f:     # every kept row lies on the branch
-                        trajs.append(dict(job=i, seq=q_main, off=f, step0=f, n_steps=jb.n_steps - f,
-                                          init_kind=1, init_index=slot_of_step[f],
-                                          ovr=[(k - f, e) for k, e in ovr], row0=0, out_from=int(g0[i] - f)))
-                    else:                # rows g0..f-1 come from the trunk
-                        trajs.append(dict(job=i, seq=q_main, off=f, step0=f, n_steps=jb.n_steps - f,
-                                          init_kind=1, init_index=slot_of_step[f],
-                                          ovr=[(k - f, e) for k, e in ovr], row0=int(f - g0[i]), out_from=0))
-                        copy_from_trunk.append((i, int(f - g0[i]), len(trunk_trajs) - 1, int(g0[i])))
-            else:
-                for i in members:
-                    jb = jobs[i]
-                    q = len(seqs)
-                    seqs.append((sset, step_shift, jb.n_steps + 1, 0))
-                    ovr = []
-                    for k, (sb, sa) in sorted(mto_maps[i].items()):
-                        ovr.append((k, len(entries)))
-                        entries.append((sset, step_shift + k, sb, sa, 1 if k > 0 else 0,
-                                        clamp_of.get(i, 0) if k >= jb.n_steps - 1 else 0))
-                    trajs.append(dict(job=i, seq=q, off=0, step0=0, n_steps=jb.n_steps, init_kind=0,
-                                      init_index=r0, ovr=ovr, row0=0, out_from=int(g0[i])))
-
-        common = dict(prob=prob, pt=pt, dt=dt, t0=t0_ref, off=(off1, off2), packed=packed, grid=grid,
-                      mats=mats, chi_pad=chi_pad, kernel=kernel, tile_T=tile_T, cluster=cluster, trunk_kernel=trunk_kernel,
-                      rho0s=np.asarray(rho0s))
-        main = dict(seqs=seqs, entries=entries, trajs=trajs, snap_steps=[], n_slots=0)
-        trunk = None
-        if trunk_trajs:
-            trunk = dict(seqs=trunk_seqs, entries=[], trajs=trunk_trajs, snap_steps=snap_steps, n_slots=n_slots)
-        return common, trunk, main, (out_off, n_rows, out_elems, copy_from_trunk)
-
-    def _materialise(self, common, part, out_off_of_traj, out_elems, out_buf=None) -> _Plan:
+    def _materialise(self, common, lv: "planner.Level", out_off_of_traj, out_elems, n_slots=0, out_buf=None) -> _Plan:
         prob, pt = common["prob"], common["pt"]
-        NL, n_out = prob.NL, prob.n_out
-        seqs = np.zeros(len(part["seqs"]), dtype=SEQ_DT)
-        for q, (sset, step0, ln, fhp) in enumerate(part["seqs"]):
-            seqs[q] = (sset, step0, ln, fhp)
+        NL = prob.NL
+        seqs = np.zeros(len(lv.seqs), dtype=SEQ_DT)
+        seqs["set"], seqs["step0"], seqs["len"], seqs["first_has_prev"] = lv.seqs.T
         seq_base = np.zeros(len(seqs) + 1, dtype=np.int64)
         seq_base[1:] = np.cumsum(seqs["len"].astype(np.int64))
-        entries = np.zeros(len(part["entries"]), dtype=ENTRY_DT)
-        for e, tup in enumerate(part["entries"]):
-            entries[e] = tup
-        tr = part["trajs"]
-        trajs = np.zeros(len(tr), dtype=TRAJ_DT)
-        for b, t in enumerate(tr):
-            r = trajs[b]
-            r["ent0"] = seq_base[t["seq"]] + t["off"]
-            r["out_off"] = out_off_of_traj[b]
-            r["step0"] = t["step0"]
-            r["n_steps"] = t["n_steps"]
-            r["init_kind"] = t["init_kind"]
-            r["init_index"] = t["init_index"]
-            r["n_ovr"] = len(t["ovr"])
-            for k, (st, en) in enumerate(t["ovr"]):
-                r["ovr_step"][k] = st
-                r["ovr_ent"][k] = en
-            r["out_from"] = t.get("out_from", 0)
-            if "snap" in t:
-                r["snap_off"], r["snap_cnt"], r["snap_slot0"] = t["snap"]
+        entries = np.zeros(len(lv.entries), dtype=ENTRY_DT)
+        if len(entries):
+            for k, name in enumerate(("set", "step", "sb", "sa", "has_prev", "clamp")):
+                entries[name] = lv.entries[:, k]
+        n = lv.n_traj
+        trajs = np.zeros(n, dtype=TRAJ_DT)
+        trajs["ent0"] = seq_base[lv.seq] + lv.off
+        trajs["out_off"] = out_off_of_traj
+        for name in ("step0", "n_steps", "init_kind", "init_index", "n_ovr", "ovr_step", "ovr_ent", "out_from",
+                     "snap_off", "snap_cnt", "snap_slot0"):
+            trajs[name] = getattr(lv, name)
         # tiling: sort by (step0, n_steps) so that tiles are homogeneous in absolute time
         order = np.lexsort((trajs["n_steps"], trajs["step0"]))
-        blk_of_alpha = self.problem_handle(prob, pt)[1]
-        rows_per_block = np.bincount(blk_of_alpha).tolist()
         t_max = self.max_tile(NL, common["chi_pad"])
         kernel = common["kernel"]
-        if len(part["snap_steps"]) and kernel in ("small", "splitk"):
+        if len(lv.snap_steps) and kernel in ("small", "splitk"):
             # trunks (few trajectories that write snapshots): not a small-bond kernel job, and a single trajectory is
             # faster on the tile kernel's pass-split cluster than on the split-K cluster
             kernel = common.get("trunk_kernel") or "tile"
@@ -763,13 +574,13 @@ class Engine:
             kernel = "splitk"     # one trajectory does not fit a CTA: spread its bond columns over a cluster
         if t_max < 1 and kernel != "splitk":
             raise EngineError(f"NL={NL}, chi={common['chi_pad']} does not fit the step kernel's shared memory")
-        T, C = self._tile_and_cluster(prob, pt, len(tr), t_max, common["tile_T"], common.get("cluster"), kernel)
-        n_tiles = -(-len(tr) // T)
+        T, C = self._tile_and_cluster(prob, pt, n, t_max, common["tile_T"], common.get("cluster"), kernel)
+        n_tiles = -(-n // T)
         tile_traj = np.full(n_tiles * T, -1, dtype=np.int32)
-        tile_traj[:len(tr)] = order
+        tile_traj[:n] = order
         mats = _c128(np.asarray(common["mats"]).reshape(-1, NL, NL)) if common["mats"] else np.zeros((0, NL, NL), complex)
         rho0 = _c128(common["rho0s"]).reshape(-1, NL)
-        snap_steps = np.asarray(part["snap_steps"], dtype=np.int32)
+        snap_steps = np.ascontiguousarray(lv.snap_steps, dtype=np.int32)
         out = out_buf if out_buf is not None else np.zeros(out_elems, dtype=np.complex128)
         packed = common["packed"]
         b = _Batch()
@@ -782,11 +593,11 @@ class Engine:
         b.n_entries, b.entries = len(entries), (entries.ctypes.data if len(entries) else None)
         b.n_mto_mats, b.mto_mats = len(mats), (mats.ctypes.data if len(mats) else None)
         b.n_rho0, b.rho0s = rho0.shape[0], rho0.ctypes.data
-        b.n_traj, b.trajs = len(trajs), trajs.ctypes.data
+        b.n_traj, b.trajs = n, trajs.ctypes.data
         b.tile_T, b.n_tiles, b.tile_traj = T, n_tiles, tile_traj.ctypes.data
         b.n_snap_steps = len(snap_steps)
         b.snap_steps = snap_steps.ctypes.data if len(snap_steps) else None
-        b.n_snap_slots = part["n_slots"]
+        b.n_snap_slots = n_slots      # the pool of the WHOLE plan in every launch: later levels read earlier slots
         b.out_elems, b.out = out_elems, out.ctypes.data
         b.device_resident = 0
         b.kernel = KERNELS[kernel]
@@ -795,6 +606,57 @@ class Engine:
                      out=out, out_off=np.asarray(out_off_of_traj), n_rows=trajs["n_steps"] + 1)
 
     # -------------------------------------------------------------- running
+    def run_arrays(self, prob: Problem, pt: Optional[ProcessTensor], arr: "planner.JobArrays", *, kernel: str = "auto",
+                   t_eval: str = "half_mid", fork: bool = True, tile_T: Optional[int] = None,
+                   cluster: Optional[int] = None, trunk_kernel: Optional[str] = None, tail_reduce=None):
+        """Propagate the jobs of ``arr``.  Returns ``(out, out_off, n_rows)``: job ``i`` owns ``out[out_off[i]:
+        out_off[i] + n_rows[i] * n_out]``, rows x outputs -- or, with ``tail_reduce``, ``[n_jobs, n_pairs]``."""
+        if pt is None:
+            pt = self._trivial(prob)
+        hp, _ = self.problem_handle(prob, pt)
+        hpt = self.pt_handle(pt)
+        common, pl = self.plan_arrays(prob, pt, arr, kernel=kernel, t_eval=t_eval, fork=fork, tile_T=tile_T,
+                                      cluster=cluster, trunk_kernel=trunk_kernel)
+        n_out = prob.n_out
+        root_out = None
+        for d, lv in enumerate(pl.levels[:-1]):
+            rows = lv.n_steps + 1 - lv.out_from
+            off = np.zeros(lv.n_traj, dtype=np.int64)
+            off[1:] = np.cumsum(rows[:-1] * n_out)
+            tp = self._materialise(common, lv, off, int(np.sum(rows * n_out)), n_slots=pl.n_slots)
+            _check(self.lib.aceqd_propagate_batch(self.ctx, hp, hpt, ctypes.byref(tp.batch)),
+                   "aceqd_propagate_batch(trunk)" if lv.group is not None else "aceqd_propagate_batch(fork level)")
+            self._log_launch("trunk" if lv.group is not None else "fork", prob, common["chi_pad"], tp)
+            if lv.group is not None:
+                root_out = (tp.out, off)
+        main = pl.levels[-1]
+        # a branch writes its rows at the tail of its job's block
+        traj_out_off = pl.out_off[main.job] + main.row0 * n_out
+        if tail_reduce is not None and not len(pl.copies):
+            pairs, spacing = tail_reduce
+            ch = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+            red = np.zeros((main.n_traj, len(ch)), dtype=np.complex128)
+            mp = self._materialise(common, main, traj_out_off, pl.out_elems, n_slots=pl.n_slots, out_buf=red.reshape(-1))
+            mp.batch.n_reduce, mp.batch.reduce_ch = len(ch), ch.ctypes.data
+            mp.batch.reduce_spacing, mp.batch.reduce_out = float(spacing), red.ctypes.data
+            mp.batch.out_elems = pl.out_elems
+            _check(self.lib.aceqd_propagate_batch(self.ctx, hp, hpt, ctypes.byref(mp.batch)),
+                   "aceqd_propagate_batch(tail_reduce)")
+            self._log_launch("main", prob, common["chi_pad"], mp)
+            return red
+        mp = self._materialise(common, main, traj_out_off, pl.out_elems, n_slots=pl.n_slots)
+        _check(self.lib.aceqd_propagate_batch(self.ctx, hp, hpt, ctypes.byref(mp.batch)),
+               "aceqd_propagate_batch")
+        self._log_launch("main", prob, common["chi_pad"], mp)
+        out = mp.out
+        for (job, n_copy, ti, row_first) in pl.copies:
+            a = root_out[1][ti] + row_first * n_out
+            out[pl.out_off[job]: pl.out_off[job] + n_copy * n_out] = root_out[0][a: a + n_copy * n_out]
+        if tail_reduce is not None:      # rows partly on the trunk: reduce on the host (same arithmetic)
+            return np.asarray([tail_trapezoid(out[o: o + r * n_out].reshape(r, n_out).T, *tail_reduce)
+                               for o, r in zip(pl.out_off, pl.n_rows)])
+        return out, pl.out_off, pl.n_rows
+
     def run_jobs(self, prob: Problem, pt: Optional[ProcessTensor], jobs: Sequence[Job], *,
                  kernel: str = "auto", t_eval: str = "half_mid", fork: bool = True,
                  tile_T: Optional[int] = None, cluster: Optional[int] = None,
@@ -806,56 +668,13 @@ class Engine:
         ``pol_entanglement/G2.py:507-533``): ``pairs = [(ch_tau, ch_zero), ...]`` output channels; the outputs stay in
         HBM and per job one ``[len(pairs)]`` array comes back -- ``spacing`` times the trapezoid over the job's kept rows,
         the first row (tau = 0) read from ``ch_zero``, the others from ``ch_tau``."""
-        if pt is None:
-            pt = self._trivial(prob)
-        hp, _ = self.problem_handle(prob, pt)
-        hpt = self.pt_handle(pt)
-        common, trunk, main, (out_off, n_rows, out_elems, copy_list) = self.plan(
-            prob, pt, jobs, kernel=kernel, t_eval=t_eval, fork=fork, tile_T=tile_T, cluster=cluster,
-            trunk_kernel=trunk_kernel)
+        res = self.run_arrays(prob, pt, planner.arrays_from_jobs(prob, jobs), kernel=kernel, t_eval=t_eval, fork=fork,
+                              tile_T=tile_T, cluster=cluster, trunk_kernel=trunk_kernel, tail_reduce=tail_reduce)
+        if tail_reduce is not None:
+            return [r.copy() for r in res]
+        out, out_off, n_rows = res
         n_out = prob.n_out
-        trunk_out = None
-        if trunk is not None:
-            t_rows = np.asarray([t["n_steps"] + 1 for t in trunk["trajs"]], dtype=np.int64)
-            t_off = np.zeros(len(t_rows), dtype=np.int64)
-            t_off[1:] = np.cumsum(t_rows[:-1] * n_out)
-            tp = self._materialise(common, trunk, t_off, int(np.sum(t_rows * n_out)))
-            _check(self.lib.aceqd_propagate_batch(self.ctx, hp, hpt, ctypes.byref(tp.batch)),
-                   "aceqd_propagate_batch(trunk)")
-            self._log_launch("trunk", prob, common["chi_pad"], tp)
-            trunk_out = (tp.out, t_off, t_rows)
-        # branch b writes its rows at the tail of its job's block
-        traj_out_off = [out_off[t["job"]] + t["row0"] * n_out for t in main["trajs"]]
-        if tail_reduce is not None and not copy_list:
-            pairs, spacing = tail_reduce
-            ch = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
-            red = np.zeros((len(main["trajs"]), len(ch)), dtype=np.complex128)
-            mp = self._materialise(common, main, traj_out_off, out_elems, out_buf=red.reshape(-1))
-            mp.batch.n_reduce, mp.batch.reduce_ch = len(ch), ch.ctypes.data
-            mp.batch.reduce_spacing, mp.batch.reduce_out = float(spacing), red.ctypes.data
-            mp.batch.out_elems = out_elems
-            _check(self.lib.aceqd_propagate_batch(self.ctx, hp, hpt, ctypes.byref(mp.batch)),
-                   "aceqd_propagate_batch(tail_reduce)")
-            self._log_launch("main", prob, common["chi_pad"], mp)
-            res = [None] * len(jobs)
-            for k, t in enumerate(main["trajs"]):
-                res[t["job"]] = red[k].copy()
-            return res
-        mp = self._materialise(common, main, traj_out_off, out_elems)
-        _check(self.lib.aceqd_propagate_batch(self.ctx, hp, hpt, ctypes.byref(mp.batch)),
-               "aceqd_propagate_batch")
-        self._log_launch("main", prob, common["chi_pad"], mp)
-        out = mp.out
-        for (job, n_copy, ti, row_first) in copy_list:
-            a = trunk_out[1][ti] + row_first * n_out
-            out[out_off[job]: out_off[job] + n_copy * n_out] = trunk_out[0][a: a + n_copy * n_out]
-        res = []
-        for i in range(len(jobs)):
-            blk = out[out_off[i]: out_off[i] + n_rows[i] * n_out].reshape(n_rows[i], n_out)
-            res.append(np.ascontiguousarray(blk.T))
-        if tail_reduce is not None:      # rows partly on the trunk: reduce on the host (same arithmetic)
-            return [tail_trapezoid(r, *tail_reduce) for r in res]
-        return res
+        return [np.ascontiguousarray(out[o: o + r * n_out].reshape(r, n_out).T) for o, r in zip(out_off, n_rows)]
 
     def _log_launch(self, kind: str, prob: Problem, chi_pad: int, plan: "_Plan"):
         if not self.record_timings:

@@ -404,6 +404,65 @@ def run_requests(reqs: List[Request], distributed: Optional[bool] = None, tail_r
     return results
 
 
+class SweepResult:
+    """Results of :func:`run_sweep_arrays`: ``res[i]`` is what the ``i``-th ``system(...)`` call returns (time row +
+    one row per output operator, only the job's kept rows); :meth:`last_rows` gives the final row of every job as
+    one ``[n_jobs, n_out]`` array without building them."""
+
+    def __init__(self, out, out_off, n_rows, n_out, t_start, dt, n_steps):
+        self.out, self.out_off, self.n_rows, self.n_out = out, out_off, n_rows, n_out
+        self.t_start, self.dt, self.n_steps = t_start, dt, n_steps
+
+    def __len__(self):
+        return len(self.out_off)
+
+    def __getitem__(self, i):
+        r, o = int(self.n_rows[i]), int(self.out_off[i])
+        res = np.empty((1 + self.n_out, r), dtype=complex)
+        res[0] = self.t_start + self.dt * np.arange(int(self.n_steps[i]) + 1 - r, int(self.n_steps[i]) + 1)
+        res[1:] = self.out[o: o + r * self.n_out].reshape(r, self.n_out).T
+        return res
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def last_rows(self):
+        idx = (self.out_off + (self.n_rows - 1) * self.n_out)[:, None] + np.arange(self.n_out)[None, :]
+        return self.out[idx]
+
+
+def run_sweep_arrays(template: Request, t_end, mto_templates, mto_times, tails, tail_reduce=None, distributed=None):
+    """A sweep whose calls differ from ``template`` (the deferred first call) only in ``t_end`` and in the times of
+    the SAME multi-time operators (``mto_times[J, M]``, NaN = absent): planned from arrays
+    (:func:`pyaceqd_b200.planner.arrays_from_sweep`), no per-call Python work.  Same results as submitting the calls
+    one by one, including the per-run length of sampled pulse files (reference ``:213``)."""
+    from pyaceqd_b200 import planner
+    from pyaceqd_b200.engine import default_engine
+    eng = default_engine()
+    prob, pt, job0 = template.problem, template.pt, template.job
+    t_end = np.asarray(t_end, dtype=float)
+    tables = template.table_maker(float(t_end.max()))
+    table_len = None
+    if template.sampled:          # len(np.arange(t_start, t_end, dt)) of every run
+        table_len = np.ceil((t_end - job0.t_start) / job0.dt).astype(np.int64)
+    parsed = prob.parse_mtos([dict(m, time=0.0) for m in mto_templates])
+    arr = planner.arrays_from_sweep(prob, dt=job0.dt, t_start=job0.t_start, t_end=t_end,
+                                    superops=[m.superop for m in parsed], before=[m.before for m in parsed],
+                                    mto_times=mto_times, tails=tails, tables=tables, table_len=table_len)
+    from pyaceqd_b200 import distributed as _dist
+    if distributed is None:
+        distributed = os.environ.get("ACEQD_DISTRIBUTED", "0") == "1"
+    if distributed and tail_reduce is None and _dist.is_multi_rank() and arr.n_jobs > 1:
+        # the sweep shards over the ranks (one GPU each) and is all-gathered once; every rank returns the full result
+        res = _dist.run_arrays_sharded(eng, prob, pt, arr)
+    else:
+        res = eng.run_arrays(prob, pt, arr, tail_reduce=tail_reduce)
+    if tail_reduce is not None:
+        return res
+    out, out_off, n_rows = res
+    return SweepResult(out, out_off, n_rows, prob.n_out, job0.t_start, job0.dt, arr.n_steps)
+
+
 def _run_dynmaps(eng, reqs: List[Request]):
     """``DynamicalMap.E`` (reference ``:328-335``) for requests of one (problem, PT) group: the physical runs in one
     batch, the NL unit vectors of EVERY request as initial states with identity outputs in a second one.  Layout as

@@ -35,6 +35,13 @@ def run_sweep(system, jobs: Sequence[dict], *pulses, options: Optional[dict] = N
     every job spec ``{"t0", "tend", "mtos", "output_ops", "tail"}`` in one batch; return results.
     ``tail_reduce = (pairs, spacing)``: per job the tau integrals of its tail (reduced on the device) instead."""
     opts = dict(options or {})
+    uniform = _uniform_sweep(jobs)
+    if uniform is not None:      # the usual case: the jobs differ in numbers only -> rows of arrays, no per-job call
+        t0, tends, templates, times, output_ops, tails = uniform
+        res = run_sweep_arrays(system, t0, tends, templates, times, *pulses, output_ops=output_ops, tails=tails,
+                               options=opts, workers=workers, tail_reduce=tail_reduce, _generic=False)
+        if res is not None:
+            return list(res)
     with BatchExecutor(max_workers=workers, tail_reduce=tail_reduce) as ex:
         futs = []
         for i, jb in enumerate(jobs):
@@ -45,6 +52,65 @@ def run_sweep(system, jobs: Sequence[dict], *pulses, options: Optional[dict] = N
                                        multitime_op=jb["mtos"], suffix=i, **kw))
         wait(futs)
     return [f.result() for f in futs]
+
+
+def _uniform_sweep(jobs):
+    """``(t0, tends, operator templates, times[J, M], output_ops, tails)`` if all jobs apply the same operators (in
+    the same file order) to the same outputs from the same start, else None."""
+    if len(jobs) < 2:
+        return None
+    as_list = lambda m: [m] if isinstance(m, dict) else list(m or [])
+    first = as_list(jobs[0]["mtos"])
+    sig = [(m.get("operator"), m.get("applyFrom", ""), str(m.get("applyBefore", "false")).strip().lower()) for m in first]
+    t0, outs = jobs[0].get("t0", 0), jobs[0].get("output_ops")
+    times = np.empty((len(jobs), len(first)))
+    for i, jb in enumerate(jobs):
+        ms = as_list(jb["mtos"])
+        if len(ms) != len(sig) or jb.get("t0", 0) != t0 or jb.get("output_ops") != outs:
+            return None
+        for k, m in enumerate(ms):
+            if (m.get("operator"), m.get("applyFrom", ""), str(m.get("applyBefore", "false")).strip().lower()) != sig[k] \
+                    or "time" not in m:
+                return None
+            times[i, k] = m["time"]
+    templates = [{k: v for k, v in m.items() if k != "time"} for m in first]
+    return (t0, np.asarray([jb["tend"] for jb in jobs], dtype=float), templates, times, outs,
+            np.asarray([jb.get("tail", 0) or 0 for jb in jobs], dtype=np.int64))
+
+
+def run_sweep_arrays(system, t0, tends, mto_templates, mto_times, *pulses, output_ops=None, tails=0,
+                     options: Optional[dict] = None, workers=None, tail_reduce=None, _generic=True):
+    """The same sweep as :func:`run_sweep` for jobs that differ only in numbers: job ``i`` is
+    ``system(t0, tends[i], *pulses, multitime_op=[dict(m, time=mto_times[i][k]) for k, m in enumerate(mto_templates)],
+    output_ops=output_ops, **options)`` (a NaN time drops the operator).  Only the first call goes through the
+    adapter; the others are rows of arrays (``general_system.run_sweep_arrays``).  An adapter that does not defer
+    (it post-processes its result) gets the calls one by one, like :func:`run_sweep`."""
+    from pyaceqd_b200.general_system import general_system as gs
+    tends = np.asarray(tends, dtype=float)
+    mto_times = np.asarray(mto_times, dtype=float).reshape(len(tends), len(mto_templates))
+    tails_arr = np.broadcast_to(np.asarray(tails, dtype=np.int64), tends.shape)
+    opts = dict(options or {})
+    if output_ops is not None:
+        opts["output_ops"] = output_ops
+
+    def mtos_of(i):
+        return [at_time(m, float(t)) for m, t in zip(mto_templates, mto_times[i]) if not np.isnan(t)]
+
+    sink: list = []
+    prev = getattr(gs._capture, "sink", None)
+    gs._capture.sink = sink
+    try:
+        first = system(t0, float(tends[0]), *pulses, multitime_op=mtos_of(0), suffix=0, **opts)
+    except Exception:      # noqa: BLE001 - an adapter that chokes on the placeholder: the generic route decides
+        first = None
+    finally:
+        gs._capture.sink = prev
+    if not isinstance(first, gs.Request) or first.calc_dynmap:
+        if not _generic:
+            return None
+        jobs = [{"t0": t0, "tend": float(tends[i]), "mtos": mtos_of(i), "tail": int(tails_arr[i])} for i in range(len(tends))]
+        return run_sweep(system, jobs, *pulses, options=opts, workers=workers, tail_reduce=tail_reduce)
+    return gs.run_sweep_arrays(first, tends, mto_templates, mto_times, tails_arr, tail_reduce=tail_reduce)
 
 
 def tail_series(res, n_after: int, i_tau: int = 1, i_zero: int = 2) -> np.ndarray:

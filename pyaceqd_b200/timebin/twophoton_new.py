@@ -17,7 +17,7 @@ from __future__ import annotations
 import numpy as np
 
 import pyaceqd_b200.constants as constants
-from pyaceqd_b200.sweeps import at_time, run_sweep, tail_series
+from pyaceqd_b200.sweeps import at_time, run_sweep, run_sweep_arrays, tail_series
 from pyaceqd_b200.timebin.timebin import TimeBin
 from pyaceqd_b200.timebin.twophoton_tl import TimeLocalTimebin
 from pyaceqd_b200.tools import concurrence, construct_t, simple_t_gaussian
@@ -86,32 +86,26 @@ class TwoPhotonTimebinNew(TimeLocalTimebin, TimeBin):
         (file) order -- the order resolves coinciding times (``:436-438``) -- and the trajectory ends at
         ``t2 + tb`` or ``t1 + tb``.  Returns the matrix of final output values: the first output, or
         the second one on the diagonal ``t2 = t1`` if ``special_first`` (``:549-552``)."""
-        t1 = self.t1
+        t1 = np.asarray(self.t1, dtype=float)
         n = len(t1)
         when = {"t1": lambda a, b: a, "t2": lambda a, b: b, "t1+tb": lambda a, b: a + self.tb,
                 "t2+tb": lambda a, b: b + self.tb}
         vals = np.zeros((n, n), dtype=complex)
-        pending, index = [], []
-
-        def flush():
-            if not pending:
-                return
-            res = run_sweep(self.system, pending, options=self.options, workers=self.workers)
-            for (i, j), r in zip(index, res):
-                vals[i, i + j] = r[2][-1] if (special_first and j == 0) else r[1][-1]
-            pending.clear()
-            index.clear()
-
-        for i in range(n):
-            for j in range(n - i):
-                a, b = t1[i], t1[i + j]
-                pending.append({"tend": when[tend_when](a, b),
-                                "mtos": [at_time(m, when[w](a, b)) for m, w in mtos_with_when],
-                                "output_ops": output_ops, "tail": 1})
-                index.append((i, j))
-            if len(pending) >= _TRI_CHUNK:
-                flush()
-        flush()
+        ii, jj = np.triu_indices(n)                    # row-major: all t2 of one t1 are neighbours
+        templates = [m for m, _ in mtos_with_when]
+        # whole t1 rows per GPU batch: the pairs of one t1 share their stretch up to t2 (two-level forking)
+        row_end = np.cumsum(n - np.arange(n))
+        lo = 0
+        while lo < len(ii):
+            hi = int(row_end[min(np.searchsorted(row_end, lo + _TRI_CHUNK), n - 1)])
+            a, b = t1[ii[lo:hi]], t1[jj[lo:hi]]
+            times = np.stack([when[w](a, b) for _, w in mtos_with_when], axis=1)
+            res = run_sweep_arrays(self.system, 0, when[tend_when](a, b), templates, times, output_ops=output_ops,
+                                   tails=1, options=self.options, workers=self.workers)
+            last = res.last_rows() if hasattr(res, "last_rows") else np.array([[x[-1] for x in r[1:]] for r in res])
+            diag = ii[lo:hi] == jj[lo:hi]
+            vals[ii[lo:hi], jj[lo:hi]] = np.where(diag, last[:, 1], last[:, 0]) if special_first else last[:, 0]
+            lo = hi
         return vals
 
     def _integrate_triangular(self, vals):

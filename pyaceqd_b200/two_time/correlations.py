@@ -16,6 +16,7 @@ from __future__ import annotations
 import numpy as np
 
 from pyaceqd_b200.batch import BatchExecutor, wait
+from pyaceqd_b200.sweeps import run_sweep_arrays
 
 
 def _product(*ops):
@@ -63,27 +64,23 @@ def _ops_two_time(system, t_axis, *pulses, mtos=[], tau_max=500, dt=0.1,
     if t_start > 0:
         raise ValueError("t_start > 0 is not supported yet. Use t_start<=0 to e.g. reach a stationary state "
                          "before applying the MTO.")
-    fixed = [dict(m) for m in mtos[n_mto:]]
-    t1 = t_axis
+    t1 = np.asarray(t_axis, dtype=float)
     n_tau = int(tau_max / dt)
     tau = np.linspace(0, tau_max, n_tau + 1)
+    # one call per t1, as the reference submits them -- but only the first goes through the adapter, the others are
+    # rows of (end time, operator times): file order of a call's operator list = moving ones first, then the fixed
+    templates = [dict(m) for m in mtos[:n_mto]] + [dict(m) for m in mtos[n_mto:]]
+    times = np.empty((len(t1), len(templates)))
+    times[:, :n_mto] = t1[:, None]
+    for k, m in enumerate(mtos[n_mto:]):
+        times[:, n_mto + k] = m["time"]
+    res = run_sweep_arrays(system, t_start, t1 + tau_max, templates, times, *pulses, tails=n_tau + 1,
+                           options=dict(options, dt=dt), workers=workers)
     G = np.empty((len(t1), len(tau)), dtype=complex)
-    with BatchExecutor(max_workers=workers) as executor:
-        futures = []
-        for i, t1_i in enumerate(t1):
-            moving = []
-            for m in mtos[:n_mto]:
-                m = dict(m)
-                m["time"] = t1_i
-                moving.append(m)
-            futures.append(executor.submit(system, t_start, t1_i + tau_max, *pulses, dt=dt, suffix=i,
-                                           multitime_op=moving + [dict(m) for m in fixed], **options))
-        wait(futures)
-    for j, f in enumerate(futures):
-        res = f.result()
-        G[j, 1:] = res[1][-n_tau:]
-        G[j, 0] = res[2][-(n_tau + 1)]
-    return t1, tau, G
+    for j, r in enumerate(res):
+        G[j, 1:] = r[1][-n_tau:]
+        G[j, 0] = r[2][-(n_tau + 1)]
+    return t_axis, tau, G
 
 
 def two_op_two_time(system, t_axis, *pulses, opA="|1><0|_2", opB="|0><1|_2", tau_max=500, dt=0.1,

@@ -34,6 +34,40 @@ class OracleEngine:
             return [tail_trapezoid(o, *kw["tail_reduce"]) for o in out]
         return out
 
+    def run_arrays(self, prob, pt, arr, **kw):
+        """The array route (``Engine.run_arrays``): every row of the job table becomes an UN-forked oracle run, its
+        merged operator products re-issued as multi-time operators at their steps."""
+        from pyaceqd_b200.jobs import FieldTable, Job
+        from pyaceqd_b200.problem import MTO
+        jobs = []
+        tabs_of_set = {}
+        for j in range(arr.n_jobs):
+            s = int(arr.set_id[j])
+            if s not in tabs_of_set:
+                tabs_of_set[s] = {pol: FieldTable(arr.grid[0], arr.grid[1], arr.packed[s, k].copy())
+                                  for k, pol in enumerate(("x", "y", "rf")) if np.any(arr.packed[s, k] != 0)}
+            t_start = arr.t0 + int(arr.shift[j]) * arr.dt
+            mtos = []
+            for e in range(int(arr.n_ev[j])):
+                t = t_start + int(arr.ev_step[j, e]) * arr.dt
+                if arr.ev_sb[j, e] >= 0:
+                    mtos.append(MTO(arr.mats[arr.ev_sb[j, e]], t, True))
+                if arr.ev_sa[j, e] >= 0:
+                    mtos.append(MTO(arr.mats[arr.ev_sa[j, e]], t, False))
+            jb = Job(t_start, t_start + int(arr.n_steps[j]) * arr.dt, arr.dt, tables=tabs_of_set[s], mtos=mtos,
+                     tail_rows=int(arr.tail[j]))
+            jb.table_len = int(arr.clamp[j])
+            if arr.r0[j]:
+                jb.rho0 = arr.rho0s[arr.r0[j]]
+            jobs.append(jb)
+        outs = self.run_jobs(prob, pt, jobs, **kw)
+        if kw.get("tail_reduce") is not None:
+            return np.asarray(outs)
+        n_rows = np.asarray([o.shape[1] for o in outs], dtype=np.int64)
+        out_off = np.zeros(len(outs), dtype=np.int64)
+        out_off[1:] = np.cumsum(n_rows[:-1] * prob.n_out)
+        return np.concatenate([o.T.reshape(-1) for o in outs]), out_off, n_rows
+
     def expm(self, mats):
         a = np.asarray(mats, dtype=complex)
         a = a[None] if a.ndim == 2 else a

@@ -425,14 +425,15 @@ def test_planner_tail_rows_and_fork_bookkeeping():
             Job(0.0, 4.0, 0.1, tables=tabs, mtos=mto(3.5), tail_rows=11),     # tail reaches back into the trunk
             Job(0.0, 5.0, 0.1, tables=tabs, mtos=mto(2.0))]                   # all rows
     eng = Engine.__new__(Engine)
-    common, trunk, main, (out_off, n_rows, out_elems, copies) = Engine.plan(eng, prob, trivial_pt(1), jobs)
-    assert n_rows.tolist() == [11, 11, 51] and out_elems == (11 + 11 + 51) * prob.n_out
-    tj = {t["job"]: t for t in main["trajs"]}
-    assert (tj[0]["step0"], tj[0]["out_from"], tj[0]["row0"]) == (10, 20, 0)     # rows 30..40, branch starts at 10
-    assert (tj[1]["step0"], tj[1]["out_from"], tj[1]["row0"]) == (35, 0, 5)      # rows 30..34 from the trunk
-    assert (tj[2]["step0"], tj[2]["out_from"], tj[2]["row0"]) == (20, 0, 20)
-    assert sorted((c[0], c[1], c[3]) for c in copies) == [(1, 5, 30), (2, 20, 0)]
-    assert trunk["snap_steps"] == [10, 20, 35] and trunk["trajs"][0]["n_steps"] == 35
+    common, plan = Engine.plan(eng, prob, trivial_pt(1), jobs)
+    trunk, main = plan.levels
+    assert plan.n_rows.tolist() == [11, 11, 51] and plan.out_elems == (11 + 11 + 51) * prob.n_out
+    assert main.job.tolist() == [0, 1, 2]
+    assert (main.step0[0], main.out_from[0], main.row0[0]) == (10, 20, 0)     # rows 30..40, branch starts at 10
+    assert (main.step0[1], main.out_from[1], main.row0[1]) == (35, 0, 5)      # rows 30..34 from the trunk
+    assert (main.step0[2], main.out_from[2], main.row0[2]) == (20, 0, 20)
+    assert sorted((c[0], c[1], c[3]) for c in plan.copies.tolist()) == [(1, 5, 30), (2, 20, 0)]
+    assert trunk.snap_steps.tolist() == [10, 20, 35] and trunk.n_steps.tolist() == [35]
 
 
 # ------------------------------------------------------------------------------------ GPU: workflow parity
