@@ -13,8 +13,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libaceqd.so")
-SOURCES = ["api.cu", "expm.cu", "step_kernel.cu", "splitk_kernel.cu", "small_kernel.cu", "tlmap.cu", "peak.cu",
-           "ptbuild.cu"]
+SOURCES = ["api.cu", "expm.cu", "step_kernel.cu", "splitk_kernel.cu", "small_kernel.cu", "tlmap.cu", "peak.cu"]
+# the on-device process-tensor builder is a library of its own: it links cuBLAS and cuSOLVER, the propagation
+# library links nothing
+PTBUILD_LIB = os.path.join(CSRC, "libaceqd_ptbuild.so")
+PTBUILD_SRC = os.path.join(CSRC, "ptbuild.cu")
+PTBUILD_HDR = os.path.join(CSRC, "..", "..", "include", "aceqd_ptbuild.h")
 HEADERS = ["common.cuh", "kernel_common.cuh", os.path.join("..", "..", "include", "aceqd.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-Xcompiler", "-fPIC"] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-diag-suppress", "177"]
@@ -68,5 +72,18 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_ptbuild_library(force: bool = False) -> str:
+    if not force and not _stale(PTBUILD_LIB, [PTBUILD_SRC, PTBUILD_HDR]):
+        return PTBUILD_LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc, "-shared"] + NVCC_FLAGS + ["-o", PTBUILD_LIB, PTBUILD_SRC, "-lcublas", "-lcusolver"]
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building libaceqd_ptbuild.so")
+    return PTBUILD_LIB
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_ptbuild_library(force="--force" in sys.argv))

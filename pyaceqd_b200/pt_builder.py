@@ -162,15 +162,33 @@ def uniform_pt_tensor(I: Sequence[np.ndarray], i0: np.ndarray, threshold: float 
     return f
 
 
+def resolve_backend(backend: Optional[str] = None) -> str:
+    """``"device"`` (iTEBD on the GPU, :mod:`pyaceqd_b200.pt_device`) or ``"host"`` (the NumPy implementation in this
+    module).  ``None`` reads ``ACEQD_PT_BUILD`` and defaults to the device whenever a CUDA device is present; asking
+    for the device explicitly without one raises."""
+    backend = backend or os.environ.get("ACEQD_PT_BUILD", "auto")
+    if backend not in ("auto", "host", "device"):
+        raise ValueError("PT build backend must be 'auto', 'host' or 'device', not {!r}".format(backend))
+    if backend == "auto":
+        from . import pt_device
+        backend = "device" if pt_device.available() else "host"
+    return backend
+
+
 def uniform_pt(keys: np.ndarray, eta: np.ndarray, dt: float, threshold: float = 1e-8, chi_max: int = 512,
-               shift_rate: float = 0.0, verbose: bool = False) -> ProcessTensor:
+               shift_rate: float = 0.0, verbose: bool = False, backend: str = "host") -> ProcessTensor:
     """Gauge-fixed uniform PT for coupling classes ``keys[n_cls, 2]`` (must contain (0, 0))."""
     keys = np.asarray(keys, dtype=float).reshape(-1, 2)
     null = np.where((np.abs(keys[:, 0]) < 1e-14) & (np.abs(keys[:, 1]) < 1e-14))[0]
     if len(null) == 0:
         raise ValueError("the coupling operator needs an uncoupled level (eigenvalue 0)")
     I, i0 = influence_factors(keys, eta, dt, shift_rate)
-    f = uniform_pt_tensor(I, i0, threshold, chi_max, verbose)
+    stats = None
+    if backend == "device":
+        from . import pt_device
+        f, stats = pt_device.uniform_pt_tensor(I, i0, threshold, chi_max, verbose=verbose)
+    else:
+        f = uniform_pt_tensor(I, i0, threshold, chi_max, verbose)
     # boundaries: times before the start / after the end sit in the uncoupled class (all I = 1)
     T0 = f[null[0]]
     ev, vr = np.linalg.eig(T0)
@@ -189,21 +207,32 @@ def uniform_pt(keys: np.ndarray, eta: np.ndarray, dt: float, threshold: float = 
     phase = (v_l / nl) @ Q[:, 0]
     Q[:, 0] = Q[:, 0] / phase                                  # now (v_l/nl) @ Q = e_0
     Qi = np.linalg.inv(Q)
-    A = np.einsum("ab,cbd,de->cae", Qi, f, Q)                  # G f G^-1 with G = Q^-1
+    A = np.matmul(np.matmul(Qi[None, :, :], f), Q[None, :, :])  # G f G^-1 with G = Q^-1 (per class: two matrix products)
     q = nl * (Qi @ v_r)
-    return ProcessTensor(slices=[A], closures=[q], n_initial=0, dt=dt, keys=keys,
-                         meta={"kind": "uniform-itebd", "threshold": threshold, "chi": A.shape[1]})
+    meta = {"kind": "uniform-itebd", "threshold": threshold, "chi": A.shape[1], "backend": backend}
+    if stats is not None:
+        meta["device_build"] = stats
+    return ProcessTensor(slices=[A], closures=[q], n_initial=0, dt=dt, keys=keys, meta=meta)
 
 
 def build_gaussian_pt(coupling_diag: Sequence[float], J: np.ndarray, w: np.ndarray, dt: float, t_mem: float,
                       temperature: float, threshold: float = 1e-8, subtract_polaron_shift: bool = True,
-                      chi_max: int = 512, dict_zero: float = 1e-12, verbose: bool = False) -> ProcessTensor:
-    """PT of a bath with tabulated spectral density ``J(w)`` (1/ps on the grid ``w`` in 1/ps)."""
+                      chi_max: int = 512, dict_zero: float = 1e-12, verbose: bool = False,
+                      backend: Optional[str] = None) -> ProcessTensor:
+    """PT of a bath with tabulated spectral density ``J(w)`` (1/ps on the grid ``w`` in 1/ps).  ``backend``: see
+    :func:`resolve_backend` -- on a GPU box the influence coefficients and the whole iTEBD contraction run on the
+    device."""
     _, keys = coupling_classes(np.asarray(coupling_diag, dtype=float), dict_zero)
     K = max(1, int(round(t_mem / dt)))
-    eta = eta_coefficients(J, w, dt, K, temperature)
+    backend = resolve_backend(backend)
+    if backend == "device":
+        from . import pt_device
+        eta = pt_device.eta_coefficients(J, w, dt, K, temperature)
+    else:
+        eta = eta_coefficients(J, w, dt, K, temperature)
     shift = polaron_shift_rate(J, w) if subtract_polaron_shift else 0.0
-    pt = uniform_pt(keys, eta, dt, threshold=threshold, chi_max=chi_max, shift_rate=shift, verbose=verbose)
+    pt = uniform_pt(keys, eta, dt, threshold=threshold, chi_max=chi_max, shift_rate=shift, verbose=verbose,
+                    backend=backend)
     pt.meta["coupling_diag"] = np.asarray(coupling_diag, dtype=float)     # travels with the file (ace_cli)
     return pt
 
@@ -211,13 +240,13 @@ def build_gaussian_pt(coupling_diag: Sequence[float], J: np.ndarray, w: np.ndarr
 def build_qd_phonon_pt(coupling_diag: Sequence[float], dt: float, t_mem: float, a_e: float = 5.0,
                        a_h: Optional[float] = None, temperature: float = 4.0, threshold: float = 1e-8,
                        e_max: float = 7.0, use_infinite: bool = True, chi_max: int = 512, n_w: int = 20001,
-                       verbose: bool = False) -> ProcessTensor:
+                       verbose: bool = False, backend: Optional[str] = None) -> ProcessTensor:
     """GaAs QD / LA-phonon PT with the parameters the reference passes to ACE
     (``general_system.py:159-192``): ``Boson_E_min 0``, ``Boson_E_max e_max`` (meV)."""
     w = np.linspace(0.0, e_max / constants.hbar, n_w)
     J = qd_phonon_spectral_density(w, a_e, a_h)
     pt = build_gaussian_pt(coupling_diag, J, w, dt, t_mem, temperature, threshold=threshold,
-                           subtract_polaron_shift=True, chi_max=chi_max, verbose=verbose)
+                           subtract_polaron_shift=True, chi_max=chi_max, verbose=verbose, backend=backend)
     pt.meta.update({"a_e": a_e, "a_h": a_h, "temperature": temperature, "t_mem": t_mem,
                     "use_infinite": bool(use_infinite)})
     if verbose:
@@ -248,7 +277,8 @@ def read_spectral_density(path: str):
 
 def build_pt_from_spectral_density_file(path: str, coupling_diag: Sequence[float], dt: float, t_mem: float,
                                         temperature: float, threshold: float = 1e-8, e_max: Optional[float] = None,
-                                        n_w: int = 20001, chi_max: int = 512, verbose: bool = False) -> ProcessTensor:
+                                        n_w: int = 20001, chi_max: int = 512, verbose: bool = False,
+                                        backend: Optional[str] = None) -> ProcessTensor:
     """PT of the bath whose spectral density is tabulated in ``path``; the table is interpolated linearly onto the
     builder's frequency grid and cut at ``e_max`` (meV, ``Boson_E_max``) or at the end of the table."""
     w_tab, j_tab = read_spectral_density(path)
@@ -256,7 +286,7 @@ def build_pt_from_spectral_density_file(path: str, coupling_diag: Sequence[float
     w = np.linspace(0.0, w_hi, n_w)
     J = np.interp(w, w_tab, j_tab, left=0.0, right=0.0)
     pt = build_gaussian_pt(coupling_diag, J, w, dt, t_mem, temperature, threshold=threshold, subtract_polaron_shift=True,
-                           chi_max=chi_max, verbose=verbose)
+                           chi_max=chi_max, verbose=verbose, backend=backend)
     pt.meta.update({"J_file": os.path.basename(path), "temperature": temperature, "t_mem": t_mem})
     return pt
 

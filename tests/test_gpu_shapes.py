@@ -113,7 +113,7 @@ def test_physical_pts_from_the_host_builder_on_the_gpu(engine):
     from pyaceqd_b200.pt_builder import build_qd_phonon_pt
     tls = tls_problem()
     pt = build_qd_phonon_pt(coupling_diag=tls.meta["coupling_diag"], dt=0.1, t_mem=6.4, a_e=5.0, temperature=4.0,
-                            threshold=1e-8)
+                            threshold=1e-8, backend="host")
     assert 16 <= pt.chi_max <= 48
     p = ChirpedPulse(tau_0=3.0, e_start=0.0, alpha=0, t0=10.0, e0=3.0)
     jobs = [Job(0.0, 25.0, 0.1, tables=make_tables([ChirpedPulse(tau_0=3.0, e_start=d, alpha=0, t0=10.0, e0=a)],
@@ -122,7 +122,7 @@ def test_physical_pts_from_the_host_builder_on_the_gpu(engine):
     _check(engine, tls, pt, jobs, range(len(jobs)))
     bx = biexciton_problem(outputs=["|0><0|_4", "|1><1|_4", "|3><3|_4", "|0><3|_4"])
     ptb = build_qd_phonon_pt(coupling_diag=bx.meta["coupling_diag"], dt=0.5, t_mem=20.48, a_e=5.0, temperature=4.0,
-                             threshold=1e-8)
+                             threshold=1e-8, backend="host")
     assert ptb.chi_max >= 64
     pb = ChirpedPulse(tau_0=3.0, e_start=-2.0, alpha=0, t0=10.0, e0=6.0, polar_x=1.0)
     tabs = make_tables([pb], 0.0, 30.0, 0.5)
