@@ -246,6 +246,9 @@ void aceqd_struct_sizes(int32_t out[4]);
 /* Largest trajectories-per-tile T for which (NL, chi_pad) fits the step kernel's shared
  * memory budget (0 if even T=1 does not fit). */
 int aceqd_max_tile(int NL, int chi_pad);
+/* The same without a shared-memory ring for the PT chunks: tiles this large read the PT fragments from global
+ * memory / L2 (launch name "... pt=global").  NL = 25, chi = 256: 2 instead of 1. */
+int aceqd_max_tile_global_pt(int NL, int chi_pad);
 
 /* Planner helper for aceqd_batch.kernel = 3: shared-memory bytes the split-K cluster kernel needs for tile_T = G
  * trajectories on a cluster of C CTAs (0: unsupported combination or does not fit). */

@@ -778,6 +778,12 @@ int aceqd_max_tile(int NL, int chi_pad) {
     return 0;
 }
 
+int aceqd_max_tile_global_pt(int NL, int chi_pad) {
+    for (int T = MAX_TILE_T; T >= 1; T >>= 1)
+        if (step_smem_bytes(NL, chi_pad, T, 0, 0, 1) <= (size_t)SMEM_BUDGET) return T;
+    return 0;
+}
+
 // End of a launch with host buffers: either the outputs go back (staged copy unless the kernel wrote them straight
 // into page-locked memory), or -- fused tail reduction -- they stay in HBM and only the per-trajectory trapezoids do.
 static int finish_outputs(aceqd_ctx* c, const aceqd_batch* b, int n_out, double* out_dev, bool zero_copy, bool reduce) {
@@ -1046,9 +1052,14 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
             if (stages) break;
         }
         if (stages < 2) {
-            set_error("NL=%d chi_pad=%d T=%d does not fit %d B of shared memory", pd.NL, chi_pad,
-                      T, SMEM_BUDGET);
-            return ACEQD_ERR_CAPACITY;
+            // last resort: no chunk ring at all, PT fragments read from global memory / L2 (gemm_pass_global)
+            stages = wov = 0;
+            wbufs = 1;
+            if (step_smem_bytes(pd.NL, chi_pad, T, 0, 0, 1) > (size_t)SMEM_BUDGET) {
+                set_error("NL=%d chi_pad=%d T=%d does not fit %d B of shared memory", pd.NL, chi_pad,
+                          T, SMEM_BUDGET);
+                return ACEQD_ERR_CAPACITY;
+            }
         }
         sp.T = T;
         sp.n_pass = (int)passes.size();

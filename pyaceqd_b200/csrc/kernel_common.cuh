@@ -178,5 +178,68 @@ __device__ __forceinline__ void gemm_pass(double (&cre)[MC][NB][2], double (&cim
     }
 }
 
+// The same pass with the PT block read straight from global memory / L2 (no shared-memory ring, no producer): used
+// when the bond states of a tile leave no room for chunk stages (NL = 25, chi = 256: one trajectory plus a ring, or
+// TWO trajectories without one -- and two trajectories fill the 8-row DMMA m-tiles 1.8x better).  The B fragments of
+// a whole chunk (two k-steps) travel through registers one chunk ahead of the DMMAs that use them; the chunk layout
+// in HBM is the shared-memory stage layout, so the fragment addressing is unchanged.  Every B element is read by
+// exactly one warp (warps own disjoint bond columns): the L2 -> SM traffic equals the ring's.
+template <int NB, int MCV, bool ALLNB>
+__device__ __forceinline__ void gemm_pass_global(double (&cre)[MC][NB][2], double (&cim)[MC][NB][2],
+                                                 const double* const (&are)[MC], const double* const (&aim)[MC],
+                                                 const bool (&aval)[MC], const bool (&nbv)[NB], const double* blk,
+                                                 int chunk_doubles, int strideB, int nch, int warp, int g, int tq) {
+    static_assert(KC == 8, "two DMMA k-steps per chunk");
+    double b_re[2][2][NB], b_im[2][2][NB];
+    auto loadB = [&](int buf, const double* bre) {
+        const double* bim = bre + KC * strideB;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                const int bo = (4 * ks + tq) * strideB + 8 * (warp + N_COMPUTE_WARPS * nb) + g;
+                b_re[buf][ks][nb] = (ALLNB || nbv[nb]) ? __ldg(bre + bo) : 0.0;
+                b_im[buf][ks][nb] = (ALLNB || nbv[nb]) ? __ldg(bim + bo) : 0.0;
+            }
+    };
+    auto compute = [&](int buf, int jc) {
+        double a_re[2][MCV], a_im[2][MCV];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int mc = 0; mc < MCV; ++mc) {
+                a_re[ks][mc] = aval[mc] ? are[mc][jc * KC + 4 * ks] : 0.0;
+                a_im[ks][mc] = aval[mc] ? aim[mc][jc * KC + 4 * ks] : 0.0;
+            }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                for (int mc = 0; mc < MCV; ++mc)
+                    if (ALLNB || nbv[nb]) {
+                        dmma(cre[mc][nb][0], cre[mc][nb][1], a_re[ks][mc], b_re[buf][ks][nb]);
+                        dmma(cim[mc][nb][0], cim[mc][nb][1], a_re[ks][mc], b_im[buf][ks][nb]);
+                    }
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                for (int mc = 0; mc < MCV; ++mc)
+                    if (ALLNB || nbv[nb]) {
+                        dmma(cre[mc][nb][0], cre[mc][nb][1], -a_im[ks][mc], b_im[buf][ks][nb]);
+                        dmma(cim[mc][nb][0], cim[mc][nb][1], a_im[ks][mc], b_re[buf][ks][nb]);
+                    }
+        }
+    };
+    if (nch <= 0) return;
+    loadB(0, blk);
+    for (int jc = 0; jc < nch; jc += 2) {
+        if (jc + 1 < nch) loadB(1, blk + (size_t)(jc + 1) * chunk_doubles);
+        compute(0, jc);
+        if (jc + 2 < nch) loadB(0, blk + (size_t)(jc + 2) * chunk_doubles);
+        if (jc + 1 < nch) compute(1, jc + 1);
+    }
+}
+
 }  // namespace
 }  // namespace aceqd

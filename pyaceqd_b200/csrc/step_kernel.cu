@@ -59,15 +59,17 @@ __host__ __device__ inline SmemLayout make_layout(int NL, int chi_pad, int T, in
 
 // NB   = n-tiles (8 bond columns) per compute warp; KSU_T = compile-time bound on the number of
 // DMMA k-steps of the system-operator product (ceil(NL/4) <= KSU_T).
-template <int NB, int KSU_T>
-__global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_constant__ StepParams p) {
+// GPT  = the tile's bond states leave no room for a PT chunk ring: PT fragments come from global memory / L2
+//        (gemm_pass_global), no producer warps (256 threads, so that the register-staged fragments fit without spills).
+template <int NB, int KSU_T, bool GPT>
+__global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) k_step_dmma(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int T = p.T, NL = p.prob.NL, R = T * NL;
     const int chi_pad = p.pt.chi_pad;
     const int strideA = chi_pad + 4;
     const int strideB = p.pt.strideB;
-    const int stages = p.stages;
-    const int wov = p.wov_doubles;          // 0: operators are read from global memory
+    const int stages = GPT ? 0 : p.stages;
+    const int wov = GPT ? 0 : p.wov_doubles;          // 0: operators are read from global memory
     const bool wsm = wov > 0;
     const int wbufs = p.wbufs;              // 2: W(n+1) is prefetched during step n; 1: during phase C of step n
     const SmemLayout L = make_layout(NL, chi_pad, T, stages, wov, wbufs);
@@ -794,6 +796,19 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
                 anynb |= nbv[nb];
             }
             TICK(3);
+            if constexpr (GPT) {
+                // no chunk ring (the bond states fill shared memory): B fragments come from global memory / L2
+                const double* blk = p.pt.blob + p.pt.off[s] + (size_t)pd.blk * nch * p.pt.chunk_doubles;
+                if (!anynb) {
+                } else if (allnb && mcn == MC)
+                    gemm_pass_global<NB, MC, true>(cre, cim, are, aim, aval, nbv, blk, p.pt.chunk_doubles, strideB, nch, warp, g, tq);
+                else if (allnb)
+                    gemm_pass_global<NB, 1, true>(cre, cim, are, aim, aval, nbv, blk, p.pt.chunk_doubles, strideB, nch, warp, g, tq);
+                else if (mcn == MC)
+                    gemm_pass_global<NB, MC, false>(cre, cim, are, aim, aval, nbv, blk, p.pt.chunk_doubles, strideB, nch, warp, g, tq);
+                else
+                    gemm_pass_global<NB, 1, false>(cre, cim, are, aim, aval, nbv, blk, p.pt.chunk_doubles, strideB, nch, warp, g, tq);
+            } else {
             if (!anynb) {  // this warp owns no bond column of the slice: keep the pipeline moving only
                 for (int jc = 0; jc < nch; ++jc) {
                     mbar_wait(bar_full + 8 * stage, phase);
@@ -812,6 +827,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step_dmma(const __grid_cons
             else
                 gemm_pass<NB, 1, false>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
                                         warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
+            }
             TICK(7);
             compute_bar();  // every warp has finished reading this pass's X rows
             if (C > 1) {    // ... and has finished writing the previous pass's rows: send them
@@ -974,17 +990,17 @@ size_t step_seg_slot_doubles(int NL, int chi_pad, int T) {
     return 2 * L.plane + 2 * (size_t)T * NL + 8;   // planes, closures, <= 16 snapshot cursors
 }
 
-template <int NB>
+template <int NB, bool GPT>
 static int launch_nb(const StepParams& p, size_t smem_bytes, cudaStream_t s) {
     const int ksu = p.prob.NLp4 / 4;
 #define ACEQD_LAUNCH(KS)                                                                        \
     do {                                                                                        \
-        ACEQD_CUDA(cudaFuncSetAttribute(k_step_dmma<NB, KS>,                                    \
+        ACEQD_CUDA(cudaFuncSetAttribute(k_step_dmma<NB, KS, GPT>,                               \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                                         (int)smem_bytes));                                      \
         cudaLaunchConfig_t cfg = {};                                                            \
         cfg.gridDim = dim3((unsigned)(p.segs ? p.n_ctas : p.n_tiles * p.cluster), 1, 1);       \
-        cfg.blockDim = dim3(STEP_THREADS, 1, 1);                                                \
+        cfg.blockDim = dim3(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1, 1);                   \
         cfg.dynamicSmemBytes = smem_bytes;                                                      \
         cfg.stream = s;                                                                         \
         cudaLaunchAttribute attr[1];                                                            \
@@ -1003,7 +1019,7 @@ static int launch_nb(const StepParams& p, size_t smem_bytes, cudaStream_t s) {
             attr[0].val.cooperative = 1;                                                        \
             cfg.numAttrs = 1;                                                                   \
         }                                                                                       \
-        ACEQD_CUDA(cudaLaunchKernelEx(&cfg, k_step_dmma<NB, KS>, p));                           \
+        ACEQD_CUDA(cudaLaunchKernelEx(&cfg, k_step_dmma<NB, KS, GPT>, p));                      \
     } while (0)
     if (ksu <= 1) ACEQD_LAUNCH(1);
     else if (ksu <= 4) ACEQD_LAUNCH(4);
@@ -1021,15 +1037,20 @@ int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, Lau
     }
     if (p.n_tiles <= 0) return ACEQD_OK;
     int rc;
-    if (chi <= 64) rc = launch_nb<1>(p, smem_bytes, s);
-    else if (chi <= 128) rc = launch_nb<2>(p, smem_bytes, s);
-    else rc = launch_nb<4>(p, smem_bytes, s);
+    if (p.stages == 0) {
+        if (chi <= 64) rc = launch_nb<1, true>(p, smem_bytes, s);
+        else if (chi <= 128) rc = launch_nb<2, true>(p, smem_bytes, s);
+        else rc = launch_nb<4, true>(p, smem_bytes, s);
+    } else if (chi <= 64) rc = launch_nb<1, false>(p, smem_bytes, s);
+    else if (chi <= 128) rc = launch_nb<2, false>(p, smem_bytes, s);
+    else rc = launch_nb<4, false>(p, smem_bytes, s);
     if (rc) return rc;
     ++log->count;
     {
         const int ksu = p.prob.NLp4 / 4;
-        log_name(log->step, "k_step_dmma<%d,%d> T=%d cluster=%d segments=%d", chi <= 64 ? 1 : (chi <= 128 ? 2 : 4),
-                 ksu <= 1 ? 1 : (ksu <= 4 ? 4 : (ksu <= 9 ? 9 : 16)), p.T, p.cluster, p.segs ? 1 : 0);
+        log_name(log->step, "k_step_dmma<%d,%d> T=%d cluster=%d segments=%d%s", chi <= 64 ? 1 : (chi <= 128 ? 2 : 4),
+                 ksu <= 1 ? 1 : (ksu <= 4 ? 4 : (ksu <= 9 ? 9 : 16)), p.T, p.cluster, p.segs ? 1 : 0,
+                 p.stages == 0 ? " pt=global" : "");
     }
     ACEQD_CUDA(cudaGetLastError());
     return ACEQD_OK;

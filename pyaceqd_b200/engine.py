@@ -127,6 +127,7 @@ def load_library():
                                     c_int, c_void_p, c_int, c_void_p, c_void_p]
     lib.aceqd_tlmap_last_ms.argtypes = [c_void_p, POINTER(c_float)]
     lib.aceqd_max_tile.argtypes = [c_int, c_int]
+    lib.aceqd_max_tile_global_pt.argtypes = [c_int, c_int]
     lib.aceqd_splitk_fit.argtypes = [c_int, c_int, c_int, c_int]
     lib.aceqd_splitk_fit.restype = c_longlong
     lib.aceqd_pass_load.argtypes = [c_void_p, c_int, c_int]
@@ -197,7 +198,11 @@ CLUSTER_CAPACITY = {1: N_SM, 2: N_SM, 4: 132, 8: 128}   # co-resident CTAs per c
 SPLITK_PASS_OVERHEAD = 128.0   # split-K planner: per-pass exchange cost in units of (m-tile x PT k-row)
 
 
-def choose_tile_cluster(n_traj: int, pass_load, t_max: int, clusters: Sequence[int] = (1, 2, 4, 8)) -> Tuple[int, int]:
+GLOBAL_PT_PENALTY = 1.15        # a tile without a shared-memory PT ring (fragments from L2) against one with it
+
+
+def choose_tile_cluster(n_traj: int, pass_load, t_max: int, clusters: Sequence[int] = (1, 2, 4, 8),
+                        t_ring: Optional[int] = None) -> Tuple[int, int]:
     """(trajectories per tile, CTAs per tile): minimise waves x (m-tiles of the most loaded CTA per
     step).  ``pass_load(T, C)`` is ``aceqd_pass_load``.  A cluster splits a tile's GEMM passes over C
     SMs, which only pays when the batch alone cannot fill the GPU; it costs a row exchange per step and
@@ -215,6 +220,8 @@ def choose_tile_cluster(n_traj: int, pass_load, t_max: int, clusters: Sequence[i
                 continue     # no point in tiles wider than the batch
             waves = -(-(tiles * c) // CLUSTER_CAPACITY[c])
             cost = waves * load * (1.0 + 0.25 * (c.bit_length() - 1))
+            if t_ring is not None and t > t_ring:      # tiles this large leave no room for the PT chunk ring
+                cost *= GLOBAL_PT_PENALTY
             if best_cost is None or cost < best_cost - 1e-9 or (abs(cost - best_cost) <= 1e-9 and c <= best[1]):
                 best, best_cost = (t, c), cost
         t *= 2
@@ -366,6 +373,10 @@ class Engine:
         return a.value, b.value
 
     def max_tile(self, NL: int, chi_pad: int) -> int:
+        """Largest tile the step kernel can hold, with or without a shared-memory ring for the PT chunks."""
+        return max(int(self.lib.aceqd_max_tile(NL, chi_pad)), int(self.lib.aceqd_max_tile_global_pt(NL, chi_pad)))
+
+    def max_tile_ring(self, NL: int, chi_pad: int) -> int:
         return int(self.lib.aceqd_max_tile(NL, chi_pad))
 
     def read_snapshot(self, slot: int, NL: int, chi_pad: int) -> np.ndarray:
@@ -446,7 +457,8 @@ class Engine:
         if tile_T:
             t = min(tile_T, t_max)
             return t, choose_tile_cluster(n_traj, lambda tt, c: load(t, c) if tt == t else 0, t)[1]
-        return choose_tile_cluster(n_traj, load, t_max, clusters=(cluster,) if cluster else (1, 2, 4, 8))
+        t_ring = self.max_tile_ring(prob.NL, -(-pt.chi_max // 8) * 8)
+        return choose_tile_cluster(n_traj, load, t_max, clusters=(cluster,) if cluster else (1, 2, 4, 8), t_ring=t_ring)
 
     def _splitk_tile(self, prob, pt, n_traj, tile_T=None, cluster=None):
         """(G, C, cost) of the split-K cluster kernel: G trajectories per tile on a cluster of C CTAs that hold

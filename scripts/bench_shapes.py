@@ -29,10 +29,14 @@ shapes = [("biexciton", biexciton_problem(outputs=["|1><1|_4", "|3><3|_4"]), 128
           ("sixls", sixls_problem(), 128, 1184, 60, 0.1),
           ("fivels", fivels_problem(), 256, 592, 60, 0.1)]
 kernel = "dmma"
+tile = None
 args = [a for a in sys.argv[1:]]
 for a in list(args):
     if a.startswith("--kernel="):
         kernel = a.split("=", 1)[1]
+        args.remove(a)
+    if a.startswith("--tile="):
+        tile = int(a.split("=", 1)[1])
         args.remove(a)
 if args:
     shapes = [s for s in shapes if s[0] in args]
@@ -42,9 +46,9 @@ for name, prob, chi, n_traj, n_steps, dt in shapes:
     for a in np.linspace(0.5, 12.0, n_traj):
         p = ChirpedPulse(tau_0=3.0, e_start=-2.0, alpha=0, t0=4.0, e0=a, polar_x=0.8)
         jobs.append(Job(0.0, n_steps * dt, dt, tables=make_tables([p], 0.0, n_steps * dt, dt), tail_rows=1))
-    eng.run_jobs(prob, pt, jobs, kernel=kernel)
+    eng.run_jobs(prob, pt, jobs, kernel=kernel, tile_T=tile)
     eng.timing_log.clear()
-    t = time.perf_counter(); out = eng.run_jobs(prob, pt, jobs, kernel=kernel); wall = time.perf_counter() - t
+    t = time.perf_counter(); out = eng.run_jobs(prob, pt, jobs, kernel=kernel, tile_T=tile); wall = time.perf_counter() - t
     l = eng.timing_log[-1]
     NL = prob.NL
     fl = 8.0 * NL * chi * (2 * NL + chi) * n_traj * n_steps

@@ -42,6 +42,8 @@ def test_tile_budget_is_pure_host_logic():
     assert lib.aceqd_max_tile(16, 128) == 4      # cfg3
     assert lib.aceqd_max_tile(36, 128) == 2      # cfg4
     assert lib.aceqd_max_tile(25, 256) == 1      # cfg5
+    assert lib.aceqd_max_tile_global_pt(25, 256) == 2    # ... two trajectories without a shared-memory PT ring
+    assert lib.aceqd_max_tile_global_pt(16, 128) == 4 and lib.aceqd_max_tile_global_pt(36, 128) == 2
     assert lib.aceqd_max_tile(64, 256) == 0      # does not fit: reported, not truncated
 
 

@@ -92,8 +92,10 @@ def test_cfg4_sixlevel_nl36_chi128_g2_reuse_pattern(engine, kernel):
     _check(engine, prob, pt, jobs, range(len(jobs)), min_signal=1e-3, kernel=kernel)
 
 
-@pytest.mark.parametrize("kernel", ["dmma", "splitk"])
-def test_cfg5_fivelevel_nl25_chi256_three_mtos(engine, kernel):
+@pytest.mark.parametrize("kernel,tile", [("dmma", 1), ("dmma", 2), ("dmma", None), ("splitk", None)])
+def test_cfg5_fivelevel_nl25_chi256_three_mtos(engine, kernel, tile):
+    """tile = 1: one trajectory per CTA and a shared-memory ring for the PT chunks; tile = 2: two trajectories fill
+    shared memory, the PT fragments come from global memory / L2 (k_step_dmma<...,GPT>, launch name "pt=global")."""
     prob = fivels_problem()
     pt = synthetic_pt(256, len(prob.cls_keys), kind="unitary", scale=0.999)
     dt = 0.1
@@ -105,7 +107,17 @@ def test_cfg5_fivelevel_nl25_chi256_three_mtos(engine, kernel):
                               {"operator": "|0><1|_5", "applyFrom": "_left", "time": b},
                               {"operator": "|1><0|_5", "applyFrom": "_right", "time": c}])
         jobs.append(Job(0.0, c + 1.0, dt, tables=tabs, mtos=mt))
-    _check(engine, prob, pt, jobs, range(len(jobs)), min_signal=1e-4, kernel=kernel)
+    engine.record_timings = True
+    engine.timing_log.clear()
+    try:
+        _check(engine, prob, pt, jobs, range(len(jobs)), min_signal=1e-4, kernel=kernel, fork=tile is None, tile_T=tile)
+        names = [l["step_kernel"] for l in engine.timing_log]
+    finally:
+        engine.record_timings = False
+    if tile == 2:
+        assert all("T=2" in n and "pt=global" in n for n in names), names
+    if tile == 1:
+        assert all("T=1" in n and "pt=global" not in n for n in names), names
 
 
 def test_physical_pts_from_the_host_builder_on_the_gpu(engine):

@@ -118,15 +118,17 @@ def test_sixlevel_and_planner_choice(engine):
     assert C in (2, 4) and G >= 4, (G, C)
 
 
-def test_shapes_too_large_for_one_cta_fall_back_to_the_cluster_kernel(engine):
-    """NL = 36 at chi = 256: even ONE trajectory (36 x 260 x 16 B = 150 KB + pipeline) does not fit a CTA; the engine
-    spreads its bond columns over a cluster instead of refusing the job."""
+def test_shapes_too_large_for_a_pt_ring_run_without_one_or_on_the_cluster_kernel(engine):
+    """NL = 36 at chi = 256: ONE trajectory (36 x 260 x 16 B = 150 KB) leaves no room for a shared-memory ring of PT
+    chunks.  The tile kernel then reads the PT fragments from global memory / L2 ("pt=global"); the split-K cluster
+    kernel (bond columns spread over a cluster) stays available for the same job."""
     six = sixls_problem()
     pt = synthetic_pt(256, len(six.cls_keys), kind="unitary", scale=0.999)
-    assert engine.max_tile(six.NL, 256) == 0
+    assert engine.max_tile_ring(six.NL, 256) == 0 and engine.max_tile(six.NL, 256) == 1
     p6 = ChirpedPulse(tau_0=1.0, e_start=-1.0, alpha=0, t0=1.0, e0=3.0, polar_x=0.7)
     jobs = [Job(0.0, 1.5, 0.1, tables=make_tables([p6], 0.0, 1.5, 0.1)) for _ in range(2)]
-    got = engine.run_jobs(six, pt, jobs)
-    assert engine.last_kernels()["step"].startswith("k_step_splitk"), engine.last_kernels()
-    for g, jb in zip(got, jobs):
-        assert np.abs(g - oracle.propagate(six, pt, jb)).max() < TOL
+    for kernel, want in (("auto", "pt=global"), ("splitk", "k_step_splitk")):
+        got = engine.run_jobs(six, pt, jobs, kernel=kernel)
+        assert want in engine.last_kernels()["step"], engine.last_kernels()
+        for g, jb in zip(got, jobs):
+            assert np.abs(g - oracle.propagate(six, pt, jb)).max() < TOL
