@@ -1041,7 +1041,10 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
         const int wov_full = pd.w_doubles + pd.ov_doubles;
         int stages = 0, wov = 0, wbufs = 1;
         struct Cand { int wov, bufs, min_stages; };
+        int wstage_max = 2;      // debug/tuning: ACEQD_WSTAGE=0 reads the operators from global memory, 1 forbids double buffering
+        if (const char* ws = getenv("ACEQD_WSTAGE")) wstage_max = atoi(ws);
         for (const Cand cd : {Cand{wov_full, 2, 3}, Cand{wov_full, 1, 3}, Cand{wov_full, 1, 2}, Cand{0, 1, 2}}) {
+            if ((cd.wov ? cd.bufs : 0) > wstage_max) continue;
             for (int st = MAX_STAGES; st >= cd.min_stages; --st)
                 if (step_smem_bytes(pd.NL, chi_pad, T, st, cd.wov, cd.bufs) <= (size_t)SMEM_BUDGET) {
                     stages = st;

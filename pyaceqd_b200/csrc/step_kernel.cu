@@ -585,6 +585,88 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
                     }
                 }
             }
+        } else if constexpr (KSU_T > 4 && !(GPT && NB == 4)) {
+            // Large Liouville spaces (NL = 25, 36: KSU_T = 9, 16).  k-steps outermost: the accumulators of ALL m-tiles of
+            // this CTA's rows are live at once (2 x MTB independent DMMA chains instead of 2), the Y fragment of a
+            // k-step is read from shared memory when it is needed, and the W fragments -- which come from global memory /
+            // L2 when the bond states leave no room to stage the operators -- are prefetched WS - 1 k-steps ahead.  (The
+            // m-tile-outer loop below re-reads W per n-tile with two dependent chains: 140k cycles per step for NL = 36,
+            // T = 2 against a DMMA floor of 23k, profiles/r06l_ticks_shapes.txt; with this loop 52k, sixls shape
+            // 33.8 -> 23.3 ms.)  Not for the ring-less chi = 256 tiles: their register-staged GEMM already fills the
+            // register file, and the extra live ranges of this block push spills into its main loop (NL = 25, chi = 256:
+            // 36 -> 53 ms, also as a function of its own that is not inlined).
+            constexpr int MTM = (KSU_T * 4 + 7) / 8;          // m-tiles of NLp8 rows
+            constexpr int WS = KSU_T > 9 ? 2 : 3;             // W fragment sets in flight
+            int arow[MTM];
+#pragma unroll
+            for (int mt = 0; mt < MTM; ++mt) arow[mt] = mt < MTB ? brow[8 * mt + g] : -1;
+            for (int j = 0; j < T; ++j) {
+                const aceqd_traj& t = trj[j];
+                if (!(full_act || (t.n_steps >= 0 && n >= t.step0 && n < t.step0 + t.n_steps))) continue;   // warp-uniform
+                const double2* Wp;
+                if (wsm) {
+                    Wp = reinterpret_cast<const double2*>(Wst + (size_t)(buf * T + j) * wov);
+                } else {
+                    const long long e = entry_of(t, n - t.step0, p.ovr_base);
+                    Wp = reinterpret_cast<const double2*>(p.W + (size_t)e * p.prob.w_doubles);
+                }
+                for (int nb = 0; nb < NB; ++nb) {
+                    const int nt = warp + N_COMPUTE_WARPS * nb;
+                    if (nt >= NT) break;                      // warp-uniform
+                    const int ncol = 8 * nt;
+                    double cr[MTM][2], ci[MTM][2];
+                    double2 w[WS][MTM];
+#pragma unroll
+                    for (int mt = 0; mt < MTM; ++mt) cr[mt][0] = cr[mt][1] = ci[mt][0] = ci[mt][1] = 0.0;
+                    auto loadW = [&](int slot, int ks) {
+#pragma unroll
+                        for (int mt = 0; mt < MTM; ++mt) {
+                            w[slot][mt] = make_double2(0.0, 0.0);
+                            if (arow[mt] >= 0) {
+                                const double2* wp = Wp + (size_t)arow[mt] * NLp4 + tq + 4 * ks;
+                                w[slot][mt] = wsm ? *wp : __ldg(wp);
+                            }
+                        }
+                    };
+#pragma unroll
+                    for (int q = 0; q < WS - 1; ++q)
+                        if (q < KSU) loadW(q, q);
+#pragma unroll
+                    for (int ks = 0; ks < KSU_T; ++ks) {
+                        if (ks < KSU) {
+                            if (ks + WS - 1 < KSU) loadW((ks + WS - 1) % WS, ks + WS - 1);
+                            const int a = 4 * ks + tq;
+                            double yr = 0.0, yi = 0.0;
+                            if (a < NL) {
+                                const size_t o = rowoff(pos[a], j) + g + ncol;
+                                yr = Xre[o];
+                                yi = Xim[o];
+                            }
+#pragma unroll
+                            for (int mt = 0; mt < MTM; ++mt)
+                                if (mt < MTB) {
+                                    dmma(cr[mt][0], cr[mt][1], w[ks % WS][mt].x, yr);
+                                    dmma(ci[mt][0], ci[mt][1], w[ks % WS][mt].x, yi);
+                                }
+#pragma unroll
+                            for (int mt = 0; mt < MTM; ++mt)
+                                if (mt < MTB) {
+                                    dmma(cr[mt][0], cr[mt][1], -w[ks % WS][mt].y, yi);
+                                    dmma(ci[mt][0], ci[mt][1], w[ks % WS][mt].y, yr);
+                                }
+                        }
+                    }
+                    __syncwarp();       // every lane has read the Y rows of these columns: write X over them
+#pragma unroll
+                    for (int mt = 0; mt < MTM; ++mt)
+                        if (arow[mt] >= 0) {
+                            const size_t o = rowoff(pos[arow[mt]], j) + ncol + 2 * tq;
+                            *reinterpret_cast<double2*>(Xre + o) = make_double2(cr[mt][0], cr[mt][1]);
+                            *reinterpret_cast<double2*>(Xim + o) = make_double2(ci[mt][0], ci[mt][1]);
+                        }
+                    __syncwarp();
+                }
+            }
         } else {
         constexpr int NBB = (KSU_T * NB <= PB_BUDGET) ? NB : 1;
         constexpr int JU_ = PB_BUDGET / (KSU_T * NBB);

@@ -574,6 +574,14 @@ class Engine:
         for name in ("step0", "n_steps", "init_kind", "init_index", "n_ovr", "ovr_step", "ovr_ent", "out_from",
                      "snap_off", "snap_cnt", "snap_slot0"):
             trajs[name] = getattr(lv, name)
+        # A uniform PT (one periodic slice, no initial block) is invariant under time translation: the step kernel
+        # needs a trajectory's absolute start only to pick PT slices and closures, the per-row operators carry the
+        # absolute times themselves (sequence / entry steps).  All trajectories are therefore rebased to start
+        # together, so the members of a tile are active in the same rows (a tile of a (t, tau) map takes n_tau steps
+        # instead of n_tau + T - 1; triangular sweeps tile by length alone).  Start row 1, not 0: a snapshot-started
+        # trajectory reads the closure of the slice BEFORE its first row.
+        if pt.n_initial == 0 and pt.n_repeat == 1 and os.environ.get("ACEQD_REBASE", "1") != "0":
+            trajs["step0"] = 1
         # tiling: sort by (step0, n_steps) so that tiles are homogeneous in absolute time
         order = np.lexsort((trajs["n_steps"], trajs["step0"]))
         t_max = self.max_tile(NL, common["chi_pad"])

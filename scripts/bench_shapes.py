@@ -38,6 +38,11 @@ for a in list(args):
     if a.startswith("--tile="):
         tile = int(a.split("=", 1)[1])
         args.remove(a)
+ticks = "--ticks" in args      # per-phase cycle clock of CTA 0 (aceqd_debug_phase_ticks)
+if ticks:
+    args.remove("--ticks")
+    import ctypes
+    eng.lib.aceqd_debug_phase_ticks.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
 if args:
     shapes = [s for s in shapes if s[0] in args]
 for name, prob, chi, n_traj, n_steps, dt in shapes:
@@ -48,7 +53,16 @@ for name, prob, chi, n_traj, n_steps, dt in shapes:
         jobs.append(Job(0.0, n_steps * dt, dt, tables=make_tables([p], 0.0, n_steps * dt, dt), tail_rows=1))
     eng.run_jobs(prob, pt, jobs, kernel=kernel, tile_T=tile)
     eng.timing_log.clear()
+    if ticks:
+        eng.lib.aceqd_debug_phase_ticks(eng.ctx, 1, None)
     t = time.perf_counter(); out = eng.run_jobs(prob, pt, jobs, kernel=kernel, tile_T=tile); wall = time.perf_counter() - t
+    if ticks:
+        tk = np.zeros(8, dtype=np.int64)
+        eng.lib.aceqd_debug_phase_ticks(eng.ctx, 0, tk.ctypes.data)
+        names = ["wait W/OV", "outputs", "system product + barrier", "GEMM main loops", "barrier after passes",
+                 "closure sums + barrier", "step tail", "after each pass (barrier, push, epilogue)"]
+        for nm, v in zip(names, tk):
+            print("  %-44s %12d cycles %5.1f%%" % (nm, v, 100.0 * v / max(1, tk.sum())))
     l = eng.timing_log[-1]
     NL = prob.NL
     fl = 8.0 * NL * chi * (2 * NL + chi) * n_traj * n_steps
