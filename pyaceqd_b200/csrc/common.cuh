@@ -20,7 +20,7 @@ constexpr int N_COMPUTE_WARPS = 8;
 // DIFFERENT warps overlap (scripts/micro/bulk_latency.cu: 67 B/clk per SM with 64+ KB in flight).  So the PT chunk
 // ring is fed by several producer warps (chunk c belongs to producer c mod P) and the per-row operators by their own.
 constexpr int N_CHUNK_PRODUCERS = 1;   // measured: more producers do not speed up the tile kernel (profiles/r05c_*)
-constexpr int N_PRODUCER_WARPS = N_CHUNK_PRODUCERS + 1;   // + the W|OV stager
+constexpr int N_PRODUCER_WARPS = N_CHUNK_PRODUCERS + 2;   // + the W|OV stager + the row pusher of cluster launches
 constexpr int STEP_THREADS = (N_COMPUTE_WARPS + N_PRODUCER_WARPS) * 32;
 constexpr int MAX_NL = 64;
 constexpr int MAX_PASSES = 96;

@@ -92,6 +92,16 @@ __device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster, uint32_t src_cta,
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// monotonic shared-memory counters (CTA scope): producer side adds with release, consumer side polls with acquire
+__device__ __forceinline__ void ctr_add_release(uint32_t addr) {
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void ctr_wait_ge(uint32_t addr, uint32_t want) {
+    uint32_t v;
+    do {
+        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    } while ((int32_t)(v - want) < 0);
+}
 __device__ __forceinline__ void compute_bar() {  // the 8 compute warps only
     asm volatile("bar.sync 1, %0;" ::"n"(N_COMPUTE_WARPS * 32) : "memory");
 }

@@ -101,6 +101,11 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
     // peer has seen its exchange barrier complete (found with NL = 36, T = 1 on 8-CTA clusters: 14 copies of 17 KB
     // were still being read when the next step began)
     const uint32_t bar_landed = smem_u32(bars + 2 * MAX_STAGES + 6);
+    // hand-over between the compute warps and the pusher warp of a cluster launch (monotonic counters, so that neither side
+    // can miss a phase): rows_done = epilogues finished (one count per compute warp and own pass), free_seen = steps
+    // for which every peer has read the previous contents of the rows it holds of mine
+    uint32_t* ctr = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 7);
+    const uint32_t ctr_rows = smem_u32(ctr), ctr_free = smem_u32(ctr + 1);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
     const uint32_t bar_wfull = smem_u32(bars + 2 * MAX_STAGES), bar_wempty = smem_u32(bars + 2 * MAX_STAGES + 2);
     // offset (doubles) of state row (pos, j) inside a plane; rows are alpha-major with a skew
@@ -132,6 +137,7 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
         mbar_init(bar_y, 1);                                 // own expect_tx; rows (bulk copies) and closures (st.async) count bytes
         mbar_init(bar_free, (uint32_t)(C > 1 ? C - 1 : 1));  // "I have read your rows" from every peer
         mbar_init(bar_landed, (uint32_t)(C > 1 ? C - 1 : 1));
+        ctr[0] = ctr[1] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -177,6 +183,37 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
     }
     __syncthreads();
     const int MTB = brow[MAX_NL + 7];
+    // Sending the rows of one finished pass to the peers (ONE thread: lane 0 of the pusher warp; thread 0 in the
+    // ring-less instantiation, which has no producer warps): wait until every compute warp has written them, before the
+    // first copy of a step until every peer has read the previous contents of its copy, then one bulk copy per plane and peer
+    uint32_t fph = 0u;         // phase of the "rows read" barrier
+    uint32_t push_ctr = 0u;    // epilogue counts of the passes sent so far
+    auto push_rows = [&](const PassDesc& pd, bool& free_waited) {
+        push_ctr += N_COMPUTE_WARPS;
+        ctr_wait_ge(ctr_rows, push_ctr);
+        if (!free_waited) {
+            mbar_wait(bar_free, fph);
+            free_waited = true;
+            ctr_add_release(ctr_free);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const int r0 = pd.row0[0];
+        const size_t off = (size_t)r0 * strideA + (size_t)(r0 / T) * SKEW;
+        const uint32_t bytes = pass_plane_bytes(pd);
+        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) {
+            if (peer == crank) continue;
+            const uint32_t rb = mapa(bar_y, peer);
+            bulk_s2s(mapa(smem_u32(Xre + off), peer), smem_u32(Xre + off), bytes, rb);
+            bulk_s2s(mapa(smem_u32(Xim + off), peer), smem_u32(Xim + off), bytes, rb);
+        }
+    };
+    auto push_step_end = [&](bool free_waited) {
+        if (!free_waited) {              // keep the phase in step without own passes
+            mbar_wait(bar_free, fph);
+            ctr_add_release(ctr_free);
+        }
+        fph ^= 1u;
+    };
 
     // A CTA works through a list of SEGMENTS (tile, step range): with more tiles than SMs the host lays
     // the tiles end to end and cuts the line into equal pieces, one per CTA (wrap-around rule), so a tile
@@ -188,6 +225,8 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
     int stage = 0;
     uint32_t phase = 0, wph0 = 0u, wph1 = 0u;
     unsigned chunk_ctr = 0u;   // producers: chunks issued by all producers together so far
+    uint32_t yph = 0u, lph = 0u;   // phases of the row-exchange barriers
+    uint32_t step_ctr = 0u;    // compute warps: steps with a PT contraction so far
     for (int si = 0; si < n_seg; ++si) {
     SegDesc sg;
     if (p.segs) {
@@ -340,31 +379,24 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
             issue_wov(n_lo);
             for (int n = n_lo; n < n_hi; ++n)
                 if (n + 1 < n_hi || final_seg) issue_wov(n + 1);   // row n_hi of an unfinished tile belongs to the next segment
+        } else if (lane == 0 && pw == N_CHUNK_PRODUCERS + 1 && C > 1) {
+            // row pusher: as soon as all compute warps have written the new rows of one of this CTA's passes, copy them
+            // into every peer's state (cp.async.bulk shared::cta -> shared::cluster, completing on the peer's exchange
+            // barrier).  Issuing a bulk copy costs its thread ~500 cycles (profiles/r05b_bulk_latency.txt): on a warp
+            // of its own that is off the compute warps' critical path, and the rows leave one pass earlier than when
+            // thread 0 sent them at the next block barrier.
+            for (int n = n_lo; n < n_hi; ++n) {
+                bool free_waited = false;
+                for (int ps = 0; ps < p.n_pass; ++ps)
+                    if (passes[ps].owner == (int)crank) push_rows(passes[ps], free_waited);
+                push_step_end(free_waited);
+            }
         }
         continue;   // next segment (all lanes meet the compute warps at its first barrier)
     }
 
     // ------------------------------------------------------------------ compute warps
     const int g = lane >> 2, tq = lane & 3;  // DMMA fragment coordinates
-    uint32_t yph = 0u, fph = 0u, lph = 0u;   // phases of the row-exchange barriers
-    bool free_waited = false;
-    // push the freshly computed rows of one pass into every peer's copy of the state (tid 0 only)
-    auto push_pass = [&](const PassDesc& pd) {
-        if (!free_waited) {              // peers have finished reading the previous contents
-            mbar_wait(bar_free, fph);
-            free_waited = true;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const int r0 = pd.row0[0];
-        const size_t off = (size_t)r0 * strideA + (size_t)(r0 / T) * SKEW;
-        const uint32_t bytes = pass_plane_bytes(pd);
-        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) {
-            if (peer == crank) continue;
-            const uint32_t rb = mapa(bar_y, peer);
-            bulk_s2s(mapa(smem_u32(Xre + off), peer), smem_u32(Xre + off), bytes, rb);
-            bulk_s2s(mapa(smem_u32(Xim + off), peer), smem_u32(Xim + off), bytes, rb);
-        }
-    };
     const int NT = chi_pad / 8;
     const int n_out = p.prob.n_out;
     const int NLp4 = p.prob.NLp4, MTU = p.prob.NLp8 / 8, KSU = NLp4 / 4;
@@ -796,8 +828,7 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
         bool nbv[NB];
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) nbv[nb] = 8 * (warp + N_COMPUTE_WARPS * nb) < nout;
-        int pending_push = -1;     // own pass whose new rows still have to be sent to the peers
-        free_waited = false;
+        bool gpt_free_waited = false;    // ring-less instantiation: thread 0 is the pusher
         // epilogue of one pass: new rows into the state (in place) + this warp's closure partials
         auto epilogue = [&](const PassDesc& pd, const double (&cre)[MC][NB][2], const double (&cim)[MC][NB][2]) {
             // both m-tiles side by side (independent dependency chains: the FP64 latency is exposed here)
@@ -843,8 +874,14 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
                 pi[mc] += __shfl_xor_sync(0xffffffffu, pi[mc], 2);
                 if (wr[mc] && tq == 0) rpart[warp * R + row[mc]] = make_double2(pr[mc], pi[mc]);
             }
-            // the rows written above are read by the bulk-copy engine (async proxy) when they are pushed to the peers
-            if (C > 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            // the rows written above are read by the bulk-copy engine (async proxy) when the pusher warp sends them to
+            // the peers: proxy fence by every writer, then one count per warp
+            if (C > 1) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) ctr_add_release(ctr_rows);
+                if (GPT && tid == 0) push_rows(pd, gpt_free_waited);
+            }
         };
         for (int ps = 0; ps < p.n_pass; ++ps) {
             const PassDesc pd = passes[ps];
@@ -912,16 +949,16 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
             }
             TICK(7);
             compute_bar();  // every warp has finished reading this pass's X rows
-            if (C > 1) {    // ... and has finished writing the previous pass's rows: send them
-                if (tid == 0 && pending_push >= 0) push_pass(passes[pending_push]);
-                pending_push = ps;
-            }
             epilogue(pd, cre, cim);
         }
         TICK(4);
         compute_bar();
         TICK(5);
-        // closure of the rows computed here: sum the per-warp partials; peers get a copy
+        // closure of the rows computed here: sum the per-warp partials; peers get a copy -- once they have left the
+        // outputs of this row behind (they read the closures there): the pusher has seen their "rows read" signals
+        ++step_ctr;
+        if (GPT && C > 1 && tid == 0) push_step_end(gpt_free_waited);
+        if (C > 1) ctr_wait_ge(ctr_free, step_ctr);
         for (int row = tid; row < R; row += N_COMPUTE_WARPS * 32) {
             if (C > 1 && !own_pos[divT(row)]) continue;
             double2 r = rpart[row];
@@ -937,11 +974,6 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
         }
         compute_bar();
         TICK(6);
-        if (C > 1 && tid == 0) {
-            if (pending_push >= 0) push_pass(passes[pending_push]);
-            if (!free_waited) mbar_wait(bar_free, fph);   // keep the phase in step without own passes
-        }
-        fph ^= 1u;
     }
     if (!final_seg && sg.save_slot >= 0) {
         // unfinished tile: bond state, closures of row n_hi and snapshot cursors go to HBM for the CTA that resumes it
