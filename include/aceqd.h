@@ -173,7 +173,7 @@ typedef struct {
                                /* 3: split-K cluster kernel k_step_splitk: `cluster` CTAs hold             */
                                /*    chi_pad/cluster bond columns each of tile_T trajectories (large NL)   */
                                /* 4: k_step_small or ACEQD_ERR_CAPACITY;  5: k_step_dmma always            */
-    int32_t cluster;           /* CTAs per tile (0/1, 2, 4 or 8): a thread-block cluster shares one tile.  */
+    int32_t cluster;           /* CTAs per tile (0/1, 2, 4, 8 or 16): a thread-block cluster shares one tile */
                                /* kernel 0/5: its GEMM passes are split, rows exchanged through            */
                                /* distributed shared memory, every CTA keeps the full bond state;          */
                                /* kernel 3: the bond columns are split (see above)                         */

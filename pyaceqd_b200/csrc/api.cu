@@ -924,8 +924,8 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
                 return ACEQD_ERR_ARG;
             }
         const int cluster = b->cluster <= 1 ? 1 : b->cluster;
-        if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) {
-            set_error("batch: cluster must be 0/1, 2, 4 or 8");
+        if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8 && cluster != 16) {
+            set_error("batch: cluster must be 0/1, 2, 4, 8 or 16");
             return ACEQD_ERR_ARG;
         }
         // ---- small-bond regime of two-level sweeps: one warp per 8 trajectories, PT resident in shared memory.

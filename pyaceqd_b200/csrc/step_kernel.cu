@@ -39,7 +39,7 @@ __host__ __device__ inline SmemLayout make_layout(int NL, int chi_pad, int T, in
     L.traj = o;  o += align_up(sizeof(aceqd_traj) * T, 16);
     L.pass = o;  o += align_up(sizeof(PassDesc) * MAX_PASSES, 16);
     L.pos = o;   o += align_up(sizeof(int) * MAX_NL, 16);
-    L.snapn = o; o += align_up(sizeof(int) * MAX_TILE_T, 16);
+    L.snapn = o; o += align_up(sizeof(int) * 2 * MAX_TILE_T, 16);   // snapshot cursors + the step of each next snapshot
     L.r = o;     o += align_up(16 * R * N_COMPUTE_WARPS, 16);   // per-warp partial closures
     L.rall = o;  o += align_up(16 * R, 16);                     // closure rho[row] of the current output row
     L.own = o;   o += align_up(sizeof(int) * MAX_NL, 16);       // alpha position computed by this CTA?
@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
     PassDesc* passes = reinterpret_cast<PassDesc*>(smem_raw + L.pass);
     int* pos = reinterpret_cast<int*>(smem_raw + L.pos);
     int* snapn = reinterpret_cast<int*>(smem_raw + L.snapn);
+    int* snapnx = snapn + MAX_TILE_T;   // step (relative to the trajectory's start) of its next snapshot, -1: none left
     double2* rpart = reinterpret_cast<double2*>(smem_raw + L.r);   // [warp][row]
     double2* rall = reinterpret_cast<double2*>(smem_raw + L.rall); // [row]
     int* own_pos = reinterpret_cast<int*>(smem_raw + L.own);       // [alpha position] rows computed here?
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
     // first copy of a step until every peer has read the previous contents of its copy, then one bulk copy per plane and peer
     uint32_t fph = 0u;         // phase of the "rows read" barrier
     uint32_t push_ctr = 0u;    // epilogue counts of the passes sent so far
-    auto push_rows = [&](const PassDesc& pd, bool& free_waited) {
+    auto push_wait = [&](bool& free_waited) {
         push_ctr += N_COMPUTE_WARPS;
         ctr_wait_ge(ctr_rows, push_ctr);
         if (!free_waited) {
@@ -196,16 +197,20 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
             free_waited = true;
             ctr_add_release(ctr_free);
         }
+    };
+    auto push_copy = [&](const PassDesc& pd, uint32_t peer) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const int r0 = pd.row0[0];
         const size_t off = (size_t)r0 * strideA + (size_t)(r0 / T) * SKEW;
         const uint32_t bytes = pass_plane_bytes(pd);
-        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) {
-            if (peer == crank) continue;
-            const uint32_t rb = mapa(bar_y, peer);
-            bulk_s2s(mapa(smem_u32(Xre + off), peer), smem_u32(Xre + off), bytes, rb);
-            bulk_s2s(mapa(smem_u32(Xim + off), peer), smem_u32(Xim + off), bytes, rb);
-        }
+        const uint32_t rb = mapa(bar_y, peer);
+        bulk_s2s(mapa(smem_u32(Xre + off), peer), smem_u32(Xre + off), bytes, rb);
+        bulk_s2s(mapa(smem_u32(Xim + off), peer), smem_u32(Xim + off), bytes, rb);
+    };
+    auto push_rows = [&](const PassDesc& pd, bool& free_waited) {      // one thread serves every peer
+        push_wait(free_waited);
+        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer)
+            if (peer != crank) push_copy(pd, peer);
     };
     auto push_step_end = [&](bool free_waited) {
         if (!free_waited) {              // keep the phase in step without own passes
@@ -250,6 +255,7 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
             trj[j] = z;
         }
         snapn[j] = 0;
+        snapnx[j] = (idx >= 0 && p.trajs[idx].snap_cnt > 0) ? p.snap_steps[p.trajs[idx].snap_off] : -1;
     }
     if (sg.load_slot < 0)
         for (size_t e = tid; e < 2 * L.plane; e += blockDim.x) Xre[e] = 0.0;
@@ -290,7 +296,10 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
         for (size_t e = tid; e < L.plane; e += blockDim.x) dst[e] = src[e];
         for (int e = tid; e < R; e += blockDim.x) rall[e] = src[L.plane + e];
         const int* sn = reinterpret_cast<const int*>(src + L.plane + R);
-        for (int e = tid; e < T; e += blockDim.x) snapn[e] = sn[e];
+        for (int e = tid; e < T; e += blockDim.x) {
+            snapn[e] = sn[e];
+            snapnx[e] = (trj[e].n_steps >= 0 && sn[e] < trj[e].snap_cnt) ? p.snap_steps[trj[e].snap_off + sn[e]] : -1;
+        }
     } else {
     // initial states (Y form)
     for (int j = 0; j < T; ++j) {
@@ -379,17 +388,23 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
             issue_wov(n_lo);
             for (int n = n_lo; n < n_hi; ++n)
                 if (n + 1 < n_hi || final_seg) issue_wov(n + 1);   // row n_hi of an unfinished tile belongs to the next segment
-        } else if (lane == 0 && pw == N_CHUNK_PRODUCERS + 1 && C > 1) {
+        } else if (pw == N_CHUNK_PRODUCERS + 1 && C > 1) {
             // row pusher: as soon as all compute warps have written the new rows of one of this CTA's passes, copy them
             // into every peer's state (cp.async.bulk shared::cta -> shared::cluster, completing on the peer's exchange
             // barrier).  Issuing a bulk copy costs its thread ~500 cycles (profiles/r05b_bulk_latency.txt): on a warp
             // of its own that is off the compute warps' critical path, and the rows leave one pass earlier than when
             // thread 0 sent them at the next block barrier.
+            // Lane 0 waits, lane r copies to peer r: bulk copies issued by different lanes overlap, a thread's own
+            // consecutive copies do not (profiles/r05b_bulk_latency.txt).
             for (int n = n_lo; n < n_hi; ++n) {
                 bool free_waited = false;
-                for (int ps = 0; ps < p.n_pass; ++ps)
-                    if (passes[ps].owner == (int)crank) push_rows(passes[ps], free_waited);
-                push_step_end(free_waited);
+                for (int ps = 0; ps < p.n_pass; ++ps) {
+                    if (passes[ps].owner != (int)crank) continue;
+                    if (lane == 0) push_wait(free_waited);
+                    __syncwarp();
+                    if (lane < C && (uint32_t)lane != crank) push_copy(passes[ps], (uint32_t)lane);
+                }
+                if (lane == 0) push_step_end(free_waited);
             }
         }
         continue;   // next segment (all lanes meet the compute warps at its first barrier)
@@ -436,8 +451,7 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
             if (t.n_steps < 0) continue;
             any_start |= (n == t.step0);
             const int i = n - t.step0;
-            any_snap |= (snapn[j] < t.snap_cnt && i >= 0 && i <= t.n_steps &&
-                         p.snap_steps[t.snap_off + snapn[j]] == i);
+            any_snap |= (snapn[j] < t.snap_cnt && i >= 0 && i <= t.n_steps && snapnx[j] == i);
         }
         if (any_start) {
             for (int row = warp; row < R; row += N_COMPUTE_WARPS) {
@@ -512,21 +526,23 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
                 }
             }
         }
-        if (any_snap && crank == 0) {
+        if (any_snap) {
+            // every CTA of a cluster holds the whole bond state: each writes its share of the snapshot (the trunk of a
+            // G2 map snapshots at every step -- 32 KB per step written by rank 0 alone were 11 % of the trunk's step)
             for (int j = 0; j < T; ++j) {
                 const aceqd_traj& t = trj[j];
                 if (t.n_steps < 0 || snapn[j] >= t.snap_cnt) continue;
                 const int i = n - t.step0;
-                if (i < 0 || i > t.n_steps || p.snap_steps[t.snap_off + snapn[j]] != i) continue;
+                if (i < 0 || i > t.n_steps || snapnx[j] != i) continue;
                 double2* dst = reinterpret_cast<double2*>(p.snaps) +
                                (size_t)(t.snap_slot0 + snapn[j]) * NL * chi_pad;
-                for (int e = tid; e < NL * chi_pad; e += N_COMPUTE_WARPS * 32) {
+                for (int e = tid + (int)crank * N_COMPUTE_WARPS * 32; e < NL * chi_pad; e += C * N_COMPUTE_WARPS * 32) {
                     const int a = e / chi_pad, d = e - a * chi_pad;
                     const size_t o = rowoff(pos[a], j) + d;
                     dst[e] = make_double2(Xre[o], Xim[o]);
                 }
                 // the closure of this row travels with the snapshot (column-distributed kernels start from it)
-                if (p.snap_r)
+                if (p.snap_r && crank == 0)
                     for (int a = tid; a < NL; a += N_COMPUTE_WARPS * 32)
                         reinterpret_cast<double2*>(p.snap_r)[(size_t)(t.snap_slot0 + snapn[j]) * NL + a] = rall[pos[a] * T + j];
             }
@@ -544,9 +560,11 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
             if (tid < T) {   // advance snapshot cursors (read again only after later barriers)
                 const aceqd_traj& t = trj[tid];
                 const int i = n - t.step0;
-                if (t.n_steps >= 0 && snapn[tid] < t.snap_cnt && i >= 0 && i <= t.n_steps &&
-                    p.snap_steps[t.snap_off + snapn[tid]] == i)
-                    snapn[tid] += 1;
+                if (t.n_steps >= 0 && snapn[tid] < t.snap_cnt && i >= 0 && i <= t.n_steps && snapnx[tid] == i) {
+                    const int k = snapn[tid] + 1;
+                    snapn[tid] = k;
+                    snapnx[tid] = k < t.snap_cnt ? p.snap_steps[t.snap_off + k] : -1;   // the only global read, off the step's path
+                }
             }
         }
 
@@ -1112,6 +1130,9 @@ static int launch_nb(const StepParams& p, size_t smem_bytes, cudaStream_t s) {
         ACEQD_CUDA(cudaFuncSetAttribute(k_step_dmma<NB, KS, GPT>,                               \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                                         (int)smem_bytes));                                      \
+        if (p.cluster > 8) /* 16 CTAs: one whole GPC's worth, beyond the portable limit */      \
+            ACEQD_CUDA(cudaFuncSetAttribute(k_step_dmma<NB, KS, GPT>,                           \
+                                            cudaFuncAttributeNonPortableClusterSizeAllowed, 1));\
         cudaLaunchConfig_t cfg = {};                                                            \
         cfg.gridDim = dim3((unsigned)(p.segs ? p.n_ctas : p.n_tiles * p.cluster), 1, 1);       \
         cfg.blockDim = dim3(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1, 1);                   \
@@ -1132,6 +1153,16 @@ static int launch_nb(const StepParams& p, size_t smem_bytes, cudaStream_t s) {
             attr[0].id = cudaLaunchAttributeCooperative;                                        \
             attr[0].val.cooperative = 1;                                                        \
             cfg.numAttrs = 1;                                                                   \
+        }                                                                                       \
+        if (p.cluster > 8) {                                                                    \
+            int ncl = 0;                                                                        \
+            ACEQD_CUDA(cudaOccupancyMaxActiveClusters(&ncl, k_step_dmma<NB, KS, GPT>, &cfg));   \
+            if (ncl < 1) {                                                                      \
+                set_error("a cluster of %d CTAs with %zu B of shared memory each cannot be "    \
+                          "scheduled on this device (ACEQD_CLUSTER16=0 keeps clusters <= 8)",   \
+                          p.cluster, smem_bytes);                                               \
+                return ACEQD_ERR_CAPACITY;                                                      \
+            }                                                                                   \
         }                                                                                       \
         ACEQD_CUDA(cudaLaunchKernelEx(&cfg, k_step_dmma<NB, KS, GPT>, p));                      \
     } while (0)

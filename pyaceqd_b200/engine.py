@@ -194,14 +194,19 @@ def choose_tile(n_traj: int, rows_per_block: Sequence[int], t_max: int, n_sm: in
     return best_t
 
 
-CLUSTER_CAPACITY = {1: N_SM, 2: N_SM, 4: 132, 8: 128}   # co-resident CTAs per cluster size (GPC packing)
+CLUSTER_CAPACITY = {1: N_SM, 2: N_SM, 4: 132, 8: 128, 16: 64}   # co-resident CTAs per cluster size (GPC packing)
 SPLITK_PASS_OVERHEAD = 128.0   # split-K planner: per-pass exchange cost in units of (m-tile x PT k-row)
 
 
 GLOBAL_PT_PENALTY = 1.15        # a tile without a shared-memory PT ring (fragments from L2) against one with it
 
 
-def choose_tile_cluster(n_traj: int, pass_load, t_max: int, clusters: Sequence[int] = (1, 2, 4, 8),
+# 16-CTA clusters (beyond the portable limit of 8; a whole GPC) serve the lone trunk of a G2 map: 9 coupling classes on
+# 16 SMs = one GEMM pass per CTA and step (cfg3 trunk 4.3 -> 3.3 ms).  ACEQD_CLUSTER16=0 keeps clusters <= 8.
+DEFAULT_CLUSTERS = (1, 2, 4, 8) if os.environ.get("ACEQD_CLUSTER16") == "0" else (1, 2, 4, 8, 16)
+
+
+def choose_tile_cluster(n_traj: int, pass_load, t_max: int, clusters: Sequence[int] = DEFAULT_CLUSTERS,
                         t_ring: Optional[int] = None) -> Tuple[int, int]:
     """(trajectories per tile, CTAs per tile): minimise waves x (m-tiles of the most loaded CTA per
     step).  ``pass_load(T, C)`` is ``aceqd_pass_load``.  A cluster splits a tile's GEMM passes over C
@@ -458,7 +463,7 @@ class Engine:
             t = min(tile_T, t_max)
             return t, choose_tile_cluster(n_traj, lambda tt, c: load(t, c) if tt == t else 0, t)[1]
         t_ring = self.max_tile_ring(prob.NL, -(-pt.chi_max // 8) * 8)
-        return choose_tile_cluster(n_traj, load, t_max, clusters=(cluster,) if cluster else (1, 2, 4, 8), t_ring=t_ring)
+        return choose_tile_cluster(n_traj, load, t_max, clusters=(cluster,) if cluster else DEFAULT_CLUSTERS, t_ring=t_ring)
 
     def _splitk_tile(self, prob, pt, n_traj, tile_T=None, cluster=None):
         """(G, C, cost) of the split-K cluster kernel: G trajectories per tile on a cluster of C CTAs that hold

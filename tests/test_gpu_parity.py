@@ -131,7 +131,7 @@ def _g2_jobs(prob, n_t=6, dt=0.25, tau_max=3.0, opA="|3><1|_4", opC="|1><3|_4", 
     return jobs
 
 
-@pytest.mark.parametrize("cluster,tile_T", [(2, 1), (2, 2), (2, 4), (4, 1), (4, 2), (4, 4), (8, 1), (8, 2)])
+@pytest.mark.parametrize("cluster,tile_T", [(2, 1), (2, 2), (2, 4), (4, 1), (4, 2), (4, 4), (8, 1), (8, 2), (16, 1), (16, 2)])
 def test_cluster_biexciton_fork_and_tails(engine, cluster, tile_T):
     """Tile shared by a cluster of CTAs: forked G2-style batch (trunk with snapshots + branches)."""
     prob = biexciton_problem(outputs=["|1><1|_4", "(|3><1|_4*|1><1|_4*|1><3|_4)", "|0><3|_4"])
@@ -177,7 +177,8 @@ def test_planner_picks_clusters_for_small_batches(engine):
     t_max = engine.max_tile(prob.NL, 128)
     T, C = engine._tile_and_cluster(prob, pt, 256, t_max)
     assert (T, C) == (4, 2)
-    assert engine._tile_and_cluster(prob, pt, 1, t_max) == (1, 8)
+    assert engine._tile_and_cluster(prob, pt, 1, t_max) == (1, 16)      # the lone trunk: one GEMM pass per CTA (9 classes)
+    assert engine._tile_and_cluster(prob, pt, 9, t_max)[1] <= 8         # 16-CTA clusters only while they are all resident
     tls = tls_problem()
     ptt = synthetic_pt(128, len(tls.cls_keys), kind="unitary", scale=0.999)
     assert engine._tile_and_cluster(tls, ptt, 4096, engine.max_tile(4, 128)) == (16, 1)
