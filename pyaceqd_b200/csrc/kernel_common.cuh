@@ -4,6 +4,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef ACEQD_GPT_BUFS
+#define ACEQD_GPT_BUFS 2
+#endif
+
 namespace aceqd {
 namespace {
 
@@ -110,6 +114,20 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
         : "+d"(c0), "+d"(c1)
         : "d"(a), "d"(b));
 }
+// N consecutive doubles through the read-only path in one instruction (N = 4: a 256-bit load, new with sm_100)
+template <int N>
+__device__ __forceinline__ void ldg_vec(const double* p, double (&v)[N]) {
+    static_assert(N == 1 || N == 2 || N == 4, "1, 2 or 4 doubles");
+    if constexpr (N == 1) {
+        v[0] = __ldg(p);
+    } else if constexpr (N == 2) {
+        const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+        v[0] = t.x;
+        v[1] = t.y;
+    } else {
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+    }
+}
 __device__ __forceinline__ int slice_of(const PtDev& pt, int n) {
     return n < pt.n_initial ? n : pt.n_initial + (n - pt.n_initial) % pt.n_repeat;
 }
@@ -200,17 +218,28 @@ __device__ __forceinline__ void gemm_pass_global(double (&cre)[MC][NB][2], doubl
                                                  const bool (&aval)[MC], const bool (&nbv)[NB], const double* blk,
                                                  int chunk_doubles, int strideB, int nch, int warp, int g, int tq) {
     static_assert(KC == 8, "two DMMA k-steps per chunk");
-    double b_re[2][2][NB], b_im[2][2][NB];
+    // chunk buffers in registers: loads run NBUF - 1 chunks ahead of their DMMAs.  Measured at NL = 25, chi = 256, T = 2
+    // (gpurun_out/r7b_*): three buffers in every pass 36.3 -> 51.2 ms, three buffers in the thin (one m-tile) passes only
+    // 49.4 ms -- more loads in flight do not help (and the register file is full at two), so the fragments' way from
+    // L2 into the SM is bound by its throughput, not by its latency.
+    constexpr int NBUF = ACEQD_GPT_BUFS;
+    double b_re[NBUF][2][NB], b_im[NBUF][2][NB];
+    // Warp w owns the bond columns [8 NB w, 8 NB (w + 1)); column 8 NB w + NB g + nb is n-index g of its n-tile nb, so the
+    // NB fragments of a lane are NB consecutive doubles of one PT row: ONE load of 8 NB bytes (LDG.256 for chi = 256)
+    // where the strided assignment of the ring kernel needs NB loads of 8 bytes that touch four cache lines each.
     auto loadB = [&](int buf, const double* bre) {
         const double* bim = bre + KC * strideB;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
+        for (int ks = 0; ks < 2; ++ks) {
+            const int bo = (4 * ks + tq) * strideB + NB * (8 * warp + g);
+            if (ALLNB || nbv[0]) {
+                ldg_vec<NB>(bre + bo, b_re[buf][ks]);
+                ldg_vec<NB>(bim + bo, b_im[buf][ks]);
+            } else {
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) {
-                const int bo = (4 * ks + tq) * strideB + 8 * (warp + N_COMPUTE_WARPS * nb) + g;
-                b_re[buf][ks][nb] = (ALLNB || nbv[nb]) ? __ldg(bre + bo) : 0.0;
-                b_im[buf][ks][nb] = (ALLNB || nbv[nb]) ? __ldg(bim + bo) : 0.0;
+                for (int nb = 0; nb < NB; ++nb) b_re[buf][ks][nb] = b_im[buf][ks][nb] = 0.0;
             }
+        }
     };
     auto compute = [&](int buf, int jc) {
         double a_re[2][MCV], a_im[2][MCV];
@@ -242,12 +271,16 @@ __device__ __forceinline__ void gemm_pass_global(double (&cre)[MC][NB][2], doubl
         }
     };
     if (nch <= 0) return;
-    loadB(0, blk);
-    for (int jc = 0; jc < nch; jc += 2) {
-        if (jc + 1 < nch) loadB(1, blk + (size_t)(jc + 1) * chunk_doubles);
-        compute(0, jc);
-        if (jc + 2 < nch) loadB(0, blk + (size_t)(jc + 2) * chunk_doubles);
-        if (jc + 1 < nch) compute(1, jc + 1);
+#pragma unroll
+    for (int q = 0; q < NBUF - 1; ++q)
+        if (q < nch) loadB(q, blk + (size_t)q * chunk_doubles);
+    for (int jc = 0; jc < nch; jc += NBUF) {
+#pragma unroll
+        for (int q = 0; q < NBUF; ++q) {
+            const int pre = jc + q + NBUF - 1;      // chunk fetched now, into the buffer compute(q - 1) released
+            if (pre < nch) loadB((q + NBUF - 1) % NBUF, blk + (size_t)pre * chunk_doubles);
+            if (jc + q < nch) compute(q, jc + q);
+        }
     }
 }
 

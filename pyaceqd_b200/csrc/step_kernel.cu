@@ -845,7 +845,8 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
         }
         bool nbv[NB];
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) nbv[nb] = 8 * (warp + N_COMPUTE_WARPS * nb) < nout;
+        for (int nb = 0; nb < NB; ++nb)     // ring-less tiles: a warp owns 8 NB CONSECUTIVE columns (gemm_pass_global), all or none
+            nbv[nb] = (GPT ? 8 * NB * warp : 8 * (warp + N_COMPUTE_WARPS * nb)) < nout;
         bool gpt_free_waited = false;    // ring-less instantiation: thread 0 is the pusher
         // epilogue of one pass: new rows into the state (in place) + this warp's closure partials
         auto epilogue = [&](const PassDesc& pd, const double (&cre)[MC][NB][2], const double (&cim)[MC][NB][2]) {
@@ -861,6 +862,38 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
                 wr[mc] = av && (full_act || (t.n_steps >= 0 && n >= t.step0 && n < t.step0 + t.n_steps));
                 pr[mc] = pi[mc] = 0.0;
             }
+            if constexpr (GPT) {
+                // accumulator (nb, e) of this lane is column cb + NB e + nb: 2 NB consecutive columns per lane
+                const int cb = 8 * NB * warp + 2 * NB * tq;
+                if (nbv[0]) {
+#pragma unroll
+                    for (int mc = 0; mc < MC; ++mc) {
+                        if (pd.nvalid[mc] <= 0) continue;   // warp-uniform
+                        double vr[2 * NB], vi[2 * NB];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+#pragma unroll
+                            for (int nb = 0; nb < NB; ++nb) {
+                                vr[e * NB + nb] = cre[mc][nb][e];
+                                vi[e * NB + nb] = cim[mc][nb][e];
+                            }
+#pragma unroll
+                        for (int c = 0; c < 2 * NB; ++c) {
+                            const double2 q = qbuf[cb + c];
+                            pr[mc] += vr[c] * q.x - vi[c] * q.y;
+                            pi[mc] += vr[c] * q.y + vi[c] * q.x;
+                        }
+                        if (wr[mc]) {
+                            const size_t o = rowoff_r(row[mc]) + cb;
+#pragma unroll
+                            for (int c = 0; c < 2 * NB; c += 2) {
+                                *reinterpret_cast<double2*>(Xre + o + c) = make_double2(vr[c], vr[c + 1]);
+                                *reinterpret_cast<double2*>(Xim + o + c) = make_double2(vi[c], vi[c + 1]);
+                            }
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) {
                 if (!nbv[nb]) continue;
@@ -879,6 +912,7 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
                         *reinterpret_cast<double2*>(Xim + o) = make_double2(i0, i1);
                     }
                 }
+            }
             }
 #pragma unroll
             for (int mc = 0; mc < MC; ++mc) {
