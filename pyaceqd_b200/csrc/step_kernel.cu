@@ -441,6 +441,18 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
             if (n < n_end && tid == 0) mbar_expect_tx(bar_y, rx_bytes);   // arm this step's exchange
         }
         TICK(0);
+        // Operators that cannot be staged in shared memory (large Liouville spaces) are read by every warp straight from
+        // global memory in the system product: pull this row's W into L1 now, so that those reads find it there instead
+        // of waiting for L2 two k-steps ahead of their DMMAs (all 8 warps read the same 11-23 KB per trajectory).
+        if (!wsm && KSU_T > 4 && n < n_end) {
+            for (int j = 0; j < T; ++j) {
+                const aceqd_traj& t = trj[j];
+                if (t.n_steps < 0 || n < t.step0 || n >= t.step0 + t.n_steps) continue;
+                const char* wp = reinterpret_cast<const char*>(p.W + (size_t)entry_of(t, n - t.step0, p.ovr_base) * p.prob.w_doubles);
+                for (int o = tid * 128; o < p.prob.w_doubles * 8; o += N_COMPUTE_WARPS * 32 * 128)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + o));
+            }
+        }
         // ---------------- phase A: outputs (closures rall[] come from the previous GEMM epilogue)
         // rows of trajectories that START at this row have no closure yet: generic closure pass
         const bool full_act = all_valid && n >= s0_max && n < e_min;   // every trajectory of the tile steps n -> n+1
@@ -635,18 +647,19 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
                     }
                 }
             }
-        } else if constexpr (KSU_T > 4 && !(GPT && NB == 4)) {
+        } else if constexpr (KSU_T > 4) {
             // Large Liouville spaces (NL = 25, 36: KSU_T = 9, 16).  k-steps outermost: the accumulators of ALL m-tiles of
             // this CTA's rows are live at once (2 x MTB independent DMMA chains instead of 2), the Y fragment of a
             // k-step is read from shared memory when it is needed, and the W fragments -- which come from global memory /
             // L2 when the bond states leave no room to stage the operators -- are prefetched WS - 1 k-steps ahead.  (The
             // m-tile-outer loop below re-reads W per n-tile with two dependent chains: 140k cycles per step for NL = 36,
             // T = 2 against a DMMA floor of 23k, profiles/r06l_ticks_shapes.txt; with this loop 52k, sixls shape
-            // 33.8 -> 23.3 ms.)  Not for the ring-less chi = 256 tiles: their register-staged GEMM already fills the
-            // register file, and the extra live ranges of this block push spills into its main loop (NL = 25, chi = 256:
-            // 36 -> 53 ms, also as a function of its own that is not inlined).
+            // 33.8 -> 23.3 ms.)
             constexpr int MTM = (KSU_T * 4 + 7) / 8;          // m-tiles of NLp8 rows
             constexpr int WS = KSU_T > 9 ? 2 : 3;             // W fragment sets in flight
+            // ring-less chi = 256 tiles: their register-staged GEMM fills the register file, so the W fragments of only two
+            // m-tiles are in registers at a time (the Y fragments are read once per group instead of once)
+            constexpr int MG = (GPT && NB == 4) ? 2 : MTM;
             int arow[MTM];
 #pragma unroll
             for (int mt = 0; mt < MTM; ++mt) arow[mt] = mt < MTB ? brow[8 * mt + g] : -1;
@@ -665,45 +678,49 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
                     if (nt >= NT) break;                      // warp-uniform
                     const int ncol = 8 * nt;
                     double cr[MTM][2], ci[MTM][2];
-                    double2 w[WS][MTM];
 #pragma unroll
                     for (int mt = 0; mt < MTM; ++mt) cr[mt][0] = cr[mt][1] = ci[mt][0] = ci[mt][1] = 0.0;
-                    auto loadW = [&](int slot, int ks) {
 #pragma unroll
-                        for (int mt = 0; mt < MTM; ++mt) {
-                            w[slot][mt] = make_double2(0.0, 0.0);
-                            if (arow[mt] >= 0) {
-                                const double2* wp = Wp + (size_t)arow[mt] * NLp4 + tq + 4 * ks;
-                                w[slot][mt] = wsm ? *wp : __ldg(wp);
+                    for (int m0 = 0; m0 < MTM; m0 += MG) {       // groups of MG m-tiles share the W fragment registers
+                        if (m0 >= MTB) break;                     // warp-uniform
+                        double2 w[WS][MG];
+                        auto loadW = [&](int slot, int ks) {
+#pragma unroll
+                            for (int mg = 0; mg < MG; ++mg) {
+                                w[slot][mg] = make_double2(0.0, 0.0);
+                                if (m0 + mg < MTM && arow[m0 + mg < MTM ? m0 + mg : 0] >= 0) {
+                                    const double2* wp = Wp + (size_t)arow[m0 + mg] * NLp4 + tq + 4 * ks;
+                                    w[slot][mg] = wsm ? *wp : __ldg(wp);
+                                }
                             }
-                        }
-                    };
+                        };
 #pragma unroll
-                    for (int q = 0; q < WS - 1; ++q)
-                        if (q < KSU) loadW(q, q);
+                        for (int q = 0; q < WS - 1; ++q)
+                            if (q < KSU) loadW(q, q);
 #pragma unroll
-                    for (int ks = 0; ks < KSU_T; ++ks) {
-                        if (ks < KSU) {
-                            if (ks + WS - 1 < KSU) loadW((ks + WS - 1) % WS, ks + WS - 1);
-                            const int a = 4 * ks + tq;
-                            double yr = 0.0, yi = 0.0;
-                            if (a < NL) {
-                                const size_t o = rowoff(pos[a], j) + g + ncol;
-                                yr = Xre[o];
-                                yi = Xim[o];
-                            }
-#pragma unroll
-                            for (int mt = 0; mt < MTM; ++mt)
-                                if (mt < MTB) {
-                                    dmma(cr[mt][0], cr[mt][1], w[ks % WS][mt].x, yr);
-                                    dmma(ci[mt][0], ci[mt][1], w[ks % WS][mt].x, yi);
+                        for (int ks = 0; ks < KSU_T; ++ks) {
+                            if (ks < KSU) {
+                                if (ks + WS - 1 < KSU) loadW((ks + WS - 1) % WS, ks + WS - 1);
+                                const int a = 4 * ks + tq;
+                                double yr = 0.0, yi = 0.0;
+                                if (a < NL) {
+                                    const size_t o = rowoff(pos[a], j) + g + ncol;
+                                    yr = Xre[o];
+                                    yi = Xim[o];
                                 }
 #pragma unroll
-                            for (int mt = 0; mt < MTM; ++mt)
-                                if (mt < MTB) {
-                                    dmma(cr[mt][0], cr[mt][1], -w[ks % WS][mt].y, yi);
-                                    dmma(ci[mt][0], ci[mt][1], w[ks % WS][mt].y, yr);
-                                }
+                                for (int mg = 0; mg < MG; ++mg)
+                                    if (m0 + mg < MTM && m0 + mg < MTB) {
+                                        dmma(cr[m0 + mg][0], cr[m0 + mg][1], w[ks % WS][mg].x, yr);
+                                        dmma(ci[m0 + mg][0], ci[m0 + mg][1], w[ks % WS][mg].x, yi);
+                                    }
+#pragma unroll
+                                for (int mg = 0; mg < MG; ++mg)
+                                    if (m0 + mg < MTM && m0 + mg < MTB) {
+                                        dmma(cr[m0 + mg][0], cr[m0 + mg][1], -w[ks % WS][mg].y, yi);
+                                        dmma(ci[m0 + mg][0], ci[m0 + mg][1], w[ks % WS][mg].y, yr);
+                                    }
+                            }
                         }
                     }
                     __syncwarp();       // every lane has read the Y rows of these columns: write X over them
