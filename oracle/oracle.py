@@ -6,7 +6,9 @@ PARITY UNPINNED: the arithmetic of this path lives in the external ACE code
 reference holds no numeric golden vector for any propagation result.  This file
 restates the published algorithm (Cygorek et al., Nat. Phys. 18, 662 (2022))
 as it is driven by the reference's call site ``pyaceqd/general_system/general_system.py:227-290``
-and is pinned only by physics known-answer tests (tests/test_oracle_kat.py).
+and is pinned by physics known-answer tests (tests/test_oracle_kat.py) and, for the coherent part of
+the path, at plot resolution (0.005) by the one ACE-made artefact the reference keeps, the plot
+``pyaceqd/tests/sixls_compare.png`` (tests/test_reference_plot.py; the phonon part stays unpinned).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl
 reference`` legs may import this module.  The product (pyaceqd_b200) never does.
