@@ -867,6 +867,330 @@ __global__ void __launch_bounds__(128) k_opbuild_dmma(OpBuildParams p, int warps
     }
 }
 
+// -------------------------------------------------------------------------------------------
+// Tensor-core operator builder for the large Liouville spaces (16 < NL <= 40: the five- and six-level models,
+// pyaceqd/four_level_system/dark_model.py:34-55, six_level_system/linear.py:28-72).  ONE CTA of 16 warps owns an entry:
+// the matrices of the scaling-and-squaring chain live in shared memory as split re/im planes [NPAD][NPAD + 4] (seven of
+// them: 197 KB for NL = 36), every product is a complex DMMA.8x8x4 GEMM whose 8x8 output tiles are dealt round-robin to
+// the warps (tile t -> warp t mod 16: the four warps of a sub-partition carry 6-7 of the 25 tiles of NL = 36), element-wise
+// passes run on all 512 threads, block barriers in between.  Same polynomial, scaling rule and operator algebra as the
+// warp-per-entry builder above, whose matrices would leave room for a single warp per SM at these sizes.
+constexpr int BM_BUFS = 7;       // A, A2, A3, A4, P0, P1, V
+constexpr int BM_WARPS = 16;
+constexpr int BM_THREADS = 32 * BM_WARPS;
+constexpr int BM_RED = 64 + BM_THREADS;   // norm reduction workspace (doubles): column sums + partial sums
+constexpr int BM_EPT = 4;        // elements per thread in element-wise passes: ceil(40 * 40 / 512)
+
+// `ksn` = ceil(n / 4) DMMA k-steps: the columns of A / rows of B beyond n are zero padding
+template <int NP, class Init>
+__device__ __forceinline__ void bmm(WMat<NP> C, WMat<NP> A, WMat<NP> B, int tid, int ksn, Init init) {
+    constexpr int LD = WMat<NP>::LD, NPAD = WMat<NP>::NPAD, NT = NP * NP, TPW = (NT + BM_WARPS - 1) / BM_WARPS;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+    double cr[TPW][2], ci[TPW][2];
+    int ao[TPW], bo[TPW];
+    bool on[TPW];
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) {
+        const int t = warp + BM_WARPS * q;
+        on[q] = t < NT;                                   // warp-uniform
+        const int mi = on[q] ? t / NP : 0, ni = on[q] ? t - (t / NP) * NP : 0;
+        ao[q] = (8 * mi + g) * LD + tq;                   // A fragment of k-step 0
+        bo[q] = tq * LD + 8 * ni + g;                     // B fragment of k-step 0
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            cr[q][h] = ci[q][h] = 0.0;
+            if (on[q]) init(8 * mi + g, 8 * ni + 2 * tq + h, cr[q][h], ci[q][h]);
+        }
+    }
+#pragma unroll 2
+    for (int ks = 0; ks < ksn; ++ks) {
+        double ar[TPW], ai[TPW], br[TPW], bi[TPW];
+#pragma unroll
+        for (int q = 0; q < TPW; ++q) {
+            ar[q] = ai[q] = br[q] = bi[q] = 0.0;
+            if (on[q]) {
+                ar[q] = A.re[ao[q] + 4 * ks];
+                ai[q] = A.im()[ao[q] + 4 * ks];
+                br[q] = B.re[bo[q] + 4 * ks * LD];
+                bi[q] = B.im()[bo[q] + 4 * ks * LD];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < TPW; ++q)
+            if (on[q]) {
+                dmma8(cr[q][0], cr[q][1], ar[q], br[q]);
+                dmma8(ci[q][0], ci[q][1], ar[q], bi[q]);
+            }
+#pragma unroll
+        for (int q = 0; q < TPW; ++q)
+            if (on[q]) {
+                dmma8(cr[q][0], cr[q][1], -ai[q], bi[q]);
+                dmma8(ci[q][0], ci[q][1], ai[q], br[q]);
+            }
+    }
+#pragma unroll
+    for (int q = 0; q < TPW; ++q)
+        if (on[q]) {
+            const int t = warp + BM_WARPS * q;
+            const int o = (8 * (t / NP) + g) * LD + 8 * (t - (t / NP) * NP) + 2 * tq;
+            *reinterpret_cast<double2*>(C.re + o) = make_double2(cr[q][0], cr[q][1]);
+            *reinterpret_cast<double2*>(C.im() + o) = make_double2(ci[q][0], ci[q][1]);
+        }
+    __syncthreads();
+}
+
+struct BlockOffs {    // plane offsets of the elements e = tid + 512 k < n*n a thread touches in element-wise passes
+    int o[BM_EPT];
+    bool diag[BM_EPT];
+    int cnt;
+};
+
+// exp(A) (A destroyed); buffers M[0..5] = A, A2, A3, A4, P0, P1; `red`: BM_RED doubles; returns the result buffer (4 or 5)
+template <int NP>
+__device__ int expm_block(WMat<NP>* M, double* red, int n, int tid, const BlockOffs& bf) {
+    constexpr int LD = WMat<NP>::LD;
+    WMat<NP> A = M[0], A2 = M[1], A3 = M[2], A4 = M[3], P0 = M[4], P1 = M[5];
+    const int ksn = (n + 3) / 4;
+    // 1-norm (largest column sum) on all threads: 8 threads share a column (a single thread per column with its chain of
+    // n square roots was 18 % of the kernel: profiles/r07g_*), partial sums in red[64 .. 64 + 512), column sums in red[0 .. n)
+    {
+        const int j = tid & 63, part = tid >> 6;
+        double ps = 0.0;
+        if (j < n)
+            for (int i = part; i < n; i += BM_THREADS / 64) {
+                const double x = A.re[i * LD + j], y = A.im()[i * LD + j];
+                ps += sqrt(x * x + y * y);
+            }
+        red[64 + part * 64 + j] = ps;
+    }
+    __syncthreads();
+    if (tid < n) {
+        double cs = 0.0;
+#pragma unroll
+        for (int part = 0; part < BM_THREADS / 64; ++part) cs += red[64 + part * 64 + tid];
+        red[tid] = cs;
+    }
+    __syncthreads();
+    double cs = 0.0;
+    for (int j = 0; j < n; ++j) cs = fmax(cs, red[j]);
+    int s = 0;
+    if (cs > THETA) {
+        int ex;
+        frexp(cs / THETA, &ex);
+        s = ex > 60 ? 60 : ex;
+    }
+    const double sc = ldexp(1.0, -s);
+#pragma unroll
+    for (int k = 0; k < BM_EPT; ++k)
+        if (k < bf.cnt) {
+            A.re[bf.o[k]] *= sc;
+            A.im()[bf.o[k]] *= sc;
+        }
+    __syncthreads();
+    constexpr double c2 = 1.0 / 2, c3 = 1.0 / 6, c4 = 1.0 / 24, c5 = 1.0 / 120, c6 = 1.0 / 720,
+                     c7 = 1.0 / 5040, c8 = 1.0 / 40320, c9 = 1.0 / 362880, c10 = 1.0 / 3628800,
+                     c11 = 1.0 / 39916800, c12 = 1.0 / 479001600;
+    auto zero = [](int, int, double& r, double& i) { r = 0.0; i = 0.0; };
+    bmm<NP>(A2, A, A, tid, ksn, zero);
+    bmm<NP>(A3, A2, A, tid, ksn, zero);
+    bmm<NP>(A4, A2, A2, tid, ksn, zero);
+#pragma unroll
+    for (int k = 0; k < BM_EPT; ++k)
+        if (k < bf.cnt) {
+            const int o = bf.o[k];
+            P0.re[o] = (bf.diag[k] ? c8 : 0.0) + c9 * A.re[o] + c10 * A2.re[o] + c11 * A3.re[o] + c12 * A4.re[o];
+            P0.im()[o] = c9 * A.im()[o] + c10 * A2.im()[o] + c11 * A3.im()[o] + c12 * A4.im()[o];
+        }
+    __syncthreads();
+    // P1 = (c4 I + c5 A + c6 A2 + c7 A3) + A4 P0 ;  P0 = (I + A + c2 A2 + c3 A3) + A4 P1
+    bmm<NP>(P1, A4, P0, tid, ksn, [&](int i, int j, double& r, double& im_) {
+        const int o = i * LD + j;
+        r = ((i == j && i < n) ? c4 : 0.0) + c5 * A.re[o] + c6 * A2.re[o] + c7 * A3.re[o];
+        im_ = c5 * A.im()[o] + c6 * A2.im()[o] + c7 * A3.im()[o];
+    });
+    bmm<NP>(P0, A4, P1, tid, ksn, [&](int i, int j, double& r, double& im_) {
+        const int o = i * LD + j;
+        r = ((i == j && i < n) ? 1.0 : 0.0) + A.re[o] + c2 * A2.re[o] + c3 * A3.re[o];
+        im_ = A.im()[o] + c2 * A2.im()[o] + c3 * A3.im()[o];
+    });
+    int cur = 4, nxt = 5;
+    for (int q = 0; q < s; ++q) {
+        bmm<NP>(M[nxt], M[cur], M[cur], tid, ksn, zero);
+        const int t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    return cur;
+}
+
+// A = delta * (L0 + sum_k f_k LA_k + conj(f_k) LB_k) at time t; `fsm`: 2 * n_fields doubles of shared memory
+template <int NP>
+__device__ void assemble_block(WMat<NP> A, const OpBuildParams& p, const double2* L0, const double2* LA, const double2* LB,
+                               double* fsm, int set, double t, double delta, int tid, int ns) {
+    constexpr int LD = WMat<NP>::LD;
+    const int n = p.prob.NL, n2 = n * n, nf = p.prob.n_fields;
+    if (tid < nf) {       // thread k samples drive field k once for the whole matrix
+        const double2* tabs = reinterpret_cast<const double2*>(p.tables);
+        const double x = (t - p.tab_t0) / p.tab_dt;
+        double2 fl = make_double2(0.0, 0.0);
+        const int tb = p.prob.field_table[tid];
+        if (tb >= 0 && tb < p.n_tables) fl = sample_table(tabs + ((size_t)set * p.n_tables + tb) * p.n_samples, ns, x);
+        fsm[2 * tid] = fl.x;
+        fsm[2 * tid + 1] = fl.y;
+    }
+    __syncthreads();
+    for (int e = tid; e < n2; e += BM_THREADS) {
+        double2 acc = L0[e];
+        for (int k = 0; k < nf; ++k) {
+            const double2 f = make_double2(fsm[2 * k], fsm[2 * k + 1]);
+            cfma(acc, f, LA[(size_t)k * n2 + e]);
+            cfma(acc, make_double2(f.x, -f.y), LB[(size_t)k * n2 + e]);
+        }
+        const int i = e / n;
+        const int o = i * LD + (e - i * n);
+        A.re[o] = acc.x * delta;
+        A.im()[o] = acc.y * delta;
+    }
+    __syncthreads();
+}
+
+constexpr int BM_MAX_FIELDS = 16;
+
+template <int NP>
+__global__ void __launch_bounds__(BM_THREADS) k_opbuild_dmma_cta(OpBuildParams p, int lsm) {
+    extern __shared__ __align__(16) double wm_smem[];
+    constexpr int LD = WMat<NP>::LD, PLANE = WMat<NP>::PLANE;
+    const int n = p.prob.NL, n2 = n * n, ksn = (n + 3) / 4;
+    const int tid = threadIdx.x;
+    WMat<NP> M[BM_BUFS];
+#pragma unroll
+    for (int b = 0; b < BM_BUFS; ++b) M[b].re = wm_smem + (size_t)b * 2 * PLANE;
+    double* red = wm_smem + (size_t)BM_BUFS * 2 * PLANE;      // [BM_RED] norm reduction workspace
+    double* fsm = red + BM_RED;                                // [2 * BM_MAX_FIELDS] drive fields of the current matrix
+    for (int e = tid; e < BM_BUFS * 2 * PLANE; e += BM_THREADS) wm_smem[e] = 0.0;    // the zero padding stays zero throughout
+    // Liouvillian pieces: a copy in shared memory when it fits (NL <= 32; they are read twice per entry)
+    const double2* L0 = reinterpret_cast<const double2*>(p.prob.L0);
+    const double2* LA = reinterpret_cast<const double2*>(p.prob.LA);
+    const double2* LB = reinterpret_cast<const double2*>(p.prob.LB);
+    if (lsm) {
+        double2* ls = reinterpret_cast<double2*>(fsm + 2 * BM_MAX_FIELDS);
+        const int nf = p.prob.n_fields;
+        for (int e = tid; e < n2; e += BM_THREADS) ls[e] = L0[e];
+        for (int e = tid; e < nf * n2; e += BM_THREADS) {
+            ls[n2 + e] = LA[e];
+            ls[(1 + nf) * n2 + e] = LB[e];
+        }
+        L0 = ls;
+        LA = ls + n2;
+        LB = ls + (size_t)(1 + nf) * n2;
+    }
+    WMat<NP> V = M[6];
+    BlockOffs bf;
+    bf.cnt = 0;
+#pragma unroll
+    for (int k = 0; k < BM_EPT; ++k) {
+        const int e = tid + BM_THREADS * k;
+        const int i = e / n, j = e - i * n;
+        bf.o[k] = e < n2 ? i * LD + j : 0;
+        bf.diag[k] = e < n2 && i == j;
+        if (e < n2) bf.cnt = k + 1;
+    }
+    __syncthreads();
+    auto load_global = [&](WMat<NP> D, const double2* src) {    // row-major complex n x n -> planes
+        for (int e = tid; e < n2; e += BM_THREADS) {
+            const int o = (e / n) * LD + e % n;
+            D.re[o] = src[e].x;
+            D.im()[o] = src[e].y;
+        }
+        __syncthreads();
+    };
+    auto copy = [&](WMat<NP> D, WMat<NP> S) {
+#pragma unroll
+        for (int k = 0; k < BM_EPT; ++k)
+            if (k < bf.cnt) {
+                D.re[bf.o[k]] = S.re[bf.o[k]];
+                D.im()[bf.o[k]] = S.im()[bf.o[k]];
+            }
+        __syncthreads();
+    };
+    auto zero = [](int, int, double& r, double& i) { r = 0.0; i = 0.0; };
+    const long long total = p.e_end > p.e_begin ? p.e_end : p.n_seq_entries + p.n_entries;
+    const double half = 0.5 * p.dt;
+    const double2* mto = reinterpret_cast<const double2*>(p.mto_mats);
+    for (long long e = p.e_begin + blockIdx.x; e < total; e += gridDim.x) {
+        int set, step, sb = -1, sa = -1, has_prev, ns = p.n_samples;
+        if (e < p.n_seq_entries) {
+            int lo = 0, hi = p.n_seq;  // seq_base[lo] <= e < seq_base[hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (p.seq_base[mid] <= e) lo = mid; else hi = mid;
+            }
+            const aceqd_seq sq = p.seqs[lo];
+            const int i = (int)(e - p.seq_base[lo]);
+            set = sq.set;
+            step = sq.step0 + i;
+            has_prev = (i > 0) || sq.first_has_prev;
+        } else {
+            const aceqd_entry en = p.entries[e - p.n_seq_entries];
+            set = en.set; step = en.step; sb = en.sb; sa = en.sa; has_prev = en.has_prev;
+            if (en.clamp > 0) ns = min(en.clamp, p.n_samples);   // this row sees only the first `clamp` samples of its drive
+        }
+        const double t_n = p.t0 + (double)step * p.dt;
+        // ---- V = Sb * M2_{n-1}
+        if (has_prev) {
+            assemble_block<NP>(M[0], p, L0, LA, LB, fsm, set, t_n - p.dt + p.eval_off2 * p.dt, half, tid, ns);
+            const int r = expm_block<NP>(M, red, n, tid, bf);
+            if (sb >= 0) {
+                load_global(M[0], mto + (size_t)sb * n2);
+                bmm<NP>(V, M[0], M[r], tid, ksn, zero);
+            } else {
+                copy(V, M[r]);
+            }
+        } else {
+            for (int q = tid; q < n2; q += BM_THREADS) {
+                const int i = q / n, j = q - i * n, o = i * LD + j;
+                const double2 v = (sb >= 0) ? mto[(size_t)sb * n2 + q] : make_double2(i == j ? 1.0 : 0.0, 0.0);
+                V.re[o] = v.x;
+                V.im()[o] = v.y;
+            }
+            __syncthreads();
+        }
+        // ---- OV = out_w * V
+        {
+            const double2* ow = reinterpret_cast<const double2*>(p.prob.out_w);
+            double2* ov = reinterpret_cast<double2*>(p.OV + (size_t)e * p.prob.ov_doubles);
+            const int cnt = p.prob.n_out * n;
+            for (int q = tid; q < cnt; q += BM_THREADS) {
+                const int j = q / n, a = q - j * n;
+                double2 acc = make_double2(0.0, 0.0);
+                for (int k = 0; k < n; ++k) cfma(acc, ow[j * n + k], make_double2(V.re[k * LD + a], V.im()[k * LD + a]));
+                ov[q] = acc;
+            }
+        }
+        // ---- X = Sa * V (in V's place, through a work buffer: V must outlive the second exponential)
+        if (sa >= 0) {
+            __syncthreads();     // OV has read V
+            load_global(M[0], mto + (size_t)sa * n2);
+            bmm<NP>(M[1], M[0], V, tid, ksn, zero);
+            copy(V, M[1]);
+        }
+        // ---- W = M1_n * X   (zero padded to [NLp8][NLp4])
+        assemble_block<NP>(M[0], p, L0, LA, LB, fsm, set, t_n + p.eval_off1 * p.dt, half, tid, ns);
+        const int r1 = expm_block<NP>(M, red, n, tid, bf);
+        WMat<NP> Wm = M[r1 == 4 ? 5 : 4];
+        bmm<NP>(Wm, M[r1], V, tid, ksn, zero);
+        {
+            double2* w = reinterpret_cast<double2*>(p.W + (size_t)e * p.prob.w_doubles);
+            const int ld = p.prob.NLp4, cnt = p.prob.NLp8 * ld;
+            for (int q = tid; q < cnt; q += BM_THREADS) {
+                const int i = q / ld, j = q - i * ld;
+                w[q] = (i < n && j < n) ? make_double2(Wm.re[i * LD + j], Wm.im()[i * LD + j]) : make_double2(0.0, 0.0);
+            }
+        }
+        __syncthreads();  // buffers are reused by the next entry
+    }
+}
+
 template <int G, bool BLK>
 __global__ void __launch_bounds__(256) k_expm_batch(int n, int count, const double* a,
                                                     double* out, double* scratch) {
@@ -960,6 +1284,31 @@ int launch_opbuild(const OpBuildParams& p, cudaStream_t s, LaunchLog* log) {
         }
         ++log->count;
         log_name(log->opbuild, "k_opbuild_dmma<%d>", np);
+        ACEQD_CUDA(cudaGetLastError());
+        return ACEQD_OK;
+    }
+    if (n > 16 && n <= 40 && p.prob.n_fields <= BM_MAX_FIELDS && !getenv("ACEQD_OPBUILD_GROUP")) {
+        // tensor-core builder, one CTA per entry (five- and six-level models)
+        const int np = (n + 7) / 8;
+        const size_t m_bytes = ((size_t)BM_BUFS * 2 * (8 * np) * (8 * np + 4) + BM_RED + 2 * BM_MAX_FIELDS) * sizeof(double);
+        const size_t l_bytes = (size_t)(1 + 2 * p.prob.n_fields) * n * n * sizeof(double2);
+        const int lsm = m_bytes + l_bytes <= (size_t)SMEM_BUDGET ? 1 : 0;
+        const size_t smem = m_bytes + (lsm ? l_bytes : 0);
+        // 512 threads of <= 128 registers: the register file holds one CTA per SM
+        const long long blocks = std::min<long long>(total, 148LL);
+        int rc;
+        if (np == 3) {
+            if ((rc = set_smem(k_opbuild_dmma_cta<3>, smem))) return rc;
+            k_opbuild_dmma_cta<3><<<(int)blocks, BM_THREADS, smem, s>>>(p, lsm);
+        } else if (np == 4) {
+            if ((rc = set_smem(k_opbuild_dmma_cta<4>, smem))) return rc;
+            k_opbuild_dmma_cta<4><<<(int)blocks, BM_THREADS, smem, s>>>(p, lsm);
+        } else {
+            if ((rc = set_smem(k_opbuild_dmma_cta<5>, smem))) return rc;
+            k_opbuild_dmma_cta<5><<<(int)blocks, BM_THREADS, smem, s>>>(p, lsm);
+        }
+        ++log->count;
+        log_name(log->opbuild, "k_opbuild_dmma_cta<%d>", np);
         ACEQD_CUDA(cudaGetLastError());
         return ACEQD_OK;
     }
