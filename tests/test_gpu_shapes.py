@@ -145,3 +145,32 @@ def test_physical_pts_from_the_host_builder_on_the_gpu(engine):
              {"operator": "|1><3|_4", "applyFrom": "_left", "time": t1}])))
     _check(engine, bx, ptb, jb, range(len(jb)), min_signal=1e-3)
     _check(engine, bx, ptb, jb, range(len(jb)), min_signal=1e-3, kernel="splitk")
+
+
+@pytest.mark.parametrize("which,name", [("fivels", "k_opbuild_dmma_cta<4>"), ("sixls", "k_opbuild_dmma_cta<5>")])
+def test_cta_per_entry_operator_builder(engine, monkeypatch, which, name):
+    """Pulse-area sweeps of the five- and six-level models (per-trajectory drives: every row needs its own two
+    exponentials) through the tensor-core builder with one CTA per entry, against the oracle and against the group
+    kernel (``ACEQD_OPBUILD_GROUP=1``); multi-time operators before and after a row included."""
+    prob = fivels_problem() if which == "fivels" else sixls_problem()
+    d = 5 if which == "fivels" else 6
+    pt = synthetic_pt(24, len(prob.cls_keys), kind="unitary", scale=0.999)
+    dt = 0.1
+    jobs = []
+    for k, a in enumerate(np.linspace(0.5, 9.0, 7)):
+        p = ChirpedPulse(tau_0=0.6, e_start=-2.0, alpha=0.1 * k, t0=1.0, e0=a, polar_x=0.8)
+        mt = None
+        if k % 2:
+            mt = prob.parse_mtos([{"operator": "|0><1|_%d" % d, "applyFrom": "_left", "time": 0.7, "applyBefore": "true"},
+                                  {"operator": "|1><0|_%d" % d, "applyFrom": "_right", "time": 1.3}])
+        jobs.append(Job(0.0, 2.5, dt, tables=make_tables([p], 0.0, 2.5, dt), mtos=mt))
+    monkeypatch.delenv("ACEQD_OPBUILD_GROUP", raising=False)
+    got = engine.run_jobs(prob, pt, jobs, kernel="dmma")
+    assert engine.last_kernels()["opbuild"] == name, engine.last_kernels()
+    monkeypatch.setenv("ACEQD_OPBUILD_GROUP", "1")
+    grp = engine.run_jobs(prob, pt, jobs, kernel="dmma")
+    assert engine.last_kernels()["opbuild"].startswith("k_opbuild<"), engine.last_kernels()
+    monkeypatch.delenv("ACEQD_OPBUILD_GROUP", raising=False)
+    for g, h, jb in zip(got, grp, jobs):
+        assert np.abs(g - h).max() < 1e-12
+        assert np.abs(g - oracle.propagate(prob, pt, jb)).max() < 1e-10
