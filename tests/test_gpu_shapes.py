@@ -159,7 +159,7 @@ def test_cta_per_entry_operator_builder(engine, monkeypatch, which, name):
     jobs = []
     for k, a in enumerate(np.linspace(0.5, 9.0, 7)):
         p = ChirpedPulse(tau_0=0.6, e_start=-2.0, alpha=0.1 * k, t0=1.0, e0=a, polar_x=0.8)
-        mt = None
+        mt = []
         if k % 2:
             mt = prob.parse_mtos([{"operator": "|0><1|_%d" % d, "applyFrom": "_left", "time": 0.7, "applyBefore": "true"},
                                   {"operator": "|1><0|_%d" % d, "applyFrom": "_right", "time": 1.3}])
