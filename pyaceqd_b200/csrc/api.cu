@@ -923,7 +923,7 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
                 set_error("batch: tile list references trajectory %d", b->tile_traj[i]);
                 return ACEQD_ERR_ARG;
             }
-        const int cluster = b->cluster <= 1 ? 1 : b->cluster;
+        int cluster = b->cluster <= 1 ? 1 : b->cluster;
         if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8 && cluster != 16) {
             set_error("batch: cluster must be 0/1, 2, 4, 8 or 16");
             return ACEQD_ERR_ARG;
@@ -1074,6 +1074,16 @@ int aceqd_run_steps(aceqd_ctx* c, const aceqd_problem* prob, const aceqd_pt* pt,
         sp.passes = (const PassDesc*)c->passes.p;
         sp.tile_traj = (const int*)c->tiles.p;
         const size_t smem = step_smem_bytes(pd.NL, chi_pad, T, stages, wov, wbufs);
+        if (cluster > 8 && (step_max_active_clusters(sp, smem) < 1 || getenv("ACEQD_CLUSTER16_UNSCHEDULABLE"))) {   // (env: tests)
+            // 16 CTAs are beyond the portable cluster size: where the device (a partition of it, a smaller part) cannot
+            // place such a cluster the tile runs on 8 CTAs instead; the launch name says which
+            cluster = 8;
+            if ((rc = build_passes(prob, T, cluster, passes))) return rc;
+            UP(c->passes, passes.data(), passes.size() * sizeof(PassDesc));
+            sp.n_pass = (int)passes.size();
+            sp.cluster = cluster;
+            sp.passes = (const PassDesc*)c->passes.p;
+        }
         if (use_segments(c, b)) {
             int n_slots = 0;
             const int n_sm = segment_ctas(c);

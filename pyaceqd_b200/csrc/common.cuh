@@ -166,6 +166,7 @@ int launch_opbuild(const OpBuildParams& p, cudaStream_t s, LaunchLog* log);
 int launch_expm_batch(int n, int count, const double* a_dev, double* out_dev, double* scratch,
                       cudaStream_t s, LaunchLog* log);
 int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, LaunchLog* log);
+int step_max_active_clusters(const StepParams& p, size_t smem_bytes);
 int launch_step_check(const StepParams& p, double* scratch, cudaStream_t s, LaunchLog* log);
 size_t step_smem_bytes(int NL, int chi_pad, int T, int stages, int wov_doubles, int wbufs);
 size_t step_seg_slot_doubles(int NL, int chi_pad, int T);

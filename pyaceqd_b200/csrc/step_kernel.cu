@@ -1173,8 +1173,9 @@ size_t step_seg_slot_doubles(int NL, int chi_pad, int T) {
     return 2 * L.plane + 2 * (size_t)T * NL + 8;   // planes, closures, <= 16 snapshot cursors
 }
 
+// query != nullptr: do not launch, report how many clusters of this configuration can be resident at once
 template <int NB, bool GPT>
-static int launch_nb(const StepParams& p, size_t smem_bytes, cudaStream_t s) {
+static int launch_nb(const StepParams& p, size_t smem_bytes, cudaStream_t s, int* query = nullptr) {
     const int ksu = p.prob.NLp4 / 4;
 #define ACEQD_LAUNCH(KS)                                                                        \
     do {                                                                                        \
@@ -1205,15 +1206,14 @@ static int launch_nb(const StepParams& p, size_t smem_bytes, cudaStream_t s) {
             attr[0].val.cooperative = 1;                                                        \
             cfg.numAttrs = 1;                                                                   \
         }                                                                                       \
-        if (p.cluster > 8) {                                                                    \
-            int ncl = 0;                                                                        \
-            ACEQD_CUDA(cudaOccupancyMaxActiveClusters(&ncl, k_step_dmma<NB, KS, GPT>, &cfg));   \
-            if (ncl < 1) {                                                                      \
-                set_error("a cluster of %d CTAs with %zu B of shared memory each cannot be "    \
-                          "scheduled on this device (ACEQD_CLUSTER16=0 keeps clusters <= 8)",   \
-                          p.cluster, smem_bytes);                                               \
-                return ACEQD_ERR_CAPACITY;                                                      \
+        if (query) {                                                                            \
+            *query = 0;                                                                         \
+            if (cudaOccupancyMaxActiveClusters(query, k_step_dmma<NB, KS, GPT>, &cfg) !=        \
+                cudaSuccess) {                                                                  \
+                cudaGetLastError();                                                             \
+                *query = 0;                                                                     \
             }                                                                                   \
+            return ACEQD_OK;                                                                    \
         }                                                                                       \
         ACEQD_CUDA(cudaLaunchKernelEx(&cfg, k_step_dmma<NB, KS, GPT>, p));                      \
     } while (0)
@@ -1223,6 +1223,20 @@ static int launch_nb(const StepParams& p, size_t smem_bytes, cudaStream_t s) {
     else ACEQD_LAUNCH(16);
 #undef ACEQD_LAUNCH
     return ACEQD_OK;
+}
+
+// clusters of p.cluster CTAs of this configuration that fit the device at once (0: such a cluster cannot be scheduled)
+int step_max_active_clusters(const StepParams& p, size_t smem_bytes) {
+    const int chi = p.pt.chi_pad;
+    int ncl = 0, rc;
+    if (p.stages == 0) {
+        if (chi <= 64) rc = launch_nb<1, true>(p, smem_bytes, nullptr, &ncl);
+        else if (chi <= 128) rc = launch_nb<2, true>(p, smem_bytes, nullptr, &ncl);
+        else rc = launch_nb<4, true>(p, smem_bytes, nullptr, &ncl);
+    } else if (chi <= 64) rc = launch_nb<1, false>(p, smem_bytes, nullptr, &ncl);
+    else if (chi <= 128) rc = launch_nb<2, false>(p, smem_bytes, nullptr, &ncl);
+    else rc = launch_nb<4, false>(p, smem_bytes, nullptr, &ncl);
+    return rc ? 0 : ncl;
 }
 
 int launch_step_dmma(const StepParams& p, size_t smem_bytes, cudaStream_t s, LaunchLog* log) {

@@ -145,6 +145,20 @@ def test_cluster_biexciton_fork_and_tails(engine, cluster, tile_T):
     assert max(np.abs(f[:, -5:] - t).max() for f, t in zip(full, tails)) < 1e-12
 
 
+def test_cluster16_falls_back_to_8_where_it_cannot_be_scheduled(engine, monkeypatch):
+    """16 CTAs are beyond the portable cluster size; the library asks cudaOccupancyMaxActiveClusters and runs the tile
+    on 8 CTAs where such a cluster cannot be placed (simulated here)."""
+    prob = biexciton_problem(outputs=["|1><1|_4", "|0><3|_4"])
+    pt = synthetic_pt(40, len(prob.cls_keys), n_slices=2, kind="unitary", scale=0.999)
+    jobs = _g2_jobs(prob)
+    monkeypatch.setenv("ACEQD_CLUSTER16_UNSCHEDULABLE", "1")
+    _compare(engine, prob, pt, jobs, "dmma", cluster=16, tile_T=1)
+    assert engine.last_kernels()["step"] == "k_step_dmma<1,4> T=1 cluster=8 segments=0"
+    monkeypatch.delenv("ACEQD_CLUSTER16_UNSCHEDULABLE")
+    _compare(engine, prob, pt, jobs, "dmma", cluster=16, tile_T=1)
+    assert engine.last_kernels()["step"] == "k_step_dmma<1,4> T=1 cluster=16 segments=0"
+
+
 @pytest.mark.parametrize("cluster", [2, 4])
 def test_cluster_tls_sweep_and_sixlevel(engine, cluster):
     prob = tls_problem()
