@@ -559,7 +559,8 @@ __global__ void __launch_bounds__(OPREG_THREADS) k_opbuild_reg(OpBuildParams p) 
 // re/im planes [NPAD][NPAD + 4] (zero padded to a multiple of 8), and every product of the scaling-and-squaring
 // chain is a complex DMMA.8x8x4 GEMM of the warp: C fragments go back to shared memory and return as A / B
 // fragments of the next product after a __syncwarp().  Same polynomial and scaling rule as expm_group.
-constexpr int WM_BUFS = 8;    // A, A2, A3, A4, P0, P1, V, X
+constexpr int WM_BUFS = 7;    // A, A2, A3, A4, P0, P1, V
+constexpr int WM_MAX_WARPS = 4;   // warps (entries in flight) per CTA: one per SM sub-partition
 
 __device__ __forceinline__ void dmma8(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -732,7 +733,7 @@ __device__ void assemble_warp(WMat<NP> A, const OpBuildParams& p, const double2*
 }
 
 template <int NP>
-__global__ void __launch_bounds__(128) k_opbuild_dmma(OpBuildParams p, int warps_per_cta, int lsm) {
+__global__ void __launch_bounds__(32 * WM_MAX_WARPS) k_opbuild_dmma(OpBuildParams p, int warps_per_cta, int lsm) {
     extern __shared__ __align__(16) double wm_smem[];
     constexpr int LD = WMat<NP>::LD, PLANE = WMat<NP>::PLANE;
     const int n = p.prob.NL, n2 = n * n;
@@ -760,7 +761,7 @@ __global__ void __launch_bounds__(128) k_opbuild_dmma(OpBuildParams p, int warps
         __syncthreads();
     }
     __syncwarp();
-    WMat<NP> V = M[6], X = M[7];
+    WMat<NP> V = M[6];
     LaneOffs lo;
     lo.cnt = 0;
 #pragma unroll
@@ -843,18 +844,18 @@ __global__ void __launch_bounds__(128) k_opbuild_dmma(OpBuildParams p, int warps
                 ov[q] = acc;
             }
         }
-        // ---- X = Sa * V
-        WMat<NP> Xp = V;
+        // ---- X = Sa * V (in V's place, through a work buffer: it must outlive the second exponential)
         if (sa >= 0) {
+            __syncwarp();     // OV has read V
             load_global(M[0], mto + (size_t)sa * n2);
-            wmm<NP>(X, M[0], V, lane, zero);
-            Xp = X;
+            wmm<NP>(M[1], M[0], V, lane, zero);
+            copy(V, M[1]);
         }
         // ---- W = M1_n * X   (zero padded to [NLp8][NLp4])
         assemble_warp<NP>(M[0], p, L0, LA, LB, set, t_n + p.eval_off1 * p.dt, half, lane, ns);
         const int r1 = expm_warp<NP>(M, n, lane, lo);
         WMat<NP> Wm = M[r1 == 4 ? 5 : 4];
-        wmm<NP>(Wm, M[r1], Xp, lane, zero);
+        wmm<NP>(Wm, M[r1], V, lane, zero);
         {
             double2* w = reinterpret_cast<double2*>(p.W + (size_t)e * p.prob.w_doubles);
             const int ld = p.prob.NLp4, cnt = p.prob.NLp8 * ld;
@@ -1265,9 +1266,12 @@ int launch_opbuild(const OpBuildParams& p, cudaStream_t s, LaunchLog* log) {
     if (n > 4 && n <= 16 && !getenv("ACEQD_OPBUILD_GROUP")) {   // tensor-core builder, one warp per entry
         const int np = (n + 7) / 8;
         const size_t per_warp = (size_t)WM_BUFS * 2 * (8 * np) * (8 * np + 4) * sizeof(double);
-        // four warps per CTA = one per SM sub-partition (a single warp with 16 independent accumulators already
-        // saturates its tensor pipe); as many CTAs per SM as the shared-memory footprint allows
-        const int wpc = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)SMEM_BUDGET / per_warp));
+        // four warps per CTA = one per SM sub-partition.  More entries in flight do NOT help: 5 / 6 warps per SM (seven
+        // instead of eight matrices per warp make room) measured 9.65 / 9.80 ms against 9.39 ms for the biexciton sweep
+        // (gpurun_out/r7i): the kernel is bound by the shared-memory pipe (fragment loads, 2-way conflicts of the C
+        // stores at LD = 20), not by the latency of one warp's chain.
+        int wpc = (int)std::max<size_t>(1, std::min<size_t>(WM_MAX_WARPS, (size_t)SMEM_BUDGET / per_warp));
+        if (const char* ev = getenv("ACEQD_OPB_WARPS")) wpc = std::max(1, std::min(wpc, atoi(ev)));   // tuning
         const size_t l_bytes = (size_t)(1 + 2 * p.prob.n_fields) * n * n * sizeof(double2);
         const int lsm = (size_t)wpc * per_warp + l_bytes <= (size_t)SMEM_BUDGET ? 1 : 0;
         const size_t smem = (size_t)wpc * per_warp + (lsm ? l_bytes : 0);
