@@ -98,6 +98,31 @@ def sample_rf(t, pulses, firstonly=False):
     return rf, px, py
 
 
+def generate_pulsefiles(t, pulses, temp_dir, system_prefix, suffix, abs_only=False):
+    """The reference's pulse-file writer under its own name (``general_system.py:55-71``): ``t Re Im`` rows with 8 decimals
+    for the x and y components; returns the two file names.  (The in-process path never writes them: it hands
+    :func:`sample_pulses` to the operator builder; scripts that call this function directly get the reference's files.)"""
+    from pyaceqd_b200.tools import export_csv
+    fx = temp_dir + "{}_pulse_x_{}.dat".format(system_prefix, suffix)
+    fy = temp_dir + "{}_pulse_y_{}.dat".format(system_prefix, suffix)
+    px, py = sample_pulses(np.asarray(t), pulses, abs_only=abs_only)
+    export_csv(fx, t, px.real, px.imag, precision=8, delimit=' ')
+    export_csv(fy, t, py.real, py.imag, precision=8, delimit=' ')
+    return fx, fy
+
+
+def generate_rf_file(t, pulses, temp_dir, system_prefix, suffix, firstonly=False):
+    """Rotating-frame file of the first pulse's instantaneous frequency, and the x / y pulse files regenerated in that
+    frame (reference ``general_system.py:73-102``); returns the rf file name."""
+    from pyaceqd_b200.tools import export_csv
+    rf_file = temp_dir + "{}_rf_{}.dat".format(system_prefix, suffix)
+    rf, px, py = sample_rf(np.asarray(t), pulses, firstonly=firstonly)
+    export_csv(rf_file, t, rf.real, rf.imag, precision=8, delimit=' ')
+    export_csv(temp_dir + "{}_pulse_x_{}.dat".format(system_prefix, suffix), t, px.real, px.imag, precision=8, delimit=' ')
+    export_csv(temp_dir + "{}_pulse_y_{}.dat".format(system_prefix, suffix), t, py.real, py.imag, precision=8, delimit=' ')
+    return rf_file
+
+
 def read_pulse_file(path: str) -> FieldTable:
     """ACE pulse-file reader: columns ``t Re Im`` (``general_system.py:69-70``), cached by mtime.  Names registered by
     ``PulseGenerator.generate_pulsefiles(in_memory=True)`` resolve without touching the disk."""
@@ -126,6 +151,21 @@ def read_result(data, n):
     result[0] = t
     for i in range(n):
         result[i + 1] = data[:, 2 * i + 1] + 1j * data[:, 2 * i + 2]
+    return result
+
+
+def read_result_1d(data):
+    """As :func:`read_result` with the number of outputs taken from the column count (reference ``:112-119``)."""
+    return read_result(data, int((data.shape[1] - 1) / 2))
+
+
+def read_hamiltonian(data):
+    """``print_H`` output rows ``[_, Re h_0, Im h_0, ...]`` -> complex ``n x n`` matrix, column by column (reference
+    ``:121-126``)."""
+    n = data.shape[0]
+    result = np.empty([n, n], dtype=complex)
+    for i in range(n):
+        result[:, i] = data[:, 2 * i + 1] + 1j * data[:, 2 * i + 2]
     return result
 
 

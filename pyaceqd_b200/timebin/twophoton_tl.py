@@ -88,6 +88,90 @@ class TimeLocalTimebin:
         g2, total = self._integrate_pairs(grid)
         return np.round(self.t1, 6), g2, total, grid
 
+    # ------------------------------------------------------------------ the reference's Python-level routines
+    def fast_propagate(self, rho, n):
+        """``E^n rho`` from the binary powers of the stationary map (reference ``:730-735``)."""
+        for i, bit in enumerate(reversed(np.binary_repr(int(n)))):
+            if bit == "1":
+                rho = self.precalc_tls[i] @ rho
+        return rho
+
+    def propagate_tb_new(self, t_start, t_stop, rho, dm_tl, verbose=False):
+        """Explicit maps ``dm_tl[n]`` while they last, then the stationary fast-forward (reference ``:737-759``);
+        ``rho`` is the row-major vectorised density matrix, maps are ``[n, NL, NL]``."""
+        n_start = int(np.round(np.round(t_start, 6) / self.dt))
+        n_steps = int(np.round(np.round(t_stop, 6) / self.dt)) - n_start
+        steps_dm = max(0, min(len(dm_tl) - n_start, n_steps))
+        if verbose:
+            print(f"propagate from {t_start} to {t_stop} using {n_steps} steps of {self.dt}, of which {steps_dm} are from dm")
+        for k in range(steps_dm):
+            rho = dm_tl[n_start + k] @ rho
+        return self.fast_propagate(rho, max(0, n_steps - steps_dm))
+
+    def four_time_tl(self, sigma_1, sigma_2, sigma_3, sigma_4, supply_mats=False):
+        """``Tr[s4 s3 (... rho s1 ... s2 ...)]`` with ``s1`` at ``t1`` and ``s2`` at ``t2`` from the right in the
+        early bin, ``s3`` at ``t1 + tb`` and ``s4`` at ``t2 + tb`` from the left in the late bin, for all
+        ``t1 <= t2`` (reference ``:925-1013``, a double Python loop there; here the chain kernel through the
+        four-operator routine).  Returns ``(t1, G2(t1), integral * gamma_e^2, G2(t1, t2))``."""
+        ops = [np.asarray(o, dtype=complex) if supply_mats else op_to_matrix(o) for o in (sigma_1, sigma_2, sigma_3, sigma_4)]
+        tl_map, dm_1, dm_2 = self._calc_dynmaps()
+        rho0 = self.get_initial_state()
+        dim = rho0.shape[0]
+        self.t1 = np.round(self.t1, 6)
+        grid = timebin_tl.four_time(self._f(dm_1), self._f(dm_2), rho0.reshape(dim * dim), self.t1,
+                                    self._f(self.precalc_tls), np.round(self.dt, 6), dim, *ops, self.tb)
+        g2, total = self._integrate_pairs(grid)
+        return self.t1, g2, total, grid
+
+    def eell_tl(self):
+        """``<ee|rho|ll>`` through :meth:`four_time_tl` (reference ``:615-627``)."""
+        t1, g2, eell, grid = self.four_time_tl(self.sigma_bdag, self.sigma_xdag, self.sigma_b, self.sigma_x)
+        return t1, g2, eell, g2, g2 * 0, grid
+
+    def dynamics_tl(self):
+        """Density matrix on the fine grid through both bins from the time-local maps (reference ``:761-790``)."""
+        tl_map, dm_1, dm_2 = self._calc_dynmaps()
+        rho0 = self.get_initial_state()
+        dim = rho0.shape[0]
+        t = np.arange(0, 2 * self.tb, self.dt)
+        rho_t = np.zeros((len(t), dim, dim), dtype=complex)
+        rho_t[0] = rho0
+        n_tb = int(self.tb / self.dt)
+        for i in range(len(t) - 1):
+            k, dm = (i, dm_1) if i < n_tb else (i - n_tb, dm_2)
+            rho_t[i + 1] = self.propagate_tb_new(k * self.dt, (k + 1) * self.dt, rho_t[i].reshape(dim * dim), dm).reshape(dim, dim)
+        return t, rho_t
+
+    def dynamics_tl_t1(self):
+        """Density matrix on the ``t1`` grid through both bins (reference ``:822-843``)."""
+        tl_map, dm_1, dm_2 = self._calc_dynmaps()
+        rho0 = self.get_initial_state()
+        dim = rho0.shape[0]
+        t1 = np.round(self.t1, 6)
+        # real maps of a Hermiticity-preserving evolution: the unconjugated [NL, NL, n] layout, as the reference passes it
+        res = timebin_tl.dynamics_t1(np.asarray(dm_1).transpose(1, 2, 0), np.asarray(dm_2).transpose(1, 2, 0),
+                                     rho0.reshape(dim * dim), t1, np.asarray(self.precalc_tls).transpose(1, 2, 0),
+                                     self.dt, dim, self.tb)
+        return np.concatenate((t1, t1[1:] + self.tb)), np.array([res[:, k].reshape(dim, dim) for k in range(res.shape[1])])
+
+    def dynamics_tl_t1_t2_f(self, _t1, _t2, sigma_1, sigma_2, sigma_3, take_IDs=False):
+        """As :meth:`dynamics_tl_t1` with ``sigma_1`` / ``sigma_2`` from the right at ``_t1`` / ``_t2`` in the early bin
+        and ``sigma_3`` from the left at ``_t1 + tb`` (reference ``:890-922``)."""
+        rho0 = self.get_initial_state()
+        dim = rho0.shape[0]
+        ops = [np.eye(dim, dtype=complex)] * 3 if take_IDs else [op_to_matrix(o) for o in (sigma_1, sigma_2, sigma_3)]
+        if not hasattr(self, "dm_tl1"):
+            self._calc_dynmaps()
+        t1 = np.round(self.t1, 6)
+        res = timebin_tl.dynamics_t1_t2(self._f(self.dm_tl1), self._f(self.dm_tl2), _t1, _t2, rho0.reshape(dim * dim), t1,
+                                        self._f(self.precalc_tls), self.dt, dim, self.tb, *ops)
+        out = np.array([res[:, k].reshape(dim, dim).T for k in range(res.shape[1])])
+        return np.concatenate((t1, t1[1:] + self.tb)), out
+
+    def dynamics_tl_t1_t2(self, t1, t2, sigma_1, sigma_2, sigma_3, take_IDs=False):
+        """The Python-level twin of :meth:`dynamics_tl_t1_t2_f` (reference ``:845-888``) on the ``t1`` grid of this object."""
+        return self.dynamics_tl_t1_t2_f(t1, t2, sigma_1, sigma_2, sigma_3, take_IDs=take_IDs)
+
     def eell_tl_8ops(self):
         """The same element through the eight-operator routine (reference ``:672-704``)."""
         tl_map, dm_1, dm_2 = self._calc_dynmaps()

@@ -319,3 +319,106 @@ def read_calibration_file(calibration_file):
     dark_energy = dark - exciton
     return (fss_bright / 2, -fss_bright / 2, dark_energy + fss_dark / 2, dark_energy - fss_dark / 2,
             -(exciton - biexciton), gamma_e, gamma_b, 0, *g)
+
+
+# ---------------------------------------------------------------------------------------------- post-processing helpers
+def ghz_to_mev(ghz):
+    """Frequency in GHz -> photon energy in meV, ``E = h f`` (reference ``tools.py:746-757``)."""
+    return ghz * (2 * np.pi * 0.6582119514) * 1e-3
+
+
+def mev_to_ghz(mev):
+    """Photon energy in meV -> frequency in GHz (reference ``tools.py:759-770``)."""
+    return mev / ((2 * np.pi * 0.6582119514) * 1e-3)
+
+
+def rotate_basis(rho, U_rot):
+    """``U rho U^dagger``: density matrix in a rotated basis, e.g. the field-mixed eigenbasis of the six-level
+    system (reference ``tools.py:375-398``)."""
+    return U_rot @ rho @ np.conj(U_rot).T
+
+
+def resample(x, y, z, s_x, s_y):
+    """Every ``s_x``-th / ``s_y``-th sample of a map ``z[y, x]`` and of its axes (reference ``tools.py:352-373``)."""
+    ix = (np.arange(int(len(x) / s_x)) * s_x).astype(int)
+    iy = (np.arange(int(len(y) / s_y)) * s_y).astype(int)
+    return np.asarray(x, dtype=float)[ix], np.asarray(y, dtype=float)[iy], np.asarray(z, dtype=float)[np.ix_(iy, ix)]
+
+
+def with_filename(func):
+    """Decorator of :func:`get_sparse_range`: with ``filename`` the result comes back as ``(range, filename +
+    "_sparse" | "_inverse")`` (reference ``tools.py:772-788``)."""
+    import functools
+
+    @functools.wraps(func)
+    def wrapper(start=0.1, stop=12, num=101, nth=10, get_inverse=False, round_to=8, filename=None):
+        result = func(start, stop, num, nth, get_inverse, round_to)
+        if filename is not None:
+            return result, filename + ("_inverse" if get_inverse else "_sparse")
+        return result
+    return wrapper
+
+
+@with_filename
+def get_sparse_range(start=0.1, stop=12, num=101, nth=10, get_inverse=False, round_to=8):
+    """Every ``nth`` point of ``linspace(start, stop, num)``, or with ``get_inverse`` all the others, sorted and
+    rounded (reference ``tools.py:790-802``): coarse and fill-in halves of a parameter sweep."""
+    full = np.linspace(start, stop, num)
+    if get_inverse:
+        keep = np.ones(num, dtype=bool)
+        keep[::nth] = False
+        return np.round(np.sort(full[keep]), round_to)
+    return full[::nth]
+
+
+def get_union(arr_x1, arr_x2, arr_z1, arr_z2, axis_z=None):
+    """Merge two sweeps: sorted union of the abscissae and the values reordered with it, duplicates taken from the first
+    sweep (reference ``tools.py:804-831``)."""
+    z1, z2 = np.asarray(arr_z1), np.asarray(arr_z2)
+    if z1.ndim == 1:
+        z1 = z1.reshape(len(arr_x1), 1)
+    if z2.ndim == 1:
+        z2 = z2.reshape(len(arr_x2), 1)
+    if axis_z is None:
+        if z1.shape[0] == z1.shape[1]:
+            raise ValueError("Cannot determine axis for z arrays.")
+        if z1.shape[0] == len(arr_x1) and z2.shape[0] == len(arr_x2):
+            axis_z = 0
+        elif z1.shape[1] == len(arr_x1) and z2.shape[1] == len(arr_x2):
+            axis_z = 1
+        else:
+            raise ValueError("Cannot determine axis for z arrays.")
+    x, idx = np.unique(np.concatenate((arr_x1, arr_x2)), return_index=True)
+    return x, np.take(np.concatenate((z1, z2), axis=axis_z), idx, axis=axis_z)
+
+
+def check_tlmap_frobenius(tl_map, times, filename="dynmap_tl_frobenius", xlim=25, check_against_i=None):
+    """Frobenius distances between adjacent time-local maps (or to map ``check_against_i``) and the norms of the maps:
+    how fast they become stationary (reference ``tools.py:677-743`` plots them; here the numbers are returned and the
+    plots are written only where matplotlib is available)."""
+    tl_map = np.asarray(tl_map)
+    times = np.asarray(times, dtype=float)
+    n = len(times) - 3
+    if check_against_i is not None:
+        diffs = np.array([np.linalg.norm(tl_map[i] - tl_map[check_against_i]) for i in range(n)])
+    else:
+        diffs = np.array([np.linalg.norm(tl_map[i] - tl_map[i + 1]) for i in range(n)])
+    norms = np.array([np.linalg.norm(m) for m in tl_map])
+    try:
+        import matplotlib.pyplot as plt
+    except ImportError:
+        return diffs, norms
+    ix = np.where((times - times[0] > 0) & (times - times[0] < xlim))[0]
+    ix = ix[ix - 1 < len(diffs)]
+    for ydata, suffix, title in ((diffs[ix - 1], "_diff", "difference of adjacent dynamical maps"),
+                                 (norms[np.minimum(ix, len(norms) - 1)], "_norm", "norm of dynamical maps")):
+        plt.clf()
+        plt.xlabel("Time")
+        plt.ylabel("Norm")
+        plt.title(title)
+        plt.plot(times[ix] - times[0], ydata)
+        plt.yscale("log")
+        plt.xlim(0, xlim)
+        plt.savefig(filename + suffix + ".png")
+    plt.clf()
+    return diffs, norms

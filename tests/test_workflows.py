@@ -476,3 +476,52 @@ def test_tail_rows_equal_tail_of_full_run():
             tails = eng.run_jobs(prob, pt, mk(11), kernel=kernel, fork=fork)
             for f, t in zip(full, tails):
                 assert t.shape[1] == 11 and np.abs(f[:, -11:] - t).max() < 1e-12
+
+
+def test_timebin_four_time_tl_kernel_route_equals_the_python_route(tmp_path):
+    """``four_time_tl`` (reference ``timebin/twophoton_new.py:925-1013``: a double Python loop over (t1, t2) of
+    ``propagate_tb_new`` calls with operator insertions and a trace) against the chain-kernel route this package
+    gives the same method, on the oracle backend; plus the time-local dynamics helpers."""
+    from pyaceqd_b200.four_level_system.linear import biexciton
+    from pyaceqd_b200.timebin.twophoton_new import TwoPhotonTimebinNew
+    from pyaceqd_b200.tools import op_to_matrix
+    tb = 4.0
+    p1 = ChirpedPulse(tau_0=0.25, e_start=-2.0, alpha=0, t0=1.5, e0=4.0)
+    p2 = ChirpedPulse(tau_0=0.25, e_start=-2.0, alpha=0, t0=1.5 + tb, e0=4.0)
+    opts = {"lindblad": True, "gamma_e": 0.5, "delta_b": 4.0, "phonons": False, "temp_dir": str(tmp_path),
+            "initial": "|0><0|_4"}
+    with oracle_backend():
+        tbn = TwoPhotonTimebinNew(biexciton, "|0><1|_4", "|1><0|_4", "|1><3|_4", "|3><1|_4", p1, p2, dt=0.25, dim=4,
+                                  tb=tb, dt_small=0.5, n_tbig=2, simple_exp=False, gaussian_t=3.0, simple_t=True,
+                                  options=opts)
+        t1, g2, eell, grid = tbn.four_time_tl(tbn.sigma_bdag, tbn.sigma_xdag, tbn.sigma_b, tbn.sigma_x)
+        _, _, eell_f, grid_f = tbn.eell_tl_f()
+        assert np.abs(grid - grid_f).max() < 1e-13 and abs(eell - eell_f) < 1e-13
+        assert tbn.eell_tl()[2] == eell
+        # the reference's Python loop, literally
+        s1, s2, s3, s4 = (op_to_matrix(o) for o in (tbn.sigma_bdag, tbn.sigma_xdag, tbn.sigma_b, tbn.sigma_x))
+        rho0 = tbn.get_initial_state()
+        dim = rho0.shape[0]
+        ref = np.zeros((len(t1), len(t1)), dtype=complex)
+        for i, a in enumerate(t1):
+            r = tbn.propagate_tb_new(0, a, rho0.copy().reshape(dim * dim), tbn.dm_tl1).reshape(dim, dim) @ s1
+            for j in range(i, len(t1)):
+                b = t1[j]
+                q = tbn.propagate_tb_new(a, b, r.copy().reshape(dim * dim), tbn.dm_tl1).reshape(dim, dim) @ s2
+                q = tbn.propagate_tb_new(b, tbn.tb, q.reshape(dim * dim), tbn.dm_tl1)
+                q = tbn.propagate_tb_new(0, a, q, tbn.dm_tl2).reshape(dim, dim)
+                q = s3 @ q
+                q = tbn.propagate_tb_new(a, b, q.reshape(dim * dim), tbn.dm_tl2).reshape(dim, dim)
+                ref[i, j] = np.trace(s4 @ q)
+        assert np.abs(ref).max() > 1e-3
+        assert np.abs(grid - ref).max() < 1e-12
+        # dynamics helpers: the t1-grid dynamics are the fine-grid dynamics at the t1 points, with trace 1
+        t_fine, rho_fine = tbn.dynamics_tl()
+        t_c, rho_c = tbn.dynamics_tl_t1()
+        assert len(t_c) == 2 * len(t1) - 1 and np.allclose(np.trace(rho_c, axis1=1, axis2=2), 1.0, atol=1e-10)
+        for k in (1, len(t1) - 1, len(t1) + 1):
+            i = int(round(t_c[k] / tbn.dt))
+            if i < len(t_fine):
+                assert np.abs(rho_c[k] - rho_fine[i]).max() < 1e-10
+        t_i, rho_i = tbn.dynamics_tl_t1_t2_f(t1[1], t1[2], None, None, None, take_IDs=True)
+        assert np.abs(rho_i - rho_c).max() < 1e-10
