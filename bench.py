@@ -332,7 +332,7 @@ def measure_small_chi(eng, chi, n_area, n_det, n_steps, dt, steps=5, warmup=3, h
     return rec
 
 
-def measure_strong(eng, world, rank, dist, n_t=48, chi=256, tb=24.0, dt=0.1):
+def measure_strong(eng, world, rank, dist, n_t=96, chi=256, tb=24.0, dt=0.1):
     """Strong scaling of ONE cfg5-shaped sweep (five-level dark model NL=25, chi=256, triangular
     (t1, t2) sweep with three multi-time operators per run, timebin/twophoton_new.py:515-557): every rank holds the
     same job list, `run_jobs_sharded` gives each a contiguous, step-balanced block and all-gathers the kept rows.
