@@ -140,7 +140,8 @@ __device__ __forceinline__ long long entry_of(const aceqd_traj& t, int i, long l
 
 // Main loop of one GEMM pass: MCV (<= MC) m-tiles x NB n-tiles of this warp over all k-chunks of
 // one PT block.  ALLNB: every n-tile of the warp is inside the slice (no predicates at all).
-template <int NB, int MCV, bool ALLNB>
+// CC: the warp owns 8 NB consecutive bond columns (see the fragment loads) instead of the n-tiles w, w + 8, ...
+template <int NB, int MCV, bool ALLNB, bool CC = false>
 __device__ __forceinline__ void gemm_pass(double (&cre)[MC][NB][2], double (&cim)[MC][NB][2],
                                           const double* const (&are)[MC], const double* const (&aim)[MC],
                                           const bool (&aval)[MC], const bool (&nbv)[NB],
@@ -161,11 +162,26 @@ __device__ __forceinline__ void gemm_pass(double (&cre)[MC][NB][2], double (&cim
             a_re[buf][mc] = aval[mc] ? are[mc][k] : 0.0;
             a_im[buf][mc] = aval[mc] ? aim[mc][k] : 0.0;
         }
+        if constexpr (CC && NB == 2) {
+            // two n-tiles per warp: the warp owns 16 CONSECUTIVE bond columns, column 16 w + 2 g + nb is n-index g of its
+            // n-tile nb, and the two fragments of a lane are one 16-byte load per plane (conflict-free: the four k-rows of
+            // a quarter-warp sit 32 bytes apart modulo 128)
+            const int bo = (4 * ks + tq) * strideB + 2 * (8 * warp + g);
+            if (ALLNB || nbv[0]) {
+                const double2 vr = *reinterpret_cast<const double2*>(bre + bo);
+                const double2 vi = *reinterpret_cast<const double2*>(bim + bo);
+                b_re[buf][0] = vr.x; b_re[buf][1] = vr.y;
+                b_im[buf][0] = vi.x; b_im[buf][1] = vi.y;
+            } else {
+                b_re[buf][0] = b_re[buf][1] = b_im[buf][0] = b_im[buf][1] = 0.0;
+            }
+        } else {
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
             const int bo = (4 * ks + tq) * strideB + 8 * (warp + N_COMPUTE_WARPS * nb) + g;
             b_re[buf][nb] = (ALLNB || nbv[nb]) ? bre[bo] : 0.0;
             b_im[buf][nb] = (ALLNB || nbv[nb]) ? bim[bo] : 0.0;
+        }
         }
     };
     auto batch = [&](int buf) {

@@ -862,8 +862,11 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
         }
         bool nbv[NB];
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb)     // ring-less tiles: a warp owns 8 NB CONSECUTIVE columns (gemm_pass_global), all or none
-            nbv[nb] = (GPT ? 8 * NB * warp : 8 * (warp + N_COMPUTE_WARPS * nb)) < nout;
+        // ring-less tiles and two n-tiles per warp: a warp owns 8 NB CONSECUTIVE columns (vector loads of the PT fragments
+        // in gemm_pass_global / gemm_pass), all or none of them inside the slice
+        constexpr bool CC = GPT || NB == 2;
+        for (int nb = 0; nb < NB; ++nb)
+            nbv[nb] = (CC ? 8 * NB * warp : 8 * (warp + N_COMPUTE_WARPS * nb)) < nout;
         bool gpt_free_waited = false;    // ring-less instantiation: thread 0 is the pusher
         // epilogue of one pass: new rows into the state (in place) + this warp's closure partials
         auto epilogue = [&](const PassDesc& pd, const double (&cre)[MC][NB][2], const double (&cim)[MC][NB][2]) {
@@ -879,7 +882,7 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
                 wr[mc] = av && (full_act || (t.n_steps >= 0 && n >= t.step0 && n < t.step0 + t.n_steps));
                 pr[mc] = pi[mc] = 0.0;
             }
-            if constexpr (GPT) {
+            if constexpr (GPT || NB == 2) {
                 // accumulator (nb, e) of this lane is column cb + NB e + nb: 2 NB consecutive columns per lane
                 const int cb = 8 * NB * warp + 2 * NB * tq;
                 if (nbv[0]) {
@@ -1004,16 +1007,16 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
             } else if (allnb && mcn == MC)
-                gemm_pass<NB, MC, true>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
+                gemm_pass<NB, MC, true, NB == 2>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
                                         warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
             else if (allnb)
-                gemm_pass<NB, 1, true>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
+                gemm_pass<NB, 1, true, NB == 2>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
                                        warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
             else if (mcn == MC)
-                gemm_pass<NB, MC, false>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
+                gemm_pass<NB, MC, false, NB == 2>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
                                          warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
             else
-                gemm_pass<NB, 1, false>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
+                gemm_pass<NB, 1, false, NB == 2>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
                                         warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
             }
             TICK(7);
