@@ -864,7 +864,9 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
 #pragma unroll
         // ring-less tiles and two n-tiles per warp: a warp owns 8 NB CONSECUTIVE columns (vector loads of the PT fragments
         // in gemm_pass_global / gemm_pass), all or none of them inside the slice
-        constexpr bool CC = GPT || NB == 2;
+        // (not for the two-level instantiation KSU_T = 1: its passes always carry two full m-tiles and it measured 0.3 %
+        // slower with the vector loads, 31.30 against 31.19 ms on cfg2, where the thin passes of larger systems gain 1-2 %)
+        constexpr bool CC = GPT || (NB == 2 && KSU_T > 1);
         for (int nb = 0; nb < NB; ++nb)
             nbv[nb] = (CC ? 8 * NB * warp : 8 * (warp + N_COMPUTE_WARPS * nb)) < nout;
         bool gpt_free_waited = false;    // ring-less instantiation: thread 0 is the pusher
@@ -882,7 +884,7 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
                 wr[mc] = av && (full_act || (t.n_steps >= 0 && n >= t.step0 && n < t.step0 + t.n_steps));
                 pr[mc] = pi[mc] = 0.0;
             }
-            if constexpr (GPT || NB == 2) {
+            if constexpr (GPT || (NB == 2 && KSU_T > 1)) {
                 // accumulator (nb, e) of this lane is column cb + NB e + nb: 2 NB consecutive columns per lane
                 const int cb = 8 * NB * warp + 2 * NB * tq;
                 if (nbv[0]) {
@@ -1007,16 +1009,16 @@ __global__ void __launch_bounds__(GPT ? N_COMPUTE_WARPS * 32 : STEP_THREADS, 1) 
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
             } else if (allnb && mcn == MC)
-                gemm_pass<NB, MC, true, NB == 2>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
+                gemm_pass<NB, MC, true, (NB == 2 && KSU_T > 1)>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
                                         warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
             else if (allnb)
-                gemm_pass<NB, 1, true, NB == 2>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
+                gemm_pass<NB, 1, true, (NB == 2 && KSU_T > 1)>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
                                        warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
             else if (mcn == MC)
-                gemm_pass<NB, MC, false, NB == 2>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
+                gemm_pass<NB, MC, false, (NB == 2 && KSU_T > 1)>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
                                          warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
             else
-                gemm_pass<NB, 1, false, NB == 2>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
+                gemm_pass<NB, 1, false, (NB == 2 && KSU_T > 1)>(cre, cim, are, aim, aval, nbv, chunks, p.pt.chunk_doubles, strideB, nch,
                                         warp, g, tq, bar_full, bar_empty, stage, phase, stages, lane);
             }
             TICK(7);
