@@ -642,7 +642,8 @@ __device__ int expm_warp(WMat<NP>* M, int n, int lane, const LaneOffs& lo) {
     if (lane < n)
         for (int i = 0; i < n; ++i) {
             const double x = A.re[i * LD + lane], y = A.im()[i * LD + lane];
-            cs += sqrt(x * x + y * y);
+            cs += fabs(x) + fabs(y);     // >= |a|, <= sqrt(2) |a|: a bound is all the scaling rule needs, and a
+                                         // double-precision square root is ~40 instructions on the only warp of its sub-partition
         }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cs = fmax(cs, __shfl_xor_sync(0xffffffffu, cs, o));
@@ -960,7 +961,7 @@ __device__ int expm_block(WMat<NP>* M, double* red, int n, int tid, const BlockO
         if (j < n)
             for (int i = part; i < n; i += BM_THREADS / 64) {
                 const double x = A.re[i * LD + j], y = A.im()[i * LD + j];
-                ps += sqrt(x * x + y * y);
+                ps += fabs(x) + fabs(y);     // a bound on |a| (see expm_warp)
             }
         red[64 + part * 64 + j] = ps;
     }
